@@ -1,0 +1,176 @@
+/* ppx.h -- C ABI of the B200-native engine for the ALS / pairwise-perturbation (PP) sweeps of CP and Tucker
+ * decomposition.  This is the drop-in boundary: the reference (LinjianMa/pairwise-perturbation) performs every
+ * operation below as a Cyclops-CTF Einstein-string expression or a ScaLAPACK-backed Matrix method; each entry point
+ * names the reference call site (file:line under /root/reference) it replaces.
+ *
+ * Conventions
+ *   - every tensor / matrix argument is a DEVICE pointer to dense FP64 data in the reference's (CTF) global order:
+ *     first index fastest; a factor matrix W is s x R, column r contiguous (leading dimension ldw >= s);
+ *   - an intermediate "T" of the dimension tree keeps its remaining tensor modes in increasing order and the rank
+ *     index LAST (reference: common.cxx:44,53; als_CP.cxx:336);
+ *   - every call is asynchronous on the context's stream and returns 0 (PPX_OK) or a negative PPX_E* code;
+ *     ppx_last_error(ctx) gives the message.  No exceptions cross this boundary, no torch / C++ types appear in it;
+ *   - buffers are caller-owned; one host thread per context.
+ *   - there is NO CPU fallback: without a CUDA device ppx_ctx_create fails with PPX_ECUDA.
+ */
+#ifndef PPX_H_
+#define PPX_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ppx_ctx ppx_ctx;
+
+enum {
+  PPX_OK = 0,
+  PPX_EINVAL = -1,       /* bad argument */
+  PPX_ECUDA = -2,        /* CUDA runtime error (message has cudaGetErrorString) */
+  PPX_ENOMEM = -3,       /* workspace / device allocation failed */
+  PPX_ENCCL = -4,        /* NCCL missing or failed */
+  PPX_EUNSUPPORTED = -5, /* shape outside what the kernels handle */
+  PPX_ENUMERIC = -6      /* factorisation broke down (non-SPD matrix in Cholesky, ...) */
+};
+
+enum { PPX_SOLVE_CHOL = 0, PPX_SOLVE_SVD_PINV = 1 };
+
+/* ---- context (replaces CTF::World; test_ALS.cxx:200) ------------------------------------------------------- */
+const char *ppx_version(void);
+/* stream: a cudaStream_t to run on, or NULL to create a private non-blocking stream. */
+int ppx_ctx_create(int device, void *stream, size_t workspace_bytes, ppx_ctx **out);
+int ppx_ctx_destroy(ppx_ctx *ctx);
+int ppx_sync(ppx_ctx *ctx);
+const char *ppx_last_error(ppx_ctx *ctx);
+void *ppx_stream(ppx_ctx *ctx);
+int ppx_device(ppx_ctx *ctx);
+int ppx_sm_count(ppx_ctx *ctx);
+/* number of kernels this context has launched so far (bench.py's gpu_launches). */
+int64_t ppx_launch_count(ppx_ctx *ctx);
+
+/* ---- memory (so the C++ host layer needs no CUDA headers) -------------------------------------------------- */
+int ppx_malloc(ppx_ctx *ctx, size_t bytes, void **dptr);
+int ppx_free(ppx_ctx *ctx, void *dptr);
+int ppx_host_alloc(ppx_ctx *ctx, size_t bytes, void **hptr); /* pinned */
+int ppx_host_free(ppx_ctx *ctx, void *hptr);
+int ppx_memcpy_h2d(ppx_ctx *ctx, void *dst, const void *src, size_t bytes); /* async on the stream */
+int ppx_memcpy_d2h(ppx_ctx *ctx, void *dst, const void *src, size_t bytes); /* async; ppx_sync before reading */
+int ppx_memcpy_d2d(ppx_ctx *ctx, void *dst, const void *src, size_t bytes);
+int ppx_memset_zero(ppx_ctx *ctx, void *dst, size_t bytes);
+int ppx_mem_info(ppx_ctx *ctx, size_t *free_bytes, size_t *total_bytes);
+
+/* ---- events / graphs (timing as als_CP.cxx:167,189 does with MPI_Wtime; CUDA graphs for the PP sweep) ------- */
+int ppx_event_create(ppx_ctx *ctx, void **ev);
+int ppx_event_destroy(ppx_ctx *ctx, void *ev);
+int ppx_event_record(ppx_ctx *ctx, void *ev);
+int ppx_event_elapsed_ms(ppx_ctx *ctx, void *ev_start, void *ev_stop, float *ms); /* synchronises ev_stop */
+int ppx_graph_begin(ppx_ctx *ctx);               /* start stream capture */
+int ppx_graph_end(ppx_ctx *ctx, void **graph);   /* end capture, instantiate; *graph is an executable graph */
+int ppx_graph_launch(ppx_ctx *ctx, void *graph);
+int ppx_graph_destroy(ppx_ctx *ctx, void *graph);
+
+/* ---- deterministic synthetic data (replaces fill_random; test_ALS.cxx:272,282,337-338) ---------------------- */
+/* out[i] = lo + (hi-lo) * u(seed, tensor_id, start+i), u = SplitMix64 finaliser of the counter (53 bits). */
+int ppx_fill_uniform(ppx_ctx *ctx, double *out, int64_t n, uint64_t seed, uint64_t tensor_id, int64_t start,
+                     double lo, double hi);
+
+/* ---- K1: first tensor-times-matrix contraction of the dimension tree ---------------------------------------
+ * out[rest, r] = sum_x V[.., x, ..] * Wx[x, r]      (remaining modes in order, rank last)
+ * replaces common.cxx:56, als_CP.cxx:378-379, cp_dt_optimizer.cxx:158-159, cp_msdt_optimizer.cxx:142-143,
+ * common.cxx:963.  FP64 tensor-core (DMMA) GEMM. */
+int ppx_ttm_first(ppx_ctx *ctx, const double *V, const int64_t *lens, int N, int x, const double *Wx, int64_t ldw,
+                  int R, double *out);
+
+/* ---- K2: Hadamard-batched contraction (rank index in all three operands) -----------------------------------
+ * out[rest', r] = sum_x T[.., x, .., r] * Wx[x, r];  lens = the k non-rank modes of T.
+ * replaces common.cxx:83,128; als_CP.cxx:258-259,407-408; cp_dt_optimizer.cxx:184-185. */
+int ppx_mttv(ppx_ctx *ctx, const double *T, const int64_t *lens, int k, int x, const double *Wx, int64_t ldw, int R,
+             double *out);
+/* two factors at once (leaf under a 3-mode node): out[rest'', r] = sum_{x1,x2} T * W1[x1,r] * W2[x2,r], x1 < x2.
+ * replaces als_CP.cxx:281-283. */
+int ppx_mttv2(ppx_ctx *ctx, const double *T, const int64_t *lens, int k, int x1, const double *W1, int64_t ldw1,
+              int x2, const double *W2, int64_t ldw2, int R, double *out);
+/* fused K1 -> K2 when the level-1 intermediate has a single consumer: contracts x1 by GEMM and x2 (x2 != x1)
+ * Hadamard-batched without writing the level-1 tensor (N=4 ALS tree: abcd x W_c x W_d -> ab*). */
+int ppx_ttm_first_mttv(ppx_ctx *ctx, const double *V, const int64_t *lens, int N, int x1, const double *W1,
+                       int64_t ldw1, int x2, const double *W2, int64_t ldw2, int R, double *out);
+
+/* ---- K3: PP first-order correction, all operators of one mode in one launch --------------------------------
+ * M_out[i', r] = M0[i', r] + sum_j  sum_q op_j[..] * dW_j[q, r]
+ * op_j is (which[j]==0) s_other[j] x s_i x R, contracted over its FIRST index (als_CP.cxx:785), or
+ *         (which[j]==1) s_i x s_other[j] x R, contracted over its SECOND index (als_CP.cxx:793).
+ * ops / dW / which / s_other are HOST arrays of n_ops entries (device pointers inside).
+ * replaces als_CP.cxx:778-794. */
+int ppx_pp_correct(ppx_ctx *ctx, const double *M0, const double *const *ops, const int *which,
+                   const double *const *dW, const int64_t *s_other, int n_ops, int64_t s_i, int R, double *M_out);
+
+/* ---- K4: Gram and Hadamard of Grams ----------------------------------------------------------------------- */
+/* G = W^T W (R x R).  replaces the W["ki"]*W["kj"] factors of als_CP.cxx:288-291. */
+int ppx_gram(ppx_ctx *ctx, const double *W, int64_t s, int64_t ldw, int R, double *G);
+/* S = Hadamard_{j != skip} G[j] + lambda*I.  G: HOST array of nG device pointers, multiplied in array order.
+ * replaces als_CP.cxx:288-292,573-579,796-802; cp_als_optimizer.cxx:33-37. */
+int ppx_hadamard_grams(ppx_ctx *ctx, const double *const *G, int nG, int skip, int R, double lambda, double *S);
+
+/* ---- K5 + K6: R x R solve fused with gradient, dW and norms ------------------------------------------------
+ * grad_out = -M + W_old * S                       (als_CP.cxx:296,582,811; cp_dt_optimizer.cxx:229-230)
+ * W_new    = M * S^-1                             (common.cxx:710-725 SVD_PINV | 727-737 CHOL)
+ * if W_init: dW_out = ratio_step*(W_new - W_init); if ratio_step != 1: W_new = W_init + dW_out (common.cxx:753-756)
+ * sq_norms_out (device, 3 doubles, may be NULL) = { ||W_new||_F^2, ||dW_out||_F^2, ||grad_out||_F^2 }.
+ * W is read (old) and overwritten (new).  grad_out / dW_out / W_init may be NULL. */
+int ppx_solve_update(ppx_ctx *ctx, const double *M, const double *S, double *W, int64_t s, int R,
+                     const double *W_init, double ratio_step, int mode, double *grad_out, double *dW_out,
+                     double *sq_norms_out);
+/* Normalize (common.cxx:680-688): every W_i scaled to the geometric mean of the Frobenius norms.  W, s: HOST
+ * arrays.  If G != NULL, G[i] (cached Gram of W_i) is rescaled consistently. */
+int ppx_normalize(ppx_ctx *ctx, double *const *W, const int64_t *s, int N, int R, double *const *G);
+/* out_dev[j] = sum of squares of X[j][0..n[j]) for j < count (norm2()^2; als_CP.cxx:176-178,598-600). */
+int ppx_sqnorms(ppx_ctx *ctx, const double *const *X, const int64_t *n, int count, double *out_dev);
+/* dW = W - W_prev; W_prev = W; sq_out_dev = { ||dW||^2, ||W||^2 }  (als_CP.cxx:596-600). */
+int ppx_diff_update(ppx_ctx *ctx, const double *W, double *W_prev, double *dW, int64_t n, double *sq_out_dev);
+/* y = alpha*x + beta*y  (elementwise; M += F, als_CP.cxx:294). */
+int ppx_axpby(ppx_ctx *ctx, double alpha, const double *x, double beta, double *y, int64_t n);
+
+/* ---- K7: residual ||V - [[W_0..W_{N-1}]]||_F without materialising the reconstruction -----------------------
+ * sq_out_dev[0] = sum of squares of the difference.  replaces common.cxx:135-197 + als_CP.cxx:183-187. */
+int ppx_cp_residual(ppx_ctx *ctx, const double *V, const int64_t *lens, int N, const double *const *W, int R,
+                    double *sq_out_dev);
+/* V_out = [[W_0..W_{N-1}]]  (build_V, common.cxx:135-197; used to make the synthetic tensor 'r'). */
+int ppx_cp_reconstruct(ppx_ctx *ctx, const int64_t *lens, int N, const double *const *W, int R, double *V_out);
+
+/* ---- Tucker (K8-K11) --------------------------------------------------------------------------------------- */
+/* out[.., q, ..] = sum_x T[.., x, ..] * Wx[x, q]  (rank replaces mode x in place).
+ * replaces als_Tucker.cxx:102,224,372,389-391,464-465,845,858. */
+int ppx_ttm(ppx_ctx *ctx, const double *T, const int64_t *lens, int k, int x, const double *Wx, int64_t ldw, int Q,
+            double *out);
+/* out += the same contraction (Tucker PP correction Y += T^(i,j) x_j dW_j, als_Tucker.cxx:845,858). */
+int ppx_ttm_acc(ppx_ctx *ctx, const double *T, const int64_t *lens, int k, int x, const double *Wx, int64_t ldw,
+                int Q, double *out);
+/* MTM[p,q] = sum_rest T[..p..] T[..q..]  (common.cxx:205-223). */
+int ppx_unfold_gram(ppx_ctx *ctx, const double *T, const int64_t *lens, int k, int i, double *MTM);
+/* U (s x r) = eigenvectors of the r largest eigenvalues of the symmetric PSD matrix MTM (s x s), in decreasing
+ * order -- what MTM.svd(U,S,VT,r) returns for such a matrix (als_Tucker.cxx:20,402,627,868).  MTM is destroyed.
+ * evals_out (device, r doubles) may be NULL. */
+int ppx_sym_eig_topk(ppx_ctx *ctx, double *MTM, int64_t s, int r, double *U, double *evals_out);
+/* U <- U * diag(sign(diag(U^T Uref))), sign(b) = +1 if b > 0 else -1  (als_Tucker.cxx:632-643,874-885). */
+int ppx_sign_align(ppx_ctx *ctx, double *U, const double *Uref, int64_t s, int r);
+/* sq_out_dev[0] = sum of squares of (a - b), nothing else is written (Tucker residual, als_Tucker.cxx:309-310). */
+int ppx_diff_sqnorm(ppx_ctx *ctx, const double *a, const double *b, int64_t n, double *sq_out_dev);
+/* B (n x m) = A^T, A is m x n column-major (W_T, als_Tucker.cxx:296-300). */
+int ppx_transpose(ppx_ctx *ctx, const double *A, int64_t m, int64_t n, double *B);
+
+/* ---- K12: collectives (replace CTF-internal MPI) ------------------------------------------------------------ */
+/* rows [*begin, *end) of a mode of size s owned by `rank` of `nranks` (first s%nranks ranks get one more). Pure host. */
+int ppx_shard_range(int64_t s, int nranks, int rank, int64_t *begin, int64_t *end);
+int ppx_comm_unique_id(void *id128);                                  /* 128 bytes; rank 0 calls, others receive */
+int ppx_comm_init(ppx_ctx *ctx, const void *id128, int nranks, int rank);
+int ppx_comm_size(ppx_ctx *ctx);
+int ppx_comm_rank(ppx_ctx *ctx);
+/* in-place sum over ranks of n buffers as ONE NCCL group (bufs/sizes: HOST arrays; no-op when nranks == 1). */
+int ppx_allreduce_packed(ppx_ctx *ctx, double *const *bufs, const int64_t *sizes, int n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PPX_H_ */

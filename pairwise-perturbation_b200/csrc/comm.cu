@@ -1,0 +1,134 @@
+// K12 -- collectives.  The reference's communication is implicit in every CTF expression (MPI all-to-all
+// redistribution, SUMMA broadcasts, allreduce inside norm2).  With the tensor sharded along one mode the only
+// exchange left is the sum over ranks of each s x R partial MTTKRP, the R x R partial Grams and a few scalars:
+// ppx_allreduce_packed issues them as ONE NCCL group on the context stream.
+//
+// NCCL is loaded lazily with dlopen so that the single-GPU path has no link-time dependency on it (inside a
+// Python process that already imported torch this resolves to torch's bundled libnccl.so.2).
+#include <dlfcn.h>
+#include <string.h>
+#include "ppx_internal.h"
+
+namespace {
+
+typedef struct { char internal[128]; } ncclUniqueId_t;
+typedef void *ncclComm_p;
+typedef int ncclResult_e;  // 0 == ncclSuccess
+enum { NCCL_FLOAT64 = 8, NCCL_SUM = 0 };
+
+struct NcclApi {
+  void *lib = nullptr;
+  ncclResult_e (*GetUniqueId)(ncclUniqueId_t *) = nullptr;
+  ncclResult_e (*CommInitRank)(ncclComm_p *, int, ncclUniqueId_t, int) = nullptr;
+  ncclResult_e (*CommDestroy)(ncclComm_p) = nullptr;
+  ncclResult_e (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_p, cudaStream_t) = nullptr;
+  ncclResult_e (*GroupStart)() = nullptr;
+  ncclResult_e (*GroupEnd)() = nullptr;
+  const char *(*GetErrorString)(ncclResult_e) = nullptr;
+  bool tried = false;
+};
+NcclApi g_nccl;
+
+bool load_nccl() {
+  if (g_nccl.tried) return g_nccl.lib != nullptr;
+  g_nccl.tried = true;
+  const char *names[] = {"libnccl.so.2", "libnccl.so", nullptr};
+  for (int i = 0; names[i] && !g_nccl.lib; i++) g_nccl.lib = dlopen(names[i], RTLD_NOW | RTLD_GLOBAL);
+  if (!g_nccl.lib) return false;
+#define LOAD(sym) *(void **)(&g_nccl.sym) = dlsym(g_nccl.lib, "nccl" #sym)
+  LOAD(GetUniqueId);
+  LOAD(CommInitRank);
+  LOAD(CommDestroy);
+  LOAD(AllReduce);
+  LOAD(GroupStart);
+  LOAD(GroupEnd);
+  LOAD(GetErrorString);
+#undef LOAD
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.GroupStart || !g_nccl.GroupEnd) {
+    g_nccl.lib = nullptr;
+    return false;
+  }
+  return true;
+}
+
+}  // namespace
+
+void ppx_comm_destroy_internal(ppx_ctx *ctx) {
+  if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_p)ctx->comm);
+  ctx->comm = nullptr;
+}
+
+extern "C" {
+
+int ppx_comm_unique_id(void *id128) {
+  if (!id128) return PPX_EINVAL;
+  if (!load_nccl()) return ppx_set_err(nullptr, PPX_ENCCL, "libnccl.so.2 not found: %s", dlerror());
+  ncclUniqueId_t id;
+  ncclResult_e r = g_nccl.GetUniqueId(&id);
+  if (r) return ppx_set_err(nullptr, PPX_ENCCL, "ncclGetUniqueId failed (%d)", r);
+  memcpy(id128, &id, 128);
+  return PPX_OK;
+}
+
+int ppx_comm_init(ppx_ctx *ctx, const void *id128, int nranks, int rank) {
+  PPX_REQUIRE(ctx, nranks >= 1 && rank >= 0 && rank < nranks, "0 <= rank < nranks");
+  ctx->nranks = nranks;
+  ctx->rank = rank;
+  if (nranks == 1) return PPX_OK;
+  PPX_REQUIRE(ctx, id128 != nullptr, "id128 != NULL");
+  if (!load_nccl()) return ppx_set_err(ctx, PPX_ENCCL, "libnccl.so.2 not found");
+  ncclUniqueId_t id;
+  memcpy(&id, id128, 128);
+  PPX_CUDA(ctx, cudaSetDevice(ctx->device));
+  ncclComm_p comm = nullptr;
+  ncclResult_e r = g_nccl.CommInitRank(&comm, nranks, id, rank);
+  if (r)
+    return ppx_set_err(ctx, PPX_ENCCL, "ncclCommInitRank failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+  ctx->comm = comm;
+  return PPX_OK;
+}
+
+int ppx_comm_size(ppx_ctx *ctx) { return ctx->nranks; }
+int ppx_comm_rank(ppx_ctx *ctx) { return ctx->rank; }
+
+int ppx_allreduce_packed(ppx_ctx *ctx, double *const *bufs, const int64_t *sizes, int n) {
+  if (ctx->nranks == 1 || n == 0) return PPX_OK;
+  PPX_REQUIRE(ctx, ctx->comm != nullptr, "communicator initialised (ppx_comm_init)");
+  PPX_REQUIRE(ctx, bufs && sizes && n > 0, "bufs, sizes non-null");
+  ncclResult_e r = g_nccl.GroupStart();
+  for (int i = 0; i < n && !r; i++)
+    if (sizes[i] > 0)
+      r = g_nccl.AllReduce(bufs[i], bufs[i], (size_t)sizes[i], NCCL_FLOAT64, NCCL_SUM, (ncclComm_p)ctx->comm, ctx->stream);
+  ncclResult_e r2 = g_nccl.GroupEnd();
+  if (r || r2)
+    return ppx_set_err(ctx, PPX_ENCCL, "ncclAllReduce failed: %s",
+                       g_nccl.GetErrorString ? g_nccl.GetErrorString(r ? r : r2) : "?");
+  ctx->launches += n;
+  return PPX_OK;
+}
+
+int ppx_ttm_first_mttv(ppx_ctx *ctx, const double *V, const int64_t *lens, int N, int x1, const double *W1,
+                       int64_t ldw1, int x2, const double *W2, int64_t ldw2, int R, double *out) {
+  // Round-1 implementation: the two contractions back to back through the context workspace (same result, the
+  // level-1 tensor still travels through HBM once).  The single-kernel fusion is tracked in DESIGN.md.
+  PPX_REQUIRE(ctx, V && lens && W1 && W2 && out, "non-null pointers");
+  PPX_REQUIRE(ctx, N >= 2 && N <= 16 && x1 >= 0 && x1 < N && x2 >= 0 && x2 < N && x1 != x2, "x1 != x2 in [0,N)");
+  int64_t P = 1;
+  for (int i = 0; i < N; i++) P *= lens[i];
+  const int64_t n1 = P / lens[x1] * R;
+  ppx_ws_reset(ctx);
+  double *tmp = (double *)ppx_ws_alloc(ctx, sizeof(double) * (size_t)n1);
+  if (!tmp)
+    return ppx_set_err(ctx, PPX_ENOMEM, "ttm_first_mttv needs %lld bytes of workspace", (long long)(8 * n1));
+  size_t keep = ctx->ws_used;
+  int rc = ppx_ttm_first(ctx, V, lens, N, x1, W1, ldw1, R, tmp);
+  if (rc) return rc;
+  int64_t lens2[16];
+  int k = 0;
+  for (int i = 0; i < N; i++)
+    if (i != x1) lens2[k++] = lens[i];
+  (void)keep;
+  return ppx_mttv(ctx, tmp, lens2, k, x2 > x1 ? x2 - 1 : x2, W2, ldw2, R, out);
+}
+
+}  // extern "C"

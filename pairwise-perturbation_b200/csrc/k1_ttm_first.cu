@@ -1,0 +1,332 @@
+// K1 -- first tensor-times-matrix contraction of the dimension tree
+//     out[l, t, r] = sum_x V[l, x, t] * W[x, r]         (V viewed as L x X x Rt, first index fastest)
+// replaces the CTF expressions at common.cxx:56, als_CP.cxx:378-379, cp_dt_optimizer.cxx:158-159,
+// cp_msdt_optimizer.cxx:142-143 and common.cxx:963 of the reference.
+//
+// Design (sm_100a): FP64 has no tcgen05 kind, so the tensor pipe is reached through warp-level DMMA
+// (mma.sync.m8n8k4.f64 -> SASS DMMA.8x8x4, measured 37.1 TFLOP/s on B200 = the FP64 peak).  Persistent CTAs
+// stream 128-row x 16-deep tiles of V and the matching 16 x R slab of W through a multi-stage cp.async pipeline
+// that runs across tile boundaries (no drain between tiles); each of the 4 warps owns a 32 x (8*NT) accumulator
+// block in registers.  Shared-memory tiles are padded (ld = 4 mod 16 doubles) so every DMMA fragment load is
+// bank-conflict free.  Two CTAs per SM.
+//   KMAJOR = true : L == 1, the contracted mode is the fastest one (rows of V are contiguous along x).
+//   KMAJOR = false: L  > 1, rows m = (l, t) are contiguous along l for a fixed x.
+#include "ppx_internal.h"
+
+namespace {
+
+constexpr int BM = 128;   // rows of the output tile per CTA
+constexpr int BK = 16;    // depth of one pipeline stage
+constexpr int LDK = 20;   // padded leading dimension of k-contiguous tiles   (20 mod 16 == 4)
+constexpr int LDM = 132;  // padded leading dimension of m-contiguous tiles   (132 mod 16 == 4)
+constexpr int THREADS = 128;
+
+struct TtmParams {
+  const double *V;
+  const double *W;
+  double *out;
+  int64_t L, X, Rt, Mtot, ldw;
+  int R;
+  int num_tiles;
+  int nk;
+  int vecA, vecW;
+  int inplace;     // 0: out[m + Mtot*col] (rank last, CP) ; 1: out[l + L*(col + R*t)] (rank replaces mode x, Tucker)
+  int accumulate;  // out += result
+};
+
+template <bool KMAJOR>
+__host__ __device__ constexpr int a_doubles() {
+  return KMAJOR ? BM * LDK : BK * LDM;
+}
+
+template <int NT, bool KMAJOR, int STAGES>
+__global__ void __launch_bounds__(THREADS, 2) ttm_first_kernel(TtmParams p) {
+  extern __shared__ __align__(16) double smem[];
+  constexpr int A_D = a_doubles<KMAJOR>();
+  constexpr int W_D = 8 * NT * LDK;
+  constexpr int STAGE_D = A_D + W_D;
+
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t4 = lane & 3;
+  const int ncol0 = blockIdx.y * 64;
+
+  int my_tiles = 0;
+  if ((int)blockIdx.x < p.num_tiles) my_tiles = (p.num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1;
+  const int total = my_tiles * p.nk;
+
+  // ---- loader state -----------------------------------------------------------------------------------
+  int ld_tile_i = 0, ld_kc = 0;  // position of the next chunk to load
+  int cached_tile = -1;
+  int64_t off0 = 0, off1 = 0;  // M-major: global offsets (without the k term) of this thread's two rows
+  int nb0 = 0, nb1 = 0;        // bytes valid for row 0 / row 1 (0 or 8)
+
+  auto load_chunk = [&](int stage) {
+    const int tile = (int)blockIdx.x + ld_tile_i * (int)gridDim.x;
+    double *As = smem + stage * STAGE_D;
+    double *Ws = As + A_D;
+    const int64_t k0 = (int64_t)ld_kc * BK;
+    if (KMAJOR) {
+      const int kp = tid & 7, mb = tid >> 3;
+      const int64_t kg = k0 + 2 * kp;
+      const int kv = (kg + 1 < p.X) ? 2 : ((kg < p.X) ? 1 : 0);
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        const int m = mb + 16 * i;
+        const int64_t mg = (int64_t)tile * BM + m;
+        const bool mv = mg < p.Mtot;
+        const double *src = p.V + (mv ? (mg * p.X + kg) : 0);
+        double *dst = As + m * LDK + 2 * kp;
+        if (p.vecA) {
+          ppx_cp_async16(dst, (mv && kv) ? src : p.V, (mv && kv == 2) ? 16 : 0);
+        } else {
+          ppx_cp_async8(dst, (mv && kv >= 1) ? src : p.V, (mv && kv >= 1) ? 8 : 0);
+          ppx_cp_async8(dst + 1, (mv && kv == 2) ? src + 1 : p.V, (mv && kv == 2) ? 8 : 0);
+        }
+      }
+    } else {
+      const int ml = 2 * (tid & 63), kb = tid >> 6;
+      if (tile != cached_tile) {
+        cached_tile = tile;
+        const int64_t mg = (int64_t)tile * BM + ml;
+        nb0 = (mg < p.Mtot) ? 8 : 0;
+        nb1 = (mg + 1 < p.Mtot) ? 8 : 0;
+        const int64_t t0 = mg / p.L, l0 = mg - t0 * p.L;
+        off0 = nb0 ? (l0 + p.L * p.X * t0) : 0;
+        if (p.vecA) {
+          off1 = off0 + 1;
+        } else {
+          const int64_t t1 = (mg + 1) / p.L, l1 = (mg + 1) - t1 * p.L;
+          off1 = nb1 ? (l1 + p.L * p.X * t1) : 0;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        const int k = kb + 2 * i;
+        const int64_t kg = k0 + k;
+        const bool kvd = kg < p.X;
+        double *dst = As + k * LDM + ml;
+        if (p.vecA) {
+          const int nb = kvd ? (nb0 + nb1) : 0;
+          ppx_cp_async16(dst, nb ? (p.V + off0 + kg * p.L) : p.V, nb);
+        } else {
+          ppx_cp_async8(dst, (kvd && nb0) ? (p.V + off0 + kg * p.L) : p.V, kvd ? nb0 : 0);
+          ppx_cp_async8(dst + 1, (kvd && nb1) ? (p.V + off1 + kg * p.L) : p.V, kvd ? nb1 : 0);
+        }
+      }
+    }
+    // W slab: Ws[n][k], n < 8*NT, k < BK
+#pragma unroll
+    for (int i = 0; i < (8 * NT * 8 + THREADS - 1) / THREADS; i++) {
+      const int idx = tid + THREADS * i;
+      if (idx < 8 * NT * 8) {
+        const int n = idx >> 3, kp = idx & 7;
+        const int col = ncol0 + n;
+        const int64_t kg = k0 + 2 * kp;
+        const int kv = (col < p.R) ? ((kg + 1 < p.X) ? 2 : ((kg < p.X) ? 1 : 0)) : 0;
+        const double *src = p.W + (kv ? ((int64_t)col * p.ldw + kg) : 0);
+        double *dst = Ws + n * LDK + 2 * kp;
+        if (p.vecW) {
+          ppx_cp_async16(dst, src, kv == 2 ? 16 : 0);
+        } else {
+          ppx_cp_async8(dst, src, kv >= 1 ? 8 : 0);
+          ppx_cp_async8(dst + 1, kv == 2 ? src + 1 : p.W, kv == 2 ? 8 : 0);
+        }
+      }
+    }
+    if (++ld_kc == p.nk) {
+      ld_kc = 0;
+      ++ld_tile_i;
+    }
+  };
+
+  // ---- accumulators ---------------------------------------------------------------------------------------
+  double acc[4][NT][2];
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < NT; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  // ---- pipeline -------------------------------------------------------------------------------------------
+#pragma unroll
+  for (int c = 0; c < STAGES - 1; c++) {
+    if (c < total) load_chunk(c);
+    ppx_cp_async_commit();
+  }
+
+  int kc = 0, tile_i = 0;
+  for (int c = 0; c < total; c++) {
+    ppx_cp_async_wait<STAGES - 2>();
+    __syncthreads();
+    {
+      const int cn = c + STAGES - 1;
+      if (cn < total) load_chunk(cn % STAGES);
+      ppx_cp_async_commit();
+    }
+    const double *As = smem + (c % STAGES) * STAGE_D;
+    const double *Ws = As + A_D;
+#pragma unroll
+    for (int kk = 0; kk < BK / 4; kk++) {
+      double a[4], b[NT];
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        if (KMAJOR)
+          a[i] = As[(32 * warp + 8 * i + g) * LDK + 4 * kk + t4];
+        else
+          a[i] = As[(4 * kk + t4) * LDM + 32 * warp + 8 * i + g];
+      }
+#pragma unroll
+      for (int j = 0; j < NT; j++) b[j] = Ws[(8 * j + g) * LDK + 4 * kk + t4];
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < NT; j++) ppx_dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+    }
+    if (++kc == p.nk) {
+      // epilogue of this tile
+      const int tile = (int)blockIdx.x + tile_i * (int)gridDim.x;
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const int64_t mg = (int64_t)tile * BM + 32 * warp + 8 * i + g;
+        int64_t base = mg, cstride = p.Mtot;
+        if (p.inplace) {
+          const int64_t tt = mg / p.L, ll = mg - tt * p.L;
+          base = ll + p.L * (int64_t)p.R * tt;
+          cstride = p.L;
+        }
+#pragma unroll
+        for (int j = 0; j < NT; j++) {
+          const int col = ncol0 + 8 * j + 2 * t4;
+          if (mg < p.Mtot) {
+            if (col < p.R) {
+              double *o = p.out + base + cstride * col;
+              *o = p.accumulate ? (*o + acc[i][j][0]) : acc[i][j][0];
+            }
+            if (col + 1 < p.R) {
+              double *o = p.out + base + cstride * (col + 1);
+              *o = p.accumulate ? (*o + acc[i][j][1]) : acc[i][j][1];
+            }
+          }
+          acc[i][j][0] = acc[i][j][1] = 0.0;
+        }
+      }
+      kc = 0;
+      ++tile_i;
+    }
+  }
+  ppx_cp_async_wait<0>();
+}
+
+template <int NT, bool KMAJOR>
+constexpr size_t ttm_smem() {
+  return sizeof(double) * (KMAJOR ? 3 : 4) * (a_doubles<KMAJOR>() + 8 * NT * LDK);
+}
+
+template <int NT, bool KMAJOR>
+int launch_ttm(ppx_ctx *ctx, const TtmParams &p, int col_blocks) {
+  constexpr int STAGES = KMAJOR ? 3 : 4;
+  auto kern = ttm_first_kernel<NT, KMAJOR, STAGES>;
+  int gx = p.num_tiles < 2 * ctx->sm_count ? p.num_tiles : 2 * ctx->sm_count;
+  dim3 grid(gx, col_blocks);
+  kern<<<grid, THREADS, ttm_smem<NT, KMAJOR>(), ctx->stream>>>(p);
+  PPX_CHECK_LAUNCH(ctx);
+  return PPX_OK;
+}
+
+template <int NT, bool KMAJOR>
+cudaError_t init_one() {
+  return cudaFuncSetAttribute(ttm_first_kernel<NT, KMAJOR, (KMAJOR ? 3 : 4)>,
+                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ttm_smem<NT, KMAJOR>());
+}
+
+template <bool KMAJOR>
+int dispatch_nt(ppx_ctx *ctx, const TtmParams &p, int nt, int col_blocks) {
+  switch (nt) {
+    case 1: return launch_ttm<1, KMAJOR>(ctx, p, col_blocks);
+    case 2: return launch_ttm<2, KMAJOR>(ctx, p, col_blocks);
+    case 3: return launch_ttm<3, KMAJOR>(ctx, p, col_blocks);
+    case 4: return launch_ttm<4, KMAJOR>(ctx, p, col_blocks);
+    case 5: return launch_ttm<5, KMAJOR>(ctx, p, col_blocks);
+    case 6: return launch_ttm<6, KMAJOR>(ctx, p, col_blocks);
+    case 7: return launch_ttm<7, KMAJOR>(ctx, p, col_blocks);
+    default: return launch_ttm<8, KMAJOR>(ctx, p, col_blocks);
+  }
+}
+
+}  // namespace
+
+int ppx_k1_init(ppx_ctx *ctx) {
+  cudaError_t e = cudaSuccess;
+#define PPX_K1_INIT(NT)                                  \
+  if (e == cudaSuccess) e = init_one<NT, true>();        \
+  if (e == cudaSuccess) e = init_one<NT, false>();
+  PPX_K1_INIT(1) PPX_K1_INIT(2) PPX_K1_INIT(3) PPX_K1_INIT(4) PPX_K1_INIT(5) PPX_K1_INIT(6) PPX_K1_INIT(7) PPX_K1_INIT(8)
+#undef PPX_K1_INIT
+  if (e != cudaSuccess) return ppx_set_err(ctx, PPX_ECUDA, "k1 init: %s", cudaGetErrorString(e));
+  return PPX_OK;
+}
+
+// Shared by ppx_ttm_first (CP, rank last) and ppx_ttm / ppx_ttm_acc (Tucker, rank in place of mode x).
+int ppx_ttm_impl(ppx_ctx *ctx, const double *V, int64_t L, int64_t X, int64_t Rt, const double *Wx, int64_t ldw,
+                 int R, double *out, int inplace, int accumulate) {
+  TtmParams p;
+  p.V = V;
+  p.W = Wx;
+  p.out = out;
+  p.L = L;
+  p.X = X;
+  p.Rt = Rt;
+  p.Mtot = L * Rt;
+  p.ldw = ldw;
+  p.R = R;
+  p.inplace = inplace;
+  p.accumulate = accumulate;
+  if (p.Mtot == 0 || R == 0) return PPX_OK;
+  int64_t tiles = (p.Mtot + BM - 1) / BM;
+  if (tiles > 0x7fffffff / 2) return ppx_set_err(ctx, PPX_EUNSUPPORTED, "ttm_first: too many row tiles");
+  p.num_tiles = (int)tiles;
+  p.nk = (int)((X + BK - 1) / BK);
+  const bool kmajor = (L == 1);
+  const bool v16 = (((uintptr_t)V) & 15) == 0;
+  p.vecA = kmajor ? (v16 && (X % 2 == 0)) : (v16 && (L % 2 == 0));
+  p.vecW = ((((uintptr_t)Wx) & 15) == 0) && (ldw % 2 == 0);
+  const int col_blocks = (R + 63) / 64;
+  // all column blocks use the same NT (the widest); narrower last blocks just mask columns
+  const int ncols = R < 64 ? R : 64;
+  const int nt = (ncols + 7) / 8;
+  return kmajor ? dispatch_nt<true>(ctx, p, nt, col_blocks) : dispatch_nt<false>(ctx, p, nt, col_blocks);
+}
+
+extern "C" {
+
+int ppx_ttm_first(ppx_ctx *ctx, const double *V, const int64_t *lens, int N, int x, const double *Wx, int64_t ldw,
+                  int R, double *out) {
+  PPX_REQUIRE(ctx, V && lens && Wx && out, "non-null pointers");
+  PPX_REQUIRE(ctx, N >= 1 && N <= 16 && x >= 0 && x < N && R >= 1, "1 <= N <= 16, 0 <= x < N, R >= 1");
+  PPX_REQUIRE(ctx, ldw >= lens[x], "ldw >= lens[x]");
+  int64_t L, X, Rt;
+  ppx_split3(lens, N, x, &L, &X, &Rt);
+  return ppx_ttm_impl(ctx, V, L, X, Rt, Wx, ldw, R, out, 0, 0);
+}
+
+int ppx_ttm(ppx_ctx *ctx, const double *T, const int64_t *lens, int k, int x, const double *Wx, int64_t ldw, int Q,
+            double *out) {
+  PPX_REQUIRE(ctx, T && lens && Wx && out, "non-null pointers");
+  PPX_REQUIRE(ctx, k >= 1 && k <= 16 && x >= 0 && x < k && Q >= 1, "1 <= k <= 16, 0 <= x < k, Q >= 1");
+  PPX_REQUIRE(ctx, ldw >= lens[x], "ldw >= lens[x]");
+  int64_t L, X, Rt;
+  ppx_split3(lens, k, x, &L, &X, &Rt);
+  return ppx_ttm_impl(ctx, T, L, X, Rt, Wx, ldw, Q, out, 1, 0);
+}
+
+int ppx_ttm_acc(ppx_ctx *ctx, const double *T, const int64_t *lens, int k, int x, const double *Wx, int64_t ldw,
+                int Q, double *out) {
+  PPX_REQUIRE(ctx, T && lens && Wx && out, "non-null pointers");
+  PPX_REQUIRE(ctx, k >= 1 && k <= 16 && x >= 0 && x < k && Q >= 1, "1 <= k <= 16, 0 <= x < k, Q >= 1");
+  PPX_REQUIRE(ctx, ldw >= lens[x], "ldw >= lens[x]");
+  int64_t L, X, Rt;
+  ppx_split3(lens, k, x, &L, &X, &Rt);
+  return ppx_ttm_impl(ctx, T, L, X, Rt, Wx, ldw, Q, out, 1, 1);
+}
+
+}  // extern "C"

@@ -1,0 +1,242 @@
+// K2 -- Hadamard-batched contraction (the rank index appears in all three operands, so it is a batch of
+//       matrix-vector products, one per rank column: no operand reuse, HBM-bound)
+//     out[l, t, r] = sum_x T[l, x, t, r] * W[x, r]            (T viewed as L x X x Rt x R)
+// replaces common.cxx:83,128; als_CP.cxx:258-259,281-283,407-408; cp_dt_optimizer.cxx:184-185.
+// K3 -- PP first-order correction  M = M0 + sum_j op_j (x) dW_j   (als_CP.cxx:778-794), all operators of one
+//       mode in ONE launch, summed in registers / shared memory in a fixed order (deterministic).
+#include "ppx_internal.h"
+
+namespace {
+
+// ---- L == 1: contiguous dot products.  A group of G lanes owns one output. ---------------------------------
+template <int G>
+__global__ void __launch_bounds__(256) mttv_first_kernel(const double *__restrict__ T, const double *__restrict__ W,
+                                                         double *__restrict__ out, int64_t X, int64_t Rt, int R,
+                                                         int64_t ldw) {
+  const int64_t n_out = Rt * (int64_t)R;
+  const int lane_g = threadIdx.x % G;
+  int64_t o = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
+  const int64_t ostride = ((int64_t)gridDim.x * blockDim.x) / G;
+  const int64_t niter = (n_out + ostride - 1) / ostride;  // same trip count for every lane (shuffles below)
+  for (int64_t it = 0; it < niter; ++it, o += ostride) {
+    double acc = 0.0;
+    if (o < n_out) {
+      const int64_t r = o / Rt;
+      const double *tp = T + o * X;
+      const double *wp = W + r * ldw;
+      for (int64_t x = lane_g; x < X; x += G) acc += tp[x] * wp[x];
+    }
+#pragma unroll
+    for (int s = G / 2; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+    if (lane_g == 0 && o < n_out) out[o] = acc;
+  }
+}
+
+// ---- L >= 32: lanes along l (coalesced), warps split x, fixed-order reduction across warps ------------------
+constexpr int MT_WY = 8;
+__global__ void __launch_bounds__(32 * MT_WY) mttv_mid_kernel(const double *__restrict__ T,
+                                                              const double *__restrict__ W,
+                                                              double *__restrict__ out, int64_t L, int64_t X,
+                                                              int64_t Rt, int R, int64_t ldw, int64_t ltiles) {
+  __shared__ double part[MT_WY][32];
+  const int lane = threadIdx.x, wy = threadIdx.y;
+  int64_t b = blockIdx.x;  // over (ltile, t, r)
+  const int64_t lt = b % ltiles;
+  b /= ltiles;
+  const int64_t t = b % Rt;
+  const int64_t r = b / Rt;
+  const int64_t l = lt * 32 + lane;
+  double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+  if (l < L) {
+    const double *tp = T + l + L * X * (t + Rt * r);
+    const double *wp = W + r * ldw;
+    int64_t x = wy;
+    for (; x + 3 * MT_WY < X; x += 4 * MT_WY) {
+      const double v0 = tp[L * x], v1 = tp[L * (x + MT_WY)], v2 = tp[L * (x + 2 * MT_WY)],
+                   v3 = tp[L * (x + 3 * MT_WY)];
+      acc0 += v0 * wp[x];
+      acc1 += v1 * wp[x + MT_WY];
+      acc2 += v2 * wp[x + 2 * MT_WY];
+      acc3 += v3 * wp[x + 3 * MT_WY];
+    }
+    for (; x < X; x += MT_WY) acc0 += tp[L * x] * wp[x];
+  }
+  part[wy][lane] = (acc0 + acc1) + (acc2 + acc3);
+  __syncthreads();
+  if (wy == 0 && l < L) {
+    double s = 0.0;
+#pragma unroll
+    for (int y = 0; y < MT_WY; y++) s += part[y][lane];
+    out[l + L * (t + Rt * r)] = s;
+  }
+}
+
+// ---- 1 < L < 32: one thread per output (l,t), loop over all x -----------------------------------------------
+__global__ void __launch_bounds__(256) mttv_small_kernel(const double *__restrict__ T, const double *__restrict__ W,
+                                                         double *__restrict__ out, int64_t L, int64_t X, int64_t Rt,
+                                                         int R, int64_t ldw) {
+  const int64_t n_out = L * Rt * (int64_t)R;
+  int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; o < n_out; o += stride) {
+    const int64_t l = o % L;
+    const int64_t tr = o / L;  // t + Rt*r
+    const int64_t r = tr / Rt;
+    const double *tp = T + l + L * X * tr;
+    const double *wp = W + r * ldw;
+    double acc = 0.0;
+    for (int64_t x = 0; x < X; x++) acc += tp[L * x] * wp[x];
+    out[o] = acc;
+  }
+}
+
+// ---- K3 ------------------------------------------------------------------------------------------------------
+constexpr int PP_MAX_OPS = 15;
+struct PpArgs {
+  const double *op[PP_MAX_OPS];
+  const double *dw[PP_MAX_OPS];
+  int64_t sj[PP_MAX_OPS];
+  int which[PP_MAX_OPS];
+  int n_ops;
+};
+
+constexpr int PP_WY = 8;
+__global__ void __launch_bounds__(32 * PP_WY) pp_correct_kernel(const double *__restrict__ M0, PpArgs a,
+                                                                int64_t s_i, int R, double *__restrict__ Mout) {
+  __shared__ double part[PP_WY][32];  // which==1 partial sums (per warp, per row)
+  __shared__ double dots[32];         // which==0 sums (per row)
+  const int lane = threadIdx.x, wy = threadIdx.y;
+  const int64_t i0 = (int64_t)blockIdx.x * 32;
+  const int r = blockIdx.y;
+  const int64_t i = i0 + lane;
+  if (wy == 0) dots[lane] = 0.0;
+  __syncthreads();
+  double acc = 0.0;
+  for (int j = 0; j < a.n_ops; j++) {
+    const int64_t sj = a.sj[j];
+    const double *dw = a.dw[j] + sj * r;
+    if (a.which[j]) {
+      // op[i', q, r]: rows contiguous along i' -> lanes along i', warps split q
+      if (i < s_i) {
+        const double *pp = a.op[j] + i + s_i * sj * (int64_t)r;
+        double a0 = 0.0, a1 = 0.0;
+        int64_t q = wy;
+        for (; q + PP_WY < sj; q += 2 * PP_WY) {
+          a0 += pp[s_i * q] * dw[q];
+          a1 += pp[s_i * (q + PP_WY)] * dw[q + PP_WY];
+        }
+        for (; q < sj; q += PP_WY) a0 += pp[s_i * q] * dw[q];
+        acc += a0 + a1;
+      }
+    } else {
+      // op[q, i', r]: contiguous along q -> one warp per row i', lanes along q
+      for (int rr = wy; rr < 32; rr += PP_WY) {
+        const int64_t ii = i0 + rr;
+        double d = 0.0;
+        if (ii < s_i) {
+          const double *pp = a.op[j] + sj * (ii + s_i * (int64_t)r);
+          for (int64_t q = lane; q < sj; q += 32) d += pp[q] * dw[q];
+        }
+        d = ppx_warp_sum(d);
+        if (lane == 0) dots[rr] += d;  // rows rr are owned by warp rr % PP_WY: no race, fixed order over j
+      }
+    }
+  }
+  part[wy][lane] = acc;
+  __syncthreads();
+  if (wy == 0 && i < s_i) {
+    double s = M0[i + s_i * r];
+#pragma unroll
+    for (int y = 0; y < PP_WY; y++) s += part[y][lane];
+    s += dots[lane];
+    Mout[i + s_i * r] = s;
+  }
+}
+
+}  // namespace
+
+int ppx_mttv_impl(ppx_ctx *ctx, const double *T, int64_t L, int64_t X, int64_t Rt, const double *Wx, int64_t ldw,
+                  int R, double *out) {
+  if (L * Rt * R == 0) return PPX_OK;
+  if (L == 1) {
+    const int64_t n_out = Rt * (int64_t)R;
+    int G = 32;
+    while (G > 4 && X < 2 * G) G >>= 1;
+    int64_t blocks = (n_out * G + 255) / 256;
+    if (blocks > (int64_t)ctx->sm_count * 32) blocks = (int64_t)ctx->sm_count * 32;
+    switch (G) {
+      case 32: mttv_first_kernel<32><<<(int)blocks, 256, 0, ctx->stream>>>(T, Wx, out, X, Rt, R, ldw); break;
+      case 16: mttv_first_kernel<16><<<(int)blocks, 256, 0, ctx->stream>>>(T, Wx, out, X, Rt, R, ldw); break;
+      case 8: mttv_first_kernel<8><<<(int)blocks, 256, 0, ctx->stream>>>(T, Wx, out, X, Rt, R, ldw); break;
+      default: mttv_first_kernel<4><<<(int)blocks, 256, 0, ctx->stream>>>(T, Wx, out, X, Rt, R, ldw); break;
+    }
+    PPX_CHECK_LAUNCH(ctx);
+  } else if (L >= 32) {
+    const int64_t ltiles = (L + 31) / 32;
+    const int64_t blocks = ltiles * Rt * R;
+    if (blocks > 0x7fffffffLL) return ppx_set_err(ctx, PPX_EUNSUPPORTED, "mttv: grid too large");
+    mttv_mid_kernel<<<(unsigned)blocks, dim3(32, MT_WY), 0, ctx->stream>>>(T, Wx, out, L, X, Rt, R, ldw, ltiles);
+    PPX_CHECK_LAUNCH(ctx);
+  } else {
+    const int64_t n_out = L * Rt * (int64_t)R;
+    int64_t blocks = (n_out + 255) / 256;
+    if (blocks > (int64_t)ctx->sm_count * 32) blocks = (int64_t)ctx->sm_count * 32;
+    mttv_small_kernel<<<(int)blocks, 256, 0, ctx->stream>>>(T, Wx, out, L, X, Rt, R, ldw);
+    PPX_CHECK_LAUNCH(ctx);
+  }
+  return PPX_OK;
+}
+
+extern "C" {
+
+int ppx_mttv(ppx_ctx *ctx, const double *T, const int64_t *lens, int k, int x, const double *Wx, int64_t ldw, int R,
+             double *out) {
+  PPX_REQUIRE(ctx, T && lens && Wx && out, "non-null pointers");
+  PPX_REQUIRE(ctx, k >= 1 && k <= 16 && x >= 0 && x < k && R >= 1, "1 <= k <= 16, 0 <= x < k, R >= 1");
+  PPX_REQUIRE(ctx, ldw >= lens[x], "ldw >= lens[x]");
+  int64_t L, X, Rt;
+  ppx_split3(lens, k, x, &L, &X, &Rt);
+  return ppx_mttv_impl(ctx, T, L, X, Rt, Wx, ldw, R, out);
+}
+
+int ppx_mttv2(ppx_ctx *ctx, const double *T, const int64_t *lens, int k, int x1, const double *W1, int64_t ldw1,
+              int x2, const double *W2, int64_t ldw2, int R, double *out) {
+  PPX_REQUIRE(ctx, T && lens && W1 && W2 && out, "non-null pointers");
+  PPX_REQUIRE(ctx, k >= 2 && k <= 16 && x1 >= 0 && x1 < x2 && x2 < k && R >= 1, "0 <= x1 < x2 < k <= 16");
+  // contract the later mode first (keeps x1's position), through the context workspace
+  int64_t L, X, Rt;
+  ppx_split3(lens, k, x2, &L, &X, &Rt);
+  ppx_ws_reset(ctx);
+  double *tmp = (double *)ppx_ws_alloc(ctx, sizeof(double) * (size_t)(L * Rt * R));
+  if (!tmp)
+    return ppx_set_err(ctx, PPX_ENOMEM, "mttv2 needs %lld bytes of workspace (have %zu)",
+                       (long long)(8 * L * Rt * R), ctx->ws_bytes);
+  int rc = ppx_mttv_impl(ctx, T, L, X, Rt, W2, ldw2, R, tmp);
+  if (rc) return rc;
+  int64_t lens2[16];
+  int kk = 0;
+  for (int i = 0; i < k; i++)
+    if (i != x2) lens2[kk++] = lens[i];
+  ppx_split3(lens2, kk, x1, &L, &X, &Rt);
+  return ppx_mttv_impl(ctx, tmp, L, X, Rt, W1, ldw1, R, out);
+}
+
+int ppx_pp_correct(ppx_ctx *ctx, const double *M0, const double *const *ops, const int *which,
+                   const double *const *dW, const int64_t *s_other, int n_ops, int64_t s_i, int R, double *M_out) {
+  PPX_REQUIRE(ctx, M0 && M_out && n_ops >= 0 && n_ops <= PP_MAX_OPS, "0 <= n_ops <= 15");
+  PPX_REQUIRE(ctx, s_i >= 1 && R >= 1 && R <= 65535, "s_i >= 1, 1 <= R <= 65535");
+  PpArgs a;
+  a.n_ops = n_ops;
+  for (int j = 0; j < n_ops; j++) {
+    a.op[j] = ops[j];
+    a.dw[j] = dW[j];
+    a.sj[j] = s_other[j];
+    a.which[j] = which[j];
+  }
+  dim3 grid(ppx_cdiv(s_i, 32), R), block(32, PP_WY);
+  pp_correct_kernel<<<grid, block, 0, ctx->stream>>>(M0, a, s_i, R, M_out);
+  PPX_CHECK_LAUNCH(ctx);
+  return PPX_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,343 @@
+// Context, memory, events/graphs, generator and small elementwise / reduction kernels behind include/ppx.h.
+#include <stdarg.h>
+#include <string.h>
+#include "ppx_internal.h"
+
+int ppx_set_err(ppx_ctx *ctx, int code, const char *fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (ctx) ctx->err = buf;
+  else fprintf(stderr, "ppx: %s\n", buf);
+  return code;
+}
+
+void *ppx_ws_alloc(ppx_ctx *ctx, size_t bytes) {
+  size_t off = (ctx->ws_used + 255) & ~(size_t)255;
+  if (off + bytes > ctx->ws_bytes) return nullptr;
+  ctx->ws_used = off + bytes;
+  return ctx->ws + off;
+}
+
+extern "C" {
+
+const char *ppx_version(void) { return "ppx 0.1 (sm_100a)"; }
+
+int ppx_ctx_create(int device, void *stream, size_t workspace_bytes, ppx_ctx **out) {
+  if (!out) return PPX_EINVAL;
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return ppx_set_err(nullptr, PPX_ECUDA, "no CUDA device (%s); there is no CPU fallback",
+                       e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+  if (device < 0 || device >= ndev) return ppx_set_err(nullptr, PPX_EINVAL, "device %d out of range", device);
+  ppx_ctx *ctx = new ppx_ctx();
+  ctx->device = device;
+  e = cudaSetDevice(device);
+  if (e != cudaSuccess) { delete ctx; return ppx_set_err(nullptr, PPX_ECUDA, "cudaSetDevice: %s", cudaGetErrorString(e)); }
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, device);
+  ctx->sm_count = prop.multiProcessorCount;
+  if (stream) {
+    ctx->stream = (cudaStream_t)stream;
+  } else {
+    e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete ctx; return ppx_set_err(nullptr, PPX_ECUDA, "stream: %s", cudaGetErrorString(e)); }
+    ctx->own_stream = true;
+  }
+  if (workspace_bytes < ((size_t)8 << 20)) workspace_bytes = (size_t)8 << 20;
+  e = cudaMalloc((void **)&ctx->ws, workspace_bytes);
+  if (e != cudaSuccess) { delete ctx; return ppx_set_err(nullptr, PPX_ENOMEM, "workspace: %s", cudaGetErrorString(e)); }
+  ctx->ws_bytes = workspace_bytes;
+  {
+    int rc = ppx_k1_init(ctx);
+    if (!rc) rc = ppx_k45_init(ctx);
+    if (!rc) rc = ppx_k7_init(ctx);
+    if (rc) {
+      fprintf(stderr, "ppx: kernel init failed: %s\n", ctx->err.c_str());
+      cudaFree(ctx->ws);
+      delete ctx;
+      return rc;
+    }
+  }
+  *out = ctx;
+  return PPX_OK;
+}
+
+int ppx_ctx_destroy(ppx_ctx *ctx) {
+  if (!ctx) return PPX_OK;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  ppx_comm_destroy_internal(ctx);
+  if (ctx->ws) cudaFree(ctx->ws);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return PPX_OK;
+}
+
+int ppx_sync(ppx_ctx *ctx) {
+  PPX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return PPX_OK;
+}
+const char *ppx_last_error(ppx_ctx *ctx) { return ctx ? ctx->err.c_str() : ""; }
+void *ppx_stream(ppx_ctx *ctx) { return (void *)ctx->stream; }
+int ppx_device(ppx_ctx *ctx) { return ctx->device; }
+int ppx_sm_count(ppx_ctx *ctx) { return ctx->sm_count; }
+int64_t ppx_launch_count(ppx_ctx *ctx) { return ctx->launches; }
+
+int ppx_malloc(ppx_ctx *ctx, size_t bytes, void **dptr) {
+  cudaError_t e = cudaMalloc(dptr, bytes ? bytes : 8);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return ppx_set_err(ctx, PPX_ENOMEM, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+  }
+  return PPX_OK;
+}
+int ppx_free(ppx_ctx *ctx, void *dptr) {
+  if (dptr) PPX_CUDA(ctx, cudaFree(dptr));
+  return PPX_OK;
+}
+int ppx_host_alloc(ppx_ctx *ctx, size_t bytes, void **hptr) {
+  PPX_CUDA(ctx, cudaMallocHost(hptr, bytes ? bytes : 8));
+  return PPX_OK;
+}
+int ppx_host_free(ppx_ctx *ctx, void *hptr) {
+  if (hptr) PPX_CUDA(ctx, cudaFreeHost(hptr));
+  return PPX_OK;
+}
+int ppx_memcpy_h2d(ppx_ctx *ctx, void *dst, const void *src, size_t bytes) {
+  PPX_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  return PPX_OK;
+}
+int ppx_memcpy_d2h(ppx_ctx *ctx, void *dst, const void *src, size_t bytes) {
+  PPX_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  return PPX_OK;
+}
+int ppx_memcpy_d2d(ppx_ctx *ctx, void *dst, const void *src, size_t bytes) {
+  PPX_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+  return PPX_OK;
+}
+int ppx_memset_zero(ppx_ctx *ctx, void *dst, size_t bytes) {
+  PPX_CUDA(ctx, cudaMemsetAsync(dst, 0, bytes, ctx->stream));
+  return PPX_OK;
+}
+int ppx_mem_info(ppx_ctx *ctx, size_t *free_bytes, size_t *total_bytes) {
+  PPX_CUDA(ctx, cudaMemGetInfo(free_bytes, total_bytes));
+  return PPX_OK;
+}
+
+int ppx_event_create(ppx_ctx *ctx, void **ev) {
+  cudaEvent_t e;
+  PPX_CUDA(ctx, cudaEventCreate(&e));
+  *ev = (void *)e;
+  return PPX_OK;
+}
+int ppx_event_destroy(ppx_ctx *ctx, void *ev) {
+  PPX_CUDA(ctx, cudaEventDestroy((cudaEvent_t)ev));
+  return PPX_OK;
+}
+int ppx_event_record(ppx_ctx *ctx, void *ev) {
+  PPX_CUDA(ctx, cudaEventRecord((cudaEvent_t)ev, ctx->stream));
+  return PPX_OK;
+}
+int ppx_event_elapsed_ms(ppx_ctx *ctx, void *a, void *b, float *ms) {
+  PPX_CUDA(ctx, cudaEventSynchronize((cudaEvent_t)b));
+  PPX_CUDA(ctx, cudaEventElapsedTime(ms, (cudaEvent_t)a, (cudaEvent_t)b));
+  return PPX_OK;
+}
+int ppx_graph_begin(ppx_ctx *ctx) {
+  PPX_CUDA(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+  return PPX_OK;
+}
+int ppx_graph_end(ppx_ctx *ctx, void **graph) {
+  cudaGraph_t g;
+  PPX_CUDA(ctx, cudaStreamEndCapture(ctx->stream, &g));
+  cudaGraphExec_t ge;
+  cudaError_t e = cudaGraphInstantiate(&ge, g, 0);
+  cudaGraphDestroy(g);
+  if (e != cudaSuccess) return ppx_set_err(ctx, PPX_ECUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e));
+  *graph = (void *)ge;
+  return PPX_OK;
+}
+int ppx_graph_launch(ppx_ctx *ctx, void *graph) {
+  PPX_CUDA(ctx, cudaGraphLaunch((cudaGraphExec_t)graph, ctx->stream));
+  return PPX_OK;
+}
+int ppx_graph_destroy(ppx_ctx *ctx, void *graph) {
+  if (graph) PPX_CUDA(ctx, cudaGraphExecDestroy((cudaGraphExec_t)graph));
+  return PPX_OK;
+}
+
+}  // extern "C"
+
+// ---- generator ----------------------------------------------------------------------------------------------
+__global__ void fill_uniform_kernel(double *out, int64_t n, uint64_t base, int64_t start, double lo, double span) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    uint64_t z = (uint64_t)(start + i) + base;
+    z += 0x9E3779B97F4A7C15ULL;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    z ^= z >> 31;
+    out[i] = lo + span * ((double)(z >> 11) * (1.0 / 9007199254740992.0));
+  }
+}
+
+// ---- small elementwise / reduction kernels --------------------------------------------------------------------
+struct SqnormArgs {
+  const double *x[16];
+  int64_t n[16];
+};
+
+// one block per array: deterministic sum of squares
+__global__ void __launch_bounds__(1024) sqnorms_kernel(SqnormArgs a, double *out) {
+  __shared__ double red[32];
+  const double *x = a.x[blockIdx.x];
+  int64_t n = a.n[blockIdx.x];
+  double s = 0;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    double v = x[i];
+    s += v * v;
+  }
+  s = ppx_block_sum(s, red);
+  if (threadIdx.x == 0) out[blockIdx.x] = s;
+}
+
+__global__ void __launch_bounds__(1024) diff_update_kernel(const double *W, double *Wp, double *dW, int64_t n,
+                                                           double *out) {
+  __shared__ double red[32];
+  double s0 = 0, s1 = 0;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    double w = W[i];
+    double d = w - Wp[i];
+    dW[i] = d;
+    Wp[i] = w;
+    s0 += d * d;
+    s1 += w * w;
+  }
+  s0 = ppx_block_sum(s0, red);
+  s1 = ppx_block_sum(s1, red);
+  if (threadIdx.x == 0) {
+    out[0] = s0;
+    out[1] = s1;
+  }
+}
+
+__global__ void axpby_kernel(double alpha, const double *x, double beta, double *y, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) y[i] = alpha * x[i] + (beta == 0.0 ? 0.0 : beta * y[i]);
+}
+
+// two-stage deterministic  out = a - b, sum of squares
+__global__ void __launch_bounds__(256) diff_sq_stage1(const double *a, const double *b, int64_t n, double *partial) {
+  __shared__ double red[32];
+  double s = 0;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    double d = a[i] - b[i];
+    s += d * d;
+  }
+  s = ppx_block_sum(s, red);
+  if (threadIdx.x == 0) partial[blockIdx.x] = s;
+}
+__global__ void __launch_bounds__(1024) sum_stage2(const double *partial, int n, double *out) {
+  __shared__ double red[32];
+  double s = 0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s += partial[i];
+  s = ppx_block_sum(s, red);
+  if (threadIdx.x == 0) out[0] = s;
+}
+
+__global__ void transpose_kernel(const double *A, int64_t m, int64_t n, double *B) {
+  __shared__ double tile[32][33];
+  int64_t bx = (int64_t)blockIdx.x * 32, by = (int64_t)blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    int64_t r = bx + threadIdx.x, c = by + j;
+    if (r < m && c < n) tile[j][threadIdx.x] = A[r + m * c];
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    int64_t c = by + threadIdx.x, r = bx + j;
+    if (r < m && c < n) B[c + n * r] = tile[threadIdx.x][j];
+  }
+}
+
+int ppx_sum_partials(ppx_ctx *ctx, const double *partial, int n, double *out) {
+  sum_stage2<<<1, 1024, 0, ctx->stream>>>(partial, n, out);
+  PPX_CHECK_LAUNCH(ctx);
+  return PPX_OK;
+}
+
+extern "C" {
+
+int ppx_fill_uniform(ppx_ctx *ctx, double *out, int64_t n, uint64_t seed, uint64_t tensor_id, int64_t start,
+                     double lo, double hi) {
+  PPX_REQUIRE(ctx, out && n >= 0, "out != NULL, n >= 0");
+  if (n == 0) return PPX_OK;
+  uint64_t base = seed * 0x9E3779B97F4A7C15ULL + tensor_id * 0xD1B54A32D192ED03ULL;
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > ctx->sm_count * 16) blocks = ctx->sm_count * 16;
+  fill_uniform_kernel<<<blocks, 256, 0, ctx->stream>>>(out, n, base, start, lo, hi - lo);
+  PPX_CHECK_LAUNCH(ctx);
+  return PPX_OK;
+}
+
+int ppx_sqnorms(ppx_ctx *ctx, const double *const *X, const int64_t *n, int count, double *out_dev) {
+  PPX_REQUIRE(ctx, count >= 1 && count <= 16, "1 <= count <= 16");
+  SqnormArgs a;
+  for (int i = 0; i < count; i++) {
+    a.x[i] = X[i];
+    a.n[i] = n[i];
+  }
+  sqnorms_kernel<<<count, 1024, 0, ctx->stream>>>(a, out_dev);
+  PPX_CHECK_LAUNCH(ctx);
+  return PPX_OK;
+}
+
+int ppx_diff_update(ppx_ctx *ctx, const double *W, double *W_prev, double *dW, int64_t n, double *sq_out_dev) {
+  diff_update_kernel<<<1, 1024, 0, ctx->stream>>>(W, W_prev, dW, n, sq_out_dev);
+  PPX_CHECK_LAUNCH(ctx);
+  return PPX_OK;
+}
+
+int ppx_axpby(ppx_ctx *ctx, double alpha, const double *x, double beta, double *y, int64_t n) {
+  if (n == 0) return PPX_OK;
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > ctx->sm_count * 16) blocks = ctx->sm_count * 16;
+  axpby_kernel<<<blocks, 256, 0, ctx->stream>>>(alpha, x, beta, y, n);
+  PPX_CHECK_LAUNCH(ctx);
+  return PPX_OK;
+}
+
+int ppx_diff_sqnorm(ppx_ctx *ctx, const double *a, const double *b, int64_t n, double *sq_out_dev) {
+  ppx_ws_reset(ctx);
+  int blocks = ctx->sm_count * 8;
+  double *partial = (double *)ppx_ws_alloc(ctx, sizeof(double) * blocks);
+  if (!partial) return ppx_set_err(ctx, PPX_ENOMEM, "workspace too small");
+  diff_sq_stage1<<<blocks, 256, 0, ctx->stream>>>(a, b, n, partial);
+  PPX_CHECK_LAUNCH(ctx);
+  return ppx_sum_partials(ctx, partial, blocks, sq_out_dev);
+}
+
+int ppx_transpose(ppx_ctx *ctx, const double *A, int64_t m, int64_t n, double *B) {
+  dim3 grid(ppx_cdiv(m, 32), ppx_cdiv(n, 32)), block(32, 8);
+  transpose_kernel<<<grid, block, 0, ctx->stream>>>(A, m, n, B);
+  PPX_CHECK_LAUNCH(ctx);
+  return PPX_OK;
+}
+
+int ppx_shard_range(int64_t s, int nranks, int rank, int64_t *begin, int64_t *end) {
+  if (nranks < 1 || rank < 0 || rank >= nranks || s < 0 || !begin || !end) return PPX_EINVAL;
+  int64_t q = s / nranks, r = s % nranks;
+  *begin = rank * q + (rank < r ? rank : r);
+  *end = *begin + q + (rank < r ? 1 : 0);
+  return PPX_OK;
+}
+
+}  // extern "C"

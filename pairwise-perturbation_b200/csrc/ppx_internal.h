@@ -1,0 +1,110 @@
+// Internal definitions shared by the kernels behind include/ppx.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include "../../include/ppx.h"
+
+struct ppx_ctx {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  char *ws = nullptr;  // workspace arena (bump allocated per call)
+  size_t ws_bytes = 0;
+  size_t ws_used = 0;
+  int64_t launches = 0;
+  std::string err;
+  // pinned staging for pointer tables handed to kernels
+  void *comm = nullptr;  // ncclComm_t
+  int nranks = 1, rank = 0;
+};
+
+int ppx_set_err(ppx_ctx *ctx, int code, const char *fmt, ...);
+// per-file one-time kernel attribute setup (opt-in shared memory), called from ppx_ctx_create
+int ppx_k1_init(ppx_ctx *ctx);
+int ppx_k45_init(ppx_ctx *ctx);
+int ppx_k7_init(ppx_ctx *ctx);
+void ppx_comm_destroy_internal(ppx_ctx *ctx);
+int ppx_sum_partials(ppx_ctx *ctx, const double *partial, int n, double *out);
+
+#define PPX_CUDA(ctx, expr)                                                                            \
+  do {                                                                                                 \
+    cudaError_t e__ = (expr);                                                                          \
+    if (e__ != cudaSuccess)                                                                            \
+      return ppx_set_err(ctx, PPX_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__),      \
+                         __FILE__, __LINE__);                                                          \
+  } while (0)
+
+#define PPX_CHECK_LAUNCH(ctx)                                                                          \
+  do {                                                                                                 \
+    (ctx)->launches++;                                                                                 \
+    cudaError_t e__ = cudaGetLastError();                                                              \
+    if (e__ != cudaSuccess)                                                                            \
+      return ppx_set_err(ctx, PPX_ECUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__),  \
+                         __FILE__, __LINE__);                                                          \
+  } while (0)
+
+#define PPX_REQUIRE(ctx, cond, msg)                                                                    \
+  do {                                                                                                 \
+    if (!(cond)) return ppx_set_err(ctx, PPX_EINVAL, "%s: requirement failed: %s", __func__, msg);     \
+  } while (0)
+
+// workspace: reset at the start of an API call that needs scratch, then bump.
+static inline void ppx_ws_reset(ppx_ctx *ctx) { ctx->ws_used = 0; }
+void *ppx_ws_alloc(ppx_ctx *ctx, size_t bytes);  // nullptr if exhausted (256-byte aligned)
+
+// split a k-mode tensor around mode x:  index = l + L*(j + X*t)
+static inline void ppx_split3(const int64_t *lens, int k, int x, int64_t *L, int64_t *X, int64_t *Rt) {
+  int64_t l = 1, r = 1;
+  for (int i = 0; i < x; i++) l *= lens[i];
+  for (int i = x + 1; i < k; i++) r *= lens[i];
+  *L = l;
+  *X = lens[x];
+  *Rt = r;
+}
+
+static inline int ppx_cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// ---- device helpers -------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ double ppx_warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// deterministic block reduction; result valid in thread 0.  `red` is >= 32 doubles of shared memory.
+__device__ __forceinline__ double ppx_block_sum(double v, double *red) {
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  v = ppx_warp_sum(v);
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  int nw = (blockDim.x + 31) >> 5;
+  v = (threadIdx.x < nw) ? red[threadIdx.x] : 0.0;
+  if (w == 0) v = ppx_warp_sum(v);
+  return v;
+}
+
+__device__ __forceinline__ void ppx_dmma(double &c0, double &c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ void ppx_cp_async16(void *smem, const void *gmem, int src_bytes) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem), "r"(src_bytes));
+}
+__device__ __forceinline__ void ppx_cp_async8(void *smem, const void *gmem, int src_bytes) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(s), "l"(gmem), "r"(src_bytes));
+}
+__device__ __forceinline__ void ppx_cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N>
+__device__ __forceinline__ void ppx_cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N));
+}
+#endif

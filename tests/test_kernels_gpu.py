@@ -1,0 +1,293 @@
+"""Parity of every CUDA kernel behind include/ppx.h against the CPU oracle (oracle/pp_oracle.py), through the C ABI.
+
+Tolerances: all arithmetic is FP64; a contraction of length K differs from the oracle only by summation order, so
+results must agree to ~K*eps relative to the magnitude of the result (checked as 1e-12 of the max-abs).  The solve
+is compared at 1e-9 (conditioning of S), well inside the north-star's 1e-8 factor tolerance."""
+import numpy as np
+import pytest
+
+from oracle import pp_oracle as o
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_err(a, b):
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+
+
+def rnd(shape, seed):
+    return o.fill_uniform(shape, 7, seed, -1.0, 1.0)
+
+
+def test_fill_uniform_matches_oracle(ctx):
+    out = ctx.empty(1000)
+    ctx.fill_uniform(out, seed=2, tensor_id=3, start=17, lo=0.5, hi=1.0)
+    ref = 0.5 + 0.5 * o.u01(2, 3, 1000, start=17)
+    assert np.array_equal(ctx.to_host(out, (1000,)), ref)  # bit exact: integer hash + one fma-free affine map
+
+
+TTM_CASES = [
+    # lens, x, R
+    ((13, 9, 11), 0, 5), ((13, 9, 11), 1, 5), ((13, 9, 11), 2, 5),
+    ((12, 10, 8, 6), 2, 4), ((12, 10, 8, 6), 0, 4), ((12, 10, 8, 6), 1, 10), ((12, 10, 8, 6), 3, 3),
+    ((7, 5, 6, 4, 5, 3), 3, 3), ((7, 5, 6, 4, 5, 3), 0, 3),
+    ((40, 40, 40), 1, 10), ((300, 37), 0, 50), ((37, 300), 1, 50), ((64, 33, 20), 1, 70),
+    ((200, 3, 50), 1, 10), ((3, 128, 16), 0, 10), ((129, 17), 1, 1), ((1, 9, 5), 1, 2), ((130,), 0, 7),
+]
+
+
+@pytest.mark.parametrize("lens,x,R", TTM_CASES)
+def test_ttm_first(ctx, lens, x, R):
+    N = len(lens)
+    V = rnd(lens, 1)
+    W = rnd((lens[x], R), 2)
+    idx = o.letters(N)
+    ref = o.contract(idx.replace(idx[x], "") + "*", V, idx, W, idx[x] + "*")
+    out = ctx.empty(ref.size)
+    ctx.ttm_first(ctx.to_device(V), lens, x, ctx.to_device(W), R, out)
+    got = ctx.to_host(out, ref.shape)
+    assert rel_err(got, ref) < 1e-12
+
+
+def test_ttm_first_unaligned_and_ldw(ctx):
+    # odd base address (8-byte aligned only) and a padded leading dimension for W
+    lens, x, R = (14, 10, 6), 1, 6
+    V = rnd(lens, 3)
+    W = rnd((lens[x], R), 4)
+    ref = o.contract("ac*", V, "abc", W, "b*")
+    Vd = ctx.empty(V.size + 1)
+    Vd[1:].copy_(ctx.to_device(V))
+    ldw = lens[x] + 3
+    Wp = np.zeros((ldw, R))
+    Wp[: lens[x]] = W
+    out = ctx.empty(ref.size)
+    ctx.ttm_first(Vd[1:], lens, x, ctx.to_device(Wp), R, out, ldw=ldw)
+    assert rel_err(ctx.to_host(out, ref.shape), ref) < 1e-12
+
+
+MTTV_CASES = [((13, 9, 11), 0, 5), ((13, 9, 11), 1, 5), ((13, 9, 11), 2, 5), ((300, 300), 1, 50), ((300, 300), 0, 50),
+              ((40, 33), 0, 10), ((3, 50, 7), 1, 4), ((70, 5, 9, 4), 2, 3), ((6,), 0, 3), ((100, 64, 3), 1, 2)]
+
+
+@pytest.mark.parametrize("lens,x,R", MTTV_CASES)
+def test_mttv(ctx, lens, x, R):
+    k = len(lens)
+    T = rnd(tuple(lens) + (R,), 5)
+    W = rnd((lens[x], R), 6)
+    idx = o.letters(k)
+    ref = o.contract(idx.replace(idx[x], "") + "*", T, idx + "*", W, idx[x] + "*")
+    out = ctx.empty(ref.size)
+    ctx.mttv(ctx.to_device(T), lens, x, ctx.to_device(W), R, out)
+    assert rel_err(ctx.to_host(out, ref.shape), ref) < 1e-12
+
+
+@pytest.mark.parametrize("lens,x1,x2,R", [((9, 8, 7), 0, 1, 4), ((9, 8, 7), 1, 2, 4), ((9, 8, 7), 0, 2, 4),
+                                          ((40, 40, 40), 0, 1, 10)])
+def test_mttv2(ctx, lens, x1, x2, R):
+    T = rnd(tuple(lens) + (R,), 8)
+    W1, W2 = rnd((lens[x1], R), 9), rnd((lens[x2], R), 10)
+    idx = "abc"
+    keep = [c for c in idx if c not in (idx[x1], idx[x2])][0]
+    ref = o.contract(keep + "*", T, "abc*", W1, idx[x1] + "*", W2, idx[x2] + "*")
+    out = ctx.empty(ref.size)
+    ctx.mttv2(ctx.to_device(T), lens, x1, ctx.to_device(W1), x2, ctx.to_device(W2), R, out)
+    assert rel_err(ctx.to_host(out, ref.shape), ref) < 1e-12
+
+
+def test_ttm_first_mttv(ctx):
+    lens, R = (12, 10, 8, 6), 5
+    V = rnd(lens, 11)
+    Wc, Wd = rnd((8, R), 12), rnd((6, R), 13)
+    ref = o.contract("ab*", V, "abcd", Wc, "c*", Wd, "d*")
+    out = ctx.empty(ref.size)
+    ctx.ttm_first_mttv(ctx.to_device(V), lens, 2, ctx.to_device(Wc), 3, ctx.to_device(Wd), R, out)
+    assert rel_err(ctx.to_host(out, ref.shape), ref) < 1e-12
+
+
+@pytest.mark.parametrize("lens,R", [((12, 10, 8, 6), 4), ((33, 40, 35), 7), ((5, 6, 4, 5, 3, 4), 3)])
+def test_pp_correct_matches_reference_formula(ctx, lens, R):
+    N = len(lens)
+    V = rnd(lens, 14)
+    W = [rnd((lens[i], R), 20 + i) for i in range(N)]
+    dW = [1e-2 * rnd((lens[i], R), 40 + i) for i in range(N)]
+    ops = o.build_pp_operators(V, W)
+    seq = o.letters(N)
+    dev_ops = {k: ctx.to_device(v) for k, v in ops.items()}
+    dev_dW = [ctx.to_device(d) for d in dW]
+    for i in range(N):
+        ref = o.pp_corrected_M(ops, dW, i, N)
+        m0 = dev_ops["".join(c for k, c in enumerate(seq) if k != i)]
+        oplist, which, dws, sother = [], [], [], []
+        for j in range(N):
+            if j == i:
+                continue
+            oplist.append(dev_ops["".join(c for k, c in enumerate(seq) if k not in (i, j))])
+            which.append(0 if j < i else 1)
+            dws.append(dev_dW[j])
+            sother.append(lens[j])
+        out = ctx.empty(ref.size)
+        ctx.pp_correct(m0, oplist, which, dws, sother, lens[i], R, out)
+        assert rel_err(ctx.to_host(out, ref.shape), ref) < 1e-12
+
+
+def test_pp_correct_zero_dw_is_identity(ctx):
+    # PP with dW = 0 reproduces the exact MTTKRP (als_CP.cxx:778)
+    s, R = 37, 5
+    M0 = rnd((s, R), 50)
+    op = rnd((s, s, R), 51)
+    z = ctx.zeros(s * R)
+    out = ctx.empty(s * R)
+    ctx.pp_correct(ctx.to_device(M0), [ctx.to_device(op)] * 2, [0, 1], [z, z], [s, s], s, R, out)
+    assert np.array_equal(ctx.to_host(out, (s, R)), M0)
+
+
+@pytest.mark.parametrize("s,R", [(300, 50), (13, 5), (7200, 10), (40, 10), (5, 1)])
+def test_gram_and_hadamard(ctx, s, R):
+    Ws = [rnd((s + i, R), 60 + i) for i in range(4)]
+    Gs = []
+    for i, w in enumerate(Ws):
+        G = ctx.empty(R * R)
+        ctx.gram(ctx.to_device(w), s + i, R, G)
+        assert rel_err(ctx.to_host(G, (R, R)), w.T @ w) < 1e-12
+        Gs.append(G)
+    S = ctx.empty(R * R)
+    ctx.hadamard_grams(Gs, 1, R, 0.25, S)
+    ref = (Ws[0].T @ Ws[0]) * (Ws[2].T @ Ws[2]) * (Ws[3].T @ Ws[3]) + 0.25 * np.eye(R)
+    assert rel_err(ctx.to_host(S, (R, R)), ref) < 1e-12
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("s,R", [(300, 50), (13, 5), (40, 10), (33, 7), (9, 1)])
+def test_solve_update(ctx, ppx, mode, s, R):
+    N = 4
+    Wf = [o.fill_uniform((s, R), 3, 70 + i) for i in range(N)]
+    S = o.gram_hadamard(Wf, 0)
+    M = rnd((s, R), 80)
+    W_old = rnd((s, R), 81)
+    W_init = rnd((s, R), 82)
+    grad_ref = -M + W_old @ S
+    for ratio in (1.0, 0.7):
+        W_ref, dW_ref = o.SVD_solve_mod(M, W_init, S, ratio)
+        Wd = ctx.to_device(W_old)
+        grad, dW, sq = ctx.empty(s * R), ctx.empty(s * R), ctx.empty(3)
+        ctx.solve_update(ctx.to_device(M), ctx.to_device(S), Wd, s, R, W_init=ctx.to_device(W_init), ratio_step=ratio,
+                         mode=mode, grad=grad, dW=dW, sq_norms=sq)
+        assert rel_err(ctx.to_host(Wd, (s, R)), W_ref) < 1e-9
+        assert rel_err(ctx.to_host(dW, (s, R)), dW_ref) < 1e-9
+        assert rel_err(ctx.to_host(grad, (s, R)), grad_ref) < 1e-12
+        sqh = ctx.to_host(sq, (3,))
+        ref_sq = np.array([np.sum(W_ref**2), np.sum(dW_ref**2), np.sum(grad_ref**2)])
+        assert np.allclose(sqh, ref_sq, rtol=1e-9)
+    # plain solve (no W_init): W = M S^-1, Cholesky and SVD semantics agree with the oracle's two solvers
+    Wd = ctx.to_device(W_old)
+    ctx.solve_update(ctx.to_device(M), ctx.to_device(S), Wd, s, R, mode=mode)
+    assert rel_err(ctx.to_host(Wd, (s, R)), o.SVD_solve(M, S)) < 1e-9
+    assert rel_err(ctx.to_host(Wd, (s, R)), o.cholesky_solve(M, S)) < 1e-9
+
+
+def test_normalize(ctx):
+    sizes, R = [13, 40, 7, 300], 6
+    W = [rnd((s, R), 90 + i) * (i + 1) for i, s in enumerate(sizes)]
+    ref = [w.copy() for w in W]
+    o.normalize(ref)
+    dW = [ctx.to_device(w) for w in W]
+    Gs = []
+    for w, s in zip(dW, sizes):
+        G = ctx.empty(R * R)
+        ctx.gram(w, s, R, G)
+        Gs.append(G)
+    ctx.normalize(dW, sizes, R, Gs)
+    for i, s in enumerate(sizes):
+        assert rel_err(ctx.to_host(dW[i], (s, R)), ref[i]) < 1e-13
+        assert rel_err(ctx.to_host(Gs[i], (R, R)), ref[i].T @ ref[i]) < 1e-12
+
+
+def test_sqnorms_and_diff_update(ctx):
+    a, b = rnd((1234,), 95), rnd((1234,), 96)
+    out = ctx.empty(2)
+    ctx.sqnorms([ctx.to_device(a), ctx.to_device(b)], out)
+    assert np.allclose(ctx.to_host(out, (2,)), [np.sum(a * a), np.sum(b * b)], rtol=1e-13)
+    Wp, dW, sq = ctx.to_device(b), ctx.empty(1234), ctx.empty(2)
+    ctx.diff_update(ctx.to_device(a), Wp, dW, sq)
+    assert np.array_equal(ctx.to_host(dW, (1234,)), a - b)
+    assert np.array_equal(ctx.to_host(Wp, (1234,)), a)
+    assert np.allclose(ctx.to_host(sq, (2,)), [np.sum((a - b) ** 2), np.sum(a * a)], rtol=1e-13)
+
+
+@pytest.mark.parametrize("lens,R", [((12, 10, 8, 6), 4), ((13, 9, 11), 5), ((5, 6, 4, 5, 3, 4), 3), ((130, 35), 50),
+                                    ((7, 200), 3)])
+def test_cp_residual_and_reconstruct(ctx, lens, R):
+    N = len(lens)
+    W = [rnd((lens[i], R), 100 + i) for i in range(N)]
+    V = rnd(lens, 110)
+    dW = [ctx.to_device(w) for w in W]
+    Vhat = ctx.empty(V.size)
+    ctx.cp_reconstruct(lens, dW, R, Vhat)
+    ref = o.build_V(W)
+    assert rel_err(ctx.to_host(Vhat, lens), ref) < 1e-13
+    sq = ctx.empty(1)
+    ctx.cp_residual(ctx.to_device(V), lens, dW, R, sq)
+    assert abs(np.sqrt(ctx.to_host(sq, (1,))[0]) - o.cp_residual(V, W)) < 1e-11 * np.linalg.norm(V)
+    # known answer: exact rank-R tensor, W = truth -> residual ~ 0 (SURVEY 8c KAT 1)
+    ctx.cp_residual(Vhat, lens, dW, R, sq)
+    assert np.sqrt(ctx.to_host(sq, (1,))[0]) <= 1e-12 * np.linalg.norm(ref)
+
+
+@pytest.mark.parametrize("lens,x,Q", [((13, 9, 11), 0, 4), ((13, 9, 11), 1, 4), ((13, 9, 11), 2, 4),
+                                      ((12, 10, 8, 6), 1, 3), ((40, 7, 40), 2, 40), ((5, 1, 6), 1, 2)])
+def test_tucker_ttm_and_acc(ctx, lens, x, Q):
+    T = rnd(lens, 120)
+    W = rnd((lens[x], Q), 121)
+    ref = o.ttm(T, x, W)
+    out = ctx.empty(ref.size)
+    ctx.ttm(ctx.to_device(T), lens, x, ctx.to_device(W), Q, out)
+    assert rel_err(ctx.to_host(out, ref.shape), ref) < 1e-12
+    ctx.ttm(ctx.to_device(T), lens, x, ctx.to_device(W), Q, out, acc=True)
+    assert rel_err(ctx.to_host(out, ref.shape), 2 * ref) < 1e-12
+
+
+@pytest.mark.parametrize("lens,i", [((13, 9, 11), 0), ((13, 9, 11), 1), ((13, 9, 11), 2), ((70, 5, 66), 2),
+                                    ((130, 40, 3), 0), ((4, 150, 5, 3), 1)])
+def test_unfold_gram(ctx, lens, i):
+    T = rnd(lens, 130)
+    ref = o.unroll_tensor_contraction(T, i)
+    out = ctx.empty(ref.size)
+    ctx.unfold_gram(ctx.to_device(T), lens, i, out)
+    assert rel_err(ctx.to_host(out, ref.shape), ref) < 1e-12
+
+
+@pytest.mark.parametrize("s,r", [(12, 3), (13, 5), (64, 8), (150, 10)])
+def test_sym_eig_topk(ctx, s, r):
+    A = rnd((s, 2 * s), 140)
+    MTM = A @ A.T
+    U, ev = ctx.empty(s * r), ctx.empty(r)
+    ctx.sym_eig_topk(ctx.to_device(MTM), s, r, U, ev)
+    Uh, evh = ctx.to_host(U, (s, r)), ctx.to_host(ev, (r,))
+    w, Q = np.linalg.eigh(MTM)
+    w, Q = w[::-1][:r], Q[:, ::-1][:, :r]
+    assert np.allclose(evh, w, rtol=1e-12)
+    assert np.abs(Uh.T @ Uh - np.eye(r)).max() < 1e-12
+    # same vectors as LAPACK up to the sign of each column (what MTM.svd(U,S,VT,r) returns)
+    assert np.abs(np.abs(np.sum(Uh * Q, axis=0)) - 1.0).max() < 1e-9
+    ref = o.top_left_singular(MTM, r)
+    assert np.abs(np.abs(np.sum(Uh * ref, axis=0)) - 1.0).max() < 1e-9
+
+
+def test_sign_align(ctx):
+    s, r = 30, 6
+    U, Uref = rnd((s, r), 150), rnd((s, r), 151)
+    Ud = ctx.to_device(U)
+    ctx.sign_align(Ud, ctx.to_device(Uref), s, r)
+    assert np.array_equal(ctx.to_host(Ud, (s, r)), o.sign_align(U, Uref))
+    # zero reference -> every column flips (b > 0 ? 1 : -1 with b == 0; als_Tucker.cxx:636-641)
+    Ud = ctx.to_device(U)
+    ctx.sign_align(Ud, ctx.zeros(s * r), s, r)
+    assert np.array_equal(ctx.to_host(Ud, (s, r)), -U)
+
+
+def test_errors_are_reported_not_swallowed(ctx, ppx):
+    out = ctx.empty(10)
+    with pytest.raises(ppx.PpxError):
+        ctx.ttm_first(out, (5, 2), 3, out, 2, out, ldw=5)  # x out of range
+    with pytest.raises(ppx.PpxError):
+        ctx.solve_update(out, out, out, 2, 5, mode=7)
