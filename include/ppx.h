@@ -125,6 +125,9 @@ int ppx_solve_update(ppx_ctx *ctx, const double *M, const double *S, double *W, 
 /* Normalize (common.cxx:680-688): every W_i scaled to the geometric mean of the Frobenius norms.  W, s: HOST
  * arrays.  If G != NULL, G[i] (cached Gram of W_i) is rescaled consistently. */
 int ppx_normalize(ppx_ctx *ctx, double *const *W, const int64_t *s, int N, int R, double *const *G);
+/* Same, but ||W_i||_F^2 is taken as trace(G[i]) instead of being recomputed from W_i: with the leading mode sharded
+ * over GPUs the local rows of W_i do not give the global norm, the (all-reduced) Gram does. */
+int ppx_normalize_g(ppx_ctx *ctx, double *const *W, const int64_t *s, int N, int R, double *const *G);
 /* out_dev[j] = sum of squares of X[j][0..n[j]) for j < count (norm2()^2; als_CP.cxx:176-178,598-600). */
 int ppx_sqnorms(ppx_ctx *ctx, const double *const *X, const int64_t *n, int count, double *out_dev);
 /* dW = W - W_prev; W_prev = W; sq_out_dev = { ||dW||^2, ||W||^2 }  (als_CP.cxx:596-600). */

@@ -65,6 +65,7 @@ SIGNATURES = {
     "ppx_hadamard_grams": (C.c_int, [_vp, C.POINTER(_dp), C.c_int, C.c_int, C.c_int, C.c_double, _dp]),
     "ppx_solve_update": (C.c_int, [_vp, _dp, _dp, _dp, _i64, C.c_int, _dp, C.c_double, C.c_int, _dp, _dp, _dp]),
     "ppx_normalize": (C.c_int, [_vp, C.POINTER(_dp), C.POINTER(_i64), C.c_int, C.c_int, C.POINTER(_dp)]),
+    "ppx_normalize_g": (C.c_int, [_vp, C.POINTER(_dp), C.POINTER(_i64), C.c_int, C.c_int, C.POINTER(_dp)]),
     "ppx_sqnorms": (C.c_int, [_vp, C.POINTER(_dp), C.POINTER(_i64), C.c_int, _dp]),
     "ppx_diff_update": (C.c_int, [_vp, _dp, _dp, _dp, _i64, _dp]),
     "ppx_axpby": (C.c_int, [_vp, C.c_double, _dp, C.c_double, _dp, _i64]),
@@ -240,6 +241,9 @@ class Ctx:
     def normalize(self, Ws, sizes, R, Gs=None):
         self._ck(self.lib.ppx_normalize(self.h, _ptrs(Ws), _lens(sizes), len(Ws), R,
                                         _ptrs(Gs) if Gs is not None else None))
+
+    def normalize_g(self, Ws, sizes, R, Gs):
+        self._ck(self.lib.ppx_normalize_g(self.h, _ptrs(Ws), _lens(sizes), len(Ws), R, _ptrs(Gs)))
 
     def sqnorms(self, Xs, out):
         self._ck(self.lib.ppx_sqnorms(self.h, _ptrs(Xs), _lens([x.numel() for x in Xs]), len(Xs), _ptr(out)))

@@ -291,6 +291,14 @@ __global__ void __launch_bounds__(1024) norm_sq_kernel(NormArgs a, double *sq) {
   s = ppx_block_sum(s, red);
   if (threadIdx.x == 0) sq[blockIdx.x] = s;
 }
+__global__ void norm_sq_from_gram_kernel(NormArgs a, double *sq) {
+  // ||W_i||_F^2 = trace(W_i^T W_i); one warp per factor
+  const int i = blockIdx.x;
+  double s = 0.0;
+  for (int k = threadIdx.x; k < a.R; k += 32) s += a.g[i][k + (int64_t)a.R * k];
+  s = ppx_warp_sum(s);
+  if (threadIdx.x == 0) sq[i] = s;
+}
 __global__ void __launch_bounds__(256) norm_scale_kernel(NormArgs a, const double *__restrict__ sq) {
   const int m = blockIdx.y;
   double prod = 1.0;
@@ -381,7 +389,22 @@ int ppx_solve_update(ppx_ctx *ctx, const double *M, const double *S, double *W, 
   return PPX_OK;
 }
 
+static int normalize_impl(ppx_ctx *ctx, double *const *W, const int64_t *s, int N, int R, double *const *G,
+                          bool from_grams);
+
 int ppx_normalize(ppx_ctx *ctx, double *const *W, const int64_t *s, int N, int R, double *const *G) {
+  return normalize_impl(ctx, W, s, N, R, G, false);
+}
+
+int ppx_normalize_g(ppx_ctx *ctx, double *const *W, const int64_t *s, int N, int R, double *const *G) {
+  PPX_REQUIRE(ctx, G != nullptr, "G != NULL");
+  return normalize_impl(ctx, W, s, N, R, G, true);
+}
+
+}  // extern "C"
+
+static int normalize_impl(ppx_ctx *ctx, double *const *W, const int64_t *s, int N, int R, double *const *G,
+                          bool from_grams) {
   PPX_REQUIRE(ctx, W && s && N >= 1 && N <= 16, "1 <= N <= 16");
   NormArgs a;
   a.N = N;
@@ -396,7 +419,10 @@ int ppx_normalize(ppx_ctx *ctx, double *const *W, const int64_t *s, int N, int R
   ppx_ws_reset(ctx);
   double *sq = (double *)ppx_ws_alloc(ctx, sizeof(double) * 16);
   if (!sq) return ppx_set_err(ctx, PPX_ENOMEM, "workspace too small");
-  norm_sq_kernel<<<N, 1024, 0, ctx->stream>>>(a, sq);
+  if (from_grams)
+    norm_sq_from_gram_kernel<<<N, 32, 0, ctx->stream>>>(a, sq);
+  else
+    norm_sq_kernel<<<N, 1024, 0, ctx->stream>>>(a, sq);
   PPX_CHECK_LAUNCH(ctx);
   int bx = ppx_cdiv(nmax, 256 * 4);
   if (bx < 1) bx = 1;
@@ -406,4 +432,4 @@ int ppx_normalize(ppx_ctx *ctx, double *const *W, const int64_t *s, int N, int R
   return PPX_OK;
 }
 
-}  // extern "C"
+

@@ -1,0 +1,698 @@
+// als_CP.cxx -- CP decomposition drivers on the ppx C ABI.  Control flow, printed lines and CSV columns follow
+// /root/reference/als_CP.cxx (cited per block); the arithmetic is one ppx_* call where the reference has a CTF
+// expression.  Differences that are deliberate are listed in DESIGN.md ("Reference quirks").
+#include "als_CP.h"
+#include <algorithm>
+#include <cmath>
+#include <numeric>
+
+namespace {
+
+const char *kCsvHeader = "[dim],[iter],[gradnorm],[tol],[pp_update],[diffV],[dtime]";
+
+double synced_time(World &dw) {
+  dw.sync();
+  return wall_time();
+}
+
+string all_modes(int N) {
+  string s;
+  for (int i = 0; i < N; i++) s.push_back((char)('a' + i));
+  return s;
+}
+string without(const string &s, int i, int j = -1) {
+  string o;
+  for (int k = 0; k < (int)s.size(); k++)
+    if (k != i && k != j) o.push_back(s[k]);
+  return o;
+}
+
+// one "[dim]= .. [iter]= .." line + CSV row (als_CP.cxx:193-201, 484-493, 724-733)
+void log_row(Tensor<> &V, int iter, double gradnorm, double tol, int pp_update, double diffV, double dtime,
+             ofstream &Plot_File, World &dw) {
+  if (trace_sink()) trace_sink()->rows.push_back({(double)iter, gradnorm, pp_update, diffV, dtime});
+  if (dw.rank != 0) return;
+  // the reference prints the GLOBAL leading dimension; with a sharded leading mode report the global size
+  const int64_t dim0 = (dw.np > 1 && dw.shard_mode == 0) ? dw.shard_global : V.lens[0];
+  if (!trace_quiet())
+    cout << "  [dim]=  " << dim0 << "  [iter]=  " << iter << "  [gradnorm]  " << gradnorm << "  [tol]  " << tol
+         << "  [pp_update]  " << pp_update << "  [diffV]  " << diffV << "  [dtime]  " << dtime << "\n";
+  if (Plot_File.is_open()) {
+    Plot_File << dim0 << "," << iter << "," << gradnorm << "," << tol << "," << pp_update << "," << diffV << ","
+              << dtime << "\n";
+    if (iter % 100 == 0 && iter != 0) Plot_File << endl;
+  }
+}
+
+double residual_or_skip(Tensor<> &V, Matrix<> *W, World &dw) {
+  if (trace_sink() && trace_sink()->skip_residual) return -1.0;
+  return cp_residual_norm(V, W, V.order, dw);
+}
+
+// local sums of squares of N matrices -> host; entry `shard_mode` is summed over ranks
+void sqnorms_global(Matrix<> *const *mats, int n, double *host, World &dw, const int *mode_of = nullptr) {
+  const double *xs[32];
+  int64_t ns[32];
+  for (int i = 0; i < n; i++) {
+    xs[i] = mats[i]->data;
+    ns[i] = mats[i]->size;
+  }
+  for (int b = 0; b < n; b += 16) {
+    const int c = std::min(16, n - b);
+    PPXCK(dw, ppx_sqnorms(dw.ctx, xs + b, ns + b, c, dw.scal_dev + b));
+  }
+  if (dw.np > 1)
+    for (int i = 0; i < n; i++) {
+      const int mode = mode_of ? mode_of[i] : i;
+      if (mode == dw.shard_mode) dw.allreduce(dw.scal_dev + i, 1);
+    }
+  dw.fetch(dw.scal_dev, host, n);
+}
+
+double gradnorm_global(Matrix<> *grad_W, int N, World &dw) {
+  Matrix<> *ptrs[16];
+  for (int i = 0; i < N; i++) ptrs[i] = &grad_W[i];
+  double h[16];
+  sqnorms_global(ptrs, N, h, dw);
+  double acc = 0;
+  for (int i = 0; i < N; i++) acc += h[i];
+  return std::sqrt(acc);
+}
+
+void normalize_with_grams(Matrix<> *W, int N, GramCache &gc, World &dw) {
+  double *wp[16], *gp[16];
+  int64_t s[16];
+  for (int i = 0; i < N; i++) {
+    wp[i] = W[i].data;
+    gp[i] = gc.G[i].data;
+    s[i] = W[i].nrow;
+  }
+  if (dw.np > 1)
+    PPXCK(dw, ppx_normalize_g(dw.ctx, wp, s, N, gc.R, gp));  // norms from trace(G): G of the sharded mode is global
+  else
+    PPXCK(dw, ppx_normalize(dw.ctx, wp, s, N, gc.R, gp));
+}
+
+// MTTKRP of leaf mode i from the dimension tree (als_CP.cxx:236-284 / 520-569).
+// Order-3 extension: a leaf whose parent is the root is contracted straight from V by the first-level rule (the
+// reference recurses forever there -- als_CP.cxx:125 "V.order should be >=4").
+Matrix<> leaf_mttkrp(map<string, Tensor<>> &mttkrp_map, map<string, string> &parent, map<string, string> &sibling,
+                     Tensor<> &V, Matrix<> *W, int i, World &dw) {
+  const string a(1, (char)('a' + i));
+  const string par = parent[a];
+  Matrix<> M(W[i].nrow, W[i].ncol, dw);
+  if ((int)par.size() == V.order) {
+    map<string, Tensor<>> tmp;
+    mttkrp_map_DT(tmp, parent, sibling, V, W, a, dw);
+    PPXCK(dw, ppx_memcpy_d2d(dw.ctx, M.data, tmp[a].data, sizeof(double) * M.size));
+  } else {
+    if (mttkrp_map.find(par) == mttkrp_map.end()) mttkrp_map_DT(mttkrp_map, parent, sibling, V, W, par, dw);
+    Tensor<> &T = mttkrp_map[par];
+    const int R = (int)W[i].ncol;
+    const int pos = (int)par.find(a[0]);
+    if (par.size() == 2) {  // als_CP.cxx:243-259
+      const int xs = 1 - pos;
+      Matrix<> &Wx = W[par[xs] - 'a'];
+      PPXCK(dw, ppx_mttv(dw.ctx, T.data, T.lens, 2, xs, Wx.data, Wx.nrow, R, M.data));
+    } else {  // als_CP.cxx:260-283: two factors at once
+      int x1 = -1, x2 = -1;
+      for (int k = 0; k < 3; k++)
+        if (k != pos) (x1 < 0 ? x1 : x2) = k;
+      Matrix<> &W1 = W[par[x1] - 'a'], &W2 = W[par[x2] - 'a'];
+      PPXCK(dw, ppx_mttv2(dw.ctx, T.data, T.lens, 3, x1, W1.data, W1.nrow, x2, W2.data, W2.nrow, R, M.data));
+    }
+  }
+  if (dw.np > 1 && i != dw.shard_mode) dw.allreduce(M.data, M.size);  // partial sums over the sharded mode
+  return M;
+}
+
+// one exact ALS sweep over all modes with the dimension tree
+void dt_sweep(Tensor<> &V, Matrix<> *W, Matrix<> *grad_W, Matrix<> *F, double lambda, bool always_regul,
+              map<string, string> &parent, map<string, string> &sibling, GramCache &gc, Matrix<> &S, World &dw) {
+  const int N = V.order;
+  map<string, Tensor<>> mttkrp_map;  // cleared every sweep (als_CP.cxx:215)
+  for (int i = 0; i < N; i++) {
+    Matrix<> M = leaf_mttkrp(mttkrp_map, parent, sibling, V, W, i, dw);
+    gc.hadamard(i, (always_regul || lambda != 0) ? lambda : 0.0, S, dw);          // :288-292 / :573-579
+    if (F) PPXCK(dw, ppx_axpby(dw.ctx, 1.0, F[i].data, 1.0, M.data, M.size));     // :294
+    solve_update_fused(M, S, W[i], nullptr, 1.0, &grad_W[i], nullptr, dw.solver, dw);  // :296-297
+    gc.refresh(W, i, dw);
+  }
+  normalize_with_grams(W, N, gc, dw);  // :303
+}
+
+}  // namespace
+
+vector<int> sort_indexes(const vector<double> &v) {
+  vector<int> idx(v.size());
+  std::iota(idx.begin(), idx.end(), 0);
+  std::stable_sort(idx.begin(), idx.end(), [&v](int i1, int i2) { return v[i1] > v[i2]; });
+  return idx;
+}
+
+bool alsCP(Tensor<> &V, Matrix<> *W, Matrix<> *grad_W, Matrix<> *F, double tol, double timelimit, int maxiter,
+           World &dw) {
+  // als_CP.cxx:20-115: one full MTTKRP per mode (KhatriRao_contract), gradient from scratch every 100 iterations
+  const int N = V.order;
+  double st_time = synced_time(dw);
+  int iter;
+  double projnorm = 0, Fnorm = 0;
+  GramCache gc;
+  gc.init(W, N, dw);
+  Matrix<> S((int64_t)W[0].ncol, (int64_t)W[0].ncol, dw);
+  for (iter = 0; iter <= maxiter; iter++) {
+    if (iter % 100 == 0 || iter == maxiter) {
+      gradient_CP(V, W, grad_W, dw);
+      double h[32];
+      Matrix<> *ptrs[32];
+      vector<Matrix<>> proj;
+      for (int i = 0; i < N; i++) {
+        proj.emplace_back(grad_W[i]);
+        PPXCK(dw, ppx_axpby(dw.ctx, -1.0, F[i].data, 1.0, proj[i].data, proj[i].size));  // grad - F  (:48)
+      }
+      int modes[32];
+      for (int i = 0; i < N; i++) {
+        ptrs[i] = &proj[i];
+        ptrs[N + i] = &F[i];
+        modes[i] = modes[N + i] = i;
+      }
+      sqnorms_global(ptrs, 2 * N, h, dw, modes);
+      projnorm = 0;
+      Fnorm = 0;
+      for (int i = 0; i < N; i++) {
+        projnorm += h[i];
+        Fnorm += std::sqrt(h[N + i]);
+      }
+      projnorm = std::sqrt(projnorm);
+      if (dw.rank == 0 && !trace_quiet())
+        cout << "  [dim]=  " << V.lens[0] << "  [iter]=  " << iter << "  [projnorm]  " << projnorm << "  [tol]  "
+             << tol << "  [Fnorm]  " << Fnorm << "\n";
+      if (trace_sink()) trace_sink()->rows.push_back({(double)iter, projnorm, 0, Fnorm, 0.0});
+      if (projnorm < tol || synced_time(dw) - st_time > timelimit) break;
+    }
+    for (int i = 0; i < N; i++) {
+      int index[16], lens_H[16];
+      for (int j = 0; j < N; j++) index[j] = j;
+      std::swap(index[i], index[N - 1]);  // :66-79
+      Matrix<> M(W[i].nrow, W[i].ncol, dw);
+      KhatriRao_contract(M, V, W, index, lens_H, dw);
+      if (dw.np > 1 && i != dw.shard_mode) dw.allreduce(M.data, M.size);
+      gc.hadamard(i, 0.0, S, dw);
+      PPXCK(dw, ppx_axpby(dw.ctx, 1.0, F[i].data, 1.0, M.data, M.size));
+      SVD_solve(M, W[i], S);
+      gc.refresh(W, i, dw);
+    }
+    if (Fnorm == 0) normalize_with_grams(W, N, gc, dw);
+    if (iter % 10 == 0 && dw.rank == 0 && !trace_quiet()) printf(".");
+  }
+  if (dw.rank == 0 && !trace_quiet()) {
+    printf("\nIter = %d Final proj-grad norm %E \n", iter, projnorm);
+    printf("tf took %lf seconds\n", synced_time(dw) - st_time);
+  }
+  return iter != maxiter + 1;
+}
+
+bool alsCP_DT(Tensor<> &V, Matrix<> *W, Matrix<> *grad_W, Matrix<> *F, double tol, double timelimit, int maxiter,
+              double lambda, ofstream &Plot_File, int resprint, bool bench, World &dw) {
+  // als_CP.cxx:127-320
+  cout.precision(13);
+  const int N = V.order;
+  if (!bench && dw.rank == 0 && Plot_File.is_open()) Plot_File << kCsvHeader << "\n";
+  double st_time = synced_time(dw);
+  int iter;
+  double projnorm = 0, diffnorm_V = 1000;
+  Matrix<> S((int64_t)W[0].ncol, (int64_t)W[0].ncol, dw);
+  map<string, string> parent, sibling;
+  Construct_Dimension_Tree(parent, sibling, 0, N - 1);
+  GramCache gc;
+  gc.init(W, N, dw);
+  for (iter = 0; iter <= maxiter; iter++) {
+    if (iter % resprint == 0 || iter == maxiter) {  // :166-213
+      const double st_time1 = synced_time(dw);
+      projnorm = gradnorm_global(grad_W, N, dw);
+      diffnorm_V = residual_or_skip(V, W, dw);
+      st_time += synced_time(dw) - st_time1;  // the residual evaluation is taken off the clock (:189)
+      const double dtime = wall_time() - st_time;
+      if (!bench) {
+        log_row(V, iter, projnorm, tol, 0, diffnorm_V, dtime, Plot_File, dw);
+      } else if (iter != 0) {
+        if (trace_sink()) trace_sink()->bench_times.push_back(dtime);
+        if (dw.rank == 0) {
+          if (!trace_quiet()) cout << "  [dimension tree step time]  " << dtime << "\n";
+          if (Plot_File.is_open()) Plot_File << "[DTtime]" << "," << dtime << "\n";
+        }
+      }
+      if (projnorm < tol || wall_time() - st_time > timelimit) break;
+    }
+    dt_sweep(V, W, grad_W, F, lambda, true, parent, sibling, gc, S, dw);
+    if (trace_sink()) trace_sink()->sweeps.push_back({0, iter});
+    if (iter % 10 == 0 && dw.rank == 0 && !trace_quiet()) printf(".");
+  }
+  if (dw.rank == 0 && !trace_quiet()) {
+    printf("\nIter = %d Final proj-grad norm %E \n", iter, projnorm);
+    printf("tf took %lf seconds\n", synced_time(dw) - st_time);
+  }
+  if (!bench && Plot_File.is_open()) Plot_File.close();
+  return iter != maxiter + 1;
+}
+
+void stringbuilder_mttkrp(const char *seq, char *seq_return, int N, World &dw) {
+  // als_CP.cxx:323-350: contracted modes -> remaining modes followed by '*'; "0" -> all modes
+  (void)dw;
+  const string s(seq);
+  string out;
+  if (s == "0") {
+    out = all_modes(N);
+  } else {
+    for (int i = 0; i < N; i++)
+      if (s.find((char)('a' + i)) == string::npos) out.push_back((char)('a' + i));
+    out.push_back('*');
+  }
+  memcpy(seq_return, out.c_str(), out.size() + 1);
+}
+
+void Build_mttkrp_map(map<string, Tensor<>> &mttkrp_map, Tensor<> &V, Matrix<> *W, const char *seq_c, World &dw) {
+  // als_CP.cxx:352-409
+  const string seq(seq_c);
+  const int N = V.order;
+  if (seq.size() == 1) {  // level 1: the first contraction with V (:360-380)
+    mttkrp_map[seq] = contract_mode(V, all_modes(N), false, seq[0], W[seq[0] - 'a'], dw);
+    return;
+  }
+  const string prefix = seq.substr(0, seq.size() - 1);  // :385-390
+  if (mttkrp_map.find(prefix) == mttkrp_map.end()) Build_mttkrp_map(mttkrp_map, V, W, prefix.c_str(), dw);
+  string kept;
+  for (int i = 0; i < N; i++)
+    if (prefix.find((char)('a' + i)) == string::npos) kept.push_back((char)('a' + i));
+  const char x = seq.back();
+  mttkrp_map[seq] = contract_mode(mttkrp_map[prefix], kept, true, x, W[x - 'a'], dw);  // :407-408
+}
+
+namespace {
+
+// all pair operators, then all singles (als_CP.cxx:676-694); afterwards only the operators the PP sweep reads are
+// kept (the reference leaves the 3 level-1 tensors -- 32 GB at N=4, s=300, R=50 -- in the map until the next clear)
+void build_pp_operators(map<string, Tensor<>> &mttkrp_map, Tensor<> &V, Matrix<> *W, World &dw) {
+  const int N = V.order;
+  const string seq = all_modes(N);
+  mttkrp_map.clear();
+  auto finish = [&](const string &key) {
+    // an operator that has contracted the sharded mode holds a partial sum over the local slab
+    if (dw.np > 1 && key.find((char)('a' + dw.shard_mode)) != string::npos)
+      dw.allreduce(mttkrp_map[key].data, mttkrp_map[key].size);
+  };
+  for (int ii = 0; ii < N; ii++)
+    for (int jj = ii + 1; jj < N; jj++) {
+      const string key = without(seq, ii, jj);
+      Build_mttkrp_map(mttkrp_map, V, W, key.c_str(), dw);
+      finish(key);
+    }
+  for (int ii = 0; ii < N; ii++) {
+    const string key = without(seq, ii);
+    Build_mttkrp_map(mttkrp_map, V, W, key.c_str(), dw);
+    // built from an already reduced pair operator: complete, nothing to reduce
+  }
+  for (auto it = mttkrp_map.begin(); it != mttkrp_map.end();) {
+    if ((int)it->first.size() < N - 2) it = mttkrp_map.erase(it);
+    else ++it;
+  }
+}
+
+// PP-corrected MTTKRP of mode i (als_CP.cxx:774-794), all operators in one launch
+void pp_corrected_mttkrp(map<string, Tensor<>> &mttkrp_map, Matrix<> *W, Matrix<> *dW, int i, int N, Matrix<> &M,
+                         Matrix<> &zero_M, World &dw) {
+  const string seq = all_modes(N);
+  const double *ops[16], *dws[16];
+  int which[16];
+  int64_t s_other[16];
+  int n = 0;
+  const bool reduce = dw.np > 1 && i != dw.shard_mode;
+  for (int j = 0; j < N; j++) {
+    if (j == i) continue;
+    // multi-GPU: P^(shard,i) is contracted over the sharded index -> partial sums; the replicated terms are added
+    // on rank 0 only and the result is summed over ranks
+    if (reduce && dw.rank != 0 && j != dw.shard_mode) continue;
+    Tensor<> &P = mttkrp_map[without(seq, std::min(i, j), std::max(i, j))];
+    ops[n] = P.data;
+    which[n] = (j < i) ? 0 : 1;  // j<i: contract the operator's first index (:785); j>i: the second (:793)
+    dws[n] = dW[j].data;
+    s_other[n] = dW[j].nrow;
+    n++;
+  }
+  const double *M0 = (reduce && dw.rank != 0) ? zero_M.data : mttkrp_map[without(seq, i)].data;  // :778
+  PPXCK(dw, ppx_pp_correct(dw.ctx, M0, ops, which, dws, s_other, n, W[i].nrow, (int)W[i].ncol, M.data));
+  if (reduce) dw.allreduce(M.data, M.size);
+}
+
+}  // namespace
+
+double alsCP_DT_sub(Tensor<> &V, Matrix<> *W, Matrix<> *grad_W, Matrix<> *dW, Matrix<> *F, double tol, double tol_init,
+                    double timelimit, int maxiter, double &st_time, double lambda, ofstream &Plot_File,
+                    double &projnorm, int &iter, int resprint, World &dw) {
+  // als_CP.cxx:418-612
+  (void)F;
+  const int N = V.order;
+  vector<Matrix<>> W_prev;  // zero-initialised: the first sweep can never switch (:428-431)
+  for (int i = 0; i < N; i++) W_prev.emplace_back(W[i].nrow, W[i].ncol, dw);
+  double diffnorm_V = 1000;
+  Matrix<> S((int64_t)W[0].ncol, (int64_t)W[0].ncol, dw);
+  map<string, string> parent, sibling;
+  Construct_Dimension_Tree(parent, sibling, 0, N - 1);
+  GramCache gc;
+  gc.init(W, N, dw);
+  for (; iter <= maxiter; iter++) {
+    if (iter % resprint == 0 || iter == maxiter) {  // :457-498
+      const double st_time1 = synced_time(dw);
+      projnorm = gradnorm_global(grad_W, N, dw);
+      diffnorm_V = residual_or_skip(V, W, dw);
+      st_time += synced_time(dw) - st_time1;
+      const double dtime = wall_time() - st_time;
+      log_row(V, iter, projnorm, tol, 0, diffnorm_V, dtime, Plot_File, dw);
+      if (projnorm < tol || wall_time() - st_time > timelimit) break;
+    }
+    dt_sweep(V, W, grad_W, nullptr, lambda, false, parent, sibling, gc, S, dw);  // :499-592
+    if (trace_sink()) trace_sink()->sweeps.push_back({0, iter});
+    // :594-605  dW = W - W_prev; W_prev = W; switch when every ||dW_i||/||W_i|| < tol_init
+    for (int i = 0; i < N; i++)
+      PPXCK(dw, ppx_diff_update(dw.ctx, W[i].data, W_prev[i].data, dW[i].data, W[i].size, dw.scal_dev + 2 * i));
+    if (dw.np > 1) dw.allreduce(dw.scal_dev + 2 * dw.shard_mode, 2);
+    double h[32];
+    dw.fetch(dw.scal_dev, h, 2 * N);
+    int num_dw_break = 0;
+    for (int i = 0; i < N; i++)
+      if (std::fabs(std::sqrt(h[2 * i]) / std::sqrt(h[2 * i + 1])) < tol_init) num_dw_break++;
+    if (num_dw_break == N) return diffnorm_V;  // returns BEFORE iter++ of this sweep (:604-605)
+    if (iter % 10 == 0 && dw.rank == 0 && !trace_quiet()) printf(".");
+  }
+  return diffnorm_V;
+}
+
+double alsCP_PP_sub(Tensor<> &V, Matrix<> *W, Matrix<> *grad_W, Matrix<> *dW, Matrix<> *F, double tol, double tol_init,
+                    double timelimit, int maxiter, double &st_time, double lambda, double ratio_step,
+                    ofstream &Plot_File, double &projnorm, int &iter, int resprint, bool bench, World &dw) {
+  // als_CP.cxx:621-833
+  (void)F;
+  const int N = V.order;
+  const int R = (int)W[0].ncol;
+  double dtime_first = 0;
+  const int init_iter = iter;
+  double diffnorm_V = 1000;
+  vector<Matrix<>> W_init(N);
+  map<string, Tensor<>> mttkrp_map;
+  Matrix<> S((int64_t)R, (int64_t)R, dw);
+  vector<Matrix<>> M;
+  for (int i = 0; i < N; i++) M.emplace_back(W[i].nrow, W[i].ncol, dw);
+  Matrix<> zero_M;
+  if (dw.np > 1) {
+    int64_t smax = 0;
+    for (int i = 0; i < N; i++) smax = std::max(smax, W[i].nrow);
+    zero_M = Matrix<>(smax, R, dw);
+  }
+  GramCache gc;
+  gc.init(W, N, dw);
+  void *graph = nullptr;  // the approximate sweep replayed as one CUDA graph (pointers are fixed within a PP phase)
+
+  // the approximate sweep: per mode correction -> Gram-Hadamard -> solve (+grad, dW) -> Gram; then Normalize and the
+  // 2N squared norms the switching test needs (:754-825, :657-664)
+  auto enqueue_sweep = [&]() {
+    for (int i = 0; i < N; i++) {
+      pp_corrected_mttkrp(mttkrp_map, W, dW, i, N, M[i], zero_M, dw);
+      gc.hadamard(i, lambda, S, dw);  // S from the CURRENT W (:796-802)
+      solve_update_fused(M[i], S, W[i], &W_init[i], ratio_step, &grad_W[i], &dW[i], dw.solver, dw);  // :811-812
+      gc.refresh(W, i, dw);
+    }
+    normalize_with_grams(W, N, gc, dw);  // after dW was taken; W_init is never rescaled (:825)
+    const double *xs[32];
+    int64_t ns[32];
+    for (int i = 0; i < N; i++) {
+      xs[2 * i] = dW[i].data;
+      xs[2 * i + 1] = W[i].data;
+      ns[2 * i] = ns[2 * i + 1] = W[i].size;
+    }
+    for (int b = 0; b < 2 * N; b += 16)
+      PPXCK(dw, ppx_sqnorms(dw.ctx, xs + b, ns + b, std::min(16, 2 * N - b), dw.scal_dev + b));
+    if (dw.np > 1) dw.allreduce(dw.scal_dev + 2 * dw.shard_mode, 2);
+    PPXCK(dw, ppx_memcpy_d2h(dw.ctx, dw.scal_host, dw.scal_dev, sizeof(double) * 2 * N));
+  };
+
+  bool norms_valid = false;  // scal_host holds ||dW_i||^2, ||W_i||^2 of the state after the last sweep
+  for (; iter <= maxiter; iter++) {
+    int num_dw_break = 0;
+    if (!bench) {  // :657-665
+      double h[32];
+      if (norms_valid) {
+        dw.sync();
+        memcpy(h, dw.scal_host, sizeof(double) * 2 * N);
+      } else {
+        Matrix<> *ptrs[32];
+        int modes[32];
+        for (int i = 0; i < N; i++) {
+          ptrs[2 * i] = &dW[i];
+          ptrs[2 * i + 1] = &W[i];
+          modes[2 * i] = modes[2 * i + 1] = i;
+        }
+        sqnorms_global(ptrs, 2 * N, h, dw, modes);
+      }
+      for (int i = 0; i < N; i++)
+        if (std::fabs(std::sqrt(h[2 * i]) / std::sqrt(h[2 * i + 1])) > tol_init) num_dw_break++;
+    }
+    if ((iter - init_iter) % 15 == 0 || num_dw_break > 0) {  // :667-695
+      if (num_dw_break > 0 || iter != init_iter) {
+        if (graph) ppx_graph_destroy(dw.ctx, graph);
+        return diffnorm_V;
+      }
+      for (int j = 0; j < N; j++) {
+        W_init[j] = W[j];
+        dW[j].set_zero();
+      }
+      build_pp_operators(mttkrp_map, V, W, dw);
+      if (trace_sink()) trace_sink()->sweeps.push_back({2, iter});
+    }
+    if (iter % resprint == 0 || iter == maxiter || iter == init_iter) {  // :697-752
+      const double st_time1 = synced_time(dw);
+      projnorm = gradnorm_global(grad_W, N, dw);
+      diffnorm_V = residual_or_skip(V, W, dw);
+      norms_valid = false;  // scal_dev was reused
+      st_time += synced_time(dw) - st_time1;
+      const double dtime = wall_time() - st_time;
+      if (!bench) {
+        log_row(V, iter, projnorm, tol, 1, diffnorm_V, dtime, Plot_File, dw);
+      } else if (iter != maxiter) {  // :736-738
+        dtime_first = dtime;
+        st_time = wall_time();
+      } else {  // :739-747
+        dtime_first = dtime_first + dtime;
+        if (trace_sink()) {
+          trace_sink()->bench_times.push_back(dtime_first);
+          trace_sink()->bench_times.push_back(dtime);
+        }
+        if (dw.rank == 0) {
+          if (!trace_quiet()) {
+            cout << "  [PP first time]  " << dtime_first << "\n";
+            cout << "  [PP second time]  " << dtime << "\n";
+          }
+          if (Plot_File.is_open()) {
+            Plot_File << "  [PPfirst]  " << "," << dtime_first << "\n";
+            Plot_File << "  [PPsecond]  " << "," << dtime << "\n";
+          }
+        }
+      }
+      if (projnorm < tol || wall_time() - st_time > timelimit) break;
+    }
+    if (dw.use_graph && dw.np == 1) {
+      if (!graph) {
+        PPXCK(dw, ppx_graph_begin(dw.ctx));
+        enqueue_sweep();
+        PPXCK(dw, ppx_graph_end(dw.ctx, &graph));
+      }
+      PPXCK(dw, ppx_graph_launch(dw.ctx, graph));
+    } else {
+      enqueue_sweep();
+    }
+    norms_valid = true;
+    if (trace_sink()) trace_sink()->sweeps.push_back({1, iter});
+    if (iter % 10 == 0 && dw.rank == 0 && !trace_quiet()) printf(".");
+  }
+  if (graph) ppx_graph_destroy(dw.ctx, graph);
+  if (bench) iter++;
+  return diffnorm_V;
+}
+
+bool alsCP_PP(Tensor<> &V, Matrix<> *W, Matrix<> *grad_W, Matrix<> *F, double tol, double tol_init, double timelimit,
+              int maxiter, double lambda, double ratio_step, ofstream &Plot_File, int resprint, bool bench,
+              World &dw) {
+  // als_CP.cxx:1082-1137
+  cout.precision(13);
+  const int N = V.order;
+  if (!bench && dw.rank == 0 && Plot_File.is_open()) Plot_File << kCsvHeader << "\n";
+  double st_time = synced_time(dw);
+  int iter = 0;
+  double gradnorm = 10.;
+  vector<Matrix<>> dW;
+  for (int j = 0; j < N; j++) dW.emplace_back(W[j].nrow, W[j].ncol, dw);
+  while (gradnorm > tol && iter <= maxiter) {
+    if (!bench) {
+      if (dw.rank == 0 && !trace_quiet()) printf("DT starts from %d\n", iter);
+      if (trace_sink()) trace_sink()->events.push_back({0, iter});
+      alsCP_DT_sub(V, W, grad_W, dW.data(), F, tol, tol_init, timelimit, maxiter, st_time, lambda, Plot_File, gradnorm,
+                   iter, resprint, dw);
+    }
+    if (dw.rank == 0 && !trace_quiet()) printf("pairwise perturbation starts from %d\n", iter);
+    if (trace_sink()) trace_sink()->events.push_back({1, iter});
+    alsCP_PP_sub(V, W, grad_W, dW.data(), F, tol, tol_init, timelimit, maxiter, st_time, lambda, ratio_step, Plot_File,
+                 gradnorm, iter, resprint, bench, dw);
+  }
+  if (dw.rank == 0 && !trace_quiet()) {
+    printf("\nIter = %d Final grad norm %E \n", iter, gradnorm);
+    printf("tf took %lf seconds\n", synced_time(dw) - st_time);
+  }
+  if (!bench && Plot_File.is_open()) Plot_File.close();
+  return iter != maxiter + 1;
+}
+
+double alsCP_PP_partupdate_sub(Tensor<> &V, Matrix<> *W, Matrix<> *grad_W, Matrix<> *dW, Matrix<> *F, double tol,
+                               double tol_init, double timelimit, int maxiter, double update_percentage,
+                               double &st_time, double lambda, double ratio_step, ofstream &Plot_File,
+                               double &projnorm, int &iter, int resprint, bool bench, World &dw) {
+  // als_CP.cxx:852-1073: like alsCP_PP_sub but the perturbation dM is PROPAGATED to the other modes after each
+  // update (:1036-1053) and only the update_size most perturbed modes are solved per sweep (:991-1001)
+  (void)F;
+  const int N = V.order;
+  const int R = (int)W[0].ncol;
+  if (dw.np > 1) throw std::runtime_error("alsCP_PP_partupdate: multi-GPU not supported yet");
+  double dtime_first = 0;
+  const int init_iter = iter;
+  double diffnorm_V = 1000;
+  vector<Matrix<>> W_init(N), dM, M;
+  for (int i = 0; i < N; i++) {
+    dM.emplace_back(W[i].nrow, W[i].ncol, dw);
+    M.emplace_back(W[i].nrow, W[i].ncol, dw);
+  }
+  map<string, Tensor<>> mttkrp_map;
+  Matrix<> S((int64_t)R, (int64_t)R, dw);
+  GramCache gc;
+  gc.init(W, N, dw);
+  vector<double> W_relative_perturbe(N, 0.);
+  const int update_size = (int)(N * update_percentage);
+  const string seq = all_modes(N);
+  for (; iter <= maxiter; iter++) {
+    int num_dw_break = 0;
+    if (!bench) {
+      Matrix<> *ptrs[32];
+      int modes[32];
+      double h[32];
+      for (int i = 0; i < N; i++) {
+        ptrs[2 * i] = &dW[i];
+        ptrs[2 * i + 1] = &W[i];
+        modes[2 * i] = modes[2 * i + 1] = i;
+      }
+      sqnorms_global(ptrs, 2 * N, h, dw, modes);
+      for (int i = 0; i < N; i++)
+        if (std::fabs(std::sqrt(h[2 * i]) / std::sqrt(h[2 * i + 1])) > tol_init) num_dw_break++;
+    }
+    if ((iter - init_iter) % 15 == 0 || num_dw_break > 0) {
+      if (num_dw_break > 0 || iter != init_iter) return diffnorm_V;
+      for (int j = 0; j < N; j++) {
+        W_init[j] = W[j];
+        dW[j].set_zero();
+      }
+      build_pp_operators(mttkrp_map, V, W, dw);
+      if (trace_sink()) trace_sink()->sweeps.push_back({2, iter});
+    }
+    if (iter % resprint == 0 || iter == maxiter || iter == init_iter) {
+      const double st_time1 = synced_time(dw);
+      projnorm = gradnorm_global(grad_W, N, dw);
+      diffnorm_V = residual_or_skip(V, W, dw);
+      st_time += synced_time(dw) - st_time1;
+      const double dtime = wall_time() - st_time;
+      if (!bench) {
+        log_row(V, iter, projnorm, tol, 1, diffnorm_V, dtime, Plot_File, dw);
+      } else if (iter != maxiter) {
+        dtime_first = dtime;
+        st_time = wall_time();
+      } else {
+        dtime_first = dtime_first + dtime;
+        if (trace_sink()) {
+          trace_sink()->bench_times.push_back(dtime_first);
+          trace_sink()->bench_times.push_back(dtime);
+        }
+        if (dw.rank == 0 && !trace_quiet()) {
+          cout << "  [PP first time]  " << dtime_first << "\n";
+          cout << "  [PP second time]  " << dtime << "\n";
+        }
+      }
+      if (projnorm < tol || wall_time() - st_time > timelimit) break;
+    }
+    const vector<int> sorted_indices = sort_indexes(W_relative_perturbe);  // :992
+    if (dw.rank == 0 && !trace_quiet()) cout << "new round" << endl;
+    for (int t = 0; t < update_size; t++) {
+      const int i = sorted_indices[t];
+      if (dw.rank == 0 && !trace_quiet()) cout << i << endl;
+      // M[i] = M_i(W_init) + dM[i]   (:1025)
+      PPXCK(dw, ppx_memcpy_d2d(dw.ctx, M[i].data, mttkrp_map[without(seq, i)].data, sizeof(double) * M[i].size));
+      PPXCK(dw, ppx_axpby(dw.ctx, 1.0, dM[i].data, 1.0, M[i].data, M[i].size));
+      gc.hadamard(i, lambda, S, dw);
+      solve_update_fused(M[i], S, W[i], &W_init[i], ratio_step, &grad_W[i], &dW[i], dw.solver, dw);  // :1034-1035
+      gc.refresh(W, i, dw);
+      dM[i].set_zero();  // :1037
+      for (int ii = 0; ii < N; ii++) {  // :1038-1053  dM[ii] += P^(ii,i) x dW[i]
+        if (ii == i) continue;
+        Tensor<> &P = mttkrp_map[without(seq, std::min(i, ii), std::max(i, ii))];
+        const double *ops[1] = {P.data}, *dws[1] = {dW[i].data};
+        const int which[1] = {i < ii ? 0 : 1};  // contract the index that belongs to mode i
+        const int64_t so[1] = {dW[i].nrow};
+        PPXCK(dw, ppx_pp_correct(dw.ctx, dM[ii].data, ops, which, dws, so, 1, W[ii].nrow, R, dM[ii].data));
+      }
+    }
+    {  // :1060-1064
+      Matrix<> *ptrs[32];
+      int modes[32];
+      double h[32];
+      for (int i = 0; i < N; i++) {
+        ptrs[2 * i] = &dM[i];
+        ptrs[2 * i + 1] = &M[i];
+        modes[2 * i] = modes[2 * i + 1] = i;
+      }
+      sqnorms_global(ptrs, 2 * N, h, dw, modes);
+      for (int i = 0; i < N; i++) W_relative_perturbe[i] = std::sqrt(h[2 * i]) / std::sqrt(h[2 * i + 1]);
+    }
+    normalize_with_grams(W, N, gc, dw);
+    if (trace_sink()) trace_sink()->sweeps.push_back({1, iter});
+    if (iter % 10 == 0 && dw.rank == 0 && !trace_quiet()) printf(".");
+  }
+  if (bench) iter++;
+  return diffnorm_V;
+}
+
+bool alsCP_PP_partupdate(Tensor<> &V, Matrix<> *W, Matrix<> *grad_W, Matrix<> *F, double tol, double tol_init,
+                         double timelimit, int maxiter, double lambda, double ratio_step, double update_percentage,
+                         ofstream &Plot_File, int resprint, bool bench, World &dw) {
+  // als_CP.cxx:1146-1207
+  cout.precision(13);
+  const int N = V.order;
+  if (dw.rank == 0 && !trace_quiet()) cout << "alsCP_PP_partupdate starts. " << endl;
+  if (!bench && dw.rank == 0 && Plot_File.is_open()) Plot_File << kCsvHeader << "\n";
+  double st_time = synced_time(dw);
+  int iter = 0;
+  double gradnorm = 10.;
+  vector<Matrix<>> dW;
+  for (int j = 0; j < N; j++) dW.emplace_back(W[j].nrow, W[j].ncol, dw);
+  while (gradnorm > tol && iter <= maxiter) {
+    if (!bench) {
+      if (dw.rank == 0 && !trace_quiet()) printf("DT starts from %d\n", iter);
+      if (trace_sink()) trace_sink()->events.push_back({0, iter});
+      alsCP_DT_sub(V, W, grad_W, dW.data(), F, tol, tol_init, timelimit, maxiter, st_time, lambda, Plot_File, gradnorm,
+                   iter, resprint, dw);
+    }
+    if (dw.rank == 0 && !trace_quiet()) printf("pairwise perturbation starts from %d\n", iter);
+    if (trace_sink()) trace_sink()->events.push_back({1, iter});
+    alsCP_PP_partupdate_sub(V, W, grad_W, dW.data(), F, tol, tol_init, timelimit, maxiter, update_percentage, st_time,
+                            lambda, ratio_step, Plot_File, gradnorm, iter, resprint, bench, dw);
+  }
+  if (dw.rank == 0 && !trace_quiet()) {
+    printf("\nIter = %d Final grad norm %E \n", iter, gradnorm);
+    printf("tf took %lf seconds\n", synced_time(dw) - st_time);
+  }
+  if (!bench && Plot_File.is_open()) Plot_File.close();
+  return iter != maxiter + 1;
+}

@@ -1,0 +1,241 @@
+// common.cxx -- see common.h.  Every function cites the reference lines whose behaviour it reproduces.
+#include "common.h"
+#include <chrono>
+#include <cmath>
+
+TraceSink *&trace_sink() {
+  static TraceSink *s = nullptr;
+  return s;
+}
+bool trace_quiet() { return trace_sink() && trace_sink()->quiet; }
+
+double wall_time() {
+  using namespace std::chrono;
+  return duration<double>(steady_clock::now().time_since_epoch()).count();
+}
+
+void vec2str(vector<int> vec, string &seq_out) {
+  // common.cxx:10-18: local indices -> letters, '*' (rank) appended
+  string s;
+  for (int v : vec) s.push_back((char)('a' + v));
+  s.push_back('*');
+  seq_out = s;
+}
+
+void Construct_Dimension_Tree(map<string, string> &parent, map<string, string> &sibling, int start, int end) {
+  // common.cxx:225-270: balanced binary split at (start+end)/2; a node is named by the modes it keeps
+  if (end <= start) return;
+  auto name = [](int lo, int hi) {
+    string s;
+    for (int i = lo; i <= hi; i++) s.push_back((char)('a' + i));
+    return s;
+  };
+  const string whole = name(start, end);
+  const int middle = (end == start + 1) ? start : (start + end) / 2;
+  const string left = name(start, middle), right = name(middle + 1, end);
+  parent[left] = whole;
+  parent[right] = whole;
+  sibling[left] = right;
+  sibling[right] = left;
+  Construct_Dimension_Tree(parent, sibling, start, middle);
+  Construct_Dimension_Tree(parent, sibling, middle + 1, end);
+}
+
+Tensor<> contract_mode(Tensor<> &in, const string &modes, bool has_rank, char x, Matrix<> &Wx, World &dw) {
+  const int k = (int)modes.size();
+  const int pos = (int)modes.find(x);
+  assert(pos >= 0 && pos < k);
+  const int R = (int)Wx.ncol;
+  int64_t out_lens[17];
+  int n = 0;
+  for (int i = 0; i < k; i++)
+    if (i != pos) out_lens[n++] = in.lens[i];
+  out_lens[n++] = R;
+  Tensor<> out(n, out_lens, dw);
+  if (!has_rank) {
+    PPXCK(dw, ppx_ttm_first(dw.ctx, in.data, in.lens, k, pos, Wx.data, Wx.nrow, R, out.data));
+  } else {
+    PPXCK(dw, ppx_mttv(dw.ctx, in.data, in.lens, k, pos, Wx.data, Wx.nrow, R, out.data));
+  }
+  return out;
+}
+
+void mttkrp_map_DT(map<string, Tensor<>> &mttkrp_map, map<string, string> &parent, map<string, string> &sibling,
+                   Tensor<> &V, Matrix<> *W, string args, World &dw) {
+  // common.cxx:20-133
+  if (mttkrp_map.find(args) != mttkrp_map.end()) return;
+  const string par = parent[args];
+  const string sib = sibling[args];
+  if ((int)par.size() == V.order) {
+    // first-level node (common.cxx:29-88): start from V, contract the sibling modes left to right; the first is
+    // the GEMM (common.cxx:56), the rest are Hadamard-batched (common.cxx:83).
+    string modes = par;
+    Tensor<> cur = contract_mode(V, modes, false, sib[0], W[sib[0] - 'a'], dw);
+    modes.erase(modes.find(sib[0]), 1);
+    for (size_t j = 1; j < sib.size(); j++) {
+      Tensor<> nxt = contract_mode(cur, modes, true, sib[j], W[sib[j] - 'a'], dw);
+      modes.erase(modes.find(sib[j]), 1);
+      cur = std::move(nxt);
+    }
+    mttkrp_map[args] = std::move(cur);
+    return;
+  }
+  if (mttkrp_map.find(par) == mttkrp_map.end()) mttkrp_map_DT(mttkrp_map, parent, sibling, V, W, par, dw);  // :89-91
+  // deeper node (common.cxx:94-131): start from the cached parent
+  string modes = par;
+  Tensor<> *src = &mttkrp_map[par];
+  Tensor<> cur;
+  for (size_t j = 0; j < sib.size(); j++) {
+    Tensor<> nxt = contract_mode(*src, modes, true, sib[j], W[sib[j] - 'a'], dw);
+    modes.erase(modes.find(sib[j]), 1);
+    cur = std::move(nxt);
+    src = &cur;
+  }
+  mttkrp_map[args] = std::move(cur);
+}
+
+void build_V(Tensor<> &V, Matrix<> *W, int order, World &dw) {
+  // common.cxx:135-197: V = [[W_0 .. W_{N-1}]]; one fused kernel instead of N-1 growing temporaries
+  int64_t lens[16];
+  const double *ptrs[16];
+  for (int i = 0; i < order; i++) {
+    lens[i] = W[i].nrow;
+    ptrs[i] = W[i].data;
+  }
+  Tensor<> out(order, lens, dw);
+  PPXCK(dw, ppx_cp_reconstruct(dw.ctx, lens, order, ptrs, (int)W[0].ncol, out.data));
+  V = std::move(out);
+}
+
+double cp_residual_norm(Tensor<> &V, Matrix<> *W, int order, World &dw) {
+  const double *ptrs[16];
+  for (int i = 0; i < order; i++) ptrs[i] = W[i].data;
+  PPXCK(dw, ppx_cp_residual(dw.ctx, V.data, V.lens, order, ptrs, (int)W[0].ncol, dw.scal_dev));
+  dw.allreduce(dw.scal_dev, 1);
+  double v;
+  dw.fetch(dw.scal_dev, &v, 1);
+  return std::sqrt(v);
+}
+
+double gradient_norm(Matrix<> *grad_W, int order, World &dw) {
+  const double *xs[16];
+  int64_t ns[16];
+  for (int i = 0; i < order; i++) {
+    xs[i] = grad_W[i].data;
+    ns[i] = grad_W[i].size;
+  }
+  PPXCK(dw, ppx_sqnorms(dw.ctx, xs, ns, order, dw.scal_dev));
+  double h[16];
+  dw.fetch(dw.scal_dev, h, order);
+  double acc = 0;
+  for (int i = 0; i < order; i++) acc += h[i];  // sum of norm2()^2, als_CP.cxx:175-180
+  return std::sqrt(acc);
+}
+
+Matrix<> unroll_tensor_contraction(Tensor<> &T, int i) {
+  // common.cxx:205-223
+  World &dw = *T.wrld;
+  Matrix<> MTM(T.lens[i], T.lens[i], dw);
+  PPXCK(dw, ppx_unfold_gram(dw.ctx, T.data, T.lens, T.order, i, MTM.data));
+  return MTM;
+}
+
+void Normalize(Matrix<> *W, int N, World &dw) {
+  // common.cxx:680-688
+  double *ptrs[16];
+  int64_t s[16];
+  for (int i = 0; i < N; i++) {
+    ptrs[i] = W[i].data;
+    s[i] = W[i].nrow;
+  }
+  PPXCK(dw, ppx_normalize(dw.ctx, ptrs, s, N, (int)W[0].ncol, nullptr));
+}
+
+void solve_update_fused(Matrix<> &M, Matrix<> &S, Matrix<> &W, Matrix<> *W_init, double ratio_step, Matrix<> *grad,
+                        Matrix<> *dW, int mode, World &dw) {
+  PPXCK(dw, ppx_solve_update(dw.ctx, M.data, S.data, W.data, W.nrow, (int)W.ncol, W_init ? W_init->data : nullptr,
+                             ratio_step, mode, grad ? grad->data : nullptr, dW ? dW->data : nullptr, nullptr));
+}
+
+void SVD_solve(Matrix<> &M, Matrix<> &W, Matrix<> &S) {
+  // common.cxx:710-725.  The world's `solver` picks the R x R factorisation (SVD pseudo-inverse semantics or the
+  // Cholesky the north star asks for); both give W = M S^-1.
+  World &dw = *M.wrld;
+  solve_update_fused(M, S, W, nullptr, 1.0, nullptr, nullptr, dw.solver, dw);
+}
+
+void cholesky_solve(Matrix<> &M, Matrix<> &W, Matrix<> &S) {
+  // common.cxx:727-737
+  World &dw = *M.wrld;
+  solve_update_fused(M, S, W, nullptr, 1.0, nullptr, nullptr, PPX_SOLVE_CHOL, dw);
+}
+
+void SVD_solve_mod(Matrix<> &M, Matrix<> &W, Matrix<> &W_init, Matrix<> &dW, Matrix<> &S, double ratio_step) {
+  // common.cxx:739-758
+  World &dw = *M.wrld;
+  solve_update_fused(M, S, W, &W_init, ratio_step, nullptr, &dW, dw.solver, dw);
+}
+
+void gradsubprob(Matrix<> &M, Matrix<> &S, Matrix<> &W, Matrix<> &grad_W) {
+  // common.cxx:1002-1004: grad = -M + W S (W unchanged): run the fused kernel on a scratch copy of W
+  World &dw = *M.wrld;
+  Matrix<> scratch(W);
+  solve_update_fused(M, S, scratch, nullptr, 1.0, &grad_W, nullptr, PPX_SOLVE_CHOL, dw);
+}
+
+void KhatriRao_contract(Matrix<> &M, Tensor<> &V, Matrix<> *W, int *index, int *lens_H, World &dw) {
+  // common.cxx:931-997: contract V with W[index[0]] (GEMM, :963) then W[index[1..N-2]] Hadamard-batched (:992).
+  // The reference permutes the remaining modes into index[] order; the result M (s_{index[N-1]} x R) is the same.
+  (void)lens_H;
+  const int N = V.order;
+  string modes;
+  for (int i = 0; i < N; i++) modes.push_back((char)('a' + i));
+  char x = (char)('a' + index[0]);
+  Tensor<> cur = contract_mode(V, modes, false, x, W[index[0]], dw);
+  modes.erase(modes.find(x), 1);
+  for (int j = 1; j < N - 1; j++) {
+    x = (char)('a' + index[j]);
+    Tensor<> nxt = contract_mode(cur, modes, true, x, W[index[j]], dw);
+    modes.erase(modes.find(x), 1);
+    cur = std::move(nxt);
+  }
+  PPXCK(dw, ppx_memcpy_d2d(dw.ctx, M.data, cur.data, sizeof(double) * M.size));
+}
+
+void GramCache::init(Matrix<> *W, int N_, World &dw) {
+  N = N_;
+  R = (int)W[0].ncol;
+  G.clear();
+  for (int i = 0; i < N; i++) G.emplace_back(R, R, dw);
+  for (int i = 0; i < N; i++) refresh(W, i, dw);
+}
+
+void GramCache::refresh(Matrix<> *W, int i, World &dw) {
+  PPXCK(dw, ppx_gram(dw.ctx, W[i].data, W[i].nrow, W[i].nrow, R, G[i].data));
+  if (dw.np > 1 && i == dw.shard_mode) dw.allreduce(G[i].data, (int64_t)R * R);  // rows of W_i are sharded
+}
+
+void GramCache::hadamard(int skip, double lambda, Matrix<> &S, World &dw) {
+  const double *ptrs[16];
+  for (int i = 0; i < N; i++) ptrs[i] = G[i].data;
+  PPXCK(dw, ppx_hadamard_grams(dw.ctx, ptrs, N, skip, R, lambda, S.data));
+}
+
+void gradient_CP(Tensor<> &V, Matrix<> *W, Matrix<> *grad_W, World &dw) {
+  // common.cxx:1009-1052: grad_W[i] = -MTTKRP_i + W[i] S_i for every mode, from scratch
+  const int N = V.order;
+  GramCache gc;
+  gc.init(W, N, dw);
+  Matrix<> S((int64_t)W[0].ncol, (int64_t)W[0].ncol, dw);
+  for (int i = 0; i < N; i++) {
+    int index[16], lens_H[16];
+    int n = 0;
+    for (int j = 0; j < N; j++)
+      if (j != i) index[n++] = j;
+    index[N - 1] = i;
+    Matrix<> M(W[i].nrow, W[i].ncol, dw);
+    KhatriRao_contract(M, V, W, index, lens_H, dw);
+    gc.hadamard(i, 0.0, S, dw);
+    gradsubprob(M, S, W[i], grad_W[i]);
+  }
+}

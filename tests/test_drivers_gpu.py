@@ -1,0 +1,310 @@
+"""Parity of the C++ host drivers (alsCP_DT, alsCP_PP, alsCP_PP_partupdate, CPD<>::als with the three optimizers,
+hosvd, alsTucker_DT, alsTucker_PP) running on the CUDA kernels, against the CPU oracle on the same seeded inputs.
+
+North-star tolerances: per-sweep fitness (residual / gradient norm) within 1e-10 relative, factors within 1e-8 after
+a fixed sweep count, identical ALS<->PP switching iterations."""
+import importlib
+
+import numpy as np
+import pytest
+
+from oracle import pp_oracle as o
+
+pytestmark = pytest.mark.gpu
+
+FIT_RTOL = 1e-10
+FACTOR_TOL = 1e-8
+
+
+@pytest.fixture(scope="module")
+def H():
+    return importlib.import_module("pairwise-perturbation_b200.host_api")
+
+
+@pytest.fixture(scope="module")
+def world(H):
+    w = H.World(0, solver=0, use_graph=True, workspace_bytes=512 << 20)
+    yield w
+    w.close()
+
+
+def problem(lens, R):
+    V, _ = o.make_tensor_r(lens, R)
+    return V, o.init_factors(lens, R), o.init_grad(lens, R)
+
+
+def to_dev(H, world, V, W, G):
+    Vd = H.Tensor.from_numpy(world, V)
+    Wd = [H.Tensor.from_numpy(world, w, matrix=True) for w in W]
+    Gd = [H.Tensor.from_numpy(world, g, matrix=True) for g in G]
+    Fd = [H.Matrix(world, w.shape[0], w.shape[1]) for w in W]
+    return Vd, Wd, Gd, Fd
+
+
+def free_all(*groups):
+    for g in groups:
+        for t in (g if isinstance(g, (list, tuple)) else [g]):
+            t.free()
+
+
+def check_rows(rows_gpu, rows_ref, vnorm):
+    assert len(rows_gpu) == len(rows_ref)
+    for rg, rr in zip(rows_gpu, rows_ref):
+        it_g, gn_g, pp_g, dv_g = rg[0], rg[1], rg[2], rg[3]
+        it_r, gn_r, pp_r, dv_r = rr
+        assert int(it_g) == it_r and int(pp_g) == pp_r
+        assert abs(gn_g - gn_r) <= FIT_RTOL * max(abs(gn_r), vnorm * 1e-6), (rg, rr)
+        # the residual is a norm of a difference: compare relative to ||V|| (fitness = 1 - residual/||V||)
+        assert abs(dv_g - dv_r) <= FIT_RTOL * vnorm, (rg, rr)
+
+
+def check_factors(Wd, W_ref):
+    for wd, wr in zip(Wd, W_ref):
+        got = wd.numpy()
+        assert np.abs(got - wr).max() <= FACTOR_TOL * max(1.0, np.abs(wr).max())
+
+
+@pytest.mark.parametrize("solver", [0, 1])
+@pytest.mark.parametrize("lens,R,sweeps", [((12, 13, 14, 15), 4, 20), ((10, 11, 12), 3, 20), ((6, 7, 6, 5, 6, 7), 3, 12),
+                                           ((9, 8, 7, 6, 5), 3, 10)])
+def test_alsCP_DT(H, world, lens, R, sweeps, solver):
+    V, W, G = problem(lens, R)
+    vnorm = np.linalg.norm(V)
+    W_ref, G_ref = [w.copy() for w in W], [g.copy() for g in G]
+    ok_ref, tr = o.alsCP_DT(V, W_ref, G_ref, 1e-10 * vnorm, sweeps, lam=0.0, resprint=5,
+                            F=[np.zeros_like(w) for w in W])
+    world.set(solver=solver)
+    Vd, Wd, Gd, Fd = to_dev(H, world, V, W, G)
+    with H.Trace() as t:
+        ok = H.alsCP_DT(world, Vd, Wd, Gd, Fd, 1e-10 * vnorm, sweeps, lam=0.0, resprint=5)
+    assert ok == ok_ref
+    check_rows(t.rows, tr.rows, vnorm)
+    check_factors(Wd, W_ref)
+    check_factors(Gd, G_ref)
+    assert [s[1] for s in t.sweeps] == [s[1] for s in tr.sweeps]
+    free_all(Vd, Wd, Gd, Fd)
+    world.set(solver=0)
+
+
+def test_alsCP_DT_regularised_and_exact_start(H, world):
+    # lambda != 0 path, and the known answer: W0 = truth on an exact rank-R tensor -> residual ~ 0, W unchanged
+    lens, R = (10, 9, 8, 7), 3
+    V, Wt = o.make_tensor_r(lens, R)
+    vnorm = np.linalg.norm(V)
+    W = o.init_factors(lens, R)
+    G = o.init_grad(lens, R)
+    W_ref, G_ref = [w.copy() for w in W], [g.copy() for g in G]
+    _, tr = o.alsCP_DT(V, W_ref, G_ref, 1e-12 * vnorm, 8, lam=1e-3, resprint=2)
+    Vd, Wd, Gd, Fd = to_dev(H, world, V, W, G)
+    with H.Trace() as t:
+        H.alsCP_DT(world, Vd, Wd, Gd, Fd, 1e-12 * vnorm, 8, lam=1e-3, resprint=2)
+    check_rows(t.rows, tr.rows, vnorm)
+    check_factors(Wd, W_ref)
+    free_all(Wd, Gd)
+    Wn = [w.copy() for w in Wt]
+    o.normalize(Wn)
+    Wd = [H.Tensor.from_numpy(world, w, matrix=True) for w in Wn]
+    Gd = [H.Tensor.from_numpy(world, g, matrix=True) for g in G]
+    with H.Trace() as t:
+        H.alsCP_DT(world, Vd, Wd, Gd, Fd, 0.0, 2, resprint=1)
+    assert t.rows[-1][3] <= 1e-12 * vnorm
+    check_factors(Wd, Wn)
+    free_all(Vd, Wd, Gd, Fd)
+
+
+@pytest.mark.parametrize("use_graph", [True, False])
+@pytest.mark.parametrize("lens,R,maxiter,tol_init", [((12, 13, 14, 15), 4, 60, 0.1), ((10, 11, 12), 3, 60, 0.1),
+                                                     ((6, 7, 6, 5, 6, 7), 3, 40, 0.1), ((20, 20, 20, 20), 5, 50, 0.05)])
+def test_alsCP_PP_switching_and_fitness(H, world, lens, R, maxiter, tol_init, use_graph):
+    V, W, G = problem(lens, R)
+    vnorm = np.linalg.norm(V)
+    W_ref, G_ref = [w.copy() for w in W], [g.copy() for g in G]
+    ok_ref, tr = o.alsCP_PP(V, W_ref, G_ref, 1e-10 * vnorm, tol_init, maxiter, resprint=5)
+    world.set(solver=0, use_graph=use_graph)
+    Vd, Wd, Gd, Fd = to_dev(H, world, V, W, G)
+    with H.Trace() as t:
+        ok = H.alsCP_PP(world, Vd, Wd, Gd, Fd, 1e-10 * vnorm, tol_init, maxiter, resprint=5)
+    assert ok == ok_ref
+    kinds = {"DT": 0, "PP": 1}
+    assert t.events == [(kinds[k], it) for k, it in tr.events]  # identical ALS<->PP switching iterations
+    sw = {"DT": 0, "PP": 1, "PPinit": 2}
+    assert t.sweeps == [(sw[k], it) for k, it in tr.sweeps]
+    check_rows(t.rows, tr.rows, vnorm)
+    check_factors(Wd, W_ref)
+    free_all(Vd, Wd, Gd, Fd)
+    world.set(solver=0, use_graph=True)
+
+
+def test_alsCP_PP_ratio_step_and_svd_solver(H, world):
+    lens, R = (11, 12, 13, 10), 4
+    V, W, G = problem(lens, R)
+    vnorm = np.linalg.norm(V)
+    W_ref, G_ref = [w.copy() for w in W], [g.copy() for g in G]
+    _, tr = o.alsCP_PP(V, W_ref, G_ref, 1e-10 * vnorm, 0.1, 40, lam=1e-4, ratio_step=0.8, resprint=4)
+    world.set(solver=1)
+    Vd, Wd, Gd, Fd = to_dev(H, world, V, W, G)
+    with H.Trace() as t:
+        H.alsCP_PP(world, Vd, Wd, Gd, Fd, 1e-10 * vnorm, 0.1, 40, lam=1e-4, ratio_step=0.8, resprint=4)
+    kinds = {"DT": 0, "PP": 1}
+    assert t.events == [(kinds[k], it) for k, it in tr.events]
+    check_rows(t.rows, tr.rows, vnorm)
+    check_factors(Wd, W_ref)
+    free_all(Vd, Wd, Gd, Fd)
+    world.set(solver=0)
+
+
+def test_alsCP_PP_bench_protocol(H, world):
+    # pp_bench: maxiter=1, bench=true -> no DT phase, prints [PP first time] and [PP second time] (als_CP.cxx:736-747)
+    lens, R = (12, 12, 12, 12), 4
+    V, W, G = problem(lens, R)
+    vnorm = np.linalg.norm(V)
+    W_ref, G_ref = [w.copy() for w in W], [g.copy() for g in G]
+    _, tr = o.alsCP_PP(V, W_ref, G_ref, 1e-10 * vnorm, 0.01, 1, bench=True, resprint=1)
+    Vd, Wd, Gd, Fd = to_dev(H, world, V, W, G)
+    with H.Trace() as t:
+        H.alsCP_PP(world, Vd, Wd, Gd, Fd, 1e-10 * vnorm, 0.01, 1, bench=True, resprint=1)
+    assert len(t.bench_times) == 2 and t.bench_times[0] >= t.bench_times[1] > 0
+    assert t.events == [(1, 0)]
+    check_factors(Wd, W_ref)
+    with H.Trace() as t:
+        H.alsCP_DT(world, Vd, Wd, Gd, Fd, 1e-10 * vnorm, 1, bench=True, resprint=1)
+    assert len(t.bench_times) == 1 and t.bench_times[0] > 0
+    free_all(Vd, Wd, Gd, Fd)
+
+
+def test_alsCP_PP_partupdate(H, world):
+    lens, R = (12, 13, 14, 15), 4
+    V, W, G = problem(lens, R)
+    vnorm = np.linalg.norm(V)
+    W_ref, G_ref = [w.copy() for w in W], [g.copy() for g in G]
+    _, tr = o.alsCP_PP_partupdate(V, W_ref, G_ref, 1e-10 * vnorm, 0.1, 30, update_percentage=1.0, resprint=5)
+    Vd, Wd, Gd, Fd = to_dev(H, world, V, W, G)
+    with H.Trace() as t:
+        H.alsCP_PP_partupdate(world, Vd, Wd, Gd, Fd, 1e-10 * vnorm, 0.1, 30, update_percentage=1.0, resprint=5)
+    kinds = {"DT": 0, "PP": 1}
+    assert t.events == [(kinds[k], it) for k, it in tr.events]
+    check_rows(t.rows, tr.rows, vnorm)
+    check_factors(Wd, W_ref)
+    free_all(Vd, Wd, Gd, Fd)
+
+
+def test_plain_alsCP(H, world):
+    lens, R = (9, 10, 11), 3
+    V, W, G = problem(lens, R)
+    vnorm = np.linalg.norm(V)
+    # oracle for the plain path = Simple optimizer steps with SVD solve + Normalize == DT sweeps (same normal equations)
+    W_ref, G_ref = [w.copy() for w in W], [g.copy() for g in G]
+    o.alsCP_DT(V, W_ref, G_ref, 0.0, 5, resprint=100, want_residual=False)
+    Vd, Wd, Gd, Fd = to_dev(H, world, V, W, G)
+    with H.Trace():
+        H.alsCP(world, Vd, Wd, Gd, Fd, 0.0, 5)
+    check_factors(Wd, W_ref)
+    free_all(Vd, Wd, Gd, Fd)
+
+
+@pytest.mark.parametrize("order,size,R", [(4, 12, 4), (3, 11, 3), (6, 6, 3)])
+def test_cpd_optimizers_match_oracle_and_each_other(H, world, order, size, R):
+    lens = (size,) * order
+    V, W, _ = problem(lens, R)
+    Vd = H.Tensor.from_numpy(world, V)
+    Wd = [H.Tensor.from_numpy(world, w, matrix=True) for w in W]
+    finals = {}
+    for kind, cls, steps in [("simple", o.CPSimpleOptimizer, 2), ("dt", o.CPDTOptimizer, 4),
+                             ("msdt", o.CPMSDTOptimizer, 3)]:
+        ref = o.CPD(order, size, R, cls)
+        ref.Init(V, [w.copy() for w in W])
+        c = H.CPD(world, kind, order, size, R)
+        c.Init(Vd, Wd)
+        for _ in range(steps):
+            f_ref = ref.optimizer.step()
+            assert abs(c.step() - f_ref) < 1e-15
+        for i in range(order):
+            assert np.abs(c.W(i) - ref.W[i]).max() <= FACTOR_TOL * max(1.0, np.abs(ref.W[i]).max())
+            assert np.abs(c.grad(i) - ref.grad_W[i]).max() <= 1e-8 * max(1.0, np.abs(ref.grad_W[i]).max())
+        finals[kind] = [c.W(i) for i in range(order)]
+        c.free()
+    # DT and Simple solve the same normal equations -> 2 full sweeps agree to round-off
+    for a, b in zip(finals["simple"], finals["dt"]):
+        assert np.abs(a - b).max() <= 1e-9 * max(1.0, np.abs(a).max())
+    free_all(Vd, Wd)
+
+
+def test_cpd_als_loop(H, world):
+    order, size, R = 4, 10, 3
+    lens = (size,) * order
+    V, W, _ = problem(lens, R)
+    vnorm = np.linalg.norm(V)
+    Vd = H.Tensor.from_numpy(world, V)
+    Wd = [H.Tensor.from_numpy(world, w, matrix=True) for w in W]
+    ref = o.CPD(order, size, R, o.CPDTOptimizer)
+    ref.Init(V, [w.copy() for w in W], grad_W=[o.fill_uniform(w.shape, 3, i) for i, w in enumerate(W)])
+    ok_ref, rows_ref = ref.als(1e-10 * vnorm, 6, 4)
+    c = H.CPD(world, "dt", order, size, R)
+    c.Init(Vd, Wd, grad_seed=3)
+    with H.Trace() as t:
+        ok = c.als(1e-10 * vnorm, 6, resprint=4)
+    assert ok == ok_ref and len(t.rows) == len(rows_ref)
+    for rg, rr in zip(t.rows, rows_ref):
+        assert abs(rg[0] - rr[0]) < 1e-12
+        assert abs(rg[1] - rr[1]) <= FIT_RTOL * max(rr[1], 1e-6 * vnorm)
+        assert abs(rg[3] - rr[2]) <= FIT_RTOL * vnorm
+    c.free()
+    free_all(Vd, Wd)
+
+
+def proj_err(A, B):
+    return np.abs(A @ A.T - B @ B.T).max()
+
+
+@pytest.mark.parametrize("lens,R", [((12, 13, 14), 3), ((9, 10, 8, 7), 3)])
+def test_hosvd_and_alsTucker_DT(H, world, lens, R):
+    N = len(lens)
+    V = o.make_tensor_r2(lens)
+    vnorm = np.linalg.norm(V)
+    core_ref, W_ref = o.hosvd(V, [R] * N)
+    Vd = H.Tensor.from_numpy(world, V)
+    Wd = [H.Matrix(world, lens[i], R) for i in range(N)]
+    cored = H.Tensor(world, (R,) * N)
+    H.hosvd(world, Vd, cored, Wd, [R] * N)
+    for i in range(N):
+        assert proj_err(Wd[i].numpy(), W_ref[i]) < 1e-8
+    assert abs(np.linalg.norm(cored.numpy()) - np.linalg.norm(core_ref)) < 1e-10 * vnorm
+    W2 = [w.copy() for w in W_ref]
+    ok_ref, rows_ref, core2 = o.alsTucker_DT(V, core_ref, W2, 1e-10 * vnorm, 12, resprint=4)
+    with H.Trace() as t:
+        ok = H.alsTucker_DT(world, Vd, cored, Wd, 1e-10 * vnorm, 12, resprint=4)
+    assert ok == ok_ref and len(t.rows) == len(rows_ref)
+    for rg, rr in zip(t.rows, rows_ref):
+        assert int(rg[0]) == rr[0]
+        assert abs(rg[1] - rr[1]) <= 1e-9 * vnorm      # | ||core|| - ||core_prev|| |
+        assert abs(rg[3] - rr[2]) <= FIT_RTOL * vnorm  # residual
+    for i in range(N):
+        assert proj_err(Wd[i].numpy(), W2[i]) < 1e-7
+    free_all(Vd, Wd, cored)
+
+
+@pytest.mark.parametrize("lens,R,tol_init", [((12, 13, 14), 3, 0.3), ((9, 10, 8, 7), 3, 0.3)])
+def test_alsTucker_PP(H, world, lens, R, tol_init):
+    N = len(lens)
+    V = o.make_tensor_r2(lens)
+    vnorm = np.linalg.norm(V)
+    core_ref, W_ref = o.hosvd(V, [R] * N)
+    Vd = H.Tensor.from_numpy(world, V)
+    # start both sides from the ORACLE's HOSVD factors so that column signs agree from the first sweep on
+    Wd = [H.Tensor.from_numpy(world, w, matrix=True) for w in W_ref]
+    cored = H.Tensor.from_numpy(world, core_ref)
+    W2 = [w.copy() for w in W_ref]
+    ok_ref, rows_ref, ev_ref, sw_ref, core2 = o.alsTucker_PP(V, core_ref, W2, 1e-10 * vnorm, tol_init, 30, resprint=5)
+    with H.Trace() as t:
+        ok = H.alsTucker_PP(world, Vd, cored, Wd, 1e-10 * vnorm, tol_init, 30, resprint=5)
+    kinds = {"DT": 0, "PP": 1}
+    assert ok == ok_ref
+    assert t.events == [(kinds[k], it) for k, it in ev_ref]
+    assert len(t.rows) == len(rows_ref)
+    for rg, rr in zip(t.rows, rows_ref):
+        assert int(rg[0]) == rr[0] and int(rg[2]) == rr[2]
+        assert abs(rg[1] - rr[1]) <= 1e-9 * vnorm
+        assert abs(rg[3] - rr[3]) <= FIT_RTOL * vnorm
+    for i in range(N):
+        assert proj_err(Wd[i].numpy(), W2[i]) < 1e-7
+    free_all(Vd, Wd, cored)
