@@ -1,0 +1,385 @@
+#!/usr/bin/env python
+"""bench.py -- ALS / pairwise-perturbation sweeps per second on the BASELINE.json headline configuration:
+CP order-4, s=300, R=50, FP64 (configs[1]), synthetic tensor 'r' built on the device from seeded random factors.
+
+    python bench.py --gpus N --steps K --warmup W            (N>1: launched under torch.distributed.run)
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+A "step" is ONE exact ALS sweep with the dimension tree over all four modes (2 first contractions, 2 level-2 and
+4 leaf Hadamard contractions, 4 Gram-Hadamard solves, Normalize) -- als_CP.cxx:215-303 of the reference.
+`value`   : sweeps/s with every input resident in HBM, device-timed (CUDA events on the engine's stream), max over
+            ranks.  The tensor (64.8 GB) is larger than L2, so nothing is flushed between steps.
+`e2e`     : the same sweep through the reference-facing driver call alsCP_DT(V, W, grad_W, F, ..., maxiter=0) with the
+            factor and gradient matrices in pinned HOST memory: per step they are copied host->device, the sweep
+            runs, and they are copied back; wall clock around the whole thing.  The tensor V is the data set of the
+            iteration (it never changes between sweeps, exactly like CTF keeps it distributed in memory) and stays
+            resident; h2d/d2h bytes are counted from the matrices copied.
+`pp`      : the PP phase with the reference's pp_bench protocol: operator build, then the approximate sweep.
+`roofline`: the first dimension-tree contraction (K1), timed alone with CUDA events; FP64 tensor pipe roofline.
+`cpu_baseline`: oracle/pp_oracle.py (NumPy/OpenBLAS restatement of the reference, all host cores) on a bounded
+            mode-0 slab of the same tensor, scaled to the full tensor.  The reference itself (Cyclops CTF + MPI)
+            cannot be built in this image.
+With N>1 the tensor is sharded along mode 0 (strong scaling: the problem is fixed); the only collectives are the
+NCCL all-reduces of the s x R partial MTTKRPs and the R x R Gram of the sharded factor.
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+FP64_PEAK_FALLBACK_TF = 35.46  # cuBLAS DGEMM 8192^3 measured on this pool's B200 (profiles/r01_fp64_peak.json)
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--size", type=int, default=300)
+    ap.add_argument("--rank", type=int, default=50)
+    ap.add_argument("--order", type=int, default=4)
+    ap.add_argument("--pp-sweeps", type=int, default=10)
+    ap.add_argument("--cpu-slab", type=int, default=4, help="mode-0 rows of the tensor used for the CPU baseline")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CPU side: the oracle as baseline (the only place bench.py touches oracle/)
+# ---------------------------------------------------------------------------------------------------------------
+def cpu_sweep_time(s, R, N, slab, reps):
+    """Seconds per exact ALS-DT sweep of the oracle on a mode-0 slab of `slab` rows; returns (sec, cores)."""
+    import numpy as np
+
+    from oracle import pp_oracle as o
+
+    lens = (slab,) + (s,) * (N - 1)
+    Wt = [o.fill_uniform((l, R), 1, i) for i, l in enumerate(lens)]
+    V = np.asfortranarray(o.build_V(Wt))
+    W = [o.fill_uniform((l, R), 2, i) for i, l in enumerate(lens)]
+    G = [np.zeros_like(w) for w in W]
+    parent, sibling = {}, {}
+    o.construct_dimension_tree(parent, sibling, 0, N - 1)
+
+    def sweep():
+        mm = {}
+        for i in range(N):
+            M = o._leaf_M(mm, parent, sibling, V, W, i)
+            S = o.gram_hadamard(W, i, 0.0, True)
+            G[i] = -M + W[i] @ S
+            W[i] = o.SVD_solve(M, S)
+        o.normalize(W)
+
+    sweep()  # warm-up (BLAS thread pool, page faults)
+    ts = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        sweep()
+        ts.append(time.perf_counter() - t0)
+    return min(ts), os.cpu_count() or 1
+
+
+def run_reference(args):
+    """The reference arm: the reference's own algorithm on the host cores (the oracle port -- CTF is not buildable
+    here), each step a bounded mode-0 slab of the same workload, scaled to the full tensor."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    s, R, N, slab = args.size, args.rank, args.order, min(args.cpu_slab, args.size)
+    t0 = time.perf_counter()
+    sec, cores = cpu_sweep_time(s, R, N, slab, max(1, min(args.steps, 3)))
+    full = sec * (s / slab)
+    val = 1.0 / full
+    line = {
+        "impl": "reference", "metric": "ALS-DT sweeps/s (CP order-%d s=%d R=%d FP64)" % (N, s, R), "value": val,
+        "unit": "sweeps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": full * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "CP-ALS dimension-tree sweep, order-%d s=%d R=%d, tensor 'r'" % (N, s, R),
+                   "sample": "mode-0 slab of %d/%d rows, time scaled x%.1f" % (slab, s, s / slab)},
+        "cpu_baseline": {"value": val, "unit": "sweeps/s", "cores": cores, "kind": "port",
+                         "sample": "oracle/pp_oracle.py (NumPy + OpenBLAS, %d threads) on a mode-0 slab of %d/%d rows; "
+                                   "seconds per sweep x %.1f" % (cores, slab, s, s / slab)},
+        "e2e": {"value": val, "unit": "sweeps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "wall_s": time.perf_counter() - t0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device, self.lines, self.proc = device, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        load = [x for x in sm if x >= 0.5 * (mx[0] if mx else 1)] or sm
+        return {"sm_mhz": load[len(load) // 2] if load else None, "sm_max_mhz": mx[0] if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import numpy as np
+    import torch
+
+    rank = int(os.environ.get("RANK", "0"))
+    nranks = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if nranks > 1:
+        import torch.distributed as dist
+
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    ppx = importlib.import_module("pairwise-perturbation_b200")
+    H = importlib.import_module("pairwise-perturbation_b200.host_api")
+    lib = ppx.load_library()
+
+    s, R, N = args.size, args.rank, args.order
+    world = H.World(local_rank, solver=0, use_graph=True, workspace_bytes=1 << 30)
+    b, e = ppx.shard_range(s, nranks, rank)
+    if nranks > 1:
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt = torch.tensor(list(ppx.comm_unique_id()), dtype=torch.uint8, device="cuda")
+        dist.broadcast(idt, 0)
+        world.comm_init(bytes(idt.cpu().tolist()), nranks, rank, 0, s, b, e)
+    rows0 = e - b
+
+    def barrier():
+        world.sync()
+        if dist is not None:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def seeded_matrix(seed, mode):
+        """s x R uniform [0,1) factor (full), sliced to the local rows for the sharded mode 0."""
+        m = H.Matrix(world, s, R)
+        m.fill(seed, mode)
+        if mode != 0 or nranks == 1:
+            return m
+        full = m.numpy()
+        m.free()
+        return H.Tensor.from_numpy(world, np.ascontiguousarray(full[b:e]), matrix=True)
+
+    # synthetic tensor 'r' (test_ALS.cxx:275-286): V = [[W_true]], local slab of mode 0
+    Wt = [seeded_matrix(1, i) for i in range(N)]
+    lens_local = (rows0,) + (s,) * (N - 1)
+    V = H.Tensor(world, lens_local)
+    H.build_V(world, V, Wt)
+    for w in Wt:
+        w.free()
+    W0_host = [seeded_matrix(2, i) for i in range(N)]
+    W = W0_host
+    G = [seeded_matrix(3, i) for i in range(N)]
+    F = [H.Matrix(world, w.lens[0], R) for w in W]
+    W_start = [w.numpy() for w in W]
+    world.sync()
+
+    def reset_W():
+        for w, h in zip(W, W_start):
+            w.write(h)
+
+    evs = [C.c_void_p() for _ in range(2)]
+    for ev in evs:
+        lib.ppx_event_create(world.ctx_handle(), C.byref(ev))
+
+    # ---- device-resident sweeps: value ---------------------------------------------------------------------------
+    H.cp_dt_sweeps(world, V, W, G, max(args.warmup, 3))
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = world.launch_count()
+    lib.ppx_event_record(world.ctx_handle(), evs[0])
+    H.cp_dt_sweeps(world, V, W, G, args.steps)
+    lib.ppx_event_record(world.ctx_handle(), evs[1])
+    ms = C.c_float(0)
+    lib.ppx_event_elapsed_ms(world.ctx_handle(), evs[0], evs[1], C.byref(ms))
+    barrier()
+    launches = world.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = max_over_ranks(float(ms.value))
+    ms_per_step = ms_total / args.steps
+    value = 1e3 / ms_per_step
+
+    # ---- PP phase (pp_bench protocol): operator build + approximate sweeps ----------------------------------------
+    reset_W()
+    H.cp_dt_sweeps(world, V, W, G, 2)  # PP starts from an ALS iterate, as alsCP_PP does
+    barrier()
+    ms_build, ms_pp = H.cp_pp_phase_timed(world, V, W, G, args.pp_sweeps)
+    ms_build, ms_pp = max_over_ranks(ms_build), max_over_ranks(ms_pp)
+    world.trim()  # the level-1 tensors of the build go back to the driver
+    pp = {"operator_build_ms": ms_build, "approx_sweep_ms": ms_pp / args.pp_sweeps,
+          "approx_sweeps_per_s": 1e3 * args.pp_sweeps / ms_pp, "sweeps_timed": args.pp_sweeps,
+          "note": "one CUDA graph per sweep (N x [correct, Gram-Hadamard, Cholesky solve+grad+dW, Gram] + Normalize + norms)"
+                  if nranks == 1 else "eager launches + NCCL all-reduce per mode (latency bound, does not scale)"}
+
+    # ---- roofline of the dominant kernel: the first dimension-tree contraction (K1) ------------------------------
+    x = 2 if N >= 3 else 0
+    out1 = H.Tensor(world, tuple(l for i, l in enumerate(lens_local) if i != x) + (R,))
+    lens_c = (C.c_int64 * N)(*lens_local)
+
+    def k1():
+        lib.ppx_ttm_first(world.ctx_handle(), C.c_void_p(V.data_ptr()), lens_c, N, x, C.c_void_p(W[x].data_ptr()),
+                          lens_local[x], R, C.c_void_p(out1.data_ptr()))
+
+    for _ in range(3):
+        k1()
+    barrier()
+    reps = 5
+    lib.ppx_event_record(world.ctx_handle(), evs[0])
+    for _ in range(reps):
+        k1()
+    lib.ppx_event_record(world.ctx_handle(), evs[1])
+    lib.ppx_event_elapsed_ms(world.ctx_handle(), evs[0], evs[1], C.byref(ms))
+    k1_ms = float(ms.value) / reps
+    out1.free()
+    P_local = float(np.prod(lens_local))
+    k1_flops = 2.0 * P_local * R
+    k1_bytes = 8.0 * (P_local + P_local / lens_local[x] * R + lens_local[x] * R)
+    peak_tf, peak_src = FP64_PEAK_FALLBACK_TF, "profiles/r01_fp64_peak.json (cuBLAS DGEMM 8192^3 on this pool's B200)"
+    try:
+        peak_tf = json.load(open(os.path.join(ROOT, "profiles", "r01_fp64_peak.json")))["fp64_tflops_burst"]
+    except Exception:
+        pass
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "k1_ncu_summary.json"))).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    achieved = k1_flops / (k1_ms * 1e-3) / 1e12
+    roofline = {"kernel": "ttm_first_kernel (K1, first dimension-tree contraction, mode %d, R=%d)" % (x, R),
+                "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
+                "traffic": traffic, "algorithmic_flops": k1_flops, "algorithmic_bytes": k1_bytes, "ms": k1_ms,
+                "hbm_gbs": k1_bytes / (k1_ms * 1e-3) / 1e9,
+                "peak_source": "FP64 peak is not in MEASURED_PEAKS.json (it holds HBM and bf16); " + peak_src,
+                "share_of_step": 2 * k1_ms / ms_per_step}
+
+    # ---- e2e: the driver call with host buffers --------------------------------------------------------------------
+    pin = [torch.from_numpy(h.ravel(order="F").copy()).pin_memory() for h in W_start]
+    pin_g = [torch.zeros(h.size, dtype=torch.float64).pin_memory() for h in W_start]
+    pin_out = [torch.empty(h.size, dtype=torch.float64).pin_memory() for h in W_start]
+    hlib = H.load_host_library()
+
+    def e2e_step():
+        for t_, w in zip(pin, W):
+            hlib.ppxh_tensor_write(w.h, C.c_void_p(t_.data_ptr()))
+        for t_, g in zip(pin_g, G):
+            hlib.ppxh_tensor_write(g.h, C.c_void_p(t_.data_ptr()))
+        H.alsCP_DT(world, V, W, G, F, 0.0, 0, lam=0.0, resprint=1 << 30, bench=True)  # exactly one sweep
+        for t_, w in zip(pin_out, W):
+            hlib.ppxh_tensor_read(w.h, C.c_void_p(t_.data_ptr()))
+        for t_, g in zip(pin_g, G):
+            hlib.ppxh_tensor_read(g.h, C.c_void_p(t_.data_ptr()))
+
+    with H.Trace(quiet=True, skip_residual=True):
+        for _ in range(max(1, min(args.warmup, 2))):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_step()
+        barrier()
+        e2e_s = max_over_ranks(time.perf_counter() - t0)
+    bytes_mats = sum(h.size for h in W_start) * 8
+    e2e = {"value": args.steps / e2e_s, "unit": "sweeps/s", "h2d_bytes_per_step": 2 * bytes_mats,
+           "d2h_bytes_per_step": 2 * bytes_mats, "ms_per_step": 1e3 * e2e_s / args.steps,
+           "call": "alsCP_DT(V, W, grad_W, F, tol, timelimit, maxiter=0, lambda, csv, resprint, bench=true, dw) with W/grad_W "
+                   "copied from/to pinned host memory every step; V (the data set) resident"}
+
+    # ---- CPU baseline ---------------------------------------------------------------------------------------------
+    cpu = None
+    if rank == 0 and nranks == 1 and not args.no_cpu_baseline:
+        slab = min(args.cpu_slab, s)
+        sec, cores = cpu_sweep_time(s, R, N, slab, 2)
+        full = sec * (s / slab)
+        cpu = {"value": 1.0 / full, "unit": "sweeps/s", "cores": cores, "kind": "port",
+               "sample": "oracle/pp_oracle.py (NumPy + OpenBLAS restatement of als_CP.cxx, %d threads) on a mode-0 slab "
+                         "of %d/%d rows: %.2f s per sweep, scaled x%.1f; the reference itself (Cyclops CTF + MPI) cannot "
+                         "be built in this image" % (cores, slab, s, sec, s / slab)}
+
+    if rank == 0:
+        line = {
+            "metric": "ALS-DT sweeps/s (CP order-%d s=%d R=%d FP64)" % (N, s, R), "value": value, "unit": "sweeps/s",
+            "n_gpus": nranks, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "CP-ALS dimension-tree sweep, order-%d s=%d R=%d, tensor 'r' (BASELINE configs[1])"
+                                   % (N, s, R),
+                       "tensor_bytes_per_gpu": 8 * P_local, "l2": "inputs (%.1f GB) larger than L2; no flush" % (8 * P_local / 1e9),
+                       "parallelism": "mode-0 shards x%d, NCCL all-reduce of s x R partial MTTKRPs" % nranks if nranks > 1
+                       else "single GPU", "solver": "cholesky"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "pp": pp,
+        }
+        print(json.dumps(line), flush=True)
+    world.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+import ctypes as C  # noqa: E402
+
+if __name__ == "__main__":
+    main()

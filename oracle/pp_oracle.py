@@ -946,7 +946,7 @@ def alsTucker_PP(V, core, W, tol, tol_init, maxiter, resprint=10, bench=False, w
 def make_tensor_r(lens, R, seed=1):
     """tensor 'r': V = [[W_true]] with W_true[i] = u(seed, id=i) in [0,1)."""
     Wt = [fill_uniform((lens[i], R), seed, i) for i in range(len(lens))]
-    return build_V(Wt), Wt
+    return np.asfortranarray(build_V(Wt)), Wt
 
 
 def make_tensor_r2(lens, seed=1, lo=0.5, hi=1.0):

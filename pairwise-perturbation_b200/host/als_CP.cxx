@@ -387,36 +387,49 @@ double alsCP_DT_sub(Tensor<> &V, Matrix<> *W, Matrix<> *grad_W, Matrix<> *dW, Ma
   return diffnorm_V;
 }
 
-double alsCP_PP_sub(Tensor<> &V, Matrix<> *W, Matrix<> *grad_W, Matrix<> *dW, Matrix<> *F, double tol, double tol_init,
-                    double timelimit, int maxiter, double &st_time, double lambda, double ratio_step,
-                    ofstream &Plot_File, double &projnorm, int &iter, int resprint, bool bench, World &dw) {
-  // als_CP.cxx:621-833
-  (void)F;
-  const int N = V.order;
-  const int R = (int)W[0].ncol;
-  double dtime_first = 0;
-  const int init_iter = iter;
-  double diffnorm_V = 1000;
-  vector<Matrix<>> W_init(N);
-  map<string, Tensor<>> mttkrp_map;
-  Matrix<> S((int64_t)R, (int64_t)R, dw);
-  vector<Matrix<>> M;
-  for (int i = 0; i < N; i++) M.emplace_back(W[i].nrow, W[i].ncol, dw);
-  Matrix<> zero_M;
-  if (dw.np > 1) {
-    int64_t smax = 0;
-    for (int i = 0; i < N; i++) smax = std::max(smax, W[i].nrow);
-    zero_M = Matrix<>(smax, R, dw);
-  }
-  GramCache gc;
-  gc.init(W, N, dw);
-  void *graph = nullptr;  // the approximate sweep replayed as one CUDA graph (pointers are fixed within a PP phase)
+namespace {
 
-  // the approximate sweep: per mode correction -> Gram-Hadamard -> solve (+grad, dW) -> Gram; then Normalize and the
-  // 2N squared norms the switching test needs (:754-825, :657-664)
-  auto enqueue_sweep = [&]() {
+// One PP phase: the operators built at W_init and the approximate sweep that reads them (als_CP.cxx:672-694 and
+// :754-825).  The sweep touches a fixed set of buffers, so it is captured once per phase as a CUDA graph.
+struct PPPhase {
+  Tensor<> &V;
+  Matrix<> *W, *grad_W, *dW;
+  double lambda, ratio_step;
+  World &dw;
+  int N, R;
+  vector<Matrix<>> W_init, M;
+  map<string, Tensor<>> ops;
+  Matrix<> S, zero_M;
+  GramCache gc;
+  void *graph = nullptr;
+
+  PPPhase(Tensor<> &V_, Matrix<> *W_, Matrix<> *grad_W_, Matrix<> *dW_, double lambda_, double ratio_step_, World &dw_)
+      : V(V_), W(W_), grad_W(grad_W_), dW(dW_), lambda(lambda_), ratio_step(ratio_step_), dw(dw_), N(V_.order),
+        R((int)W_[0].ncol), W_init(V_.order), S((int64_t)W_[0].ncol, (int64_t)W_[0].ncol, dw_) {
+    for (int i = 0; i < N; i++) M.emplace_back(W[i].nrow, W[i].ncol, dw);
+    if (dw.np > 1) {
+      int64_t smax = 0;
+      for (int i = 0; i < N; i++) smax = std::max(smax, W[i].nrow);
+      zero_M = Matrix<>(smax, R, dw);
+    }
+    gc.init(W, N, dw);
+  }
+  ~PPPhase() {
+    if (graph) ppx_graph_destroy(dw.ctx, graph);
+  }
+  // W_init = W, dW = 0, build all pair operators and singles (:672-694)
+  void build() {
+    for (int j = 0; j < N; j++) {
+      W_init[j] = W[j];
+      dW[j].set_zero();
+    }
+    build_pp_operators(ops, V, W, dw);
+  }
+  // per mode: correction -> Gram-Hadamard -> solve (+grad, dW) -> Gram; then Normalize and the 2N squared norms
+  // the switching test needs, copied to pinned host memory (:754-825, :657-664)
+  void enqueue_sweep() {
     for (int i = 0; i < N; i++) {
-      pp_corrected_mttkrp(mttkrp_map, W, dW, i, N, M[i], zero_M, dw);
+      pp_corrected_mttkrp(ops, W, dW, i, N, M[i], zero_M, dw);
       gc.hadamard(i, lambda, S, dw);  // S from the CURRENT W (:796-802)
       solve_update_fused(M[i], S, W[i], &W_init[i], ratio_step, &grad_W[i], &dW[i], dw.solver, dw);  // :811-812
       gc.refresh(W, i, dw);
@@ -433,8 +446,33 @@ double alsCP_PP_sub(Tensor<> &V, Matrix<> *W, Matrix<> *grad_W, Matrix<> *dW, Ma
       PPXCK(dw, ppx_sqnorms(dw.ctx, xs + b, ns + b, std::min(16, 2 * N - b), dw.scal_dev + b));
     if (dw.np > 1) dw.allreduce(dw.scal_dev + 2 * dw.shard_mode, 2);
     PPXCK(dw, ppx_memcpy_d2h(dw.ctx, dw.scal_host, dw.scal_dev, sizeof(double) * 2 * N));
-  };
+  }
+  void sweep() {
+    if (dw.use_graph && dw.np == 1) {
+      if (!graph) {
+        PPXCK(dw, ppx_graph_begin(dw.ctx));
+        enqueue_sweep();
+        PPXCK(dw, ppx_graph_end(dw.ctx, &graph));
+      }
+      PPXCK(dw, ppx_graph_launch(dw.ctx, graph));
+    } else {
+      enqueue_sweep();
+    }
+  }
+};
 
+}  // namespace
+
+double alsCP_PP_sub(Tensor<> &V, Matrix<> *W, Matrix<> *grad_W, Matrix<> *dW, Matrix<> *F, double tol, double tol_init,
+                    double timelimit, int maxiter, double &st_time, double lambda, double ratio_step,
+                    ofstream &Plot_File, double &projnorm, int &iter, int resprint, bool bench, World &dw) {
+  // als_CP.cxx:621-833
+  (void)F;
+  const int N = V.order;
+  double dtime_first = 0;
+  const int init_iter = iter;
+  double diffnorm_V = 1000;
+  PPPhase phase(V, W, grad_W, dW, lambda, ratio_step, dw);
   bool norms_valid = false;  // scal_host holds ||dW_i||^2, ||W_i||^2 of the state after the last sweep
   for (; iter <= maxiter; iter++) {
     int num_dw_break = 0;
@@ -457,15 +495,8 @@ double alsCP_PP_sub(Tensor<> &V, Matrix<> *W, Matrix<> *grad_W, Matrix<> *dW, Ma
         if (std::fabs(std::sqrt(h[2 * i]) / std::sqrt(h[2 * i + 1])) > tol_init) num_dw_break++;
     }
     if ((iter - init_iter) % 15 == 0 || num_dw_break > 0) {  // :667-695
-      if (num_dw_break > 0 || iter != init_iter) {
-        if (graph) ppx_graph_destroy(dw.ctx, graph);
-        return diffnorm_V;
-      }
-      for (int j = 0; j < N; j++) {
-        W_init[j] = W[j];
-        dW[j].set_zero();
-      }
-      build_pp_operators(mttkrp_map, V, W, dw);
+      if (num_dw_break > 0 || iter != init_iter) return diffnorm_V;
+      phase.build();
       if (trace_sink()) trace_sink()->sweeps.push_back({2, iter});
     }
     if (iter % resprint == 0 || iter == maxiter || iter == init_iter) {  // :697-752
@@ -499,23 +530,51 @@ double alsCP_PP_sub(Tensor<> &V, Matrix<> *W, Matrix<> *grad_W, Matrix<> *dW, Ma
       }
       if (projnorm < tol || wall_time() - st_time > timelimit) break;
     }
-    if (dw.use_graph && dw.np == 1) {
-      if (!graph) {
-        PPXCK(dw, ppx_graph_begin(dw.ctx));
-        enqueue_sweep();
-        PPXCK(dw, ppx_graph_end(dw.ctx, &graph));
-      }
-      PPXCK(dw, ppx_graph_launch(dw.ctx, graph));
-    } else {
-      enqueue_sweep();
-    }
+    phase.sweep();
     norms_valid = true;
     if (trace_sink()) trace_sink()->sweeps.push_back({1, iter});
     if (iter % 10 == 0 && dw.rank == 0 && !trace_quiet()) printf(".");
   }
-  if (graph) ppx_graph_destroy(dw.ctx, graph);
   if (bench) iter++;
   return diffnorm_V;
+}
+
+// ---- timing helpers for bench.py (no logging, nothing but the sweeps on the stream) -----------------------------
+void alsCP_DT_sweeps(Tensor<> &V, Matrix<> *W, Matrix<> *grad_W, int n_sweeps, double lambda, World &dw) {
+  const int N = V.order;
+  Matrix<> S((int64_t)W[0].ncol, (int64_t)W[0].ncol, dw);
+  map<string, string> parent, sibling;
+  Construct_Dimension_Tree(parent, sibling, 0, N - 1);
+  GramCache gc;
+  gc.init(W, N, dw);
+  for (int it = 0; it < n_sweeps; it++) dt_sweep(V, W, grad_W, nullptr, lambda, true, parent, sibling, gc, S, dw);
+}
+
+void alsCP_PP_phase_timed(Tensor<> &V, Matrix<> *W, Matrix<> *grad_W, int n_sweeps, double lambda, double ratio_step,
+                          World &dw, float *ms_build, float *ms_sweeps) {
+  const int N = V.order;
+  vector<Matrix<>> dW;
+  for (int j = 0; j < N; j++) dW.emplace_back(W[j].nrow, W[j].ncol, dw);
+  PPPhase phase(V, W, grad_W, dW.data(), lambda, ratio_step, dw);
+  void *e0, *e1, *e2;
+  PPXCK(dw, ppx_event_create(dw.ctx, &e0));
+  PPXCK(dw, ppx_event_create(dw.ctx, &e1));
+  PPXCK(dw, ppx_event_create(dw.ctx, &e2));
+  PPXCK(dw, ppx_event_record(dw.ctx, e0));
+  phase.build();
+  PPXCK(dw, ppx_event_record(dw.ctx, e1));
+  phase.sweep();  // first sweep captures the graph; not timed
+  dw.sync();
+  PPXCK(dw, ppx_event_record(dw.ctx, e2));
+  PPXCK(dw, ppx_event_elapsed_ms(dw.ctx, e0, e1, ms_build));
+  void *t0, *t1;
+  PPXCK(dw, ppx_event_create(dw.ctx, &t0));
+  PPXCK(dw, ppx_event_create(dw.ctx, &t1));
+  PPXCK(dw, ppx_event_record(dw.ctx, t0));
+  for (int it = 0; it < n_sweeps; it++) phase.sweep();
+  PPXCK(dw, ppx_event_record(dw.ctx, t1));
+  PPXCK(dw, ppx_event_elapsed_ms(dw.ctx, t0, t1, ms_sweeps));
+  for (void *e : {e0, e1, e2, t0, t1}) ppx_event_destroy(dw.ctx, e);
 }
 
 bool alsCP_PP(Tensor<> &V, Matrix<> *W, Matrix<> *grad_W, Matrix<> *F, double tol, double tol_init, double timelimit,

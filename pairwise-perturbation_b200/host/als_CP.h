@@ -43,4 +43,11 @@ bool alsCP_PP_partupdate(Tensor<> &V, Matrix<> *W, Matrix<> *grad_W, Matrix<> *F
 
 vector<int> sort_indexes(const vector<double> &v);  // als_CP.cxx:835-843
 
+// ---- timing helpers (bench.py): exactly n exact sweeps / one PP phase, no logging, no host synchronisation ----
+void alsCP_DT_sweeps(Tensor<> &V, Matrix<> *W, Matrix<> *grad_W, int n_sweeps, double lambda, World &dw);
+// builds the PP operators at W (timed: ms_build), captures the approximate sweep, then runs n_sweeps of it
+// (timed: ms_sweeps); both with CUDA events on the world's stream
+void alsCP_PP_phase_timed(Tensor<> &V, Matrix<> *W, Matrix<> *grad_W, int n_sweeps, double lambda, double ratio_step,
+                          World &dw, float *ms_build, float *ms_sweeps);
+
 #endif

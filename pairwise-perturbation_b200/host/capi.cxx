@@ -233,6 +233,22 @@ int ppxh_alsCP_PP_partupdate(void *V, void **W, void **grad_W, void **F, int N, 
   });
 }
 
+// ---- timing helpers (bench.py) ---------------------------------------------------------------------------------
+int ppxh_cp_dt_sweeps(void *V, void **W, void **grad_W, int N, int n_sweeps, double lambda, void *w) {
+  return guarded([&] {
+    MatArray Wa(W, N), Ga(grad_W, N);
+    alsCP_DT_sweeps(*(Tensor<> *)V, Wa.ptr(), Ga.ptr(), n_sweeps, lambda, *(World *)w);
+  });
+}
+int ppxh_cp_pp_phase_timed(void *V, void **W, void **grad_W, int N, int n_sweeps, double lambda, double ratio_step,
+                           void *w, float *ms_build, float *ms_sweeps) {
+  return guarded([&] {
+    MatArray Wa(W, N), Ga(grad_W, N);
+    alsCP_PP_phase_timed(*(Tensor<> *)V, Wa.ptr(), Ga.ptr(), n_sweeps, lambda, ratio_step, *(World *)w, ms_build,
+                         ms_sweeps);
+  });
+}
+
 // ---- OO path (src/CP.h + src/optimizer) ---------------------------------------------------------------------
 // kind: 0 = CPSimpleOptimizer, 1 = CPDTOptimizer, 2 = CPMSDTOptimizer  (run.cxx -pp 4 / 0 / 1)
 void *ppxh_cpd_create(int kind, int order, int size, int r, void *w) {

@@ -63,6 +63,9 @@ def load_host_library():
                                   PI]
     lib.ppxh_alsCP_PP_partupdate.argtypes = [_vp, PV, PV, PV, C.c_int, d, d, d, C.c_int, d, d, d, C.c_char_p, C.c_int,
                                              C.c_int, _vp, PI]
+    lib.ppxh_cp_dt_sweeps.argtypes = [_vp, PV, PV, C.c_int, C.c_int, d, _vp]
+    lib.ppxh_cp_pp_phase_timed.argtypes = [_vp, PV, PV, C.c_int, C.c_int, d, d, _vp, C.POINTER(C.c_float),
+                                           C.POINTER(C.c_float)]
     lib.ppxh_cpd_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, _vp]
     lib.ppxh_cpd_destroy.argtypes = [_vp]
     lib.ppxh_cpd_init.argtypes = [_vp, _vp, PV, C.c_int, d, C.c_uint64]
@@ -241,6 +244,19 @@ def alsCP_PP_partupdate(world, V, W, grad_W, F, tol, tol_init, maxiter, lam=0.0,
                                            maxiter, lam, ratio_step, update_percentage, csv.encode() if csv else None,
                                            resprint, int(bench), world.h, C.byref(st)))
     return bool(st.value)
+
+
+def cp_dt_sweeps(world, V, W, grad_W, n_sweeps, lam=0.0):
+    """Exactly n exact ALS-DT sweeps on the world's stream, no logging, no host synchronisation (bench.py)."""
+    _ck(world.lib.ppxh_cp_dt_sweeps(V.h, _harr(W), _harr(grad_W), len(W), n_sweeps, lam, world.h))
+
+
+def cp_pp_phase_timed(world, V, W, grad_W, n_sweeps, lam=0.0, ratio_step=1.0):
+    """One PP phase: operator build (ms) and n approximate sweeps (ms), CUDA events on the world's stream."""
+    a, b = C.c_float(0), C.c_float(0)
+    _ck(world.lib.ppxh_cp_pp_phase_timed(V.h, _harr(W), _harr(grad_W), len(W), n_sweeps, lam, ratio_step, world.h,
+                                         C.byref(a), C.byref(b)))
+    return a.value, b.value
 
 
 class CPD:

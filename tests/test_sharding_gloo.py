@@ -1,0 +1,98 @@
+"""World-size-2 test of the multi-GPU design on CPU (gloo): the tensor is sharded along mode 0, every rank runs the
+oracle's contractions on its slab, and the ONLY exchanges are the all-reduce of the s x R partial MTTKRPs of the
+non-sharded modes and of the R x R Gram of the sharded factor.  The sharded sweep must
+reproduce the unsharded oracle sweep.  Shard ranges come from the C ABI's host function ppx_shard_range."""
+import importlib
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _sharded_sweep(rank, nranks, port, lens, R, out_dir):
+    sys.path.insert(0, ROOT)
+    from oracle import pp_oracle as o
+
+    ppx = importlib.import_module("pairwise-perturbation_b200")
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=nranks)
+    N = len(lens)
+    V, _ = o.make_tensor_r(lens, R)
+    W = o.init_factors(lens, R)
+    b, e = ppx.shard_range(lens[0], nranks, rank)
+    Vl = V[b:e]                       # local slab of mode 0
+    Wl = [w.copy() for w in W]
+    Wl[0] = W[0][b:e].copy()          # rows of W_0 are sharded the same way; the other factors are replicated
+
+    def allreduce(x):
+        t = torch.from_numpy(np.ascontiguousarray(x))
+        dist.all_reduce(t)
+        return t.numpy()
+
+    parent, sibling = {}, {}
+    o.construct_dimension_tree(parent, sibling, 0, N - 1)
+    grams = [w.T @ w for w in Wl]
+    grams[0] = allreduce(grams[0])
+    n_allreduce = 1
+    for sweep in range(2):
+        mm = {}
+        for i in range(N):
+            M = o._leaf_M(mm, parent, sibling, Vl, Wl, i)
+            if i != 0:
+                M = allreduce(M)      # partial sums over the local slab
+                n_allreduce += 1
+            S = np.ones((R, R))
+            for j in range(N):
+                if j != i:
+                    S = S * grams[j]
+            Wl[i] = o.cholesky_solve(M, S)
+            grams[i] = Wl[i].T @ Wl[i]
+            if i == 0:
+                grams[0] = allreduce(grams[0])
+                n_allreduce += 1
+        norms = [np.sqrt(np.trace(g)) for g in grams]   # global norms from the (reduced) Grams
+        gm = np.prod(norms) ** (1.0 / N)
+        for i in range(N):
+            Wl[i] = Wl[i] * (gm / norms[i])
+            grams[i] = grams[i] * (gm / norms[i]) ** 2
+    np.savez(os.path.join(out_dir, "rank%d.npz" % rank), b=b, e=e, n_allreduce=n_allreduce,
+             **{"W%d" % i: w for i, w in enumerate(Wl)})
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("lens,R", [((9, 6, 5, 4), 3), ((7, 5, 6), 2)])
+def test_mode0_sharded_sweep_equals_unsharded(tmp_path, lens, R):
+    sys.path.insert(0, ROOT)
+    from oracle import pp_oracle as o
+
+    nranks = 2
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_sharded_sweep, args=(nranks, port, lens, R, str(tmp_path)), nprocs=nranks, join=True)
+    N = len(lens)
+    V, _ = o.make_tensor_r(lens, R)
+    W = o.init_factors(lens, R)
+    parent, sibling = {}, {}
+    o.construct_dimension_tree(parent, sibling, 0, N - 1)
+    for sweep in range(2):
+        mm = {}
+        for i in range(N):
+            M = o._leaf_M(mm, parent, sibling, V, W, i)
+            S = o.gram_hadamard(W, i)
+            W[i] = o.cholesky_solve(M, S)
+        o.normalize(W)
+    parts = [np.load(os.path.join(str(tmp_path), "rank%d.npz" % r)) for r in range(nranks)]
+    W0 = np.concatenate([p["W0"] for p in parts], axis=0)
+    assert np.abs(W0 - W[0]).max() < 1e-10
+    for i in range(1, N):
+        for p in parts:
+            assert np.abs(p["W%d" % i] - W[i]).max() < 1e-10   # replicated factors agree on every rank
+    # N-1 MTTKRP all-reduces + 1 Gram all-reduce per sweep (+1 initial Gram)
+    assert int(parts[0]["n_allreduce"]) == 1 + 2 * N
+    assert sum(int(p["e"]) - int(p["b"]) for p in parts) == lens[0]
