@@ -83,6 +83,14 @@ int ppx_fill_uniform(ppx_ctx *ctx, double *out, int64_t n, uint64_t seed, uint64
 int ppx_ttm_first(ppx_ctx *ctx, const double *V, const int64_t *lens, int N, int x, const double *Wx, int64_t ldw,
                   int R, double *out);
 
+/* Several ADJACENT modes x_first .. x_first+n_modes-1 contracted at once:
+ *   out[rest, r] = sum_{x_1..x_n} V[.., x_1, .., x_n, ..] * prod_j W[j][x_j, r]
+ * i.e. the first contraction followed by the Hadamard-batched contractions of the reference's tree
+ * (common.cxx:56 then :83) as ONE GEMM against the Khatri-Rao rows of the factors; the level-1 intermediates are
+ * never written.  W / ldw: HOST arrays of n_modes entries.  Needs 8*R*prod(lens[x_j]) bytes of workspace. */
+int ppx_ttm_multi(ppx_ctx *ctx, const double *V, const int64_t *lens, int N, int x_first, int n_modes,
+                  const double *const *W, const int64_t *ldw, int R, double *out);
+
 /* ---- K2: Hadamard-batched contraction (rank index in all three operands) -----------------------------------
  * out[rest', r] = sum_x T[.., x, .., r] * Wx[x, r];  lens = the k non-rank modes of T.
  * replaces common.cxx:83,128; als_CP.cxx:258-259,407-408; cp_dt_optimizer.cxx:184-185. */
@@ -122,12 +130,37 @@ int ppx_hadamard_grams(ppx_ctx *ctx, const double *const *G, int nG, int skip, i
 int ppx_solve_update(ppx_ctx *ctx, const double *M, const double *S, double *W, int64_t s, int R,
                      const double *W_init, double ratio_step, int mode, double *grad_out, double *dW_out,
                      double *sq_norms_out);
+/* Same with S = Hadamard_{j != skip} G[j] + lambda*I formed inside the inverse kernel from the cached Grams
+ * (G: HOST array of nG device pointers) -- one launch less per mode update of the PP sweep. */
+int ppx_solve_update_g(ppx_ctx *ctx, const double *M, const double *const *G, int nG, int skip, double lambda,
+                       double *W, int64_t s, int R, const double *W_init, double ratio_step, int mode,
+                       double *grad_out, double *dW_out, double *sq_norms_out);
+/* The two halves of ppx_solve_update_g as separate calls, so that the R x R inverse (which depends only on the
+ * Grams) can overlap the PP correction of the same mode on the side stream (ppx_side_begin/end/join):
+ *   S_out (may be NULL) = Hadamard_{j != skip} G[j] + lambda*I ;  Sinv_out = S^-1   (R x R device buffers)         */
+int ppx_spd_inverse_g(ppx_ctx *ctx, const double *const *G, int nG, int skip, double lambda, int R, int mode,
+                      double *S_out, double *Sinv_out);
+/*   grad_out = -M + W_old*S ; W = M*Sinv ; dW_out = ratio_step*(W - W_init)  (S may be NULL iff grad_out is NULL)  */
+int ppx_solve_apply(ppx_ctx *ctx, const double *M, const double *S, const double *Sinv, double *W, int64_t s, int R,
+                    const double *W_init, double ratio_step, double *grad_out, double *dW_out);
+/* Fork / join for work that may overlap the main stream; valid eagerly and inside ppx_graph_begin/end:
+ *   ppx_side_begin: the side stream waits for everything enqueued so far; subsequent calls go to the side stream
+ *   ppx_side_end  : subsequent calls go to the main stream again (the side work keeps running concurrently)
+ *   ppx_side_join : the main stream waits for the side work enqueued between begin and end                         */
+int ppx_side_begin(ppx_ctx *ctx);
+int ppx_side_end(ppx_ctx *ctx);
+int ppx_side_join(ppx_ctx *ctx);
 /* Normalize (common.cxx:680-688): every W_i scaled to the geometric mean of the Frobenius norms.  W, s: HOST
  * arrays.  If G != NULL, G[i] (cached Gram of W_i) is rescaled consistently. */
 int ppx_normalize(ppx_ctx *ctx, double *const *W, const int64_t *s, int N, int R, double *const *G);
 /* Same, but ||W_i||_F^2 is taken as trace(G[i]) instead of being recomputed from W_i: with the leading mode sharded
  * over GPUs the local rows of W_i do not give the global norm, the (all-reduced) Gram does. */
 int ppx_normalize_g(ppx_ctx *ctx, double *const *W, const int64_t *s, int N, int R, double *const *G);
+/* ppx_normalize_g fused with the 2N squared norms the PP switching test reads after every approximate sweep
+ * (als_CP.cxx:657-664, :825), one launch:  sq_out_dev[2i] = ||dW[i]||^2 (0 if dW == NULL),
+ * sq_out_dev[2i+1] = ||W[i]||^2 after the rescale. */
+int ppx_normalize_norms(ppx_ctx *ctx, double *const *W, const double *const *dW, const int64_t *s, int N, int R,
+                        double *const *G, double *sq_out_dev);
 /* out_dev[j] = sum of squares of X[j][0..n[j]) for j < count (norm2()^2; als_CP.cxx:176-178,598-600). */
 int ppx_sqnorms(ppx_ctx *ctx, const double *const *X, const int64_t *n, int count, double *out_dev);
 /* dW = W - W_prev; W_prev = W; sq_out_dev = { ||dW||^2, ||W||^2 }  (als_CP.cxx:596-600). */

@@ -15,7 +15,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libppx.so")
+LIB_PATH = os.environ.get("PPX_LIB_PATH") or os.path.join(_HERE, "libppx.so")  # override: A/B tests of kernel builds
 HOST_LIB_PATH = os.path.join(_HERE, "libppx_host.so")
 
 PPX_SOLVE_CHOL = 0
@@ -55,6 +55,8 @@ SIGNATURES = {
     "ppx_graph_destroy": (C.c_int, [_vp, _vp]),
     "ppx_fill_uniform": (C.c_int, [_vp, _dp, _i64, C.c_uint64, C.c_uint64, _i64, C.c_double, C.c_double]),
     "ppx_ttm_first": (C.c_int, [_vp, _dp, C.POINTER(_i64), C.c_int, C.c_int, _dp, _i64, C.c_int, _dp]),
+    "ppx_ttm_multi": (C.c_int, [_vp, _dp, C.POINTER(_i64), C.c_int, C.c_int, C.c_int, C.POINTER(_dp), C.POINTER(_i64),
+                                C.c_int, _dp]),
     "ppx_mttv": (C.c_int, [_vp, _dp, C.POINTER(_i64), C.c_int, C.c_int, _dp, _i64, C.c_int, _dp]),
     "ppx_mttv2": (C.c_int, [_vp, _dp, C.POINTER(_i64), C.c_int, C.c_int, _dp, _i64, C.c_int, _dp, _i64, C.c_int, _dp]),
     "ppx_ttm_first_mttv": (C.c_int, [_vp, _dp, C.POINTER(_i64), C.c_int, C.c_int, _dp, _i64, C.c_int, _dp, _i64,
@@ -64,6 +66,15 @@ SIGNATURES = {
     "ppx_gram": (C.c_int, [_vp, _dp, _i64, _i64, C.c_int, _dp]),
     "ppx_hadamard_grams": (C.c_int, [_vp, C.POINTER(_dp), C.c_int, C.c_int, C.c_int, C.c_double, _dp]),
     "ppx_solve_update": (C.c_int, [_vp, _dp, _dp, _dp, _i64, C.c_int, _dp, C.c_double, C.c_int, _dp, _dp, _dp]),
+    "ppx_solve_update_g": (C.c_int, [_vp, _dp, C.POINTER(_dp), C.c_int, C.c_int, C.c_double, _dp, _i64, C.c_int, _dp,
+                                     C.c_double, C.c_int, _dp, _dp, _dp]),
+    "ppx_spd_inverse_g": (C.c_int, [_vp, C.POINTER(_dp), C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, _dp, _dp]),
+    "ppx_solve_apply": (C.c_int, [_vp, _dp, _dp, _dp, _dp, _i64, C.c_int, _dp, C.c_double, _dp, _dp]),
+    "ppx_side_begin": (C.c_int, [_vp]),
+    "ppx_side_end": (C.c_int, [_vp]),
+    "ppx_side_join": (C.c_int, [_vp]),
+    "ppx_normalize_norms": (C.c_int, [_vp, C.POINTER(_dp), C.POINTER(_dp), C.POINTER(_i64), C.c_int, C.c_int,
+                                      C.POINTER(_dp), _dp]),
     "ppx_normalize": (C.c_int, [_vp, C.POINTER(_dp), C.POINTER(_i64), C.c_int, C.c_int, C.POINTER(_dp)]),
     "ppx_normalize_g": (C.c_int, [_vp, C.POINTER(_dp), C.POINTER(_i64), C.c_int, C.c_int, C.POINTER(_dp)]),
     "ppx_sqnorms": (C.c_int, [_vp, C.POINTER(_dp), C.POINTER(_i64), C.c_int, _dp]),
@@ -210,6 +221,11 @@ class Ctx:
         self._ck(self.lib.ppx_ttm_first(self.h, _ptr(V), _lens(lens), len(lens), x, _ptr(W),
                                         ldw if ldw is not None else lens[x], R, _ptr(out)))
 
+    def ttm_multi(self, V, lens, x_first, Ws, R, out):
+        n = len(Ws)
+        self._ck(self.lib.ppx_ttm_multi(self.h, _ptr(V), _lens(lens), len(lens), x_first, n, _ptrs(Ws),
+                                        _lens([lens[x_first + j] for j in range(n)]), R, _ptr(out)))
+
     def mttv(self, T, lens, x, W, R, out, ldw=None):
         self._ck(self.lib.ppx_mttv(self.h, _ptr(T), _lens(lens), len(lens), x, _ptr(W),
                                    ldw if ldw is not None else lens[x], R, _ptr(out)))
@@ -237,6 +253,11 @@ class Ctx:
                      sq_norms=None):
         self._ck(self.lib.ppx_solve_update(self.h, _ptr(M), _ptr(S), _ptr(W), s, R, _ptr(W_init), ratio_step, mode,
                                            _ptr(grad), _ptr(dW), _ptr(sq_norms)))
+
+    def solve_update_g(self, M, Gs, skip, lam, W, s, R, W_init=None, ratio_step=1.0, mode=PPX_SOLVE_CHOL, grad=None,
+                       dW=None, sq_norms=None):
+        self._ck(self.lib.ppx_solve_update_g(self.h, _ptr(M), _ptrs(Gs), len(Gs), skip, lam, _ptr(W), s, R,
+                                             _ptr(W_init), ratio_step, mode, _ptr(grad), _ptr(dW), _ptr(sq_norms)))
 
     def normalize(self, Ws, sizes, R, Gs=None):
         self._ck(self.lib.ppx_normalize(self.h, _ptrs(Ws), _lens(sizes), len(Ws), R,

@@ -109,26 +109,35 @@ int ppx_allreduce_packed(ppx_ctx *ctx, double *const *bufs, const int64_t *sizes
 
 int ppx_ttm_first_mttv(ppx_ctx *ctx, const double *V, const int64_t *lens, int N, int x1, const double *W1,
                        int64_t ldw1, int x2, const double *W2, int64_t ldw2, int R, double *out) {
-  // Round-1 implementation: the two contractions back to back through the context workspace (same result, the
-  // level-1 tensor still travels through HBM once).  The single-kernel fusion is tracked in DESIGN.md.
+  // adjacent modes: one GEMM against the Khatri-Rao rows (ppx_ttm_multi); otherwise the two contractions back to
+  // back through the context workspace
   PPX_REQUIRE(ctx, V && lens && W1 && W2 && out, "non-null pointers");
   PPX_REQUIRE(ctx, N >= 2 && N <= 16 && x1 >= 0 && x1 < N && x2 >= 0 && x2 < N && x1 != x2, "x1 != x2 in [0,N)");
+  if (x2 == x1 + 1 || x1 == x2 + 1) {
+    const double *W[2] = {x1 < x2 ? W1 : W2, x1 < x2 ? W2 : W1};
+    const int64_t ld[2] = {x1 < x2 ? ldw1 : ldw2, x1 < x2 ? ldw2 : ldw1};
+    return ppx_ttm_multi(ctx, V, lens, N, x1 < x2 ? x1 : x2, 2, W, ld, R, out);
+  }
   int64_t P = 1;
   for (int i = 0; i < N; i++) P *= lens[i];
   const int64_t n1 = P / lens[x1] * R;
-  ppx_ws_reset(ctx);
-  double *tmp = (double *)ppx_ws_alloc(ctx, sizeof(double) * (size_t)n1);
-  if (!tmp)
-    return ppx_set_err(ctx, PPX_ENOMEM, "ttm_first_mttv needs %lld bytes of workspace", (long long)(8 * n1));
-  size_t keep = ctx->ws_used;
+  double *tmp = nullptr;
+  cudaError_t e = cudaMalloc((void **)&tmp, sizeof(double) * (size_t)n1);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return ppx_set_err(ctx, PPX_ENOMEM, "ttm_first_mttv: cannot allocate the %lld-byte level-1 tensor", (long long)(8 * n1));
+  }
   int rc = ppx_ttm_first(ctx, V, lens, N, x1, W1, ldw1, R, tmp);
-  if (rc) return rc;
-  int64_t lens2[16];
-  int k = 0;
-  for (int i = 0; i < N; i++)
-    if (i != x1) lens2[k++] = lens[i];
-  (void)keep;
-  return ppx_mttv(ctx, tmp, lens2, k, x2 > x1 ? x2 - 1 : x2, W2, ldw2, R, out);
+  if (!rc) {
+    int64_t lens2[16];
+    int k = 0;
+    for (int i = 0; i < N; i++)
+      if (i != x1) lens2[k++] = lens[i];
+    rc = ppx_mttv(ctx, tmp, lens2, k, x2 > x1 ? x2 - 1 : x2, W2, ldw2, R, out);
+  }
+  cudaStreamSynchronize(ctx->stream);
+  cudaFree(tmp);
+  return rc;
 }
 
 }  // extern "C"

@@ -1,16 +1,25 @@
 // K1 -- first tensor-times-matrix contraction of the dimension tree
 //     out[l, t, r] = sum_x V[l, x, t] * W[x, r]         (V viewed as L x X x Rt, first index fastest)
 // replaces the CTF expressions at common.cxx:56, als_CP.cxx:378-379, cp_dt_optimizer.cxx:158-159,
-// cp_msdt_optimizer.cxx:142-143 and common.cxx:963 of the reference.
+// cp_msdt_optimizer.cxx:142-143 and common.cxx:963 of the reference; with `inplace` it is the Tucker TTM
+// (als_Tucker.cxx:102,224,464-465).
 //
 // Design (sm_100a): FP64 has no tcgen05 kind, so the tensor pipe is reached through warp-level DMMA
 // (mma.sync.m8n8k4.f64 -> SASS DMMA.8x8x4, measured 37.1 TFLOP/s on B200 = the FP64 peak).  Persistent CTAs
 // stream 128-row x 16-deep tiles of V and the matching 16 x R slab of W through a multi-stage cp.async pipeline
-// that runs across tile boundaries (no drain between tiles); each of the 4 warps owns a 32 x (8*NT) accumulator
-// block in registers.  Shared-memory tiles are padded (ld = 4 mod 16 doubles) so every DMMA fragment load is
-// bank-conflict free.  Two CTAs per SM.
+// that runs across work-unit boundaries (no drain between tiles); each of the 4 warps owns a 32 x (8*NT)
+// accumulator block in registers.  Shared-memory tiles are padded (ld = 4 mod 16 doubles) so every DMMA fragment
+// load is bank-conflict free.  Two CTAs per SM.
 //   KMAJOR = true : L == 1, the contracted mode is the fastest one (rows of V are contiguous along x).
 //   KMAJOR = false: L  > 1, rows m = (l, t) are contiguous along l for a fixed x.
+// A work unit is (row tile, K split): when there are too few row tiles to balance 2 x 148 persistent CTAs (the
+// fused contraction of several adjacent modes has K = prod of their sizes and few rows) the K range is split and the
+// partial tiles are summed by a second kernel in a fixed order (deterministic).
+//
+// ppx_ttm_multi: several ADJACENT modes contracted at once.  sum_{x1..xn} V[l, x1..xn, t] prod_j W_j[x_j, r] is one
+// GEMM with the Khatri-Rao product of the factors as right-hand side: K[(x1..xn), r] = prod_j W_j[x_j, r] is formed
+// by a small kernel (K*R doubles, L2 resident) and the level-1 intermediates of the reference's tree
+// (common.cxx:56 followed by :83) are never written to HBM.
 #include "ppx_internal.h"
 
 namespace {
@@ -26,9 +35,12 @@ struct TtmParams {
   const double *W;
   double *out;
   int64_t L, X, Rt, Mtot, ldw;
+  int64_t split_stride;  // elements between the partial outputs of consecutive K splits
   int R;
   int num_tiles;
-  int nk;
+  int nk;          // 16-deep chunks along K
+  int ksplit;      // number of K splits (1 = none)
+  int cps;         // chunks per split
   int vecA, vecW;
   int inplace;     // 0: out[m + Mtot*col] (rank last, CP) ; 1: out[l + L*(col + R*t)] (rank replaces mode x, Tucker)
   int accumulate;  // out += result
@@ -51,21 +63,53 @@ __global__ void __launch_bounds__(THREADS, 2) ttm_first_kernel(TtmParams p) {
   const int g = lane >> 2, t4 = lane & 3;
   const int ncol0 = blockIdx.y * 64;
 
-  int my_tiles = 0;
-  if ((int)blockIdx.x < p.num_tiles) my_tiles = (p.num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1;
-  const int total = my_tiles * p.nk;
+  const int num_units = p.num_tiles * p.ksplit;
+  // unit u = (tile, split); chunks [split*cps, min(nk, (split+1)*cps))
+  struct Unit {
+    int u, tile, split, count;
+  };
+  auto set_unit = [&](Unit &q, int u) {
+    q.u = u;
+    q.tile = 0;
+    q.split = 0;
+    q.count = 0;
+    if (u >= num_units) return;
+    if (p.ksplit == 1) {
+      q.tile = u;
+      q.count = p.nk;
+    } else {
+      q.tile = u / p.ksplit;
+      q.split = u - q.tile * p.ksplit;
+      const int kb = q.split * p.cps;
+      const int ke = min(p.nk, kb + p.cps);
+      q.count = ke > kb ? ke - kb : 0;
+    }
+  };
+  int total = 0;
+  if (p.ksplit == 1) {
+    if ((int)blockIdx.x < num_units) total = ((num_units - 1 - (int)blockIdx.x) / (int)gridDim.x + 1) * p.nk;
+  } else {
+    Unit q;
+    for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
+      set_unit(q, u);
+      total += q.count;
+    }
+  }
 
   // ---- loader state -----------------------------------------------------------------------------------
-  int ld_tile_i = 0, ld_kc = 0;  // position of the next chunk to load
+  Unit ld;  // work unit of the next chunk to load
+  set_unit(ld, blockIdx.x);
+  int ld_kc = 0;
   int cached_tile = -1;
   int64_t off0 = 0, off1 = 0;  // M-major: global offsets (without the k term) of this thread's two rows
   int nb0 = 0, nb1 = 0;        // bytes valid for row 0 / row 1 (0 or 8)
 
   auto load_chunk = [&](int stage) {
-    const int tile = (int)blockIdx.x + ld_tile_i * (int)gridDim.x;
+    while (ld.count == 0) set_unit(ld, ld.u + gridDim.x);  // skip empty units (only possible for the last split)
+    const int tile = ld.tile, split = ld.split;
     double *As = smem + stage * STAGE_D;
     double *Ws = As + A_D;
-    const int64_t k0 = (int64_t)ld_kc * BK;
+    const int64_t k0 = (int64_t)(split * p.cps + ld_kc) * BK;
     if (KMAJOR) {
       const int kp = tid & 7, mb = tid >> 3;
       const int64_t kg = k0 + 2 * kp;
@@ -134,9 +178,9 @@ __global__ void __launch_bounds__(THREADS, 2) ttm_first_kernel(TtmParams p) {
         }
       }
     }
-    if (++ld_kc == p.nk) {
+    if (++ld_kc == ld.count) {
       ld_kc = 0;
-      ++ld_tile_i;
+      set_unit(ld, ld.u + gridDim.x);
     }
   };
 
@@ -154,8 +198,11 @@ __global__ void __launch_bounds__(THREADS, 2) ttm_first_kernel(TtmParams p) {
     ppx_cp_async_commit();
   }
 
-  int kc = 0, tile_i = 0;
+  Unit cu;  // work unit being computed
+  set_unit(cu, blockIdx.x);
+  int kc = 0;
   for (int c = 0; c < total; c++) {
+    while (cu.count == 0) set_unit(cu, cu.u + gridDim.x);
     ppx_cp_async_wait<STAGES - 2>();
     __syncthreads();
     {
@@ -182,9 +229,10 @@ __global__ void __launch_bounds__(THREADS, 2) ttm_first_kernel(TtmParams p) {
 #pragma unroll
         for (int j = 0; j < NT; j++) ppx_dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
     }
-    if (++kc == p.nk) {
-      // epilogue of this tile
-      const int tile = (int)blockIdx.x + tile_i * (int)gridDim.x;
+    if (++kc == cu.count) {
+      // epilogue of this work unit
+      const int tile = cu.tile, split = cu.split;
+      double *outp = p.out + (int64_t)split * p.split_stride;
 #pragma unroll
       for (int i = 0; i < 4; i++) {
         const int64_t mg = (int64_t)tile * BM + 32 * warp + 8 * i + g;
@@ -199,11 +247,11 @@ __global__ void __launch_bounds__(THREADS, 2) ttm_first_kernel(TtmParams p) {
           const int col = ncol0 + 8 * j + 2 * t4;
           if (mg < p.Mtot) {
             if (col < p.R) {
-              double *o = p.out + base + cstride * col;
+              double *o = outp + base + cstride * col;
               *o = p.accumulate ? (*o + acc[i][j][0]) : acc[i][j][0];
             }
             if (col + 1 < p.R) {
-              double *o = p.out + base + cstride * (col + 1);
+              double *o = outp + base + cstride * (col + 1);
               *o = p.accumulate ? (*o + acc[i][j][1]) : acc[i][j][1];
             }
           }
@@ -211,10 +259,46 @@ __global__ void __launch_bounds__(THREADS, 2) ttm_first_kernel(TtmParams p) {
         }
       }
       kc = 0;
-      ++tile_i;
+      set_unit(cu, cu.u + gridDim.x);
     }
   }
   ppx_cp_async_wait<0>();
+}
+
+// out[i] = sum_s part[s][i], fixed order
+__global__ void __launch_bounds__(256) split_reduce_kernel(const double *__restrict__ part, int64_t n, int nsplit,
+                                                           double *__restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    double s = part[i];
+    for (int k = 1; k < nsplit; k++) s += part[(int64_t)k * n + i];
+    out[i] = s;
+  }
+}
+
+// Khatri-Rao rows of n adjacent modes: K[k, r] = prod_j W_j[idx_j(k), r], k = x_1 + X_1*(x_2 + X_2*(...))
+struct KrpArgs {
+  const double *w[8];
+  int64_t x[8];
+  int64_t ld[8];
+  int n;
+};
+__global__ void __launch_bounds__(256) krp_kernel(KrpArgs a, int64_t K, int R, double *__restrict__ out) {
+  const int64_t total = K * (int64_t)R;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < total; i += stride) {
+    const int64_t r = i / K;
+    int64_t k = i - r * K;
+    double v = 1.0;
+    for (int j = 0; j < a.n; j++) {
+      const int64_t xj = k % a.x[j];
+      k /= a.x[j];
+      v *= a.w[j][xj + a.ld[j] * r];
+    }
+    out[i] = v;
+  }
 }
 
 template <int NT, bool KMAJOR>
@@ -226,7 +310,8 @@ template <int NT, bool KMAJOR>
 int launch_ttm(ppx_ctx *ctx, const TtmParams &p, int col_blocks) {
   constexpr int STAGES = KMAJOR ? 3 : 4;
   auto kern = ttm_first_kernel<NT, KMAJOR, STAGES>;
-  int gx = p.num_tiles < 2 * ctx->sm_count ? p.num_tiles : 2 * ctx->sm_count;
+  const int units = p.num_tiles * p.ksplit;
+  int gx = units < 2 * ctx->sm_count ? units : 2 * ctx->sm_count;
   dim3 grid(gx, col_blocks);
   kern<<<grid, THREADS, ttm_smem<NT, KMAJOR>(), ctx->stream>>>(p);
   PPX_CHECK_LAUNCH(ctx);
@@ -266,9 +351,10 @@ int ppx_k1_init(ppx_ctx *ctx) {
   return PPX_OK;
 }
 
-// Shared by ppx_ttm_first (CP, rank last) and ppx_ttm / ppx_ttm_acc (Tucker, rank in place of mode x).
+// Shared by ppx_ttm_first (CP, rank last), ppx_ttm / ppx_ttm_acc (Tucker, rank in place of mode x) and ppx_ttm_multi.
+// Uses the context workspace for split-K partials (callers that hold workspace memory pass ws_keep = true).
 int ppx_ttm_impl(ppx_ctx *ctx, const double *V, int64_t L, int64_t X, int64_t Rt, const double *Wx, int64_t ldw,
-                 int R, double *out, int inplace, int accumulate) {
+                 int R, double *out, int inplace, int accumulate, bool ws_keep) {
   TtmParams p;
   p.V = V;
   p.W = Wx;
@@ -281,20 +367,63 @@ int ppx_ttm_impl(ppx_ctx *ctx, const double *V, int64_t L, int64_t X, int64_t Rt
   p.R = R;
   p.inplace = inplace;
   p.accumulate = accumulate;
+  p.ksplit = 1;
+  p.split_stride = 0;
   if (p.Mtot == 0 || R == 0) return PPX_OK;
   int64_t tiles = (p.Mtot + BM - 1) / BM;
-  if (tiles > 0x7fffffff / 2) return ppx_set_err(ctx, PPX_EUNSUPPORTED, "ttm_first: too many row tiles");
+  if (tiles > 0x7fffffff / 64) return ppx_set_err(ctx, PPX_EUNSUPPORTED, "ttm_first: too many row tiles");
   p.num_tiles = (int)tiles;
-  p.nk = (int)((X + BK - 1) / BK);
+  const int64_t nk64 = (X + BK - 1) / BK;
+  if (nk64 > 0x7fffffff) return ppx_set_err(ctx, PPX_EUNSUPPORTED, "ttm_first: contracted extent too large");
+  p.nk = (int)nk64;
+  p.cps = p.nk;
   const bool kmajor = (L == 1);
   const bool v16 = (((uintptr_t)V) & 15) == 0;
   p.vecA = kmajor ? (v16 && (X % 2 == 0)) : (v16 && (L % 2 == 0));
   p.vecW = ((((uintptr_t)Wx) & 15) == 0) && (ldw % 2 == 0);
   const int col_blocks = (R + 63) / 64;
-  // all column blocks use the same NT (the widest); narrower last blocks just mask columns
   const int ncols = R < 64 ? R : 64;
   const int nt = (ncols + 7) / 8;
-  return kmajor ? dispatch_nt<true>(ctx, p, nt, col_blocks) : dispatch_nt<false>(ctx, p, nt, col_blocks);
+
+  // K split: only when the row tiles cannot balance the persistent grid and K is deep enough to amortise it
+  double *partial = nullptr;
+  const int G = 2 * ctx->sm_count;
+  if (!inplace && !accumulate && col_blocks == 1 && p.nk >= 64 && p.num_tiles < 8 * G) {
+    auto eff = [&](int S) {
+      const int64_t units = (int64_t)p.num_tiles * S;
+      const int64_t waves = (units + G - 1) / G;
+      return (double)units / (double)(waves * G);
+    };
+    int best = 1;
+    double best_eff = eff(1);
+    for (int S = 2; S <= 32 && p.nk / S >= 16; S++) {
+      const double e = eff(S);
+      if (e > best_eff + 0.02) {
+        best_eff = e;
+        best = S;
+      }
+    }
+    if (best > 1) {
+      if (!ws_keep) ppx_ws_reset(ctx);
+      partial = (double *)ppx_ws_alloc(ctx, sizeof(double) * (size_t)best * p.Mtot * R);
+      if (partial) {
+        p.ksplit = best;
+        p.cps = (p.nk + best - 1) / best;
+        p.split_stride = p.Mtot * (int64_t)R;
+        p.out = partial;
+      }  // else: not enough workspace -> run unsplit (correct, just less balanced)
+    }
+  }
+  int rc = kmajor ? dispatch_nt<true>(ctx, p, nt, col_blocks) : dispatch_nt<false>(ctx, p, nt, col_blocks);
+  if (rc) return rc;
+  if (p.ksplit > 1) {
+    const int64_t n = p.Mtot * (int64_t)R;
+    int blocks = ppx_cdiv(n, 256 * 4);
+    if (blocks > ctx->sm_count * 8) blocks = ctx->sm_count * 8;
+    split_reduce_kernel<<<blocks, 256, 0, ctx->stream>>>(partial, n, p.ksplit, out);
+    PPX_CHECK_LAUNCH(ctx);
+  }
+  return PPX_OK;
 }
 
 extern "C" {
@@ -306,7 +435,39 @@ int ppx_ttm_first(ppx_ctx *ctx, const double *V, const int64_t *lens, int N, int
   PPX_REQUIRE(ctx, ldw >= lens[x], "ldw >= lens[x]");
   int64_t L, X, Rt;
   ppx_split3(lens, N, x, &L, &X, &Rt);
-  return ppx_ttm_impl(ctx, V, L, X, Rt, Wx, ldw, R, out, 0, 0);
+  return ppx_ttm_impl(ctx, V, L, X, Rt, Wx, ldw, R, out, 0, 0, false);
+}
+
+int ppx_ttm_multi(ppx_ctx *ctx, const double *V, const int64_t *lens, int N, int x_first, int n_modes,
+                  const double *const *W, const int64_t *ldw, int R, double *out) {
+  PPX_REQUIRE(ctx, V && lens && W && ldw && out, "non-null pointers");
+  PPX_REQUIRE(ctx, N >= 1 && N <= 16 && n_modes >= 1 && n_modes <= 8 && x_first >= 0 && x_first + n_modes <= N && R >= 1,
+              "1 <= n_modes <= 8 adjacent modes inside [0, N)");
+  if (n_modes == 1) return ppx_ttm_first(ctx, V, lens, N, x_first, W[0], ldw[0], R, out);
+  int64_t L = 1, K = 1, Rt = 1;
+  for (int i = 0; i < x_first; i++) L *= lens[i];
+  KrpArgs a;
+  a.n = n_modes;
+  for (int j = 0; j < n_modes; j++) {
+    PPX_REQUIRE(ctx, W[j] && ldw[j] >= lens[x_first + j], "ldw[j] >= lens of the contracted mode");
+    a.w[j] = W[j];
+    a.x[j] = lens[x_first + j];
+    a.ld[j] = ldw[j];
+    K *= lens[x_first + j];
+  }
+  for (int i = x_first + n_modes; i < N; i++) Rt *= lens[i];
+  ppx_ws_reset(ctx);
+  double *krp = (double *)ppx_ws_alloc(ctx, sizeof(double) * (size_t)K * R);  // K x R, column-major, ld = K
+  if (!krp)
+    return ppx_set_err(ctx, PPX_ENOMEM, "ttm_multi needs %lld bytes of workspace for the Khatri-Rao rows",
+                       (long long)(8 * K * R));
+  const int64_t ld = K;
+  const int64_t total = K * (int64_t)R;
+  int blocks = ppx_cdiv(total, 256 * 2);
+  if (blocks > ctx->sm_count * 16) blocks = ctx->sm_count * 16;
+  krp_kernel<<<blocks, 256, 0, ctx->stream>>>(a, K, R, krp);
+  PPX_CHECK_LAUNCH(ctx);
+  return ppx_ttm_impl(ctx, V, L, K, Rt, krp, ld, R, out, 0, 0, true);
 }
 
 int ppx_ttm(ppx_ctx *ctx, const double *T, const int64_t *lens, int k, int x, const double *Wx, int64_t ldw, int Q,
@@ -316,7 +477,7 @@ int ppx_ttm(ppx_ctx *ctx, const double *T, const int64_t *lens, int k, int x, co
   PPX_REQUIRE(ctx, ldw >= lens[x], "ldw >= lens[x]");
   int64_t L, X, Rt;
   ppx_split3(lens, k, x, &L, &X, &Rt);
-  return ppx_ttm_impl(ctx, T, L, X, Rt, Wx, ldw, Q, out, 1, 0);
+  return ppx_ttm_impl(ctx, T, L, X, Rt, Wx, ldw, Q, out, 1, 0, false);
 }
 
 int ppx_ttm_acc(ppx_ctx *ctx, const double *T, const int64_t *lens, int k, int x, const double *Wx, int64_t ldw,
@@ -326,7 +487,7 @@ int ppx_ttm_acc(ppx_ctx *ctx, const double *T, const int64_t *lens, int k, int x
   PPX_REQUIRE(ctx, ldw >= lens[x], "ldw >= lens[x]");
   int64_t L, X, Rt;
   ppx_split3(lens, k, x, &L, &X, &Rt);
-  return ppx_ttm_impl(ctx, T, L, X, Rt, Wx, ldw, Q, out, 1, 1);
+  return ppx_ttm_impl(ctx, T, L, X, Rt, Wx, ldw, Q, out, 1, 1, false);
 }
 
 }  // extern "C"

@@ -100,9 +100,12 @@ struct PpArgs {
   int n_ops;
 };
 
-constexpr int PP_WY = 8;
+constexpr int PP_WY = 16;  // warps per CTA
+constexpr int PP_B = 10;   // loads in flight per thread and batch
 __global__ void __launch_bounds__(32 * PP_WY) pp_correct_kernel(const double *__restrict__ M0, PpArgs a,
                                                                 int64_t s_i, int R, double *__restrict__ Mout) {
+  // At PP-operator sizes (tens of MB) the kernel is latency bound: every thread keeps PP_B independent loads in
+  // flight and the next batch is issued before the current one is consumed.
   __shared__ double part[PP_WY][32];  // which==1 partial sums (per warp, per row)
   __shared__ double dots[32];         // which==0 sums (per row)
   const int lane = threadIdx.x, wy = threadIdx.y;
@@ -119,14 +122,32 @@ __global__ void __launch_bounds__(32 * PP_WY) pp_correct_kernel(const double *__
       // op[i', q, r]: rows contiguous along i' -> lanes along i', warps split q
       if (i < s_i) {
         const double *pp = a.op[j] + i + s_i * sj * (int64_t)r;
-        double a0 = 0.0, a1 = 0.0;
-        int64_t q = wy;
-        for (; q + PP_WY < sj; q += 2 * PP_WY) {
-          a0 += pp[s_i * q] * dw[q];
-          a1 += pp[s_i * (q + PP_WY)] * dw[q + PP_WY];
+        double cur[PP_B], nxt[PP_B];
+#pragma unroll
+        for (int u = 0; u < PP_B; u++) {
+          const int64_t q = wy + (int64_t)u * PP_WY;
+          cur[u] = q < sj ? pp[s_i * q] : 0.0;
         }
-        for (; q < sj; q += PP_WY) a0 += pp[s_i * q] * dw[q];
-        acc += a0 + a1;
+        for (int64_t q0 = wy; q0 < sj; q0 += PP_B * PP_WY) {
+          const int64_t q1 = q0 + PP_B * PP_WY;
+          if (q1 < sj) {
+#pragma unroll
+            for (int u = 0; u < PP_B; u++) {
+              const int64_t q = q1 + (int64_t)u * PP_WY;
+              nxt[u] = q < sj ? pp[s_i * q] : 0.0;
+            }
+          }
+          double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+          for (int u = 0; u < PP_B; u += 2) {
+            const int64_t qa = q0 + (int64_t)u * PP_WY, qb = qa + PP_WY;
+            a0 += cur[u] * (qa < sj ? dw[qa] : 0.0);
+            a1 += cur[u + 1] * (qb < sj ? dw[qb] : 0.0);
+          }
+          acc += a0 + a1;
+#pragma unroll
+          for (int u = 0; u < PP_B; u++) cur[u] = nxt[u];
+        }
       }
     } else {
       // op[q, i', r]: contiguous along q -> one warp per row i', lanes along q
@@ -135,7 +156,32 @@ __global__ void __launch_bounds__(32 * PP_WY) pp_correct_kernel(const double *__
         double d = 0.0;
         if (ii < s_i) {
           const double *pp = a.op[j] + sj * (ii + s_i * (int64_t)r);
-          for (int64_t q = lane; q < sj; q += 32) d += pp[q] * dw[q];
+          double cur[PP_B], nxt[PP_B];
+#pragma unroll
+          for (int u = 0; u < PP_B; u++) {
+            const int64_t q = lane + 32 * (int64_t)u;
+            cur[u] = q < sj ? pp[q] : 0.0;
+          }
+          for (int64_t q0 = lane; q0 < sj; q0 += 32 * PP_B) {
+            const int64_t q1 = q0 + 32 * PP_B;
+            if (q1 < sj) {
+#pragma unroll
+              for (int u = 0; u < PP_B; u++) {
+                const int64_t q = q1 + 32 * (int64_t)u;
+                nxt[u] = q < sj ? pp[q] : 0.0;
+              }
+            }
+            double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+            for (int u = 0; u < PP_B; u += 2) {
+              const int64_t qa = q0 + 32 * (int64_t)u, qb = qa + 32;
+              a0 += cur[u] * (qa < sj ? dw[qa] : 0.0);
+              a1 += cur[u + 1] * (qb < sj ? dw[qb] : 0.0);
+            }
+            d += a0 + a1;
+#pragma unroll
+            for (int u = 0; u < PP_B; u++) cur[u] = nxt[u];
+          }
         }
         d = ppx_warp_sum(d);
         if (lane == 0) dots[rr] += d;  // rows rr are owned by warp rr % PP_WY: no race, fixed order over j

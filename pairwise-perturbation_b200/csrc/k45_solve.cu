@@ -6,7 +6,9 @@
 //
 // The R x R inverse is formed once by ONE CTA (Cholesky: S = L L^T, S^-1 = L^-T L^-1; or, for the reference's
 // SVD_solve semantics, a cyclic Jacobi eigen-decomposition S = Q diag(e) Q^T, S^-1 = Q diag(1/e) Q^T with no
-// truncation, common.cxx:720-722), then applied to the s x R right-hand side by a grid of row tiles.
+// truncation, common.cxx:720-722), then applied to the s x R right-hand side by a grid of 8-row tiles.  The
+// Hadamard product of the cached Grams is fused into the inverse kernel (ppx_solve_update_g), so one mode update of
+// the PP sweep is: correction kernel, inverse kernel, apply kernel, Gram kernel.
 #include "ppx_internal.h"
 
 namespace {
@@ -26,14 +28,16 @@ __global__ void __launch_bounds__(256) gram_kernel(const double *__restrict__ W,
   }
   const int b = a + rem;
   const double *wa = W + (int64_t)a * ldw, *wb = W + (int64_t)b * ldw;
-  double acc0 = 0.0, acc1 = 0.0;
+  double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
   int64_t i = lane;
-  for (; i + 32 < s; i += 64) {
+  for (; i + 96 < s; i += 128) {
     acc0 += wa[i] * wb[i];
     acc1 += wa[i + 32] * wb[i + 32];
+    acc2 += wa[i + 64] * wb[i + 64];
+    acc3 += wa[i + 96] * wb[i + 96];
   }
   for (; i < s; i += 32) acc0 += wa[i] * wb[i];
-  double v = ppx_warp_sum(acc0 + acc1);
+  double v = ppx_warp_sum((acc0 + acc1) + (acc2 + acc3));
   if (lane == 0) {
     G[a + R * b] = v;
     G[b + R * a] = v;
@@ -44,63 +48,128 @@ struct HadArgs {
   const double *g[16];
   int n;
 };
-__global__ void hadamard_kernel(HadArgs h, int R, double lambda, double *__restrict__ S) {
-  int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= R * R) return;
+__device__ __forceinline__ double hadamard_at(const HadArgs &h, int idx, int R, double lambda) {
   double v = h.g[0][idx];
   for (int j = 1; j < h.n; j++) v *= h.g[j][idx];
   if (lambda != 0.0 && (idx / R) == (idx % R)) v += lambda;
-  S[idx] = v;
+  return v;
+}
+__global__ void hadamard_kernel(HadArgs h, int R, double lambda, double *__restrict__ S) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= R * R) return;
+  S[idx] = hadamard_at(h, idx, R, lambda);
 }
 
-// ---- R x R inverse, one CTA ------------------------------------------------------------------------------------
-// shared: A[R][ld] (ld = R+1) and B[R][ld]
-__global__ void __launch_bounds__(256) spd_inverse_chol_kernel(const double *__restrict__ S, int R,
-                                                               double *__restrict__ Sinv) {
+// ---- R x R inverse by Cholesky, one CTA of 16 x 16 threads, matrix in registers -----------------------------------
+// S is the Hadamard product of h.n matrices (+ lambda I); it is written to S_out (the apply kernel needs it for the
+// gradient) and inverted.  Thread (tx, ty) owns the elements (i, j) with i = ty (mod 16), j = tx (mod 16) of S and of
+// Y (initially I) in REGISTERS (T x T each, T = ceil(R/16)).  Step k of the right-looking Cholesky S = L L^T needs
+// only column k of the partially updated S and, to carry L^-1 along, row k of Y: their owners publish them through
+// double-buffered shared vectors, so there is ONE barrier per column and nothing else touches shared memory:
+//      l_ik = s_ik / sqrt(s_kk)  (one rsqrt, no divide),   s_ij -= l_ik l_jk,
+//      y_k: = y_k: / l_kk,   y_i: -= l_ik y_k:   (i > k)            =>  after R steps  Y = L^-1.
+// Finally S^-1 = Y^T Y.
+// B = edge of the thread grid (16 -> 256 threads, T <= 7; 32 -> 1024 threads, T <= 2: with more warps the
+// per-column critical path -- barrier, rsqrt, a handful of dependent FP64 operations -- is issue bound, not latency bound)
+template <int T, int B>
+__global__ void __launch_bounds__(B * B) spd_inverse_chol_kernel(HadArgs h, int R, double lambda,
+                                                                       double *__restrict__ S_out,
+                                                                       double *__restrict__ Sinv) {
   extern __shared__ double sm[];
   const int ld = R + 1;
-  double *A = sm;           // becomes L (lower)
-  double *B = sm + R * ld;  // becomes L^-1 (lower)
-  const int tid = threadIdx.x, nt = blockDim.x;
-  for (int idx = tid; idx < R * R; idx += nt) {
-    int i = idx % R, j = idx / R;
-    A[i * ld + j] = S[idx];
-    B[i * ld + j] = 0.0;
-  }
-  __syncthreads();
-  // right-looking Cholesky, lower triangle
-  for (int k = 0; k < R; k++) {
-    const double d = sqrt(A[k * ld + k]);  // every thread reads the same (pre-update) value
-    __syncthreads();
-    if (tid == 0) A[k * ld + k] = d;
-    for (int i = k + 1 + tid; i < R; i += nt) A[i * ld + k] /= d;
-    __syncthreads();
-    const int m = R - k - 1;  // trailing update on the lower triangle of the m x m block
-    for (int idx = tid; idx < m * m; idx += nt) {
-      int i = k + 1 + idx / m, j = k + 1 + idx % m;
-      if (j <= i) A[i * ld + j] -= A[i * ld + k] * A[j * ld + k];
-    }
-    __syncthreads();
-  }
-  // L^-1 by forward substitution, one thread per column
-  for (int j = tid; j < R; j += nt) {
-    for (int i = j; i < R; i++) {
-      double v = (i == j) ? 1.0 : 0.0;
-      for (int k = j; k < i; k++) v -= A[i * ld + k] * B[k * ld + j];
-      B[i * ld + j] = v / A[i * ld + i];
-    }
-  }
-  __syncthreads();
-  // S^-1 = L^-T L^-1 :  Sinv[i][j] = sum_{k >= max(i,j)} Linv[k][i] Linv[k][j]
-  for (int idx = tid; idx < R * R; idx += nt) {
-    int i = idx % R, j = idx / R;
-    if (i >= j) {
+  double *colraw = sm;            // [2][R]
+  double *rowraw = sm + 2 * R;    // [2][R]
+  double *Ys = sm + 4 * R;        // [R][ld]
+  const int tx = threadIdx.x % B, ty = threadIdx.x / B;
+  double a[T][T], y[T][T];
+#pragma unroll
+  for (int ii = 0; ii < T; ii++)
+#pragma unroll
+    for (int jj = 0; jj < T; jj++) {
+      const int i = ty + B * ii, j = tx + B * jj;
       double v = 0.0;
-      for (int k = i; k < R; k++) v += B[k * ld + i] * B[k * ld + j];
-      Sinv[i + R * j] = v;
-      Sinv[j + R * i] = v;
+      if (i < R && j < R) {
+        const int idx = i + R * j;
+        v = h.g[0][idx];
+        for (int m = 1; m < h.n; m++) v *= h.g[m][idx];
+        if (i == j) v += lambda;
+        if (S_out) S_out[idx] = v;
+      }
+      a[ii][jj] = v;
+      y[ii][jj] = (i == j) ? 1.0 : 0.0;
+    }
+#pragma unroll
+  for (int kk = 0; kk < T; kk++) {
+    for (int kt = 0; kt < B; kt++) {
+      const int k = B * kk + kt;
+      if (k >= R) break;
+      double *cr = colraw + (k & 1) * R, *rr = rowraw + (k & 1) * R;
+      if (tx == kt) {  // owners of column k of S
+#pragma unroll
+        for (int ii = 0; ii < T; ii++) {
+          const int i = ty + B * ii;
+          if (i >= k && i < R) cr[i] = a[ii][kk];
+        }
+      }
+      if (ty == kt) {  // owners of row k of Y
+#pragma unroll
+        for (int jj = 0; jj < T; jj++) {
+          const int j = tx + B * jj;
+          if (j <= k) rr[j] = y[kk][jj];
+        }
+      }
+      __syncthreads();
+      const double rs = rsqrt(cr[k]);
+      double ci[T], cj[T], yk[T];
+#pragma unroll
+      for (int ii = 0; ii < T; ii++) {
+        const int i = ty + B * ii;
+        ci[ii] = (i > k && i < R) ? cr[i] * rs : 0.0;
+      }
+#pragma unroll
+      for (int jj = 0; jj < T; jj++) {
+        const int j = tx + B * jj;
+        cj[jj] = (j > k && j < R) ? cr[j] * rs : 0.0;
+        yk[jj] = (j <= k) ? rr[j] * rs : 0.0;
+      }
+#pragma unroll
+      for (int ii = 0; ii < T; ii++)
+#pragma unroll
+        for (int jj = 0; jj < T; jj++) {
+          a[ii][jj] -= ci[ii] * cj[jj];
+          y[ii][jj] -= ci[ii] * yk[jj];
+        }
+      if (ty == kt) {
+#pragma unroll
+        for (int jj = 0; jj < T; jj++) y[kk][jj] = yk[jj];  // row k of Y is final
+      }
     }
   }
+  // Y = L^-1 (lower triangular) -> shared, then S^-1 = Y^T Y
+#pragma unroll
+  for (int ii = 0; ii < T; ii++)
+#pragma unroll
+    for (int jj = 0; jj < T; jj++) {
+      const int i = ty + B * ii, j = tx + B * jj;
+      if (i < R && j < R) Ys[i * ld + j] = (j <= i) ? y[ii][jj] : 0.0;
+    }
+  __syncthreads();
+#pragma unroll
+  for (int ii = 0; ii < T; ii++)
+#pragma unroll
+    for (int jj = 0; jj < T; jj++) {
+      const int i = ty + B * ii, j = tx + B * jj;
+      if (i < R && j < R) {
+        double v0 = 0.0, v1 = 0.0;
+        int k = (i > j ? i : j);
+        for (; k + 1 < R; k += 2) {
+          v0 += Ys[k * ld + i] * Ys[k * ld + j];
+          v1 += Ys[(k + 1) * ld + i] * Ys[(k + 1) * ld + j];
+        }
+        if (k < R) v0 += Ys[k * ld + i] * Ys[k * ld + j];
+        Sinv[i + R * j] = v0 + v1;
+      }
+    }
 }
 
 // Cyclic Jacobi (parallel round-robin ordering) on a symmetric matrix in shared memory.
@@ -196,8 +265,9 @@ __device__ void jacobi_eig_shared(double *A, double *Q, double *cs, int n, int l
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(256) sym_inverse_jacobi_kernel(const double *__restrict__ S, int R,
-                                                                 double *__restrict__ Sinv) {
+__global__ void __launch_bounds__(1024) sym_inverse_jacobi_kernel(HadArgs h, int R, double lambda,
+                                                                         double *__restrict__ S_out,
+                                                                         double *__restrict__ Sinv) {
   extern __shared__ double sm[];
   const int n = (R + 1) & ~1;
   const int ld = n + 1;
@@ -205,10 +275,23 @@ __global__ void __launch_bounds__(256) sym_inverse_jacobi_kernel(const double *_
   double *Q = sm + n * ld;
   double *cs = Q + n * ld;
   const int tid = threadIdx.x, nt = blockDim.x;
+  for (int idx = tid; idx < R * R; idx += nt) {
+    const double v = hadamard_at(h, idx, R, lambda);
+    if (S_out) S_out[idx] = v;
+    A[(idx % R) * ld + idx / R] = v;
+  }
+  __syncthreads();
   for (int idx = tid; idx < n * n; idx += nt) {
     int i = idx / n, j = idx % n;
-    double v = (i < R && j < R) ? 0.5 * (S[i + R * j] + S[j + R * i]) : (i == j ? 1.0 : 0.0);
-    A[i * ld + j] = v;
+    if (i < R && j < R) {
+      if (i < j) {  // symmetrise in place (each pair once)
+        const double v = 0.5 * (A[i * ld + j] + A[j * ld + i]);
+        A[i * ld + j] = v;
+        A[j * ld + i] = v;
+      }
+    } else {
+      A[i * ld + j] = (i == j) ? 1.0 : 0.0;
+    }
     Q[i * ld + j] = (i == j) ? 1.0 : 0.0;
   }
   __syncthreads();
@@ -219,7 +302,7 @@ __global__ void __launch_bounds__(256) sym_inverse_jacobi_kernel(const double *_
     if (i >= j) {
       double v = 0.0;
       for (int k = 0; k < n; k++) {
-        if (n != R && k == n - 1 && fabs(Q[(n - 1) * ld + k]) > 0.5) continue;  // the padding eigenvector
+        if (n != R && fabs(Q[(n - 1) * ld + k]) > 0.5) continue;  // the padding eigenvector
         v += Q[i * ld + k] * Q[j * ld + k] / A[k * ld + k];
       }
       Sinv[i + R * j] = v;
@@ -228,49 +311,57 @@ __global__ void __launch_bounds__(256) sym_inverse_jacobi_kernel(const double *_
   }
 }
 
-// ---- apply: row tiles of 32 rows ----------------------------------------------------------------------------
-constexpr int AP_WY = 8;
-__global__ void __launch_bounds__(32 * AP_WY) solve_apply_kernel(const double *__restrict__ M,
-                                                                 const double *__restrict__ S,
-                                                                 const double *__restrict__ Sinv,
-                                                                 double *__restrict__ W, int64_t s, int R,
-                                                                 const double *__restrict__ W_init,
-                                                                 double ratio_step, double *__restrict__ grad_out,
-                                                                 double *__restrict__ dW_out) {
+// ---- apply: 8-row tiles; warp = row, lanes = columns --------------------------------------------------------------
+constexpr int AP_ROWS = 8;
+__global__ void __launch_bounds__(32 * AP_ROWS) solve_apply_kernel(const double *__restrict__ M,
+                                                                   const double *__restrict__ S,
+                                                                   const double *__restrict__ Sinv,
+                                                                   double *__restrict__ W, int64_t s, int R,
+                                                                   const double *__restrict__ W_init,
+                                                                   double ratio_step, double *__restrict__ grad_out,
+                                                                   double *__restrict__ dW_out) {
   extern __shared__ double sm[];
-  double *Ss = sm;              // R*R  (S, column-major as given)
-  double *Si = Ss + R * R;      // R*R
-  double *Mt = Si + R * R;      // R*32: Mt[r*32 + lane]
-  double *Wt = Mt + R * 32;     // R*32: old W
-  const int lane = threadIdx.x, wy = threadIdx.y;
-  const int tid = wy * 32 + lane, nt = 32 * AP_WY;
-  const int64_t i = (int64_t)blockIdx.x * 32 + lane;
+  double *Ss = sm;                 // R*R
+  double *Si = Ss + R * R;         // R*R
+  double *Mt = Si + R * R;         // AP_ROWS * R : Mt[row*R + r]
+  double *Wt = Mt + AP_ROWS * R;   // old W
+  const int lane = threadIdx.x, row = threadIdx.y;
+  const int tid = row * 32 + lane, nt = 32 * AP_ROWS;
+  const int64_t i = (int64_t)blockIdx.x * AP_ROWS + row;
   for (int idx = tid; idx < R * R; idx += nt) {
     Ss[idx] = grad_out ? S[idx] : 0.0;
     Si[idx] = Sinv[idx];
   }
-  for (int r = wy; r < R; r += AP_WY) {
-    Mt[r * 32 + lane] = (i < s) ? M[i + s * r] : 0.0;
-    Wt[r * 32 + lane] = (i < s) ? W[i + s * r] : 0.0;
+  for (int r = lane; r < R; r += 32) {
+    Mt[row * R + r] = (i < s) ? M[i + s * r] : 0.0;
+    Wt[row * R + r] = (i < s) ? W[i + s * r] : 0.0;
   }
   __syncthreads();
-  for (int c = wy; c < R; c += AP_WY) {
-    double w = 0.0, g = 0.0;
-    for (int r = 0; r < R; r++) {
-      w += Mt[r * 32 + lane] * Si[r + R * c];
-      g += Wt[r * 32 + lane] * Ss[r + R * c];
+  if (i >= s) return;
+  for (int c = lane; c < R; c += 32) {
+    double w0 = 0.0, w1 = 0.0, g0 = 0.0, g1 = 0.0;
+    int r = 0;
+    for (; r + 1 < R; r += 2) {
+      w0 += Mt[row * R + r] * Si[r + R * c];
+      w1 += Mt[row * R + r + 1] * Si[r + 1 + R * c];
+      g0 += Wt[row * R + r] * Ss[r + R * c];
+      g1 += Wt[row * R + r + 1] * Ss[r + 1 + R * c];
     }
-    if (i < s) {
-      const int64_t o = i + s * c;
-      if (grad_out) grad_out[o] = -Mt[c * 32 + lane] + g;
-      if (W_init) {
-        const double wi = W_init[o];
-        const double d = ratio_step * (w - wi);
-        if (dW_out) dW_out[o] = d;
-        if (ratio_step != 1.0) w = wi + d;
-      }
-      W[o] = w;
+    if (r < R) {
+      w0 += Mt[row * R + r] * Si[r + R * c];
+      g0 += Wt[row * R + r] * Ss[r + R * c];
     }
+    double w = w0 + w1;
+    const double g = g0 + g1;
+    const int64_t o = i + s * c;
+    if (grad_out) grad_out[o] = -Mt[row * R + c] + g;
+    if (W_init) {
+      const double wi = W_init[o];
+      const double d = ratio_step * (w - wi);
+      if (dW_out) dW_out[o] = d;
+      if (ratio_step != 1.0) w = wi + d;
+    }
+    W[o] = w;
   }
 }
 
@@ -316,70 +407,95 @@ __global__ void __launch_bounds__(256) norm_scale_kernel(NormArgs a, const doubl
   }
 }
 
-}  // namespace
-
-int ppx_sum_partials(ppx_ctx *ctx, const double *partial, int n, double *out);
-
-int ppx_k45_init(ppx_ctx *ctx) {
-  const int big = 220 * 1024;
-  PPX_CUDA(ctx, cudaFuncSetAttribute(spd_inverse_chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-  PPX_CUDA(ctx, cudaFuncSetAttribute(sym_inverse_jacobi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-  PPX_CUDA(ctx, cudaFuncSetAttribute(solve_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-  return PPX_OK;
+// Normalize from the cached Grams + the squared norms the PP switching test needs, one launch, one block per mode:
+// ||W_j||^2 = trace(G_j) for all j (recomputed by every block), W_i and G_i rescaled, sq[2i] = ||dW_i||^2,
+// sq[2i+1] = ||W_i||^2 after the rescale.
+struct NormNormsArgs {
+  double *w[16];
+  double *g[16];
+  const double *dw[16];
+  int64_t n[16];
+  int N;
+  int R;
+};
+__global__ void __launch_bounds__(1024) normalize_norms_kernel(NormNormsArgs a, double *__restrict__ sq_out) {
+  __shared__ double red[32];
+  __shared__ double tr[16];
+  const int m = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (warp < a.N) {
+    double s = 0.0;
+    for (int k = lane; k < a.R; k += 32) s += a.g[warp][k + (int64_t)a.R * k];
+    s = ppx_warp_sum(s);
+    if (lane == 0) tr[warp] = s;
+  }
+  __syncthreads();
+  double prod = 1.0;
+  for (int j = 0; j < a.N; j++) prod *= sqrt(tr[j]);
+  const double f = pow(prod, 1.0 / a.N) / sqrt(tr[m]);
+  double *x = a.w[m];
+  const double *d = a.dw[m];
+  const int64_t n = a.n[m];
+  double sw = 0.0, sd = 0.0;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const double v = f * x[i];
+    x[i] = v;
+    sw += v * v;
+    if (d) {
+      const double e = d[i];
+      sd += e * e;
+    }
+  }
+  double *g = a.g[m];
+  for (int i = threadIdx.x; i < a.R * a.R; i += blockDim.x) g[i] = (f * f) * g[i];
+  sw = ppx_block_sum(sw, red);
+  sd = ppx_block_sum(sd, red);
+  if (threadIdx.x == 0) {
+    sq_out[2 * m] = sd;
+    sq_out[2 * m + 1] = sw;
+  }
 }
 
-extern "C" {
-
-int ppx_gram(ppx_ctx *ctx, const double *W, int64_t s, int64_t ldw, int R, double *G) {
-  PPX_REQUIRE(ctx, W && G && s >= 0 && R >= 1 && ldw >= s, "W, G non-null; ldw >= s; R >= 1");
-  const int npairs = R * (R + 1) / 2;
-  const int blocks = (npairs * 32 + 255) / 256;
-  gram_kernel<<<blocks, 256, 0, ctx->stream>>>(W, s, ldw, R, G);
-  PPX_CHECK_LAUNCH(ctx);
-  return PPX_OK;
-}
-
-int ppx_hadamard_grams(ppx_ctx *ctx, const double *const *G, int nG, int skip, int R, double lambda, double *S) {
-  PPX_REQUIRE(ctx, G && S && nG >= 1 && nG <= 16, "1 <= nG <= 16");
-  HadArgs h;
-  h.n = 0;
-  for (int j = 0; j < nG; j++)
-    if (j != skip) h.g[h.n++] = G[j];
-  PPX_REQUIRE(ctx, h.n >= 1, "at least one Gram after skipping");
-  hadamard_kernel<<<(R * R + 255) / 256, 256, 0, ctx->stream>>>(h, R, lambda, S);
-  PPX_CHECK_LAUNCH(ctx);
-  return PPX_OK;
-}
-
-int ppx_spd_inverse(ppx_ctx *ctx, const double *S, int R, int mode, double *Sinv) {
+int inverse_launch(ppx_ctx *ctx, const HadArgs &h, int R, double lambda, int mode, double *S_out, double *Sinv) {
   if (mode == PPX_SOLVE_CHOL) {
-    const size_t smem = sizeof(double) * 2 * R * (R + 1);
-    if (smem > 220 * 1024) return ppx_set_err(ctx, PPX_EUNSUPPORTED, "solve: R=%d too large for the one-CTA inverse", R);
-    spd_inverse_chol_kernel<<<1, 256, smem, ctx->stream>>>(S, R, Sinv);
+    if (R > 112) return ppx_set_err(ctx, PPX_EUNSUPPORTED, "solve: R=%d too large for the one-CTA inverse (max 112)", R);
+    const size_t smem = sizeof(double) * (4 * (size_t)R + (size_t)R * (R + 1));
+#define PPX_INV_LAUNCH(T, B) \
+  spd_inverse_chol_kernel<T, B><<<1, B * B, smem, ctx->stream>>>(h, R, lambda, S_out, Sinv)
+    if (R <= 16) PPX_INV_LAUNCH(1, 16);
+    else if (R <= 32) PPX_INV_LAUNCH(1, 32);
+    else if (R <= 64) PPX_INV_LAUNCH(2, 32);
+    else if (R <= 80) PPX_INV_LAUNCH(5, 16);
+    else if (R <= 96) PPX_INV_LAUNCH(6, 16);
+    else PPX_INV_LAUNCH(7, 16);
+#undef PPX_INV_LAUNCH
   } else {
     const int n = (R + 1) & ~1;
-    const size_t smem = sizeof(double) * (2 * n * (n + 1) + 4 * (n / 2 + 1));
+    const size_t smem = sizeof(double) * (2 * (size_t)n * (n + 1) + 4 * (n / 2 + 1));
     if (smem > 220 * 1024) return ppx_set_err(ctx, PPX_EUNSUPPORTED, "solve: R=%d too large for the one-CTA inverse", R);
-    sym_inverse_jacobi_kernel<<<1, 256, smem, ctx->stream>>>(S, R, Sinv);
+    sym_inverse_jacobi_kernel<<<1, 1024, smem, ctx->stream>>>(h, R, lambda, S_out, Sinv);
   }
   PPX_CHECK_LAUNCH(ctx);
   return PPX_OK;
 }
 
-int ppx_solve_update(ppx_ctx *ctx, const double *M, const double *S, double *W, int64_t s, int R,
-                     const double *W_init, double ratio_step, int mode, double *grad_out, double *dW_out,
-                     double *sq_norms_out) {
-  PPX_REQUIRE(ctx, M && S && W && s >= 1 && R >= 1, "M, S, W non-null; s, R >= 1");
+int solve_impl(ppx_ctx *ctx, const double *M, const HadArgs &h, double lambda, const double *S_given, double *W,
+               int64_t s, int R, const double *W_init, double ratio_step, int mode, double *grad_out,
+               double *dW_out, double *sq_norms_out) {
+  PPX_REQUIRE(ctx, M && W && s >= 1 && R >= 1, "M, W non-null; s, R >= 1");
   PPX_REQUIRE(ctx, mode == PPX_SOLVE_CHOL || mode == PPX_SOLVE_SVD_PINV, "mode is CHOL or SVD_PINV");
   ppx_ws_reset(ctx);
   double *Sinv = (double *)ppx_ws_alloc(ctx, sizeof(double) * R * R);
-  if (!Sinv) return ppx_set_err(ctx, PPX_ENOMEM, "workspace too small");
-  int rc = ppx_spd_inverse(ctx, S, R, mode, Sinv);
+  double *Sws = (double *)ppx_ws_alloc(ctx, sizeof(double) * R * R);
+  if (!Sinv || !Sws) return ppx_set_err(ctx, PPX_ENOMEM, "workspace too small");
+  // S is needed by the apply kernel only for the gradient
+  int rc = inverse_launch(ctx, h, R, lambda, mode, (grad_out && !S_given) ? Sws : nullptr, Sinv);
   if (rc) return rc;
-  const size_t smem = sizeof(double) * (2 * (size_t)R * R + 64 * (size_t)R);
+  const double *S_apply = S_given ? S_given : Sws;
+  const size_t smem = sizeof(double) * (2 * (size_t)R * R + 2 * AP_ROWS * (size_t)R);
   if (smem > 220 * 1024) return ppx_set_err(ctx, PPX_EUNSUPPORTED, "solve: R=%d too large", R);
-  solve_apply_kernel<<<ppx_cdiv(s, 32), dim3(32, AP_WY), smem, ctx->stream>>>(M, S, Sinv, W, s, R, W_init, ratio_step,
-                                                                             grad_out, dW_out);
+  solve_apply_kernel<<<ppx_cdiv(s, AP_ROWS), dim3(32, AP_ROWS), smem, ctx->stream>>>(M, S_apply, Sinv, W, s, R, W_init,
+                                                                                    ratio_step, grad_out, dW_out);
   PPX_CHECK_LAUNCH(ctx);
   if (sq_norms_out) {
     const double *xs[3] = {W, dW_out ? dW_out : W, grad_out ? grad_out : W};
@@ -389,19 +505,17 @@ int ppx_solve_update(ppx_ctx *ctx, const double *M, const double *S, double *W, 
   return PPX_OK;
 }
 
-static int normalize_impl(ppx_ctx *ctx, double *const *W, const int64_t *s, int N, int R, double *const *G,
-                          bool from_grams);
+}  // namespace
 
-int ppx_normalize(ppx_ctx *ctx, double *const *W, const int64_t *s, int N, int R, double *const *G) {
-  return normalize_impl(ctx, W, s, N, R, G, false);
+int ppx_k45_init(ppx_ctx *ctx) {
+  const int big = 220 * 1024;
+  PPX_CUDA(ctx, cudaFuncSetAttribute(spd_inverse_chol_kernel<5, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  PPX_CUDA(ctx, cudaFuncSetAttribute(spd_inverse_chol_kernel<6, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  PPX_CUDA(ctx, cudaFuncSetAttribute(spd_inverse_chol_kernel<7, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  PPX_CUDA(ctx, cudaFuncSetAttribute(sym_inverse_jacobi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  PPX_CUDA(ctx, cudaFuncSetAttribute(solve_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  return PPX_OK;
 }
-
-int ppx_normalize_g(ppx_ctx *ctx, double *const *W, const int64_t *s, int N, int R, double *const *G) {
-  PPX_REQUIRE(ctx, G != nullptr, "G != NULL");
-  return normalize_impl(ctx, W, s, N, R, G, true);
-}
-
-}  // extern "C"
 
 static int normalize_impl(ppx_ctx *ctx, double *const *W, const int64_t *s, int N, int R, double *const *G,
                           bool from_grams) {
@@ -432,4 +546,100 @@ static int normalize_impl(ppx_ctx *ctx, double *const *W, const int64_t *s, int 
   return PPX_OK;
 }
 
+extern "C" {
 
+int ppx_gram(ppx_ctx *ctx, const double *W, int64_t s, int64_t ldw, int R, double *G) {
+  PPX_REQUIRE(ctx, W && G && s >= 0 && R >= 1 && ldw >= s, "W, G non-null; ldw >= s; R >= 1");
+  const int npairs = R * (R + 1) / 2;
+  const int blocks = (npairs * 32 + 255) / 256;
+  gram_kernel<<<blocks, 256, 0, ctx->stream>>>(W, s, ldw, R, G);
+  PPX_CHECK_LAUNCH(ctx);
+  return PPX_OK;
+}
+
+int ppx_hadamard_grams(ppx_ctx *ctx, const double *const *G, int nG, int skip, int R, double lambda, double *S) {
+  PPX_REQUIRE(ctx, G && S && nG >= 1 && nG <= 16, "1 <= nG <= 16");
+  HadArgs h;
+  h.n = 0;
+  for (int j = 0; j < nG; j++)
+    if (j != skip) h.g[h.n++] = G[j];
+  PPX_REQUIRE(ctx, h.n >= 1, "at least one Gram after skipping");
+  hadamard_kernel<<<(R * R + 255) / 256, 256, 0, ctx->stream>>>(h, R, lambda, S);
+  PPX_CHECK_LAUNCH(ctx);
+  return PPX_OK;
+}
+
+int ppx_solve_update(ppx_ctx *ctx, const double *M, const double *S, double *W, int64_t s, int R,
+                     const double *W_init, double ratio_step, int mode, double *grad_out, double *dW_out,
+                     double *sq_norms_out) {
+  PPX_REQUIRE(ctx, S != nullptr, "S != NULL");
+  HadArgs h;
+  h.n = 1;
+  h.g[0] = S;
+  return solve_impl(ctx, M, h, 0.0, S, W, s, R, W_init, ratio_step, mode, grad_out, dW_out, sq_norms_out);
+}
+
+int ppx_solve_update_g(ppx_ctx *ctx, const double *M, const double *const *G, int nG, int skip, double lambda,
+                       double *W, int64_t s, int R, const double *W_init, double ratio_step, int mode,
+                       double *grad_out, double *dW_out, double *sq_norms_out) {
+  PPX_REQUIRE(ctx, G && nG >= 1 && nG <= 16, "1 <= nG <= 16");
+  HadArgs h;
+  h.n = 0;
+  for (int j = 0; j < nG; j++)
+    if (j != skip) h.g[h.n++] = G[j];
+  PPX_REQUIRE(ctx, h.n >= 1, "at least one Gram after skipping");
+  return solve_impl(ctx, M, h, lambda, nullptr, W, s, R, W_init, ratio_step, mode, grad_out, dW_out, sq_norms_out);
+}
+
+int ppx_spd_inverse_g(ppx_ctx *ctx, const double *const *G, int nG, int skip, double lambda, int R, int mode,
+                      double *S_out, double *Sinv_out) {
+  PPX_REQUIRE(ctx, G && Sinv_out && nG >= 1 && nG <= 16 && R >= 1, "1 <= nG <= 16, R >= 1, Sinv_out != NULL");
+  PPX_REQUIRE(ctx, mode == PPX_SOLVE_CHOL || mode == PPX_SOLVE_SVD_PINV, "mode is CHOL or SVD_PINV");
+  HadArgs h;
+  h.n = 0;
+  for (int j = 0; j < nG; j++)
+    if (j != skip) h.g[h.n++] = G[j];
+  PPX_REQUIRE(ctx, h.n >= 1, "at least one Gram after skipping");
+  return inverse_launch(ctx, h, R, lambda, mode, S_out, Sinv_out);
+}
+
+int ppx_solve_apply(ppx_ctx *ctx, const double *M, const double *S, const double *Sinv, double *W, int64_t s, int R,
+                    const double *W_init, double ratio_step, double *grad_out, double *dW_out) {
+  PPX_REQUIRE(ctx, M && Sinv && W && s >= 1 && R >= 1, "M, Sinv, W non-null; s, R >= 1");
+  PPX_REQUIRE(ctx, S || !grad_out, "S is required when the gradient is requested");
+  const size_t smem = sizeof(double) * (2 * (size_t)R * R + 2 * AP_ROWS * (size_t)R);
+  if (smem > 220 * 1024) return ppx_set_err(ctx, PPX_EUNSUPPORTED, "solve: R=%d too large", R);
+  solve_apply_kernel<<<ppx_cdiv(s, AP_ROWS), dim3(32, AP_ROWS), smem, ctx->stream>>>(M, S, Sinv, W, s, R, W_init,
+                                                                                    ratio_step, grad_out, dW_out);
+  PPX_CHECK_LAUNCH(ctx);
+  return PPX_OK;
+}
+
+int ppx_normalize_norms(ppx_ctx *ctx, double *const *W, const double *const *dW, const int64_t *s, int N, int R,
+                        double *const *G, double *sq_out_dev) {
+  PPX_REQUIRE(ctx, W && s && G && sq_out_dev && N >= 1 && N <= 16, "W, s, G, sq_out_dev non-null; 1 <= N <= 16");
+  NormNormsArgs a;
+  a.N = N;
+  a.R = R;
+  for (int i = 0; i < N; i++) {
+    PPX_REQUIRE(ctx, W[i] && G[i], "W[i], G[i] non-null");
+    a.w[i] = W[i];
+    a.g[i] = G[i];
+    a.dw[i] = dW ? dW[i] : nullptr;
+    a.n[i] = s[i] * R;
+  }
+  normalize_norms_kernel<<<N, 1024, 0, ctx->stream>>>(a, sq_out_dev);
+  PPX_CHECK_LAUNCH(ctx);
+  return PPX_OK;
+}
+
+int ppx_normalize(ppx_ctx *ctx, double *const *W, const int64_t *s, int N, int R, double *const *G) {
+  return normalize_impl(ctx, W, s, N, R, G, false);
+}
+
+int ppx_normalize_g(ppx_ctx *ctx, double *const *W, const int64_t *s, int N, int R, double *const *G) {
+  PPX_REQUIRE(ctx, G != nullptr, "G != NULL");
+  return normalize_impl(ctx, W, s, N, R, G, true);
+}
+
+}  // extern "C"

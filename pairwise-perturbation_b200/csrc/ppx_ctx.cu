@@ -48,6 +48,11 @@ int ppx_ctx_create(int device, void *stream, size_t workspace_bytes, ppx_ctx **o
     if (e != cudaSuccess) { delete ctx; return ppx_set_err(nullptr, PPX_ECUDA, "stream: %s", cudaGetErrorString(e)); }
     ctx->own_stream = true;
   }
+  ctx->main_stream = ctx->stream;
+  e = cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
+  if (e != cudaSuccess) { delete ctx; return ppx_set_err(nullptr, PPX_ECUDA, "side stream: %s", cudaGetErrorString(e)); }
   if (workspace_bytes < ((size_t)8 << 20)) workspace_bytes = (size_t)8 << 20;
   e = cudaMalloc((void **)&ctx->ws, workspace_bytes);
   if (e != cudaSuccess) { delete ctx; return ppx_set_err(nullptr, PPX_ENOMEM, "workspace: %s", cudaGetErrorString(e)); }
@@ -70,20 +75,43 @@ int ppx_ctx_create(int device, void *stream, size_t workspace_bytes, ppx_ctx **o
 int ppx_ctx_destroy(ppx_ctx *ctx) {
   if (!ctx) return PPX_OK;
   cudaSetDevice(ctx->device);
-  cudaStreamSynchronize(ctx->stream);
+  cudaStreamSynchronize(ctx->main_stream);
+  cudaStreamSynchronize(ctx->side_stream);
   ppx_comm_destroy_internal(ctx);
   if (ctx->ws) cudaFree(ctx->ws);
-  if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->side_stream) cudaStreamDestroy(ctx->side_stream);
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->main_stream);
   delete ctx;
   return PPX_OK;
 }
 
 int ppx_sync(ppx_ctx *ctx) {
-  PPX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  PPX_CUDA(ctx, cudaStreamSynchronize(ctx->main_stream));
+  return PPX_OK;
+}
+// Fork/join for work that may overlap the main stream (works eagerly and inside a graph capture):
+//   ppx_side_begin  : the side stream waits for everything enqueued so far; later calls go to the side stream
+//   ppx_side_end    : later calls go to the main stream again (the side work keeps running concurrently)
+//   ppx_side_join   : the main stream waits for the side work enqueued between begin and end
+int ppx_side_begin(ppx_ctx *ctx) {
+  PPX_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->main_stream));
+  PPX_CUDA(ctx, cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0));
+  ctx->stream = ctx->side_stream;
+  return PPX_OK;
+}
+int ppx_side_end(ppx_ctx *ctx) {
+  PPX_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->side_stream));
+  ctx->stream = ctx->main_stream;
+  return PPX_OK;
+}
+int ppx_side_join(ppx_ctx *ctx) {
+  PPX_CUDA(ctx, cudaStreamWaitEvent(ctx->main_stream, ctx->ev_join, 0));
   return PPX_OK;
 }
 const char *ppx_last_error(ppx_ctx *ctx) { return ctx ? ctx->err.c_str() : ""; }
-void *ppx_stream(ppx_ctx *ctx) { return (void *)ctx->stream; }
+void *ppx_stream(ppx_ctx *ctx) { return (void *)ctx->main_stream; }
 int ppx_device(ppx_ctx *ctx) { return ctx->device; }
 int ppx_sm_count(ppx_ctx *ctx) { return ctx->sm_count; }
 int64_t ppx_launch_count(ppx_ctx *ctx) { return ctx->launches; }
@@ -140,7 +168,7 @@ int ppx_event_destroy(ppx_ctx *ctx, void *ev) {
   return PPX_OK;
 }
 int ppx_event_record(ppx_ctx *ctx, void *ev) {
-  PPX_CUDA(ctx, cudaEventRecord((cudaEvent_t)ev, ctx->stream));
+  PPX_CUDA(ctx, cudaEventRecord((cudaEvent_t)ev, ctx->main_stream));
   return PPX_OK;
 }
 int ppx_event_elapsed_ms(ppx_ctx *ctx, void *a, void *b, float *ms) {
@@ -149,12 +177,12 @@ int ppx_event_elapsed_ms(ppx_ctx *ctx, void *a, void *b, float *ms) {
   return PPX_OK;
 }
 int ppx_graph_begin(ppx_ctx *ctx) {
-  PPX_CUDA(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+  PPX_CUDA(ctx, cudaStreamBeginCapture(ctx->main_stream, cudaStreamCaptureModeThreadLocal));
   return PPX_OK;
 }
 int ppx_graph_end(ppx_ctx *ctx, void **graph) {
   cudaGraph_t g;
-  PPX_CUDA(ctx, cudaStreamEndCapture(ctx->stream, &g));
+  PPX_CUDA(ctx, cudaStreamEndCapture(ctx->main_stream, &g));
   cudaGraphExec_t ge;
   cudaError_t e = cudaGraphInstantiate(&ge, g, 0);
   cudaGraphDestroy(g);
@@ -163,7 +191,7 @@ int ppx_graph_end(ppx_ctx *ctx, void **graph) {
   return PPX_OK;
 }
 int ppx_graph_launch(ppx_ctx *ctx, void *graph) {
-  PPX_CUDA(ctx, cudaGraphLaunch((cudaGraphExec_t)graph, ctx->stream));
+  PPX_CUDA(ctx, cudaGraphLaunch((cudaGraphExec_t)graph, ctx->main_stream));
   return PPX_OK;
 }
 int ppx_graph_destroy(ppx_ctx *ctx, void *graph) {

@@ -9,7 +9,10 @@
 struct ppx_ctx {
   int device = 0;
   int sm_count = 148;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;       // the stream operators are enqueued on (main, or side between side_begin/end)
+  cudaStream_t main_stream = nullptr;
+  cudaStream_t side_stream = nullptr;  // for work that may overlap the main stream (ppx_side_*)
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool own_stream = false;
   char *ws = nullptr;  // workspace arena (bump allocated per call)
   size_t ws_bytes = 0;

@@ -100,7 +100,7 @@ Matrix<> leaf_mttkrp(map<string, Tensor<>> &mttkrp_map, map<string, string> &par
                      Tensor<> &V, Matrix<> *W, int i, World &dw) {
   const string a(1, (char)('a' + i));
   const string par = parent[a];
-  Matrix<> M(W[i].nrow, W[i].ncol, dw);
+  Matrix<> M(W[i].nrow, W[i].ncol, dw, false);
   if ((int)par.size() == V.order) {
     map<string, Tensor<>> tmp;
     mttkrp_map_DT(tmp, parent, sibling, V, W, a, dw);
@@ -133,9 +133,9 @@ void dt_sweep(Tensor<> &V, Matrix<> *W, Matrix<> *grad_W, Matrix<> *F, double la
   map<string, Tensor<>> mttkrp_map;  // cleared every sweep (als_CP.cxx:215)
   for (int i = 0; i < N; i++) {
     Matrix<> M = leaf_mttkrp(mttkrp_map, parent, sibling, V, W, i, dw);
-    gc.hadamard(i, (always_regul || lambda != 0) ? lambda : 0.0, S, dw);          // :288-292 / :573-579
     if (F) PPXCK(dw, ppx_axpby(dw.ctx, 1.0, F[i].data, 1.0, M.data, M.size));     // :294
-    solve_update_fused(M, S, W[i], nullptr, 1.0, &grad_W[i], nullptr, dw.solver, dw);  // :296-297
+    // S = Hadamard of the cached Grams (+ lambda I) (:288-292 / :573-579), gradient and solve (:296-297), one call
+    gc.solve(i, (always_regul || lambda != 0) ? lambda : 0.0, M, W[i], nullptr, 1.0, &grad_W[i], nullptr, dw.solver, dw);
     gc.refresh(W, i, dw);
   }
   normalize_with_grams(W, N, gc, dw);  // :303
@@ -399,13 +399,14 @@ struct PPPhase {
   int N, R;
   vector<Matrix<>> W_init, M;
   map<string, Tensor<>> ops;
-  Matrix<> S, zero_M;
+  Matrix<> S, Sinv, zero_M;
   GramCache gc;
   void *graph = nullptr;
 
   PPPhase(Tensor<> &V_, Matrix<> *W_, Matrix<> *grad_W_, Matrix<> *dW_, double lambda_, double ratio_step_, World &dw_)
       : V(V_), W(W_), grad_W(grad_W_), dW(dW_), lambda(lambda_), ratio_step(ratio_step_), dw(dw_), N(V_.order),
-        R((int)W_[0].ncol), W_init(V_.order), S((int64_t)W_[0].ncol, (int64_t)W_[0].ncol, dw_) {
+        R((int)W_[0].ncol), W_init(V_.order), S((int64_t)W_[0].ncol, (int64_t)W_[0].ncol, dw_),
+        Sinv((int64_t)W_[0].ncol, (int64_t)W_[0].ncol, dw_) {
     for (int i = 0; i < N; i++) M.emplace_back(W[i].nrow, W[i].ncol, dw);
     if (dw.np > 1) {
       int64_t smax = 0;
@@ -429,22 +430,44 @@ struct PPPhase {
   // the switching test needs, copied to pinned host memory (:754-825, :657-664)
   void enqueue_sweep() {
     for (int i = 0; i < N; i++) {
+      // S from the CURRENT W (:796-802) and its inverse depend only on the Grams: they run on the side stream while
+      // the main stream forms the corrected MTTKRP (:774-794); then gradient + SVD_solve_mod (:811-812)
+      const double *gp[16];
+      for (int j = 0; j < N; j++) gp[j] = gc.G[j].data;
+      PPXCK(dw, ppx_side_begin(dw.ctx));
+      PPXCK(dw, ppx_spd_inverse_g(dw.ctx, gp, N, i, lambda, R, dw.solver, S.data, Sinv.data));
+      PPXCK(dw, ppx_side_end(dw.ctx));
       pp_corrected_mttkrp(ops, W, dW, i, N, M[i], zero_M, dw);
-      gc.hadamard(i, lambda, S, dw);  // S from the CURRENT W (:796-802)
-      solve_update_fused(M[i], S, W[i], &W_init[i], ratio_step, &grad_W[i], &dW[i], dw.solver, dw);  // :811-812
+      PPXCK(dw, ppx_side_join(dw.ctx));
+      PPXCK(dw, ppx_solve_apply(dw.ctx, M[i].data, S.data, Sinv.data, W[i].data, W[i].nrow, R, W_init[i].data,
+                                ratio_step, grad_W[i].data, dW[i].data));
       gc.refresh(W, i, dw);
     }
-    normalize_with_grams(W, N, gc, dw);  // after dW was taken; W_init is never rescaled (:825)
-    const double *xs[32];
-    int64_t ns[32];
-    for (int i = 0; i < N; i++) {
-      xs[2 * i] = dW[i].data;
-      xs[2 * i + 1] = W[i].data;
-      ns[2 * i] = ns[2 * i + 1] = W[i].size;
+    // Normalize after dW was taken -- W_init is never rescaled (:825) -- and the 2N squared norms of the switching test
+    if (dw.np == 1) {
+      double *wp[16], *gp[16];
+      const double *dp[16];
+      int64_t s[16];
+      for (int i = 0; i < N; i++) {
+        wp[i] = W[i].data;
+        gp[i] = gc.G[i].data;
+        dp[i] = dW[i].data;
+        s[i] = W[i].nrow;
+      }
+      PPXCK(dw, ppx_normalize_norms(dw.ctx, wp, dp, s, N, R, gp, dw.scal_dev));
+    } else {
+      normalize_with_grams(W, N, gc, dw);
+      const double *xs[32];
+      int64_t ns[32];
+      for (int i = 0; i < N; i++) {
+        xs[2 * i] = dW[i].data;
+        xs[2 * i + 1] = W[i].data;
+        ns[2 * i] = ns[2 * i + 1] = W[i].size;
+      }
+      for (int b = 0; b < 2 * N; b += 16)
+        PPXCK(dw, ppx_sqnorms(dw.ctx, xs + b, ns + b, std::min(16, 2 * N - b), dw.scal_dev + b));
+      dw.allreduce(dw.scal_dev + 2 * dw.shard_mode, 2);
     }
-    for (int b = 0; b < 2 * N; b += 16)
-      PPXCK(dw, ppx_sqnorms(dw.ctx, xs + b, ns + b, std::min(16, 2 * N - b), dw.scal_dev + b));
-    if (dw.np > 1) dw.allreduce(dw.scal_dev + 2 * dw.shard_mode, 2);
     PPXCK(dw, ppx_memcpy_d2h(dw.ctx, dw.scal_host, dw.scal_dev, sizeof(double) * 2 * N));
   }
   void sweep() {

@@ -31,7 +31,7 @@ Tensor<> ttm_mode(Tensor<> &T, int x, Matrix<> &Wx, World &dw) {
   int64_t lens[16];
   for (int i = 0; i < T.order; i++) lens[i] = T.lens[i];
   lens[x] = Wx.ncol;
-  Tensor<> out(T.order, lens, dw);
+  Tensor<> out(T.order, lens, dw, false);
   PPXCK(dw, ppx_ttm(dw.ctx, T.data, T.lens, T.order, x, Wx.data, Wx.nrow, (int)Wx.ncol, out.data));
   return out;
 }

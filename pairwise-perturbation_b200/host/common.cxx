@@ -51,7 +51,7 @@ Tensor<> contract_mode(Tensor<> &in, const string &modes, bool has_rank, char x,
   for (int i = 0; i < k; i++)
     if (i != pos) out_lens[n++] = in.lens[i];
   out_lens[n++] = R;
-  Tensor<> out(n, out_lens, dw);
+  Tensor<> out(n, out_lens, dw, false);
   if (!has_rank) {
     PPXCK(dw, ppx_ttm_first(dw.ctx, in.data, in.lens, k, pos, Wx.data, Wx.nrow, R, out.data));
   } else {
@@ -69,6 +69,30 @@ void mttkrp_map_DT(map<string, Tensor<>> &mttkrp_map, map<string, string> &paren
   if ((int)par.size() == V.order) {
     // first-level node (common.cxx:29-88): start from V, contract the sibling modes left to right; the first is
     // the GEMM (common.cxx:56), the rest are Hadamard-batched (common.cxx:83).
+    // The sibling modes of a tree node are adjacent, so the whole chain is ONE GEMM against the Khatri-Rao rows of
+    // their factors (ppx_ttm_multi): the level-1 tensors the reference materialises (10.8 GB each at N=4, s=300,
+    // R=50) have a single consumer here and are never written.
+    const int R = (int)W[0].ncol;
+    const int x_first = sib[0] - 'a';
+    const int n = (int)sib.size();
+    int64_t out_lens[17];
+    int k = 0;
+    for (char c : args) out_lens[k++] = V.lens[c - 'a'];
+    out_lens[k++] = R;
+    Tensor<> out(k, out_lens, dw, false);
+    const double *wp[8];
+    int64_t ld[8];
+    bool adjacent = n <= 8;
+    for (int j = 0; j < n && adjacent; j++) {
+      adjacent = (sib[j] - 'a') == x_first + j;
+      wp[j] = W[sib[j] - 'a'].data;
+      ld[j] = W[sib[j] - 'a'].nrow;
+    }
+    if (adjacent) {
+      PPXCK(dw, ppx_ttm_multi(dw.ctx, V.data, V.lens, V.order, x_first, n, wp, ld, R, out.data));
+      mttkrp_map[args] = std::move(out);
+      return;
+    }
     string modes = par;
     Tensor<> cur = contract_mode(V, modes, false, sib[0], W[sib[0] - 'a'], dw);
     modes.erase(modes.find(sib[0]), 1);
@@ -102,7 +126,7 @@ void build_V(Tensor<> &V, Matrix<> *W, int order, World &dw) {
     lens[i] = W[i].nrow;
     ptrs[i] = W[i].data;
   }
-  Tensor<> out(order, lens, dw);
+  Tensor<> out(order, lens, dw, false);
   PPXCK(dw, ppx_cp_reconstruct(dw.ctx, lens, order, ptrs, (int)W[0].ncol, out.data));
   V = std::move(out);
 }
@@ -219,6 +243,15 @@ void GramCache::hadamard(int skip, double lambda, Matrix<> &S, World &dw) {
   const double *ptrs[16];
   for (int i = 0; i < N; i++) ptrs[i] = G[i].data;
   PPXCK(dw, ppx_hadamard_grams(dw.ctx, ptrs, N, skip, R, lambda, S.data));
+}
+
+void GramCache::solve(int skip, double lambda, Matrix<> &M, Matrix<> &W, Matrix<> *W_init, double ratio_step,
+                      Matrix<> *grad, Matrix<> *dW, int mode, World &dw) {
+  const double *ptrs[16];
+  for (int i = 0; i < N; i++) ptrs[i] = G[i].data;
+  PPXCK(dw, ppx_solve_update_g(dw.ctx, M.data, ptrs, N, skip, lambda, W.data, W.nrow, R,
+                               W_init ? W_init->data : nullptr, ratio_step, mode, grad ? grad->data : nullptr,
+                               dW ? dW->data : nullptr, nullptr));
 }
 
 void gradient_CP(Tensor<> &V, Matrix<> *W, Matrix<> *grad_W, World &dw) {

@@ -49,6 +49,10 @@ struct GramCache {
   void refresh(Matrix<> *W, int i, World &dw);
   // S = Hadamard_{j != skip} G[j] (+ lambda I)
   void hadamard(int skip, double lambda, Matrix<> &S, World &dw);
+  // W = M S^-1 with S = Hadamard_{j != skip} G[j] + lambda I formed inside the inverse kernel; also the gradient
+  // -M + W_old S and (W_init != NULL) dW = ratio (W - W_init).  Does NOT refresh G[skip].
+  void solve(int skip, double lambda, Matrix<> &M, Matrix<> &W, Matrix<> *W_init, double ratio_step, Matrix<> *grad,
+             Matrix<> *dW, int mode, World &dw);
 };
 
 // ||V - [[W]]||_F without materialising the reconstruction (replaces build_V + subtraction + norm2 at

@@ -291,3 +291,58 @@ def test_errors_are_reported_not_swallowed(ctx, ppx):
         ctx.ttm_first(out, (5, 2), 3, out, 2, out, ldw=5)  # x out of range
     with pytest.raises(ppx.PpxError):
         ctx.solve_update(out, out, out, 2, 5, mode=7)
+
+
+MULTI_CASES = [
+    # lens, x_first, n_modes, R
+    ((12, 10, 8, 6), 2, 2, 4), ((12, 10, 8, 6), 0, 2, 4), ((12, 10, 8, 6), 1, 2, 5), ((12, 10, 8, 6), 1, 3, 3),
+    ((7, 5, 6, 4, 5, 3), 3, 3, 3), ((7, 5, 6, 4, 5, 3), 0, 3, 3), ((13, 9, 11), 1, 2, 5), ((13, 9, 11), 0, 2, 5),
+    ((20, 64, 70), 1, 2, 10),   # few rows, deep K: exercises the K split (20 rows, K = 4480)
+    ((64, 70, 3), 0, 2, 50),    # k-major, 3 rows, K = 4480
+    ((9, 7, 5), 0, 3, 2),       # everything contracted: a single row
+]
+
+
+@pytest.mark.parametrize("lens,x_first,n,R", MULTI_CASES)
+def test_ttm_multi(ctx, lens, x_first, n, R):
+    N = len(lens)
+    V = rnd(lens, 160)
+    Ws = [rnd((lens[x_first + j], R), 161 + j) for j in range(n)]
+    idx = o.letters(N)
+    ops = [V, idx]
+    keep = idx
+    for j in range(n):
+        c = idx[x_first + j]
+        ops += [Ws[j], c + "*"]
+        keep = keep.replace(c, "")
+    ref = o.contract(keep + "*", *ops)
+    out = ctx.empty(ref.size)
+    ctx.ttm_multi(ctx.to_device(V), lens, x_first, [ctx.to_device(w) for w in Ws], R, out)
+    got = ctx.to_host(out, ref.shape if ref.ndim else (1,))
+    assert rel_err(got.reshape(ref.shape), ref) < 1e-12
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("s,R", [(300, 50), (13, 5), (33, 7), (200, 96)])
+def test_solve_update_g_fuses_hadamard(ctx, mode, s, R):
+    N = 4
+    Wf = [o.fill_uniform((s + j, R), 3, 170 + j) for j in range(N)]
+    Gs = []
+    for j, w in enumerate(Wf):
+        G = ctx.empty(R * R)
+        ctx.gram(ctx.to_device(w), s + j, R, G)
+        Gs.append(G)
+    skip, lam = 1, 1e-3
+    S = np.ones((R, R))
+    for j in range(N):
+        if j != skip:
+            S = S * (Wf[j].T @ Wf[j])
+    S = S + lam * np.eye(R)
+    M, W_old, W_init = rnd((s, R), 180), rnd((s, R), 181), rnd((s, R), 182)
+    W_ref, dW_ref = o.SVD_solve_mod(M, W_init, S, 1.0)
+    Wd, grad, dW = ctx.to_device(W_old), ctx.empty(s * R), ctx.empty(s * R)
+    ctx.solve_update_g(ctx.to_device(M), Gs, skip, lam, Wd, s, R, W_init=ctx.to_device(W_init), mode=mode, grad=grad,
+                       dW=dW)
+    assert rel_err(ctx.to_host(Wd, (s, R)), W_ref) < 1e-9
+    assert rel_err(ctx.to_host(dW, (s, R)), dW_ref) < 1e-9
+    assert rel_err(ctx.to_host(grad, (s, R)), -M + W_old @ S) < 1e-12

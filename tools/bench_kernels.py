@@ -77,6 +77,12 @@ if not args.only or "k1" in args.only:
             b, m = timeit(lambda: ctx.ttm_first(V, lens, x, W10, 10, out))
             report(f"k1 ttm_first x={x} R=10", b, m, 2.0 * P * 10, 8.0 * (P + P // s * 10 + s * 10))
 
+if (not args.only or "k1f" in args.only) and N == 4:
+    outf = ctx.empty(s * s * R)
+    for xf in [2, 0]:
+        b, m = timeit(lambda: ctx.ttm_multi(V, lens, xf, [W[xf], W[xf + 1]], R, outf))
+        report(f"k1 fused ttm_multi x={xf},{xf+1} R={R}", b, m, 2.0 * P * R, 8.0 * (P + s * s * R + 2 * s * R))
+
 if (not args.only or "k2" in args.only) and N == 4:
     T = ctx.empty(s**3 * R)
     ctx.fill_uniform(T, 3, 0)
