@@ -278,13 +278,20 @@ def main():
                   if nranks == 1 else "eager launches + NCCL all-reduce per mode (latency bound, does not scale)"}
 
     # ---- roofline of the dominant kernel: the first dimension-tree contraction (K1) ------------------------------
-    x = 2 if N >= 3 else 0
-    out1 = H.Tensor(world, tuple(l for i, l in enumerate(lens_local) if i != x) + (R,))
+    # The sweep contracts the sibling modes of the first-level tree node in ONE launch (ppx_ttm_multi: DMMA GEMM against
+    # the Khatri-Rao rows of their factors); that call is what is timed here.
+    x_first = (N - 1) // 2 + 1
+    n_modes = N - x_first
+    keep = lens_local[:x_first]
+    out1 = H.Tensor(world, tuple(keep) + (R,))
     lens_c = (C.c_int64 * N)(*lens_local)
+    wptrs = (C.c_void_p * n_modes)(*[W[x_first + j].data_ptr() for j in range(n_modes)])
+    wld = (C.c_int64 * n_modes)(*[lens_local[x_first + j] for j in range(n_modes)])
 
     def k1():
-        lib.ppx_ttm_first(world.ctx_handle(), C.c_void_p(V.data_ptr()), lens_c, N, x, C.c_void_p(W[x].data_ptr()),
-                          lens_local[x], R, C.c_void_p(out1.data_ptr()))
+        rc = lib.ppx_ttm_multi(world.ctx_handle(), C.c_void_p(V.data_ptr()), lens_c, N, x_first, n_modes, wptrs, wld, R,
+                               C.c_void_p(out1.data_ptr()))
+        assert rc == 0, lib.ppx_last_error(world.ctx_handle())
 
     for _ in range(3):
         k1()
@@ -298,8 +305,9 @@ def main():
     k1_ms = float(ms.value) / reps
     out1.free()
     P_local = float(np.prod(lens_local))
+    Kc = float(np.prod(lens_local[x_first:]))
     k1_flops = 2.0 * P_local * R
-    k1_bytes = 8.0 * (P_local + P_local / lens_local[x] * R + lens_local[x] * R)
+    k1_bytes = 8.0 * (P_local + P_local / Kc * R + sum(lens_local[x_first:]) * R)
     peak_tf, peak_src = FP64_PEAK_FALLBACK_TF, "profiles/r01_fp64_peak.json (cuBLAS DGEMM 8192^3 on this pool's B200)"
     try:
         peak_tf = json.load(open(os.path.join(ROOT, "profiles", "r01_fp64_peak.json")))["fp64_tflops_burst"]
@@ -307,11 +315,14 @@ def main():
         pass
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "k1_ncu_summary.json"))).get("dram_bytes_per_launch")
+        prof = json.load(open(os.path.join(ROOT, "profiles", "k1_ncu_summary.json")))
+        if nranks == 1 and [s, R, N] == prof.get("size_rank_order"):
+            traffic = prof.get("dram_bytes_per_launch")
     except Exception:
         pass
     achieved = k1_flops / (k1_ms * 1e-3) / 1e12
-    roofline = {"kernel": "ttm_first_kernel (K1, first dimension-tree contraction, mode %d, R=%d)" % (x, R),
+    roofline = {"kernel": "ttm_first_kernel via ppx_ttm_multi (K1, first dimension-tree contraction, modes %d..%d at once, "
+                          "R=%d)" % (x_first, N - 1, R),
                 "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
                 "traffic": traffic, "algorithmic_flops": k1_flops, "algorithmic_bytes": k1_bytes, "ms": k1_ms,
                 "hbm_gbs": k1_bytes / (k1_ms * 1e-3) / 1e9,

@@ -100,6 +100,14 @@ int ppxh_world_comm_init(void *w_, const void *id128, int nranks, int rank, int 
     w->row_end = row_end;
   });
 }
+int ppxh_world_set_shard(void *w_, int shard_mode, int64_t shard_global, int64_t row_begin, int64_t row_end) {
+  World *w = (World *)w_;
+  w->shard_mode = shard_mode;
+  w->shard_global = shard_global;
+  w->row_begin = row_begin;
+  w->row_end = row_end;
+  return 0;
+}
 void ppxh_world_trim(void *w) { ((World *)w)->trim(); }
 
 void *ppxh_tensor_create(void *w, int order, const int64_t *lens) {

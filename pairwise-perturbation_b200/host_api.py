@@ -104,6 +104,10 @@ class World:
         _ck(self.lib.ppxh_world_comm_init(self.h, buf, nranks, rank, shard_mode, shard_global, row_begin, row_end))
         self.rank, self.np = rank, nranks
 
+    def set_shard(self, shard_mode, shard_global, row_begin, row_end):
+        self.lib.ppxh_world_set_shard.argtypes = [_vp, C.c_int, _i64, _i64, _i64]
+        self.lib.ppxh_world_set_shard(self.h, shard_mode, shard_global, row_begin, row_end)
+
     def ctx_handle(self):
         return self.lib.ppxh_world_ctx(self.h)
 

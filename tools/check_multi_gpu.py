@@ -1,0 +1,80 @@
+"""Multi-GPU parity check (run under torch.distributed.run on a box with >= 2 GPUs; not part of the single-GPU
+`-m gpu` suite):  the tensor is sharded along mode 0, alsCP_DT and alsCP_PP run through the C++ drivers with the NCCL
+all-reduces, and every rank compares its rows of W_0 / the replicated W_j and the logged fitness with the CPU oracle.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tools/check_multi_gpu.py
+"""
+import importlib
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import pp_oracle as o  # noqa: E402  (checker)
+
+rank, nranks, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+ppx = importlib.import_module("pairwise-perturbation_b200")
+H = importlib.import_module("pairwise-perturbation_b200.host_api")
+
+world = H.World(local, solver=0, use_graph=True, workspace_bytes=256 << 20)
+idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+if rank == 0:
+    idt = torch.tensor(list(ppx.comm_unique_id()), dtype=torch.uint8, device="cuda")
+dist.broadcast(idt, 0)
+
+ok_all = True
+for lens, R, maxiter, tol_init in [((13, 12, 11, 10), 4, 40, 0.1), ((9, 10, 11), 3, 30, 0.1), ((6, 7, 6, 5, 6, 7), 3, 40, 0.1)]:
+    N = len(lens)
+    b, e = ppx.shard_range(lens[0], nranks, rank)
+    if world.np == 1:
+        world.comm_init(bytes(idt.cpu().tolist()), nranks, rank, 0, lens[0], b, e)  # NCCL communicator, once
+    else:
+        world.set_shard(0, lens[0], b, e)  # only the shard layout changes between problems
+    V, _ = o.make_tensor_r(lens, R)
+    W, G = o.init_factors(lens, R), o.init_grad(lens, R)
+    vnorm = np.linalg.norm(V)
+    for driver in ("DT", "PP"):
+        W_ref, G_ref = [w.copy() for w in W], [g.copy() for g in G]
+        if driver == "DT":
+            _, tr = o.alsCP_DT(V, W_ref, G_ref, 1e-10 * vnorm, 12, resprint=4, F=None)
+        else:
+            _, tr = o.alsCP_PP(V, W_ref, G_ref, 1e-10 * vnorm, tol_init, maxiter, resprint=4)
+        Vd = H.Tensor.from_numpy(world, np.ascontiguousarray(V[b:e]))
+        Wd = [H.Tensor.from_numpy(world, (w[b:e] if i == 0 else w), matrix=True) for i, w in enumerate(W)]
+        Gd = [H.Tensor.from_numpy(world, (g[b:e] if i == 0 else g), matrix=True) for i, g in enumerate(G)]
+        Fd = [H.Matrix(world, w.lens[0], R) for w in Wd]
+        with H.Trace(quiet=True) as t:
+            if driver == "DT":
+                H.alsCP_DT(world, Vd, Wd, Gd, Fd, 1e-10 * vnorm, 12, resprint=4)
+            else:
+                H.alsCP_PP(world, Vd, Wd, Gd, Fd, 1e-10 * vnorm, tol_init, maxiter, resprint=4)
+        ok = len(t.rows) == len(tr.rows)
+        worst_fit = worst_fac = 0.0
+        for rg, rr in zip(t.rows, tr.rows):
+            ok &= int(rg[0]) == rr[0] and abs(rg[3] - rr[3]) <= 1e-10 * vnorm and abs(rg[1] - rr[1]) <= 1e-9 * max(rr[1], 1e-6 * vnorm)
+            worst_fit = max(worst_fit, abs(rg[3] - rr[3]) / vnorm)
+        if driver == "PP":
+            ok &= t.events == [(0 if k == "DT" else 1, it) for k, it in tr.events]
+        for i in range(N):
+            ref = W_ref[i][b:e] if i == 0 else W_ref[i]
+            err = float(np.abs(Wd[i].numpy() - ref).max() / max(1.0, np.abs(ref).max()))
+            worst_fac = max(worst_fac, err)
+            ok &= err <= 1e-8
+        print(f"rank {rank} lens {lens} R {R} {driver}: {'OK' if ok else 'MISMATCH'} rows {len(t.rows)} "
+              f"fit_err {worst_fit:.2e} factor_err {worst_fac:.2e} events {t.events if driver == 'PP' else ''}", flush=True)
+        ok_all &= ok
+        for x in [Vd] + Wd + Gd + Fd:
+            x.free()
+flag = torch.tensor([1 if ok_all else 0], device="cuda")
+dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+if rank == 0:
+    print("MULTI-GPU PARITY", "PASS" if int(flag.item()) == 1 else "FAIL", flush=True)
+world.close()
+dist.destroy_process_group()
+sys.exit(0 if int(flag.item()) == 1 else 1)
