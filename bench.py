@@ -269,6 +269,10 @@ def main():
     reset_W()
     H.cp_dt_sweeps(world, V, W, G, 2)  # PP starts from an ALS iterate, as alsCP_PP does
     barrier()
+    H.cp_pp_phase_timed(world, V, W, G, 1)  # warm-up: first-use kernel loading and the 3 x 10.8 GB allocations
+    reset_W()
+    H.cp_dt_sweeps(world, V, W, G, 2)
+    barrier()
     ms_build, ms_pp = H.cp_pp_phase_timed(world, V, W, G, args.pp_sweeps)
     ms_build, ms_pp = max_over_ranks(ms_build), max_over_ranks(ms_pp)
     world.trim()  # the level-1 tensors of the build go back to the driver

@@ -110,6 +110,47 @@ __global__ void __launch_bounds__(THREADS, 2) ttm_first_kernel(TtmParams p) {
     double *As = smem + stage * STAGE_D;
     double *Ws = As + A_D;
     const int64_t k0 = (int64_t)(split * p.cps + ld_kc) * BK;
+    // Fast path (all but the K-tail chunk and the last row tile of aligned problems): full 16-byte copies from a
+    // per-thread base pointer plus a constant stride -- a handful of integer instructions per cp.async instead of
+    // the bounds / zero-fill logic of the general path below.
+    if (p.vecA && p.vecW && k0 + BK <= p.X && (int64_t)(tile + 1) * BM <= p.Mtot) {
+      if (KMAJOR) {
+        const int kp = tid & 7, mb = tid >> 3;
+        const double *src = p.V + ((int64_t)tile * BM + mb) * p.X + k0 + 2 * kp;
+        const int64_t stride = 16 * p.X;
+        double *dst = As + mb * LDK + 2 * kp;
+#pragma unroll
+        for (int i = 0; i < 8; i++) ppx_cp_async16(dst + i * 16 * LDK, src + i * stride, 16);
+      } else {
+        const int ml = 2 * (tid & 63), kb = tid >> 6;
+        if (tile != cached_tile) {
+          cached_tile = tile;
+          const int64_t mg = (int64_t)tile * BM + ml;
+          nb0 = nb1 = 8;
+          const int64_t t0 = mg / p.L, l0 = mg - t0 * p.L;
+          off0 = l0 + p.L * p.X * t0;
+          off1 = off0 + 1;
+        }
+        const double *src = p.V + off0 + (k0 + kb) * p.L;
+        const int64_t stride = 2 * p.L;
+        double *dst = As + kb * LDM + ml;
+#pragma unroll
+        for (int i = 0; i < 8; i++) ppx_cp_async16(dst + i * 2 * LDM, src + i * stride, 16);
+      }
+      {
+        const int n0 = tid >> 3, kp = tid & 7;  // slab rows n0, n0+16, ...: same kp, constant row stride
+        const double *src = p.W + (int64_t)(ncol0 + n0) * p.ldw + k0 + 2 * kp;
+        const int64_t stride = 16 * p.ldw;
+        double *dst = Ws + n0 * LDK + 2 * kp;
+#pragma unroll
+        for (int i = 0; i < (8 * NT + 15) / 16; i++) {
+          if (n0 + 16 * i < 8 * NT) {
+            const bool cv = ncol0 + n0 + 16 * i < p.R;
+            ppx_cp_async16(dst + i * 16 * LDK, cv ? src + i * stride : p.W, cv ? 16 : 0);
+          }
+        }
+      }
+    } else {
     if (KMAJOR) {
       const int kp = tid & 7, mb = tid >> 3;
       const int64_t kg = k0 + 2 * kp;
@@ -178,6 +219,7 @@ __global__ void __launch_bounds__(THREADS, 2) ttm_first_kernel(TtmParams p) {
         }
       }
     }
+    }  // general path
     if (++ld_kc == ld.count) {
       ld_kc = 0;
       set_unit(ld, ld.u + gridDim.x);
@@ -301,14 +343,19 @@ __global__ void __launch_bounds__(256) krp_kernel(KrpArgs a, int64_t K, int R, d
   }
 }
 
+// pipeline depth: as deep as two CTAs per SM allow (about 113 KB of shared memory each)
+template <int NT, bool KMAJOR>
+constexpr int ttm_stages() {
+  return KMAJOR ? (NT <= 4 ? 4 : 3) : (NT <= 3 ? 5 : 4);
+}
 template <int NT, bool KMAJOR>
 constexpr size_t ttm_smem() {
-  return sizeof(double) * (KMAJOR ? 3 : 4) * (a_doubles<KMAJOR>() + 8 * NT * LDK);
+  return sizeof(double) * ttm_stages<NT, KMAJOR>() * (a_doubles<KMAJOR>() + 8 * NT * LDK);
 }
 
 template <int NT, bool KMAJOR>
 int launch_ttm(ppx_ctx *ctx, const TtmParams &p, int col_blocks) {
-  constexpr int STAGES = KMAJOR ? 3 : 4;
+  constexpr int STAGES = ttm_stages<NT, KMAJOR>();
   auto kern = ttm_first_kernel<NT, KMAJOR, STAGES>;
   const int units = p.num_tiles * p.ksplit;
   int gx = units < 2 * ctx->sm_count ? units : 2 * ctx->sm_count;
@@ -320,7 +367,7 @@ int launch_ttm(ppx_ctx *ctx, const TtmParams &p, int col_blocks) {
 
 template <int NT, bool KMAJOR>
 cudaError_t init_one() {
-  return cudaFuncSetAttribute(ttm_first_kernel<NT, KMAJOR, (KMAJOR ? 3 : 4)>,
+  return cudaFuncSetAttribute(ttm_first_kernel<NT, KMAJOR, ttm_stages<NT, KMAJOR>()>,
                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ttm_smem<NT, KMAJOR>());
 }
 
@@ -354,7 +401,7 @@ int ppx_k1_init(ppx_ctx *ctx) {
 // Shared by ppx_ttm_first (CP, rank last), ppx_ttm / ppx_ttm_acc (Tucker, rank in place of mode x) and ppx_ttm_multi.
 // Uses the context workspace for split-K partials (callers that hold workspace memory pass ws_keep = true).
 int ppx_ttm_impl(ppx_ctx *ctx, const double *V, int64_t L, int64_t X, int64_t Rt, const double *Wx, int64_t ldw,
-                 int R, double *out, int inplace, int accumulate, bool ws_keep) {
+                 int R, double *out, int inplace, int accumulate, bool ws_keep, bool try_tma = true) {
   TtmParams p;
   p.V = V;
   p.W = Wx;
@@ -370,6 +417,12 @@ int ppx_ttm_impl(ppx_ctx *ctx, const double *V, int64_t L, int64_t X, int64_t Rt
   p.ksplit = 1;
   p.split_stride = 0;
   if (p.Mtot == 0 || R == 0) return PPX_OK;
+  if (try_tma) {  // TMA-staged tiles when the shape allows it
+    const double *fac[1] = {Wx};
+    const int64_t ld1[1] = {ldw}, xs1[1] = {X};
+    const int rc = ppx_ttm_tma_try(ctx, V, L, X, Rt, fac, ld1, xs1, 1, R, out, inplace, accumulate, ws_keep);
+    if (rc != 1) return rc;
+  }
   int64_t tiles = (p.Mtot + BM - 1) / BM;
   if (tiles > 0x7fffffff / 64) return ppx_set_err(ctx, PPX_EUNSUPPORTED, "ttm_first: too many row tiles");
   p.num_tiles = (int)tiles;
@@ -457,6 +510,13 @@ int ppx_ttm_multi(ppx_ctx *ctx, const double *V, const int64_t *lens, int N, int
   }
   for (int i = x_first + n_modes; i < N; i++) Rt *= lens[i];
   ppx_ws_reset(ctx);
+  {  // TMA path: the Khatri-Rao rows are packed straight into the per-chunk slabs the kernel streams
+    int64_t xs[8];
+    for (int j = 0; j < n_modes; j++) xs[j] = lens[x_first + j];
+    const int rc = ppx_ttm_tma_try(ctx, V, L, K, Rt, W, ldw, xs, n_modes, R, out, 0, 0, true);
+    if (rc != 1) return rc;
+    ppx_ws_reset(ctx);
+  }
   double *krp = (double *)ppx_ws_alloc(ctx, sizeof(double) * (size_t)K * R);  // K x R, column-major, ld = K
   if (!krp)
     return ppx_set_err(ctx, PPX_ENOMEM, "ttm_multi needs %lld bytes of workspace for the Khatri-Rao rows",
@@ -467,7 +527,7 @@ int ppx_ttm_multi(ppx_ctx *ctx, const double *V, const int64_t *lens, int N, int
   if (blocks > ctx->sm_count * 16) blocks = ctx->sm_count * 16;
   krp_kernel<<<blocks, 256, 0, ctx->stream>>>(a, K, R, krp);
   PPX_CHECK_LAUNCH(ctx);
-  return ppx_ttm_impl(ctx, V, L, K, Rt, krp, ld, R, out, 0, 0, true);
+  return ppx_ttm_impl(ctx, V, L, K, Rt, krp, ld, R, out, 0, 0, true, false);
 }
 
 int ppx_ttm(ppx_ctx *ctx, const double *T, const int64_t *lens, int k, int x, const double *Wx, int64_t ldw, int Q,

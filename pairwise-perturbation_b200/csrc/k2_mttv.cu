@@ -24,7 +24,23 @@ __global__ void __launch_bounds__(256) mttv_first_kernel(const double *__restric
       const int64_t r = o / Rt;
       const double *tp = T + o * X;
       const double *wp = W + r * ldw;
-      for (int64_t x = lane_g; x < X; x += G) acc += tp[x] * wp[x];
+      // 8 independent loads in flight per lane (the dot products are short: latency, not bandwidth, limits them)
+      for (int64_t x0 = lane_g; x0 < X; x0 += 8 * G) {
+        double v[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+          const int64_t x = x0 + (int64_t)u * G;
+          v[u] = x < X ? tp[x] : 0.0;
+        }
+        double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+        for (int u = 0; u < 8; u += 2) {
+          const int64_t xa = x0 + (int64_t)u * G, xb = xa + G;
+          a0 += v[u] * (xa < X ? wp[xa] : 0.0);
+          a1 += v[u + 1] * (xb < X ? wp[xb] : 0.0);
+        }
+        acc += a0 + a1;
+      }
     }
 #pragma unroll
     for (int s = G / 2; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
@@ -33,41 +49,77 @@ __global__ void __launch_bounds__(256) mttv_first_kernel(const double *__restric
 }
 
 // ---- L >= 32: lanes along l (coalesced), warps split x, fixed-order reduction across warps ------------------
+// VEC = 2: every lane owns two consecutive l (16-byte loads, 64 l per block); VEC = 1: one l per lane.
+// MT_B loads are in flight per thread and the next batch is requested before the current one is consumed: with
+// tens of thousands of small blocks the kernel is otherwise bound by the number of dependent round trips per block.
 constexpr int MT_WY = 8;
+constexpr int MT_B = 8;
+template <int VEC>
 __global__ void __launch_bounds__(32 * MT_WY) mttv_mid_kernel(const double *__restrict__ T,
                                                               const double *__restrict__ W,
                                                               double *__restrict__ out, int64_t L, int64_t X,
                                                               int64_t Rt, int R, int64_t ldw, int64_t ltiles) {
-  __shared__ double part[MT_WY][32];
+  __shared__ double part[MT_WY][32 * VEC];
   const int lane = threadIdx.x, wy = threadIdx.y;
   int64_t b = blockIdx.x;  // over (ltile, t, r)
   const int64_t lt = b % ltiles;
   b /= ltiles;
   const int64_t t = b % Rt;
   const int64_t r = b / Rt;
-  const int64_t l = lt * 32 + lane;
-  double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+  const int64_t l = (lt * 32 + lane) * VEC;
+  double acc[VEC];
+#pragma unroll
+  for (int v = 0; v < VEC; v++) acc[v] = 0.0;
   if (l < L) {
     const double *tp = T + l + L * X * (t + Rt * r);
     const double *wp = W + r * ldw;
-    int64_t x = wy;
-    for (; x + 3 * MT_WY < X; x += 4 * MT_WY) {
-      const double v0 = tp[L * x], v1 = tp[L * (x + MT_WY)], v2 = tp[L * (x + 2 * MT_WY)],
-                   v3 = tp[L * (x + 3 * MT_WY)];
-      acc0 += v0 * wp[x];
-      acc1 += v1 * wp[x + MT_WY];
-      acc2 += v2 * wp[x + 2 * MT_WY];
-      acc3 += v3 * wp[x + 3 * MT_WY];
+    double cur[MT_B][VEC], nxt[MT_B][VEC];
+    auto load = [&](double (&dst)[MT_B][VEC], int64_t x0) {
+#pragma unroll
+      for (int u = 0; u < MT_B; u++) {
+        const int64_t x = x0 + (int64_t)u * MT_WY;
+        if (x < X) {
+          if (VEC == 2) {
+            const double2 v = *reinterpret_cast<const double2 *>(tp + L * x);
+            dst[u][0] = v.x;
+            dst[u][VEC - 1] = v.y;
+          } else {
+            dst[u][0] = tp[L * x];
+          }
+        } else {
+#pragma unroll
+          for (int v = 0; v < VEC; v++) dst[u][v] = 0.0;
+        }
+      }
+    };
+    load(cur, wy);
+    for (int64_t x0 = wy; x0 < X; x0 += MT_B * MT_WY) {
+      const int64_t x1 = x0 + MT_B * MT_WY;
+      if (x1 < X) load(nxt, x1);
+#pragma unroll
+      for (int u = 0; u < MT_B; u++) {
+        const int64_t x = x0 + (int64_t)u * MT_WY;
+        const double w = x < X ? wp[x] : 0.0;
+#pragma unroll
+        for (int v = 0; v < VEC; v++) acc[v] += cur[u][v] * w;
+      }
+#pragma unroll
+      for (int u = 0; u < MT_B; u++)
+#pragma unroll
+        for (int v = 0; v < VEC; v++) cur[u][v] = nxt[u][v];
     }
-    for (; x < X; x += MT_WY) acc0 += tp[L * x] * wp[x];
   }
-  part[wy][lane] = (acc0 + acc1) + (acc2 + acc3);
+#pragma unroll
+  for (int v = 0; v < VEC; v++) part[wy][lane * VEC + v] = acc[v];
   __syncthreads();
   if (wy == 0 && l < L) {
-    double s = 0.0;
 #pragma unroll
-    for (int y = 0; y < MT_WY; y++) s += part[y][lane];
-    out[l + L * (t + Rt * r)] = s;
+    for (int v = 0; v < VEC; v++) {
+      double s = 0.0;
+#pragma unroll
+      for (int y = 0; y < MT_WY; y++) s += part[y][lane * VEC + v];
+      out[l + v + L * (t + Rt * r)] = s;
+    }
   }
 }
 
@@ -218,10 +270,14 @@ int ppx_mttv_impl(ppx_ctx *ctx, const double *T, int64_t L, int64_t X, int64_t R
     }
     PPX_CHECK_LAUNCH(ctx);
   } else if (L >= 32) {
-    const int64_t ltiles = (L + 31) / 32;
+    const bool vec = (L % 2 == 0) && ((((uintptr_t)T) & 15) == 0) && L >= 64;
+    const int64_t ltiles = vec ? (L + 63) / 64 : (L + 31) / 32;
     const int64_t blocks = ltiles * Rt * R;
     if (blocks > 0x7fffffffLL) return ppx_set_err(ctx, PPX_EUNSUPPORTED, "mttv: grid too large");
-    mttv_mid_kernel<<<(unsigned)blocks, dim3(32, MT_WY), 0, ctx->stream>>>(T, Wx, out, L, X, Rt, R, ldw, ltiles);
+    if (vec)
+      mttv_mid_kernel<2><<<(unsigned)blocks, dim3(32, MT_WY), 0, ctx->stream>>>(T, Wx, out, L, X, Rt, R, ldw, ltiles);
+    else
+      mttv_mid_kernel<1><<<(unsigned)blocks, dim3(32, MT_WY), 0, ctx->stream>>>(T, Wx, out, L, X, Rt, R, ldw, ltiles);
     PPX_CHECK_LAUNCH(ctx);
   } else {
     const int64_t n_out = L * Rt * (int64_t)R;

@@ -59,6 +59,7 @@ int ppx_ctx_create(int device, void *stream, size_t workspace_bytes, ppx_ctx **o
   ctx->ws_bytes = workspace_bytes;
   {
     int rc = ppx_k1_init(ctx);
+    if (!rc) rc = ppx_k1_tma_init(ctx);
     if (!rc) rc = ppx_k45_init(ctx);
     if (!rc) rc = ppx_k7_init(ctx);
     if (rc) {

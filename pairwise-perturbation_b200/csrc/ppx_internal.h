@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string>
 #include "../../include/ppx.h"
 
@@ -27,6 +28,11 @@ struct ppx_ctx {
 int ppx_set_err(ppx_ctx *ctx, int code, const char *fmt, ...);
 // per-file one-time kernel attribute setup (opt-in shared memory), called from ppx_ctx_create
 int ppx_k1_init(ppx_ctx *ctx);
+int ppx_k1_tma_init(ppx_ctx *ctx);
+// TMA path of the first contraction; returns 1 when the shape is not eligible (caller falls back to cp.async)
+int ppx_ttm_tma_try(ppx_ctx *ctx, const double *V, int64_t L, int64_t K, int64_t Rt, const double *const *fac,
+                    const int64_t *ld, const int64_t *xs, int n_fac, int R, double *out, int inplace, int accumulate,
+                    bool ws_keep);
 int ppx_k45_init(ppx_ctx *ctx);
 int ppx_k7_init(ppx_ctx *ctx);
 void ppx_comm_destroy_internal(ppx_ctx *ctx);

@@ -33,6 +33,9 @@ TTM_CASES = [
     ((7, 5, 6, 4, 5, 3), 3, 3), ((7, 5, 6, 4, 5, 3), 0, 3),
     ((40, 40, 40), 1, 10), ((300, 37), 0, 50), ((37, 300), 1, 50), ((64, 33, 20), 1, 70),
     ((200, 3, 50), 1, 10), ((3, 128, 16), 0, 10), ((129, 17), 1, 1), ((1, 9, 5), 1, 2), ((130,), 0, 7),
+    # TMA-eligible shapes (even leading extent, rows fill the 128-row tiles): M-major 3-D maps and k-major 2-D maps
+    ((256, 24, 6), 1, 5), ((512, 17, 3), 1, 50), ((1024, 20), 1, 10), ((128, 8, 4, 6), 1, 7), ((384, 33, 2), 1, 64),
+    ((300, 150), 0, 50), ((18, 700), 0, 3), ((64, 129), 0, 56), ((2560, 9), 1, 9),
 ]
 
 
@@ -300,6 +303,8 @@ MULTI_CASES = [
     ((20, 64, 70), 1, 2, 10),   # few rows, deep K: exercises the K split (20 rows, K = 4480)
     ((64, 70, 3), 0, 2, 50),    # k-major, 3 rows, K = 4480
     ((9, 7, 5), 0, 3, 2),       # everything contracted: a single row
+    ((256, 6, 5, 3), 1, 2, 4), ((128, 30, 40), 1, 2, 50), ((10, 12, 130, 3), 0, 2, 50),  # TMA-eligible fused cases
+    ((640, 4, 5, 6), 1, 3, 10),
 ]
 
 
