@@ -12,7 +12,7 @@
 //     warps on one SM sub-partition and caps the kernel at 168 registers, which spills the 56-double accumulator.)
 //   * the V tile is stored dense with the hardware 128-byte swizzle; the k index each lane takes in an MMA step is
 //     permuted so that every DMMA fragment load is bank-conflict free on the swizzled tile;
-//   * B is packed once per call (krp_pack_kernel) into per-chunk slabs [chunk][8*NT columns][20] with the same k
+//   * B is packed once per call (krp_pack_kernel) into per-chunk slabs [chunk][8*NT + TAIL columns][20] with the same k
 //     permutation, zero padded in k and in the columns, so a stage's slab is ONE contiguous bulk copy.
 // Layouts:  KMAJOR (L == 1): tensor map 2-D {K, M}, one 16 x 128 box per stage;
 //           M-major (L > 1): tensor map 3-D {L, K, Rt}, eight 16(l) x 16(k) boxes per stage, row tiles do not straddle t.
@@ -41,6 +41,7 @@ struct TmaParams {
   int num_tiles;
   int nk, ksplit, cps;
   int inplace, accumulate;
+  int onebox;  // M-major with L % 16 == 0: the eight 16 x 16 boxes of a stage are one 4-D box (see ppx_ttm_tma_try)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -79,6 +80,14 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, u
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
           smem_u32(dst)),
       "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
 __device__ __forceinline__ void bulk_load(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
@@ -141,10 +150,16 @@ __global__ void __launch_bounds__(256) tma_split_reduce_kernel(const double *__r
   }
 }
 
-template <int NT, bool KMAJOR>
+// NT full 8-column DMMA tiles + TAIL (0..4) extra columns.  R = 50 as 7 DMMA tiles wastes 6 of 56 columns of the FP64
+// pipe; DMMA and DFMA share that pipe (tools/dmma_bench.cu: interleaving them adds their times), so the R mod 8 <= 4
+// leftover columns are cheaper as plain DFMA on the A fragments the thread already holds: per 16-deep chunk 16*TAIL
+// DFMA per thread (about 2.9*TAIL DMMA-equivalents) instead of the 16 DMMA of a padded tile.  Each lane accumulates
+// the partial sum over its own k positions; the four lanes of a group are combined by shuffles in the epilogue.
+template <int NT, int TAIL, bool KMAJOR>
 __global__ void __launch_bounds__(TTHREADS, 2) ttm_tma_kernel(const __grid_constant__ CUtensorMap tmap, TmaParams p) {
   extern __shared__ uint8_t smem_raw[];
-  constexpr int W_STAGE_BYTES = 8 * NT * TLDW * 8;
+  constexpr int NCOLS = 8 * NT + TAIL;
+  constexpr int W_STAGE_BYTES = NCOLS * TLDW * 8;
   // 1024-byte aligned base (the 128-byte swizzle pattern is a function of the shared address)
   uint8_t *base = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t *A_base = base;
@@ -213,10 +228,14 @@ __global__ void __launch_bounds__(TTHREADS, 2) ttm_tma_kernel(const __grid_const
     } else {
       const int t = ld.tile / p.tiles_per_t;
       const int l0 = (ld.tile - t * p.tiles_per_t) * TBM;
+      if (p.onebox) {
+        tma_load_4d(As, &tmap, &full[stage], 0, chunk * TBK, l0 >> 4, t);
+      } else {
 #pragma unroll
-      for (int b = 0; b < 8; b++) tma_load_3d(As + b * 2048, &tmap, &full[stage], l0 + 16 * b, chunk * TBK, t);
+        for (int b = 0; b < 8; b++) tma_load_3d(As + b * 2048, &tmap, &full[stage], l0 + 16 * b, chunk * TBK, t);
+      }
     }
-    bulk_load(W_base + stage * W_STAGE_BYTES, p.Wpp + (int64_t)chunk * (8 * NT * TLDW), W_STAGE_BYTES, &full[stage]);
+    bulk_load(W_base + stage * W_STAGE_BYTES, p.Wpp + (int64_t)chunk * (NCOLS * TLDW), W_STAGE_BYTES, &full[stage]);
     if (++ld_kc == ld.count) {
       ld_kc = 0;
       set_unit(ld, ld.u + gridDim.x);
@@ -253,6 +272,11 @@ __global__ void __launch_bounds__(TTHREADS, 2) ttm_tma_kernel(const __grid_const
   for (int i = 0; i < 4; i++)
 #pragma unroll
     for (int j = 0; j < NT; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+  double tacc[4][TAIL > 0 ? TAIL : 1];
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int c = 0; c < (TAIL > 0 ? TAIL : 1); c++) tacc[i][c] = 0.0;
 
   Unit cu;
   set_unit(cu, blockIdx.x);
@@ -279,6 +303,15 @@ __global__ void __launch_bounds__(TTHREADS, 2) ttm_tma_kernel(const __grid_const
       for (int i = 0; i < 4; i++)
 #pragma unroll
         for (int j = 0; j < NT; j++) ppx_dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+      if (TAIL > 0) {
+        double bt[TAIL > 0 ? TAIL : 1];
+#pragma unroll
+        for (int c = 0; c < TAIL; c++) bt[c] = Ws[(8 * NT + c) * TLDW + 4 * q + t4];
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+          for (int c = 0; c < TAIL; c++) tacc[i][c] = fma(a[i], bt[c], tacc[i][c]);
+      }
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[stage]);  // this warp is done reading the stage
@@ -326,6 +359,22 @@ __global__ void __launch_bounds__(TTHREADS, 2) ttm_tma_kernel(const __grid_const
           }
           acc[i][j][0] = acc[i][j][1] = 0.0;
         }
+        if (TAIL > 0) {
+          // combine the four lanes of the group (fixed order), lane t4 == c stores column 8*NT + c
+          double mine = 0.0;
+#pragma unroll
+          for (int c = 0; c < TAIL; c++) {
+            double v = tacc[i][c];
+            v += __shfl_xor_sync(0xffffffffu, v, 1);
+            v += __shfl_xor_sync(0xffffffffu, v, 2);
+            if (t4 == c) mine = v;
+            tacc[i][c] = 0.0;
+          }
+          if (rv && t4 < TAIL) {
+            double *o = outp + basei + cstride * (8 * NT + t4);
+            *o = p.accumulate ? (*o + mine) : mine;
+          }
+        }
       }
       kc = 0;
       set_unit(cu, cu.u + gridDim.x);
@@ -333,41 +382,47 @@ __global__ void __launch_bounds__(TTHREADS, 2) ttm_tma_kernel(const __grid_const
   }
 }
 
-template <int NT>
+template <int NT, int TAIL>
 constexpr size_t tma_smem() {
-  return 1024 + (size_t)TSTAGES * (A_STAGE_BYTES + 8 * NT * TLDW * 8) + 2 * TSTAGES * sizeof(uint64_t);
+  return 1024 + (size_t)TSTAGES * (A_STAGE_BYTES + (8 * NT + TAIL) * TLDW * 8) + 2 * TSTAGES * sizeof(uint64_t);
 }
 
-template <int NT, bool KMAJOR>
-int launch_tma(ppx_ctx *ctx, const CUtensorMap &map, const TmaParams &p) {
+constexpr int TAIL_MAX = 4;  // leftover columns done as DFMA; 5..7 leftover columns get a padded DMMA tile
+constexpr int NT_MAX = 8;
+
+// (NT, TAIL) table of the instantiated kernels: NT = 1..8 with TAIL = 0, NT = 1..7 with TAIL = 1..4
+typedef void (*TmaKernel)(const CUtensorMap, TmaParams);
+struct TmaEntry {
+  TmaKernel kern[2];  // [kmajor]
+  size_t smem;
+};
+template <int NT, int TAIL>
+constexpr TmaEntry tma_entry() {
+  return TmaEntry{{ttm_tma_kernel<NT, TAIL, false>, ttm_tma_kernel<NT, TAIL, true>}, tma_smem<NT, TAIL>()};
+}
+#define PPX_TMA_ROW(NT) {tma_entry<NT, 0>(), tma_entry<NT, 1>(), tma_entry<NT, 2>(), tma_entry<NT, 3>(), tma_entry<NT, 4>()}
+const TmaEntry g_tma_table[NT_MAX][TAIL_MAX + 1] = {PPX_TMA_ROW(1), PPX_TMA_ROW(2), PPX_TMA_ROW(3), PPX_TMA_ROW(4),
+                                                    PPX_TMA_ROW(5), PPX_TMA_ROW(6), PPX_TMA_ROW(7),
+                                                    {tma_entry<8, 0>(), {}, {}, {}, {}}};
+
+// R <= 64 -> (NT full tiles, TAIL DFMA columns)
+inline void tma_split_rank(int R, int *nt, int *tail) {
+  int n = R / 8, t = R % 8;
+  if (n == 0 || t > TAIL_MAX) {
+    n += 1;
+    t = 0;
+  }
+  *nt = n;
+  *tail = t;
+}
+
+int launch_tma(ppx_ctx *ctx, const CUtensorMap &map, const TmaParams &p, int nt, int tail, bool kmajor) {
+  const TmaEntry &e = g_tma_table[nt - 1][tail];
   const int units = p.num_tiles * p.ksplit;
   const int gx = units < 2 * ctx->sm_count ? units : 2 * ctx->sm_count;
-  ttm_tma_kernel<NT, KMAJOR><<<gx, TTHREADS, tma_smem<NT>(), ctx->stream>>>(map, p);
+  e.kern[kmajor ? 1 : 0]<<<gx, TTHREADS, e.smem, ctx->stream>>>(map, p);
   PPX_CHECK_LAUNCH(ctx);
   return PPX_OK;
-}
-
-template <bool KMAJOR>
-int dispatch_tma(ppx_ctx *ctx, const CUtensorMap &map, const TmaParams &p, int nt) {
-  switch (nt) {
-    case 1: return launch_tma<1, KMAJOR>(ctx, map, p);
-    case 2: return launch_tma<2, KMAJOR>(ctx, map, p);
-    case 3: return launch_tma<3, KMAJOR>(ctx, map, p);
-    case 4: return launch_tma<4, KMAJOR>(ctx, map, p);
-    case 5: return launch_tma<5, KMAJOR>(ctx, map, p);
-    case 6: return launch_tma<6, KMAJOR>(ctx, map, p);
-    case 7: return launch_tma<7, KMAJOR>(ctx, map, p);
-    default: return launch_tma<8, KMAJOR>(ctx, map, p);
-  }
-}
-
-template <int NT>
-cudaError_t tma_init_nt() {
-  cudaError_t e = cudaFuncSetAttribute(ttm_tma_kernel<NT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)tma_smem<NT>());
-  if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(ttm_tma_kernel<NT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tma_smem<NT>());
-  return e;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
@@ -379,15 +434,15 @@ bool g_encode_tried = false;
 }  // namespace
 
 int ppx_k1_tma_init(ppx_ctx *ctx) {
-  cudaError_t e = tma_init_nt<1>();
-  if (e == cudaSuccess) e = tma_init_nt<2>();
-  if (e == cudaSuccess) e = tma_init_nt<3>();
-  if (e == cudaSuccess) e = tma_init_nt<4>();
-  if (e == cudaSuccess) e = tma_init_nt<5>();
-  if (e == cudaSuccess) e = tma_init_nt<6>();
-  if (e == cudaSuccess) e = tma_init_nt<7>();
-  if (e == cudaSuccess) e = tma_init_nt<8>();
-  if (e != cudaSuccess) return ppx_set_err(ctx, PPX_ECUDA, "k1 tma init: %s", cudaGetErrorString(e));
+  for (int n = 0; n < NT_MAX; n++)
+    for (int t = 0; t <= TAIL_MAX; t++)
+      for (int k = 0; k < 2; k++) {
+        const TmaEntry &e = g_tma_table[n][t];
+        if (!e.kern[k]) continue;
+        cudaError_t err = cudaFuncSetAttribute((const void *)e.kern[k], cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               (int)e.smem);
+        if (err != cudaSuccess) return ppx_set_err(ctx, PPX_ECUDA, "k1 tma init: %s", cudaGetErrorString(err));
+      }
   if (!g_encode_tried) {
     g_encode_tried = true;
     void *fn = nullptr;
@@ -444,8 +499,10 @@ int ppx_ttm_tma_try(ppx_ctx *ctx, const double *V, int64_t L, int64_t K, int64_t
   p.split_stride = 0;
   p.inplace = inplace;
   p.accumulate = accumulate;
-  const int nt = (R + 7) / 8;
-  const int ncols = 8 * nt;
+  p.onebox = (!kmajor && L % 16 == 0) ? 1 : 0;
+  int nt, tail;
+  tma_split_rank(R, &nt, &tail);
+  const int ncols = 8 * nt + tail;
 
   if (!ws_keep) ppx_ws_reset(ctx);
   double *Wpp = (double *)ppx_ws_alloc(ctx, sizeof(double) * (size_t)p.nk * ncols * TLDW);
@@ -491,6 +548,18 @@ int ppx_ttm_tma_try(ppx_ctx *ctx, const double *V, int64_t L, int64_t K, int64_t
     cr = g_encode(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void *)V, dims, strides, box, es,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  } else if (p.onebox) {
+    // L = 16 * Lo: view V as {li = 16, k = K, lo = Lo, t = Rt}; a {16, 16, 8, 1} box lands in shared memory as
+    // [lo][k][li] -- byte for byte the image of eight consecutive {16 l, 16 k} boxes, in ONE instruction per stage
+    // (rows past the last full group of a partial row tile are out of bounds in `lo` and read as zero).
+    cuuint64_t dims[4] = {16, (cuuint64_t)K, (cuuint64_t)(L / 16), (cuuint64_t)Rt};
+    cuuint64_t strides[3] = {(cuuint64_t)L * 8, 128, (cuuint64_t)L * (cuuint64_t)K * 8};
+    cuuint32_t box[4] = {16, TBK, 8, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    if (strides[2] >= ((cuuint64_t)1 << 40)) return 1;
+    cr = g_encode(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, (void *)V, dims, strides, box, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   } else {
     cuuint64_t dims[3] = {(cuuint64_t)L, (cuuint64_t)K, (cuuint64_t)Rt};
     cuuint64_t strides[2] = {(cuuint64_t)L * 8, (cuuint64_t)L * (cuuint64_t)K * 8};
@@ -520,7 +589,7 @@ int ppx_ttm_tma_try(ppx_ctx *ctx, const double *V, int64_t L, int64_t K, int64_t
     PPX_CHECK_LAUNCH(ctx);
   }
   p.Wpp = Wpp;
-  int rc = kmajor ? dispatch_tma<true>(ctx, map, p, nt) : dispatch_tma<false>(ctx, map, p, nt);
+  int rc = launch_tma(ctx, map, p, nt, tail, kmajor);
   if (rc) return rc;
   if (p.ksplit > 1) {
     const int64_t n = Mtot * (int64_t)R;

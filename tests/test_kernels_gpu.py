@@ -36,6 +36,13 @@ TTM_CASES = [
     # TMA-eligible shapes (even leading extent, rows fill the 128-row tiles): M-major 3-D maps and k-major 2-D maps
     ((256, 24, 6), 1, 5), ((512, 17, 3), 1, 50), ((1024, 20), 1, 10), ((128, 8, 4, 6), 1, 7), ((384, 33, 2), 1, 64),
     ((300, 150), 0, 50), ((18, 700), 0, 3), ((64, 129), 0, 56), ((2560, 9), 1, 9),
+    # leftover rank columns (R mod 8 in 1..4) run as DFMA beside the DMMA tiles: every tail width, both layouts
+    ((40, 260), 0, 9), ((40, 260), 0, 10), ((34, 300), 0, 11), ((34, 300), 0, 12), ((34, 300), 0, 13),
+    ((50, 131), 0, 17), ((20, 400), 0, 27), ((20, 400), 0, 36), ((22, 129), 0, 60),
+    ((256, 19, 3), 1, 25), ((256, 19, 3), 1, 26), ((384, 10, 2), 1, 27), ((128, 33, 4), 1, 28), ((256, 9, 5), 1, 33),
+    ((128, 21, 3), 1, 41), ((640, 7, 2), 1, 58), ((256, 12, 3), 1, 59),
+    # M-major with L % 16 != 0: eight 16 x 16 boxes per stage instead of the single 4-D box
+    ((250, 12, 3), 1, 50), ((378, 9, 2), 1, 33), ((122, 40, 2), 1, 26),
 ]
 
 
@@ -237,7 +244,9 @@ def test_cp_residual_and_reconstruct(ctx, lens, R):
 
 
 @pytest.mark.parametrize("lens,x,Q", [((13, 9, 11), 0, 4), ((13, 9, 11), 1, 4), ((13, 9, 11), 2, 4),
-                                      ((12, 10, 8, 6), 1, 3), ((40, 7, 40), 2, 40), ((5, 1, 6), 1, 2)])
+                                      ((12, 10, 8, 6), 1, 3), ((40, 7, 40), 2, 40), ((5, 1, 6), 1, 2),
+                                      # TMA path with the rank written in place (+ DFMA tail columns)
+                                      ((256, 14, 5), 1, 26), ((22, 130), 0, 27), ((128, 9, 3, 2), 1, 35)])
 def test_tucker_ttm_and_acc(ctx, lens, x, Q):
     T = rnd(lens, 120)
     W = rnd((lens[x], Q), 121)
@@ -304,7 +313,7 @@ MULTI_CASES = [
     ((64, 70, 3), 0, 2, 50),    # k-major, 3 rows, K = 4480
     ((9, 7, 5), 0, 3, 2),       # everything contracted: a single row
     ((256, 6, 5, 3), 1, 2, 4), ((128, 30, 40), 1, 2, 50), ((10, 12, 130, 3), 0, 2, 50),  # TMA-eligible fused cases
-    ((640, 4, 5, 6), 1, 3, 10),
+    ((640, 4, 5, 6), 1, 3, 10), ((128, 9, 11), 1, 2, 26), ((12, 14, 140), 0, 2, 11), ((256, 5, 4, 3), 1, 3, 43),
 ]
 
 

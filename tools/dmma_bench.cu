@@ -40,6 +40,45 @@ __global__ void __launch_bounds__(1024) dfma_kernel(double* out, int iters, doub
   out[blockIdx.x*blockDim.x+threadIdx.x]=s;
 }
 
+
+// DMMA and DFMA interleaved: do they share one FP64 pipe?  NM DMMA + NF DFMA per iteration, independent accumulators.
+template<int NM, int NF>
+__global__ void __launch_bounds__(1024) mixed_kernel(double* out, int iters, double av, double bv){
+  double c[NM][2]; double f[NF > 0 ? NF : 1];
+  #pragma unroll
+  for(int i=0;i<NM;i++){c[i][0]=0;c[i][1]=0;}
+  #pragma unroll
+  for(int i=0;i<NF;i++) f[i]=i;
+  double a=av+threadIdx.x*1e-9, b=bv;
+  for(int it=0; it<iters; ++it){
+    #pragma unroll
+    for(int i=0;i<NM;i++){
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                   : "+d"(c[i][0]),"+d"(c[i][1]) : "d"(a),"d"(b));
+      #pragma unroll
+      for(int j=0;j<NF/NM;j++) asm volatile("fma.rn.f64 %0, %1, %0, %2;" : "+d"(f[i*(NF/NM)+j]) : "d"(a),"d"(b));
+    }
+  }
+  double s=0;
+  #pragma unroll
+  for(int i=0;i<NM;i++) s+=c[i][0]+c[i][1];
+  #pragma unroll
+  for(int i=0;i<NF;i++) s+=f[i];
+  out[blockIdx.x*blockDim.x+threadIdx.x]=s;
+}
+template<int NM,int NF>
+void run_mixed(double* out,int sms,cudaEvent_t e0,cudaEvent_t e1){
+  const int iters=20000, threads=128, bps=2;
+  mixed_kernel<NM,NF><<<sms*bps,threads>>>(out,100,0.999,1e-3);
+  CK(cudaDeviceSynchronize());
+  CK(cudaEventRecord(e0));
+  mixed_kernel<NM,NF><<<sms*bps,threads>>>(out,iters,0.999,1e-3);
+  CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
+  float ms; CK(cudaEventElapsedTime(&ms,e0,e1));
+  double fm=2.0*8*8*4*NM*(double)iters*(threads/32)*sms*bps, ff=2.0*NF*(double)iters*threads*sms*bps;
+  printf("mixed NM=%d DMMA + NF=%d DFMA per iter: %.3f ms  DMMA-only-equivalent %.2f TF/s, total %.2f TF/s\n",NM,NF,ms,fm/ms*1e-9,(fm+ff)/ms*1e-9);
+}
+
 int main(){
   int dev=0; CK(cudaSetDevice(dev));
   cudaDeviceProp p; CK(cudaGetDeviceProperties(&p,dev));
@@ -76,6 +115,7 @@ int main(){
       printf("DFMA       nacc=16 threads=%4d blocks/SM=%d : %.2f TFLOP/s (%.3f ms)\n",threads,bps,flops/ms*1e-9,ms);
     }
   }
+  run_mixed<8,0>(out,sms,e0,e1); run_mixed<8,8>(out,sms,e0,e1); run_mixed<8,16>(out,sms,e0,e1); run_mixed<8,32>(out,sms,e0,e1); run_mixed<8,64>(out,sms,e0,e1);
   // latency of a dependent DMMA chain (1 warp)
   CK(cudaEventRecord(e0));
   dmma_kernel<1><<<1,32>>>(out,200000,1.0,1e-3);
