@@ -5,11 +5,12 @@
 // B is one factor (ppx_ttm_first, Tucker ppx_ttm) or the Khatri-Rao rows of several adjacent factors
 // (ppx_ttm_multi).  Same math and same DMMA (mma.sync m8n8k4 f64) consumer layout as k1_ttm_first.cu; what changes is
 // how the operands reach shared memory:
-//   * ONE elected thread per CTA issues cp.async.bulk.tensor (TMA) loads of V straight from a CUtensorMap and one
-//     cp.async.bulk copy of the pre-packed B slab per stage; completion is signalled on a per-stage "full" mbarrier
-//     (complete_tx), the warps hand a stage back through an "empty" mbarrier -- no __syncthreads in the main loop and
-//     no per-thread load/address instructions.  (A separate producer warp was tried first: a fifth warp puts three
-//     warps on one SM sub-partition and caps the kernel at 168 registers, which spills the 56-double accumulator.)
+//   * one elected thread issues cp.async.bulk.tensor (TMA) loads of V straight from a CUtensorMap and one
+//     cp.async.bulk copy of the pre-packed B slab per stage (the duty rotates over the four warps, chunk by chunk);
+//     completion is signalled on a per-stage "full" mbarrier (complete_tx), the warps hand a stage back through an
+//     "empty" mbarrier -- no __syncthreads in the main loop and no per-thread load/address instructions.  (A separate
+//     producer warp was tried first: a fifth warp puts three warps on one SM sub-partition and caps the kernel at 168
+//     registers, which spills the accumulators.)
 //   * the V tile is stored dense with the hardware 128-byte swizzle; the k index each lane takes in an MMA step is
 //     permuted so that every DMMA fragment load is bank-conflict free on the swizzled tile;
 //   * B is packed once per call (krp_pack_kernel) into per-chunk slabs [chunk][8*NT + TAIL columns][20] with the same k
@@ -27,7 +28,7 @@ constexpr int TBM = 128;          // rows per tile
 constexpr int TBK = 16;           // depth per stage
 constexpr int TLDW = 20;          // padded leading dimension of the packed B slab (20 mod 16 == 4: conflict free)
 constexpr int TSTAGES = 4;
-constexpr int TCONSUMERS = 128;   // 4 warps, all of them consume; lane 0 of warp 0 also issues the TMA loads
+constexpr int TCONSUMERS = 128;   // 4 warps, all of them consume; they take turns issuing the TMA loads
 constexpr int TTHREADS = 128;
 constexpr int A_STAGE_BYTES = TBM * TBK * 8;  // 16 KB
 
@@ -161,7 +162,8 @@ __global__ void __launch_bounds__(TTHREADS, 2) ttm_tma_kernel(const __grid_const
   constexpr int NCOLS = 8 * NT + TAIL;
   constexpr int W_STAGE_BYTES = NCOLS * TLDW * 8;
   // 1024-byte aligned base (the 128-byte swizzle pattern is a function of the shared address)
-  uint8_t *base = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  // (offset arithmetic on the __shared__ array keeps the address space: LDS, not generic LD)
+  uint8_t *base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t *A_base = base;
   uint8_t *W_base = base + TSTAGES * A_STAGE_BYTES;
   uint64_t *full = (uint64_t *)(W_base + TSTAGES * W_STAGE_BYTES);
@@ -211,12 +213,28 @@ __global__ void __launch_bounds__(TTHREADS, 2) ttm_tma_kernel(const __grid_const
     }
   }
 
-  // ---- producer duty (lane 0 of warp 0): issue the loads of chunk `n` of this CTA's flat chunk stream ---------------
+  // ---- producer duty, rotated over the warps: chunk n of this CTA's flat chunk stream is issued by lane 0 of warp
+  // n % 4 (one producer warp would make its scheduler partition -- shared with the producer warp of the SM's other
+  // CTA -- the slowest of the four, and every other warp waits for the data it issues).  Each warp tracks the
+  // position (unit, chunk inside the unit) of the chunk it issues next.
   Unit ld;
   set_unit(ld, blockIdx.x);
-  int ld_kc = 0;
+  int ld_kc = 0, ld_n = 0;  // ld/ld_kc describe chunk ld_n
   auto issue_chunk = [&](int n) {
-    while (ld.count == 0) set_unit(ld, ld.u + gridDim.x);
+    int d = n - ld_n;
+    ld_n = n;
+    while (true) {
+      while (ld.count == 0) set_unit(ld, ld.u + gridDim.x);
+      const int rem = ld.count - ld_kc;
+      if (d < rem) {
+        ld_kc += d;
+        break;
+      }
+      d -= rem;
+      ld_kc = 0;
+      set_unit(ld, ld.u + gridDim.x);
+    }
+    if (lane != 0) return;
     const int stage = n % TSTAGES;
     const int round = n / TSTAGES;
     if (round > 0) mbar_wait(&empty[stage], (round - 1) & 1);  // every warp has released the stage
@@ -236,15 +254,12 @@ __global__ void __launch_bounds__(TTHREADS, 2) ttm_tma_kernel(const __grid_const
       }
     }
     bulk_load(W_base + stage * W_STAGE_BYTES, p.Wpp + (int64_t)chunk * (NCOLS * TLDW), W_STAGE_BYTES, &full[stage]);
-    if (++ld_kc == ld.count) {
-      ld_kc = 0;
-      set_unit(ld, ld.u + gridDim.x);
-    }
   };
-  const bool producer = (tid == 0);
-  if (producer) {
-    for (int n = 0; n < TSTAGES - 1 && n < total; n++) issue_chunk(n);
-  }
+  // (measured at order-4 s=300 R=50: rotation gains 3 % for the M-major layout, whose issue path is longer, and
+  // loses 3 % for the k-major one, so that one keeps warp 0 as its only producer)
+  constexpr int ROT = KMAJOR ? 0 : 3;
+  for (int n = 0; n < TSTAGES - 1 && n < total; n++)
+    if (warp == (n & ROT)) issue_chunk(n);
 
   // ===================================== consumer warps =====================================
   const int g = lane >> 2, t4 = lane & 3;
@@ -315,7 +330,7 @@ __global__ void __launch_bounds__(TTHREADS, 2) ttm_tma_kernel(const __grid_const
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[stage]);  // this warp is done reading the stage
-    if (producer && c + TSTAGES - 1 < total) issue_chunk(c + TSTAGES - 1);  // refills the stage of chunk c-1
+    if (warp == ((c + TSTAGES - 1) & ROT) && c + TSTAGES - 1 < total) issue_chunk(c + TSTAGES - 1);  // stage of c-1
     __syncwarp();
     if (++kc == cu.count) {
       const int tile = cu.tile, split = cu.split;

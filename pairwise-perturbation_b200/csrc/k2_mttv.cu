@@ -152,102 +152,125 @@ struct PpArgs {
   int n_ops;
 };
 
-constexpr int PP_WY = 16;  // warps per CTA
-constexpr int PP_B = 10;   // loads in flight per thread and batch
-__global__ void __launch_bounds__(32 * PP_WY) pp_correct_kernel(const double *__restrict__ M0, PpArgs a,
-                                                                int64_t s_i, int R, double *__restrict__ Mout) {
-  // At PP-operator sizes (tens of MB) the kernel is latency bound: every thread keeps PP_B independent loads in
-  // flight and the next batch is issued before the current one is consumed.
+// One CTA per (32 rows of M, rank column r); 8 warps; up to 4 CTAs per SM, so the whole grid (500 CTAs at s = 300,
+// R = 50) is resident at once and every thread keeps PP_B 16-byte loads in flight: at PP-operator sizes (3 x 36 MB per
+// mode) the kernel lives or dies by memory-level parallelism, not by instruction count.
+//   which == 1, op[i', q, r] (rows contiguous along i'): lanes along i', warps (and half-warps when VEC == 2) split q;
+//   which == 0, op[q, i', r] (contiguous along q): one warp per row i', lanes along q.
+// VEC == 2 needs even s_i / s_j and 16-byte aligned operators (checked by the launcher per call).
+constexpr int PP_WY = 8;  // warps per CTA
+constexpr int PP_B = 8;   // loads in flight per thread and batch
+template <int VEC>
+__global__ void __launch_bounds__(32 * PP_WY, 4) pp_correct_kernel(const double *__restrict__ M0, PpArgs a,
+                                                                   int64_t s_i, int R, double *__restrict__ Mout) {
   __shared__ double part[PP_WY][32];  // which==1 partial sums (per warp, per row)
-  __shared__ double dots[32];         // which==0 sums (per row)
-  const int lane = threadIdx.x, wy = threadIdx.y;
+  __shared__ double dots[32];         // which==0 sums (per row; row rr is owned by warp rr % PP_WY)
+  const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;
   const int64_t i0 = (int64_t)blockIdx.x * 32;
   const int r = blockIdx.y;
-  const int64_t i = i0 + lane;
-  if (wy == 0) dots[lane] = 0.0;
-  __syncthreads();
-  double acc = 0.0;
+  const int lrow = VEC == 2 ? 2 * (lane & 15) : lane;  // which==1: first row owned by this lane
+  const int qlane = VEC == 2 ? (lane >> 4) : 0;        // which==1, VEC==2: the two half-warps take alternate q
+  double acc[VEC];
+#pragma unroll
+  for (int v = 0; v < VEC; v++) acc[v] = 0.0;
+  double dsum[32 / PP_WY];
+#pragma unroll
+  for (int k = 0; k < 32 / PP_WY; k++) dsum[k] = 0.0;
+
   for (int j = 0; j < a.n_ops; j++) {
     const int64_t sj = a.sj[j];
     const double *dw = a.dw[j] + sj * r;
     if (a.which[j]) {
-      // op[i', q, r]: rows contiguous along i' -> lanes along i', warps split q
-      if (i < s_i) {
-        const double *pp = a.op[j] + i + s_i * sj * (int64_t)r;
-        double cur[PP_B], nxt[PP_B];
+      if (i0 + lrow < s_i) {
+        const double *pp = a.op[j] + i0 + lrow + s_i * sj * (int64_t)r;
+        constexpr int QSTEP = PP_WY * VEC;
+        for (int64_t q0 = wy * VEC + qlane; q0 < sj; q0 += PP_B * QSTEP) {
+          double v[PP_B][VEC];
 #pragma unroll
-        for (int u = 0; u < PP_B; u++) {
-          const int64_t q = wy + (int64_t)u * PP_WY;
-          cur[u] = q < sj ? pp[s_i * q] : 0.0;
-        }
-        for (int64_t q0 = wy; q0 < sj; q0 += PP_B * PP_WY) {
-          const int64_t q1 = q0 + PP_B * PP_WY;
-          if (q1 < sj) {
+          for (int u = 0; u < PP_B; u++) {
+            const int64_t q = q0 + u * QSTEP;
+            if (q < sj) {
+              if (VEC == 2) {
+                const double2 t = *reinterpret_cast<const double2 *>(pp + s_i * q);
+                v[u][0] = t.x;
+                v[u][VEC - 1] = t.y;
+              } else {
+                v[u][0] = pp[s_i * q];
+              }
+            } else {
 #pragma unroll
-            for (int u = 0; u < PP_B; u++) {
-              const int64_t q = q1 + (int64_t)u * PP_WY;
-              nxt[u] = q < sj ? pp[s_i * q] : 0.0;
+              for (int e = 0; e < VEC; e++) v[u][e] = 0.0;
             }
           }
-          double a0 = 0.0, a1 = 0.0;
 #pragma unroll
-          for (int u = 0; u < PP_B; u += 2) {
-            const int64_t qa = q0 + (int64_t)u * PP_WY, qb = qa + PP_WY;
-            a0 += cur[u] * (qa < sj ? dw[qa] : 0.0);
-            a1 += cur[u + 1] * (qb < sj ? dw[qb] : 0.0);
+          for (int u = 0; u < PP_B; u++) {
+            const int64_t q = q0 + u * QSTEP;
+            const double w = q < sj ? dw[q] : 0.0;
+#pragma unroll
+            for (int e = 0; e < VEC; e++) acc[e] = fma(v[u][e], w, acc[e]);
           }
-          acc += a0 + a1;
-#pragma unroll
-          for (int u = 0; u < PP_B; u++) cur[u] = nxt[u];
         }
       }
     } else {
-      // op[q, i', r]: contiguous along q -> one warp per row i', lanes along q
-      for (int rr = wy; rr < 32; rr += PP_WY) {
-        const int64_t ii = i0 + rr;
+#pragma unroll
+      for (int k = 0; k < 32 / PP_WY; k++) {
+        const int64_t ii = i0 + wy + PP_WY * k;
         double d = 0.0;
         if (ii < s_i) {
           const double *pp = a.op[j] + sj * (ii + s_i * (int64_t)r);
-          double cur[PP_B], nxt[PP_B];
+          for (int64_t q0 = lane * VEC; q0 < sj; q0 += 32 * VEC * PP_B) {
+            double v[PP_B][VEC];
 #pragma unroll
-          for (int u = 0; u < PP_B; u++) {
-            const int64_t q = lane + 32 * (int64_t)u;
-            cur[u] = q < sj ? pp[q] : 0.0;
-          }
-          for (int64_t q0 = lane; q0 < sj; q0 += 32 * PP_B) {
-            const int64_t q1 = q0 + 32 * PP_B;
-            if (q1 < sj) {
+            for (int u = 0; u < PP_B; u++) {
+              const int64_t q = q0 + 32 * VEC * u;
+              if (q < sj) {
+                if (VEC == 2) {
+                  const double2 t = *reinterpret_cast<const double2 *>(pp + q);
+                  v[u][0] = t.x;
+                  v[u][VEC - 1] = t.y;
+                } else {
+                  v[u][0] = pp[q];
+                }
+              } else {
 #pragma unroll
-              for (int u = 0; u < PP_B; u++) {
-                const int64_t q = q1 + 32 * (int64_t)u;
-                nxt[u] = q < sj ? pp[q] : 0.0;
+                for (int e = 0; e < VEC; e++) v[u][e] = 0.0;
               }
             }
-            double a0 = 0.0, a1 = 0.0;
 #pragma unroll
-            for (int u = 0; u < PP_B; u += 2) {
-              const int64_t qa = q0 + 32 * (int64_t)u, qb = qa + 32;
-              a0 += cur[u] * (qa < sj ? dw[qa] : 0.0);
-              a1 += cur[u + 1] * (qb < sj ? dw[qb] : 0.0);
+            for (int u = 0; u < PP_B; u++) {
+              const int64_t q = q0 + 32 * VEC * u;
+              if (q < sj) {
+#pragma unroll
+                for (int e = 0; e < VEC; e++) d = fma(v[u][e], dw[q + e], d);
+              }
             }
-            d += a0 + a1;
-#pragma unroll
-            for (int u = 0; u < PP_B; u++) cur[u] = nxt[u];
           }
         }
-        d = ppx_warp_sum(d);
-        if (lane == 0) dots[rr] += d;  // rows rr are owned by warp rr % PP_WY: no race, fixed order over j
+        dsum[k] += ppx_warp_sum(d);
       }
     }
   }
-  part[wy][lane] = acc;
+  if (VEC == 2) {
+#pragma unroll
+    for (int e = 0; e < VEC; e++) acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 16);
+    if (lane < 16) {
+#pragma unroll
+      for (int e = 0; e < VEC; e++) part[wy][lrow + e] = acc[e];
+    }
+  } else {
+    part[wy][lane] = acc[0];
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < 32 / PP_WY; k++) dots[wy + PP_WY * k] = dsum[k];
+  }
   __syncthreads();
-  if (wy == 0 && i < s_i) {
-    double s = M0[i + s_i * r];
+  if (wy == 0 && i0 + lane < s_i) {
+    double s = M0[i0 + lane + s_i * r];
 #pragma unroll
     for (int y = 0; y < PP_WY; y++) s += part[y][lane];
     s += dots[lane];
-    Mout[i + s_i * r] = s;
+    Mout[i0 + lane + s_i * r] = s;
   }
 }
 
@@ -335,8 +358,15 @@ int ppx_pp_correct(ppx_ctx *ctx, const double *M0, const double *const *ops, con
     a.sj[j] = s_other[j];
     a.which[j] = which[j];
   }
-  dim3 grid(ppx_cdiv(s_i, 32), R), block(32, PP_WY);
-  pp_correct_kernel<<<grid, block, 0, ctx->stream>>>(M0, a, s_i, R, M_out);
+  // 16-byte loads when every operator slab and dW column stays 16-byte aligned
+  bool vec = (s_i % 2 == 0);
+  for (int j = 0; j < n_ops && vec; j++)
+    vec = (s_other[j] % 2 == 0) && ((((uintptr_t)ops[j]) | ((uintptr_t)dW[j])) & 15) == 0;
+  dim3 grid(ppx_cdiv(s_i, 32), R), block(32 * PP_WY);
+  if (vec)
+    pp_correct_kernel<2><<<grid, block, 0, ctx->stream>>>(M0, a, s_i, R, M_out);
+  else
+    pp_correct_kernel<1><<<grid, block, 0, ctx->stream>>>(M0, a, s_i, R, M_out);
   PPX_CHECK_LAUNCH(ctx);
   return PPX_OK;
 }
