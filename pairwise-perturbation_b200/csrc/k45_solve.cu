@@ -4,7 +4,7 @@
 //       dW = ratio*(W - W_init)   (common.cxx:710-758; als_CP.cxx:296,582,811-812)
 // K6 -- Normalize (common.cxx:680-688)
 //
-// The R x R inverse is formed once by ONE CTA (Cholesky: S = L L^T, S^-1 = L^-T L^-1; or, for the reference's
+// The R x R inverse is formed once by ONE CTA (square-root-free Cholesky: S = L D L^T, S^-1 = L^-T D^-1 L^-1; or, for the reference's
 // SVD_solve semantics, a cyclic Jacobi eigen-decomposition S = Q diag(e) Q^T, S^-1 = Q diag(1/e) Q^T with no
 // truncation, common.cxx:720-722), then applied to the s x R right-hand side by a grid of 8-row tiles.  The
 // Hadamard product of the cached Grams is fused into the inverse kernel (ppx_solve_update_g), so one mode update of
@@ -60,116 +60,171 @@ __global__ void hadamard_kernel(HadArgs h, int R, double lambda, double *__restr
   S[idx] = hadamard_at(h, idx, R, lambda);
 }
 
-// ---- R x R inverse by Cholesky, one CTA of 16 x 16 threads, matrix in registers -----------------------------------
+// ---- R x R SPD inverse, one CTA of 16 x 16 threads, matrix in registers -------------------------------------------
 // S is the Hadamard product of h.n matrices (+ lambda I); it is written to S_out (the apply kernel needs it for the
-// gradient) and inverted.  Thread (tx, ty) owns the elements (i, j) with i = ty (mod 16), j = tx (mod 16) of S and of
-// Y (initially I) in REGISTERS (T x T each, T = ceil(R/16)).  Step k of the right-looking Cholesky S = L L^T needs
-// only column k of the partially updated S and, to carry L^-1 along, row k of Y: their owners publish them through
-// double-buffered shared vectors, so there is ONE barrier per column and nothing else touches shared memory:
-//      l_ik = s_ik / sqrt(s_kk)  (one rsqrt, no divide),   s_ij -= l_ik l_jk,
-//      y_k: = y_k: / l_kk,   y_i: -= l_ik y_k:   (i > k)            =>  after R steps  Y = L^-1.
-// Finally S^-1 = Y^T Y.
-// B = edge of the thread grid (16 -> 256 threads, T <= 7; 32 -> 1024 threads, T <= 2: with more warps the
-// per-column critical path -- barrier, rsqrt, a handful of dependent FP64 operations -- is issue bound, not latency bound)
-template <int T, int B>
-__global__ void __launch_bounds__(B * B) spd_inverse_chol_kernel(HadArgs h, int R, double lambda,
+// gradient) and inverted through the square-root-free Cholesky factorisation S = L D L^T (L unit lower triangular):
+//      S^-1 = Y^T D^-1 Y = sum_k (1/d_k) y_k^T y_k,   Y = L^-1,  y_k = row k of Y.
+// Thread (tx, ty) owns the elements (i, j), i = ty (mod 16), j = tx (mod 16), of a T x T register tile Z that holds
+// the partially factorised S in its columns j > k and the rows of Y built so far in the columns j <= k (every position
+// is touched by exactly one of the two updates, so they share storage), and of a second tile that accumulates S^-1:
+//      step k:  p_j = z_jk (j > k, column k of S),  p_j = z_kj (j < k, row k of Y),  p_k = 1,  t_i = p_i / d_k,
+//               rows i >  k:  z_ij   -= t_i p_j            (column k was zeroed by its owners: z_ik = -t_i)
+//               rows i <= k:  inv_ij += t_i p_j  (j <= k)  (row k of Y is final: its term of S^-1)
+// The owners publish p through a double-buffered shared vector: ONE barrier per column.
+// The kernel is ONE CTA with two warps per scheduler: it runs at the latency of its dependent instruction stream
+// (measured with clock64 probes, tools/inv_bench.cu: about 5 cycles per instruction, 365 for an IEEE division), so
+//   * tile indices are compile-time (unrolled over the tile column kk, a real loop over the 16 columns inside it)
+//     and the update has no selects;
+//   * the reciprocal of the NEXT pivot is computed one step ahead, off the critical path: the owner of z_{k+1,k+1}
+//     publishes it (before the update) with column k, and every thread forms d_{k+1} = z_{k+1,k+1} - p_{k+1}^2 / d_k
+//     and its Newton reciprocal while the updates of step k are in flight;
+//   * S^-1 is accumulated inside the loop (the latency-bound loop has issue slots to spare) instead of a separate
+//     triangular product through shared memory.
+constexpr int INV_B = 16;
+
+// 1/d for the pivots of an SPD matrix: float seed + three Newton steps (full double precision); IEEE division outside
+// the float range.
+__device__ __forceinline__ double inv_pivot(double d) {
+  const float f = (float)d;
+  if (!(fabsf(f) > 1e-30f && fabsf(f) < 1e30f)) return 1.0 / d;
+  double x = (double)__fdividef(1.0f, f);
+  x = fma(x, fma(-d, x, 1.0), x);
+  x = fma(x, fma(-d, x, 1.0), x);
+  x = fma(x, fma(-d, x, 1.0), x);
+  return x;
+}
+
+template <int T>
+__global__ void __launch_bounds__(INV_B *INV_B) spd_inverse_ldl_kernel(HadArgs h, int R, double lambda,
                                                                        double *__restrict__ S_out,
                                                                        double *__restrict__ Sinv) {
+  constexpr int B = INV_B;
+  constexpr int NTH = B * B;
+  constexpr int RP = B * T;   // padded order
+  constexpr int PV = RP + 2;  // p_0..p_{RP-1}, slot RP: z_{k+1,k+1} before the update of step k
   extern __shared__ double sm[];
   const int ld = R + 1;
-  double *colraw = sm;            // [2][R]
-  double *rowraw = sm + 2 * R;    // [2][R]
-  double *Ys = sm + 4 * R;        // [R][ld]
+  double *pv = sm;            // [2][PV]
+  double *Ss = sm + 2 * PV;   // [R][ld] staging of S
   const int tx = threadIdx.x % B, ty = threadIdx.x / B;
-  double a[T][T], y[T][T];
+#ifdef PPX_INV_PROFILE
+#define PPX_PROF(slot) if (threadIdx.x == 0) g_prof[slot] = clock64()
+#else
+#define PPX_PROF(slot)
+#endif
+  PPX_PROF(0);
+  // S = Hadamard product (+ lambda I) -> S_out and, through shared memory, the registers; four independent elements
+  // per thread and pass keep the global loads of a pass in flight together
+  for (int e0 = threadIdx.x; e0 < R * R; e0 += 4 * NTH) {
+    double v[4];
 #pragma unroll
-  for (int ii = 0; ii < T; ii++)
+    for (int u = 0; u < 4; u++) {
+      const int e = e0 + u * NTH;
+      v[u] = e < R * R ? h.g[0][e] : 0.0;
+    }
+#pragma unroll 1
+    for (int m = 1; m < h.n; m++) {
+      const double *g = h.g[m];
 #pragma unroll
-    for (int jj = 0; jj < T; jj++) {
-      const int i = ty + B * ii, j = tx + B * jj;
-      double v = 0.0;
-      if (i < R && j < R) {
-        const int idx = i + R * j;
-        v = h.g[0][idx];
-        for (int m = 1; m < h.n; m++) v *= h.g[m][idx];
-        if (i == j) v += lambda;
-        if (S_out) S_out[idx] = v;
+      for (int u = 0; u < 4; u++) {
+        const int e = e0 + u * NTH;
+        if (e < R * R) v[u] *= g[e];
       }
-      a[ii][jj] = v;
-      y[ii][jj] = (i == j) ? 1.0 : 0.0;
     }
 #pragma unroll
-  for (int kk = 0; kk < T; kk++) {
-    for (int kt = 0; kt < B; kt++) {
-      const int k = B * kk + kt;
-      if (k >= R) break;
-      double *cr = colraw + (k & 1) * R, *rr = rowraw + (k & 1) * R;
-      if (tx == kt) {  // owners of column k of S
-#pragma unroll
-        for (int ii = 0; ii < T; ii++) {
-          const int i = ty + B * ii;
-          if (i >= k && i < R) cr[i] = a[ii][kk];
-        }
-      }
-      if (ty == kt) {  // owners of row k of Y
-#pragma unroll
-        for (int jj = 0; jj < T; jj++) {
-          const int j = tx + B * jj;
-          if (j <= k) rr[j] = y[kk][jj];
-        }
-      }
-      __syncthreads();
-      const double rs = rsqrt(cr[k]);
-      double ci[T], cj[T], yk[T];
-#pragma unroll
-      for (int ii = 0; ii < T; ii++) {
-        const int i = ty + B * ii;
-        ci[ii] = (i > k && i < R) ? cr[i] * rs : 0.0;
-      }
-#pragma unroll
-      for (int jj = 0; jj < T; jj++) {
-        const int j = tx + B * jj;
-        cj[jj] = (j > k && j < R) ? cr[j] * rs : 0.0;
-        yk[jj] = (j <= k) ? rr[j] * rs : 0.0;
-      }
-#pragma unroll
-      for (int ii = 0; ii < T; ii++)
-#pragma unroll
-        for (int jj = 0; jj < T; jj++) {
-          a[ii][jj] -= ci[ii] * cj[jj];
-          y[ii][jj] -= ci[ii] * yk[jj];
-        }
-      if (ty == kt) {
-#pragma unroll
-        for (int jj = 0; jj < T; jj++) y[kk][jj] = yk[jj];  // row k of Y is final
+    for (int u = 0; u < 4; u++) {
+      const int e = e0 + u * NTH;
+      if (e < R * R) {
+        const int j = e / R, i = e - j * R;
+        if (i == j) v[u] += lambda;
+        if (S_out) S_out[e] = v[u];
+        Ss[i * ld + j] = v[u];
       }
     }
   }
-  // Y = L^-1 (lower triangular) -> shared, then S^-1 = Y^T Y
-#pragma unroll
-  for (int ii = 0; ii < T; ii++)
-#pragma unroll
-    for (int jj = 0; jj < T; jj++) {
-      const int i = ty + B * ii, j = tx + B * jj;
-      if (i < R && j < R) Ys[i * ld + j] = (j <= i) ? y[ii][jj] : 0.0;
-    }
   __syncthreads();
+  double z[T][T], acc[T][T];
 #pragma unroll
   for (int ii = 0; ii < T; ii++)
 #pragma unroll
     for (int jj = 0; jj < T; jj++) {
       const int i = ty + B * ii, j = tx + B * jj;
-      if (i < R && j < R) {
-        double v0 = 0.0, v1 = 0.0;
-        int k = (i > j ? i : j);
-        for (; k + 1 < R; k += 2) {
-          v0 += Ys[k * ld + i] * Ys[k * ld + j];
-          v1 += Ys[(k + 1) * ld + i] * Ys[(k + 1) * ld + j];
-        }
-        if (k < R) v0 += Ys[k * ld + i] * Ys[k * ld + j];
-        Sinv[i + R * j] = v0 + v1;
-      }
+      // identity padding keeps the factorisation of the padded matrix trivial
+      z[ii][jj] = (i < R && j < R) ? Ss[i * ld + j] : ((i == j) ? 1.0 : 0.0);
+      acc[ii][jj] = 0.0;
     }
+  double inv = inv_pivot(Ss[0]);  // 1 / d_0
+  PPX_PROF(1);
+#pragma unroll
+  for (int kk = 0; kk < T; kk++) {
+#pragma unroll 1
+    for (int kt = 0; kt < B; kt++) {
+      const int k = B * kk + kt;
+      if (k >= R) break;
+      double *p = pv + (k & 1) * PV;
+      if (tx == kt) {  // owners of column k: p_i = z_ik (i > k); the column is cleared for Y; p_k = 1
+#pragma unroll
+        for (int ii = 0; ii < T; ii++) {
+          const int i = ty + B * ii;
+          if (i > k) {
+            p[i] = z[ii][kk];
+            z[ii][kk] = 0.0;
+          } else if (i == k) {
+            p[i] = 1.0;
+          }
+        }
+      }
+      if (ty == kt) {  // owners of row k: p_j = z_kj for j < k
+#pragma unroll
+        for (int jj = 0; jj < T; jj++) {
+          const int j = tx + B * jj;
+          if (j < k) p[j] = z[kk][jj];
+        }
+      }
+      if (tx == ty) {  // owner of the next diagonal element
+        if (kt + 1 < B) {
+          if (tx == kt + 1) p[RP] = z[kk][kk];
+        } else if (kk + 1 < T) {
+          if (tx == 0) p[RP] = z[kk + 1 < T ? kk + 1 : kk][kk + 1 < T ? kk + 1 : kk];
+        }
+      }
+      __syncthreads();
+      double t[T], pj[T], pjy[T];
+#pragma unroll
+      for (int ii = 0; ii < T; ii++) t[ii] = p[ty + B * ii] * inv;
+#pragma unroll
+      for (int jj = 0; jj < T; jj++) {
+        pj[jj] = p[tx + B * jj];
+        pjy[jj] = (tx + B * jj <= k) ? pj[jj] : 0.0;
+      }
+      // next pivot and its reciprocal (used in the next step)
+      double inv_next = 0.0;
+      if (k + 1 < R) {
+        const double pn = p[k + 1];
+        inv_next = inv_pivot(fma(-(pn * inv), pn, p[RP]));
+      }
+#pragma unroll
+      for (int ii = 0; ii < T; ii++) {
+        if (ty + B * ii > k) {
+#pragma unroll
+          for (int jj = 0; jj < T; jj++) z[ii][jj] = fma(-t[ii], pj[jj], z[ii][jj]);
+        } else {
+#pragma unroll
+          for (int jj = 0; jj < T; jj++) acc[ii][jj] = fma(t[ii], pjy[jj], acc[ii][jj]);
+        }
+      }
+      inv = inv_next;
+    }
+  }
+  PPX_PROF(2);
+#pragma unroll
+  for (int ii = 0; ii < T; ii++)
+#pragma unroll
+    for (int jj = 0; jj < T; jj++) {
+      const int i = ty + B * ii, j = tx + B * jj;
+      if (i < R && j < R) Sinv[i + R * j] = acc[ii][jj];
+    }
+  PPX_PROF(4);
 }
 
 // Cyclic Jacobi (parallel round-robin ordering) on a symmetric matrix in shared memory.
@@ -328,33 +383,40 @@ __global__ void __launch_bounds__(32 * AP_ROWS) solve_apply_kernel(const double 
   const int lane = threadIdx.x, row = threadIdx.y;
   const int tid = row * 32 + lane, nt = 32 * AP_ROWS;
   const int64_t i = (int64_t)blockIdx.x * AP_ROWS + row;
+  // (compact loops: the kernel runs once per launch on cold instruction caches, code size is latency)
+#pragma unroll 1
   for (int idx = tid; idx < R * R; idx += nt) {
     Ss[idx] = grad_out ? S[idx] : 0.0;
     Si[idx] = Sinv[idx];
   }
+#pragma unroll 1
   for (int r = lane; r < R; r += 32) {
     Mt[row * R + r] = (i < s) ? M[i + s * r] : 0.0;
     Wt[row * R + r] = (i < s) ? W[i + s * r] : 0.0;
   }
   __syncthreads();
   if (i >= s) return;
+  const double *mrow = Mt + row * R, *wrow = Wt + row * R;
+#pragma unroll 1
   for (int c = lane; c < R; c += 32) {
+    // S and S^-1 are symmetric: column c is read as row c, contiguous across the lanes (no bank conflicts)
     double w0 = 0.0, w1 = 0.0, g0 = 0.0, g1 = 0.0;
     int r = 0;
+#pragma unroll 1
     for (; r + 1 < R; r += 2) {
-      w0 += Mt[row * R + r] * Si[r + R * c];
-      w1 += Mt[row * R + r + 1] * Si[r + 1 + R * c];
-      g0 += Wt[row * R + r] * Ss[r + R * c];
-      g1 += Wt[row * R + r + 1] * Ss[r + 1 + R * c];
+      w0 = fma(mrow[r], Si[c + R * r], w0);
+      w1 = fma(mrow[r + 1], Si[c + R * (r + 1)], w1);
+      g0 = fma(wrow[r], Ss[c + R * r], g0);
+      g1 = fma(wrow[r + 1], Ss[c + R * (r + 1)], g1);
     }
     if (r < R) {
-      w0 += Mt[row * R + r] * Si[r + R * c];
-      g0 += Wt[row * R + r] * Ss[r + R * c];
+      w0 = fma(mrow[r], Si[c + R * r], w0);
+      g0 = fma(wrow[r], Ss[c + R * r], g0);
     }
     double w = w0 + w1;
     const double g = g0 + g1;
     const int64_t o = i + s * c;
-    if (grad_out) grad_out[o] = -Mt[row * R + c] + g;
+    if (grad_out) grad_out[o] = -mrow[c] + g;
     if (W_init) {
       const double wi = W_init[o];
       const double d = ratio_step * (w - wi);
@@ -459,15 +521,19 @@ __global__ void __launch_bounds__(1024) normalize_norms_kernel(NormNormsArgs a, 
 int inverse_launch(ppx_ctx *ctx, const HadArgs &h, int R, double lambda, int mode, double *S_out, double *Sinv) {
   if (mode == PPX_SOLVE_CHOL) {
     if (R > 112) return ppx_set_err(ctx, PPX_EUNSUPPORTED, "solve: R=%d too large for the one-CTA inverse (max 112)", R);
-    const size_t smem = sizeof(double) * (4 * (size_t)R + (size_t)R * (R + 1));
-#define PPX_INV_LAUNCH(T, B) \
-  spd_inverse_chol_kernel<T, B><<<1, B * B, smem, ctx->stream>>>(h, R, lambda, S_out, Sinv)
-    if (R <= 16) PPX_INV_LAUNCH(1, 16);
-    else if (R <= 32) PPX_INV_LAUNCH(1, 32);
-    else if (R <= 64) PPX_INV_LAUNCH(2, 32);
-    else if (R <= 80) PPX_INV_LAUNCH(5, 16);
-    else if (R <= 96) PPX_INV_LAUNCH(6, 16);
-    else PPX_INV_LAUNCH(7, 16);
+    const int T = (R + INV_B - 1) / INV_B;
+    const size_t smem = sizeof(double) * (2 * ((size_t)INV_B * T + 2) + (size_t)R * (R + 1));
+#define PPX_INV_LAUNCH(T) \
+  spd_inverse_ldl_kernel<T><<<1, INV_B * INV_B, smem, ctx->stream>>>(h, R, lambda, S_out, Sinv)
+    switch (T) {
+      case 1: PPX_INV_LAUNCH(1); break;
+      case 2: PPX_INV_LAUNCH(2); break;
+      case 3: PPX_INV_LAUNCH(3); break;
+      case 4: PPX_INV_LAUNCH(4); break;
+      case 5: PPX_INV_LAUNCH(5); break;
+      case 6: PPX_INV_LAUNCH(6); break;
+      default: PPX_INV_LAUNCH(7); break;
+    }
 #undef PPX_INV_LAUNCH
   } else {
     const int n = (R + 1) & ~1;
@@ -509,9 +575,10 @@ int solve_impl(ppx_ctx *ctx, const double *M, const HadArgs &h, double lambda, c
 
 int ppx_k45_init(ppx_ctx *ctx) {
   const int big = 220 * 1024;
-  PPX_CUDA(ctx, cudaFuncSetAttribute(spd_inverse_chol_kernel<5, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-  PPX_CUDA(ctx, cudaFuncSetAttribute(spd_inverse_chol_kernel<6, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-  PPX_CUDA(ctx, cudaFuncSetAttribute(spd_inverse_chol_kernel<7, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  PPX_CUDA(ctx, cudaFuncSetAttribute(spd_inverse_ldl_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  PPX_CUDA(ctx, cudaFuncSetAttribute(spd_inverse_ldl_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  PPX_CUDA(ctx, cudaFuncSetAttribute(spd_inverse_ldl_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  PPX_CUDA(ctx, cudaFuncSetAttribute(spd_inverse_ldl_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   PPX_CUDA(ctx, cudaFuncSetAttribute(sym_inverse_jacobi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   PPX_CUDA(ctx, cudaFuncSetAttribute(solve_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   return PPX_OK;
