@@ -189,6 +189,12 @@ int ppx_unfold_gram(ppx_ctx *ctx, const double *T, const int64_t *lens, int k, i
  * order -- what MTM.svd(U,S,VT,r) returns for such a matrix (als_Tucker.cxx:20,402,627,868).  MTM is destroyed.
  * evals_out (device, r doubles) may be NULL. */
 int ppx_sym_eig_topk(ppx_ctx *ctx, double *MTM, int64_t s, int r, double *U, double *evals_out);
+/* Same, warm started: `basis` (device, s x s, column-major) is an orthogonal matrix the iteration starts from when
+ * basis_valid != 0 -- typically the eigenvectors this call left there for the same mode one HOOI sweep earlier -- and
+ * receives ALL s eigenvectors on return.  Any orthogonal start gives the same result up to rounding; a close one
+ * leaves a few Jacobi sweeps instead of a dozen.  basis may be NULL (cold start, nothing stored). */
+int ppx_sym_eig_topk_warm(ppx_ctx *ctx, double *MTM, int64_t s, int r, double *U, double *evals_out, double *basis,
+                          int basis_valid);
 /* U <- U * diag(sign(diag(U^T Uref))), sign(b) = +1 if b > 0 else -1  (als_Tucker.cxx:632-643,874-885). */
 int ppx_sign_align(ppx_ctx *ctx, double *U, const double *Uref, int64_t s, int r);
 /* sq_out_dev[0] = sum of squares of (a - b), nothing else is written (Tucker residual, als_Tucker.cxx:309-310). */

@@ -86,6 +86,7 @@ SIGNATURES = {
     "ppx_ttm_acc": (C.c_int, [_vp, _dp, C.POINTER(_i64), C.c_int, C.c_int, _dp, _i64, C.c_int, _dp]),
     "ppx_unfold_gram": (C.c_int, [_vp, _dp, C.POINTER(_i64), C.c_int, C.c_int, _dp]),
     "ppx_sym_eig_topk": (C.c_int, [_vp, _dp, _i64, C.c_int, _dp, _dp]),
+    "ppx_sym_eig_topk_warm": (C.c_int, [_vp, _dp, _i64, C.c_int, _dp, _dp, _dp, C.c_int]),
     "ppx_sign_align": (C.c_int, [_vp, _dp, _dp, _i64, C.c_int]),
     "ppx_diff_sqnorm": (C.c_int, [_vp, _dp, _dp, _i64, _dp]),
     "ppx_transpose": (C.c_int, [_vp, _dp, _i64, _i64, _dp]),
@@ -289,8 +290,12 @@ class Ctx:
     def unfold_gram(self, T, lens, i, MTM):
         self._ck(self.lib.ppx_unfold_gram(self.h, _ptr(T), _lens(lens), len(lens), i, _ptr(MTM)))
 
-    def sym_eig_topk(self, MTM, s, r, U, evals=None):
-        self._ck(self.lib.ppx_sym_eig_topk(self.h, _ptr(MTM), s, r, _ptr(U), _ptr(evals)))
+    def sym_eig_topk(self, MTM, s, r, U, evals=None, basis=None, basis_valid=False):
+        if basis is None:
+            self._ck(self.lib.ppx_sym_eig_topk(self.h, _ptr(MTM), s, r, _ptr(U), _ptr(evals)))
+        else:
+            self._ck(self.lib.ppx_sym_eig_topk_warm(self.h, _ptr(MTM), s, r, _ptr(U), _ptr(evals), _ptr(basis),
+                                                    1 if basis_valid else 0))
 
     def sign_align(self, U, Uref, s, r):
         self._ck(self.lib.ppx_sign_align(self.h, _ptr(U), _ptr(Uref), s, r))

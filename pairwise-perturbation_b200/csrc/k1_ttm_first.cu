@@ -401,7 +401,7 @@ int ppx_k1_init(ppx_ctx *ctx) {
 // Shared by ppx_ttm_first (CP, rank last), ppx_ttm / ppx_ttm_acc (Tucker, rank in place of mode x) and ppx_ttm_multi.
 // Uses the context workspace for split-K partials (callers that hold workspace memory pass ws_keep = true).
 int ppx_ttm_impl(ppx_ctx *ctx, const double *V, int64_t L, int64_t X, int64_t Rt, const double *Wx, int64_t ldw,
-                 int R, double *out, int inplace, int accumulate, bool ws_keep, bool try_tma = true) {
+                 int R, double *out, int inplace, int accumulate, bool ws_keep, bool try_tma) {
   TtmParams p;
   p.V = V;
   p.W = Wx;
@@ -488,7 +488,7 @@ int ppx_ttm_first(ppx_ctx *ctx, const double *V, const int64_t *lens, int N, int
   PPX_REQUIRE(ctx, ldw >= lens[x], "ldw >= lens[x]");
   int64_t L, X, Rt;
   ppx_split3(lens, N, x, &L, &X, &Rt);
-  return ppx_ttm_impl(ctx, V, L, X, Rt, Wx, ldw, R, out, 0, 0, false);
+  return ppx_ttm_impl(ctx, V, L, X, Rt, Wx, ldw, R, out, 0, 0, false, true);
 }
 
 int ppx_ttm_multi(ppx_ctx *ctx, const double *V, const int64_t *lens, int N, int x_first, int n_modes,
@@ -537,7 +537,7 @@ int ppx_ttm(ppx_ctx *ctx, const double *T, const int64_t *lens, int k, int x, co
   PPX_REQUIRE(ctx, ldw >= lens[x], "ldw >= lens[x]");
   int64_t L, X, Rt;
   ppx_split3(lens, k, x, &L, &X, &Rt);
-  return ppx_ttm_impl(ctx, T, L, X, Rt, Wx, ldw, Q, out, 1, 0, false);
+  return ppx_ttm_impl(ctx, T, L, X, Rt, Wx, ldw, Q, out, 1, 0, false, true);
 }
 
 int ppx_ttm_acc(ppx_ctx *ctx, const double *T, const int64_t *lens, int k, int x, const double *Wx, int64_t ldw,
@@ -547,7 +547,7 @@ int ppx_ttm_acc(ppx_ctx *ctx, const double *T, const int64_t *lens, int k, int x
   PPX_REQUIRE(ctx, ldw >= lens[x], "ldw >= lens[x]");
   int64_t L, X, Rt;
   ppx_split3(lens, k, x, &L, &X, &Rt);
-  return ppx_ttm_impl(ctx, T, L, X, Rt, Wx, ldw, Q, out, 1, 1, false);
+  return ppx_ttm_impl(ctx, T, L, X, Rt, Wx, ldw, Q, out, 1, 1, false, true);
 }
 
 }  // extern "C"

@@ -92,136 +92,182 @@ __global__ void unfold_gram_reduce_kernel(const double *__restrict__ parts, int6
   MTM[idx] = s;
 }
 
-// ---- cooperative two-sided Jacobi in global memory (matrix is L2 resident) ----------------------------------------
-// A (n x n, symmetric, destroyed), Q (n x n) column-major, cs: 4*(n/2) doubles, flag: 2 doubles (off, diag norms)
-__global__ void __launch_bounds__(256) jacobi_global_kernel(double *__restrict__ A, double *__restrict__ Q,
-                                                            double *__restrict__ cs, double *__restrict__ norms,
-                                                            int n, int max_sweeps) {
+// ---- cooperative one-sided (Hestenes) Jacobi in global memory (matrix is L2 resident) -----------------------------
+// B = A (n x n symmetric positive semi-definite, column-major, destroyed).  Plane rotations of column pairs make the
+// columns mutually orthogonal: at convergence B = A V = V Lambda, i.e. column j is lambda_j v_j -- the eigenvalue is
+// its norm and the eigenvector its direction, so the rotations never have to be accumulated separately.
+// Every round of the round-robin ordering holds n/2 disjoint pairs: one CTA per pair, which reads its two columns
+// once, forms the three inner products, rotates and writes back; pairs of a round touch disjoint columns, so a round
+// needs ONE grid barrier (the two-sided variant this replaces needed five and also updated rows).  The iteration ends
+// when a whole sweep applied no rotation above the threshold.  (Writing the pair back larger-column-first, de Rijk's
+// sorting, was tried: with the round-robin ordering it DOUBLES the number of sweeps -- 20 instead of 11 at n = 128.)
+// Warm start: any orthogonal V0 is a valid start, B = A V0; with V0 = the eigenvectors of a nearby matrix (the same
+// mode in the previous HOOI sweep) the columns start almost orthogonal and few sweeps remain.  `Vout` (optional)
+// receives all n normalised columns for that purpose.
+// `count`: one int per sweep (zeroed by the launcher), rotations applied in that sweep (integer atomics: exact).
+constexpr int JT = 128;   // threads per CTA
+constexpr int JE = 8;     // column elements per thread held in registers per pass (n <= JT*JE in one pass)
+__global__ void __launch_bounds__(JT) jacobi_onesided_kernel(double *__restrict__ B, int n, int ncols, int max_sweeps,
+                                                             int *__restrict__ count, double *__restrict__ evals,
+                                                             int *__restrict__ sweeps_done, double *__restrict__ Vout) {
   cg::grid_group grid = cg::this_grid();
-  const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t gsz = (int64_t)gridDim.x * blockDim.x;
-  const int half = n / 2;
-  for (int64_t idx = gtid; idx < (int64_t)n * n; idx += gsz) Q[idx] = (idx % n == idx / n) ? 1.0 : 0.0;
-  grid.sync();
-  for (int sweep = 0; sweep < max_sweeps; sweep++) {
-    if (gtid == 0) {
-      norms[0] = 0.0;
-      norms[1] = 0.0;
-    }
-    grid.sync();
-    {
-      double o = 0.0, d = 0.0;
-      for (int64_t idx = gtid; idx < (int64_t)n * n; idx += gsz) {
-        const double v = A[idx];
-        if (idx % n == idx / n) d += v * v;
-        else o += v * v;
-      }
-      o = ppx_warp_sum(o);
-      d = ppx_warp_sum(d);
-      if ((threadIdx.x & 31) == 0) {  // stopping test only
-        atomicAdd(&norms[0], o);
-        atomicAdd(&norms[1], d);
-      }
-    }
-    grid.sync();
-    if (norms[0] <= 1e-30 * norms[1]) break;
-    for (int round = 0; round < n - 1; round++) {
-      for (int64_t pr = gtid; pr < half; pr += gsz) {
+  __shared__ double red[3][JT / 32];
+  __shared__ double bc[3];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int m = ncols;            // even number of seats; seat index >= number of real columns: idle
+  const double tol = 2.3e-16 * sqrt((double)n);
+  const int half = m / 2;
+  int sweep = 0;
+  for (; sweep < max_sweeps; sweep++) {
+    for (int round = 0; round < m - 1; round++) {
+      for (int pr = blockIdx.x; pr < half; pr += gridDim.x) {
         int p, q;
         if (pr == 0) {
-          p = n - 1;
-          q = round % (n - 1);
+          p = m - 1;
+          q = round % (m - 1);
         } else {
-          p = (int)((round + pr) % (n - 1));
-          q = (int)((round + n - 1 - pr) % (n - 1));
+          p = (round + pr) % (m - 1);
+          q = (round + m - 1 - pr) % (m - 1);
         }
         if (p > q) {
-          int t = p;
+          const int t = p;
           p = q;
           q = t;
         }
-        const double app = A[p + (int64_t)n * p], aqq = A[q + (int64_t)n * q], apq = A[p + (int64_t)n * q];
-        double c = 1.0, s = 0.0;
-        if (fabs(apq) > 1e-300) {
-          const double tau = (aqq - app) / (2.0 * apq);
-          const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
-          c = 1.0 / sqrt(1.0 + t * t);
-          s = t * c;
+        if (q >= n) continue;  // padded seat (odd n)
+        double *bp = B + (int64_t)n * p, *bq = B + (int64_t)n * q;
+        double a = 0.0, b = 0.0, g = 0.0;
+        double xp[JE], xq[JE];
+        const bool onepass = n <= JT * JE;
+        if (onepass) {
+#pragma unroll
+          for (int u = 0; u < JE; u++) {
+            const int i = tid + JT * u;
+            xp[u] = i < n ? bp[i] : 0.0;
+            xq[u] = i < n ? bq[i] : 0.0;
+          }
+#pragma unroll
+          for (int u = 0; u < JE; u++) {
+            a = fma(xp[u], xp[u], a);
+            b = fma(xq[u], xq[u], b);
+            g = fma(xp[u], xq[u], g);
+          }
+        } else {
+          for (int i = tid; i < n; i += JT) {
+            const double vp = bp[i], vq = bq[i];
+            a = fma(vp, vp, a);
+            b = fma(vq, vq, b);
+            g = fma(vp, vq, g);
+          }
         }
-        cs[4 * pr + 0] = c;
-        cs[4 * pr + 1] = s;
-        cs[4 * pr + 2] = (double)p;
-        cs[4 * pr + 3] = (double)q;
+        a = ppx_warp_sum(a);
+        b = ppx_warp_sum(b);
+        g = ppx_warp_sum(g);
+        __syncthreads();  // previous pair's broadcast has been read
+        if (lane == 0) {
+          red[0][warp] = a;
+          red[1][warp] = b;
+          red[2][warp] = g;
+        }
+        __syncthreads();
+        if (tid < 3) {
+          double v = 0.0;
+#pragma unroll
+          for (int w = 0; w < JT / 32; w++) v += red[tid][w];
+          bc[tid] = v;
+        }
+        __syncthreads();
+        a = bc[0];
+        b = bc[1];
+        g = bc[2];
+        // rotate when the columns are not orthogonal to working precision
+        // (threshold sqrt(n) eps, as LAPACK's dgesvj: a recomputed inner product of orthogonal columns is that large)
+        const bool rot = fabs(g) > tol * sqrt(a * b) && fabs(g) > 1e-300;
+        double c = 1.0, sn = 0.0;
+        if (rot) {
+          const double zeta = (b - a) / (2.0 * g);
+          const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+          c = 1.0 / sqrt(1.0 + t * t);
+          sn = c * t;
+          if (tid == 0) atomicAdd(&count[sweep], 1);
+        }
+        if (!rot) continue;
+        if (onepass) {
+#pragma unroll
+          for (int u = 0; u < JE; u++) {
+            const int i = tid + JT * u;
+            if (i < n) {
+              bp[i] = c * xp[u] - sn * xq[u];
+              bq[i] = sn * xp[u] + c * xq[u];
+            }
+          }
+        } else {
+          for (int i = tid; i < n; i += JT) {
+            const double vp = bp[i], vq = bq[i];
+            bp[i] = c * vp - sn * vq;
+            bq[i] = sn * vp + c * vq;
+          }
+        }
       }
       grid.sync();
-      // columns p,q of A and Q (contiguous along i)
-      for (int64_t idx = gtid; idx < (int64_t)half * n; idx += gsz) {
-        const int pr = (int)(idx / n), i = (int)(idx % n);
-        const double c = cs[4 * pr], s = cs[4 * pr + 1];
-        const int64_t p = (int64_t)cs[4 * pr + 2], q = (int64_t)cs[4 * pr + 3];
-        const double aip = A[i + n * p], aiq = A[i + n * q];
-        A[i + n * p] = c * aip - s * aiq;
-        A[i + n * q] = s * aip + c * aiq;
-        const double qip = Q[i + n * p], qiq = Q[i + n * q];
-        Q[i + n * p] = c * qip - s * qiq;
-        Q[i + n * q] = s * qip + c * qiq;
-      }
-      grid.sync();
-      // rows p,q of A
-      for (int64_t idx = gtid; idx < (int64_t)half * n; idx += gsz) {
-        const int pr = (int)(idx % half), j = (int)(idx / half);
-        const double c = cs[4 * pr], s = cs[4 * pr + 1];
-        const int64_t p = (int64_t)cs[4 * pr + 2], q = (int64_t)cs[4 * pr + 3];
-        const double apj = A[p + (int64_t)n * j], aqj = A[q + (int64_t)n * j];
-        A[p + (int64_t)n * j] = c * apj - s * aqj;
-        A[q + (int64_t)n * j] = s * apj + c * aqj;
-      }
-      grid.sync();
-      for (int64_t pr = gtid; pr < half; pr += gsz) {
-        const int64_t p = (int64_t)cs[4 * pr + 2], q = (int64_t)cs[4 * pr + 3];
-        A[p + n * q] = 0.0;
-        A[q + n * p] = 0.0;
-      }
-      // no sync needed here: the next round's parameter phase reads A[p][p], A[q][q], A[p][q] of OTHER pairs only
-      // after this loop?  No -- pairs change between rounds, so order it:
-      grid.sync();
+    }
+    if (count[sweep] == 0) {
+      sweep++;
+      break;
+    }
+  }
+  if (blockIdx.x == 0 && tid == 0 && sweeps_done) *sweeps_done = sweep;
+  // eigenvalue estimates: column norms
+  for (int j = blockIdx.x; j < n; j += gridDim.x) {
+    const double *bj = B + (int64_t)n * j;
+    double a = 0.0;
+    for (int i = tid; i < n; i += JT) a = fma(bj[i], bj[i], a);
+    a = ppx_warp_sum(a);
+    __syncthreads();
+    if (lane == 0) red[0][warp] = a;
+    __syncthreads();
+    if (tid == 0) {
+      double v = 0.0;
+#pragma unroll
+      for (int w = 0; w < JT / 32; w++) v += red[0][w];
+      evals[j] = sqrt(v);
+      bc[0] = sqrt(v);
+    }
+    if (Vout) {
+      __syncthreads();
+      const double nrm = bc[0];
+      double *vj = Vout + (int64_t)n * j;
+      for (int i = tid; i < n; i += JT) vj[i] = nrm > 0.0 ? bj[i] / nrm : (i == j ? 1.0 : 0.0);
     }
   }
 }
 
-// pick the r largest eigenvalues (diag of A), write eigenvectors in decreasing order; pad index (if any) excluded
-__global__ void __launch_bounds__(256) eig_select_kernel(const double *__restrict__ A, const double *__restrict__ Q,
-                                                         int n, int s, int r, double *__restrict__ U,
-                                                         double *__restrict__ evals) {
-  // one block per candidate eigen-index i < n
-  const int i = blockIdx.x;
+// pick the r largest eigenvalues, write the normalised columns in decreasing order, largest component positive
+__global__ void __launch_bounds__(256) eig_select_kernel(const double *__restrict__ B, const double *__restrict__ ev,
+                                                         int n, int r, double *__restrict__ U,
+                                                         double *__restrict__ evals_out) {
+  const int i = blockIdx.x;  // one block per candidate column
   __shared__ int rank_s;
-  __shared__ int is_pad;
-  if (threadIdx.x == 0) {
-    rank_s = 0;
-    is_pad = (n != s) && (fabs(Q[(int64_t)(n - 1) + (int64_t)n * i]) > 0.5);
-  }
+  if (threadIdx.x == 0) rank_s = 0;
   __syncthreads();
-  const double li = A[i + (int64_t)n * i];
+  const double li = ev[i];
   int cnt = 0;
   for (int j = threadIdx.x; j < n; j += blockDim.x) {
     if (j == i) continue;
-    const bool jpad = (n != s) && (fabs(Q[(int64_t)(n - 1) + (int64_t)n * j]) > 0.5);
-    if (jpad) continue;
-    const double lj = A[j + (int64_t)n * j];
+    const double lj = ev[j];
     if (lj > li || (lj == li && j < i)) cnt++;
   }
   atomicAdd(&rank_s, cnt);  // integer: order independent
   __syncthreads();
-  if (is_pad || rank_s >= r) return;
+  if (rank_s >= r) return;
   const int k = rank_s;
-  // deterministic sign: make the largest-magnitude component positive
+  const double *bi_ = B + (int64_t)n * i;
   __shared__ double red_v[256];
   __shared__ int red_i[256];
   double best = -1.0;
   int bi = 0;
-  for (int j = threadIdx.x; j < s; j += blockDim.x) {
-    const double v = fabs(Q[j + (int64_t)n * i]);
+  for (int j = threadIdx.x; j < n; j += blockDim.x) {
+    const double v = fabs(bi_[j]);
     if (v > best) {
       best = v;
       bi = j;
@@ -240,16 +286,20 @@ __global__ void __launch_bounds__(256) eig_select_kernel(const double *__restric
     }
     __syncthreads();
   }
-  const double sgn = Q[red_i[0] + (int64_t)n * i] < 0.0 ? -1.0 : 1.0;
-  for (int j = threadIdx.x; j < s; j += blockDim.x) U[j + (int64_t)s * k] = sgn * Q[j + (int64_t)n * i];
-  if (threadIdx.x == 0 && evals) evals[k] = li;
+  // a zero column (rank-deficient input) has no direction: emit the unit vector of its own index
+  const double nrm = li;
+  const double sc = nrm > 0.0 ? (bi_[red_i[0]] < 0.0 ? -1.0 : 1.0) / nrm : 0.0;
+  for (int j = threadIdx.x; j < n; j += blockDim.x)
+    U[j + (int64_t)n * k] = nrm > 0.0 ? sc * bi_[j] : (j == i ? 1.0 : 0.0);
+  if (threadIdx.x == 0 && evals_out) evals_out[k] = li;
 }
 
-__global__ void pad_copy_kernel(const double *__restrict__ M, int s, int n, double *__restrict__ A) {
+// symmetrised copy of the input (the Gram kernels mirror exactly, callers' matrices may not)
+__global__ void sym_copy_kernel(const double *__restrict__ M, int n, double *__restrict__ A) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (int64_t)n * n) return;
   const int i = (int)(idx % n), j = (int)(idx / n);
-  A[idx] = (i < s && j < s) ? 0.5 * (M[i + (int64_t)s * j] + M[j + (int64_t)s * i]) : (i == j ? 1.0 : 0.0);
+  A[idx] = 0.5 * (M[i + (int64_t)n * j] + M[j + (int64_t)n * i]);
 }
 
 __global__ void __launch_bounds__(256) sign_align_kernel(double *__restrict__ U, const double *__restrict__ Uref,
@@ -296,36 +346,58 @@ int ppx_unfold_gram(ppx_ctx *ctx, const double *T, const int64_t *lens, int k, i
   return PPX_OK;
 }
 
-int ppx_sym_eig_topk(ppx_ctx *ctx, double *MTM, int64_t s, int r, double *U, double *evals_out) {
+int ppx_sym_eig_topk_warm(ppx_ctx *ctx, double *MTM, int64_t s, int r, double *U, double *evals_out, double *basis,
+                          int basis_valid) {
   PPX_REQUIRE(ctx, MTM && U && s >= 1 && r >= 1 && r <= s, "1 <= r <= s");
   PPX_REQUIRE(ctx, s <= 16384, "s <= 16384");
-  const int n = (int)((s + 1) & ~(int64_t)1);
+  const int n = (int)s;
+  const int seats = (n + 1) & ~1;
+  const int max_sweeps = 40;
+  const bool warm = basis && basis_valid && n > 1;
   ppx_ws_reset(ctx);
-  double *A = (double *)ppx_ws_alloc(ctx, sizeof(double) * (size_t)n * n);
-  double *Q = (double *)ppx_ws_alloc(ctx, sizeof(double) * (size_t)n * n);
-  double *cs = (double *)ppx_ws_alloc(ctx, sizeof(double) * (4 * (size_t)(n / 2) + 8));
-  if (!A || !Q || !cs)
-    return ppx_set_err(ctx, PPX_ENOMEM, "sym_eig_topk needs %lld bytes of workspace", (long long)(16LL * n * n + 4096));
-  double *norms = cs + 4 * (n / 2);
-  pad_copy_kernel<<<ppx_cdiv((int64_t)n * n, 256), 256, 0, ctx->stream>>>(MTM, (int)s, n, A);
+  double *B = (double *)ppx_ws_alloc(ctx, sizeof(double) * (size_t)n * n);
+  double *A = warm ? (double *)ppx_ws_alloc(ctx, sizeof(double) * (size_t)n * n) : B;
+  double *ev = (double *)ppx_ws_alloc(ctx, sizeof(double) * (size_t)n);
+  int *count = (int *)ppx_ws_alloc(ctx, sizeof(int) * (max_sweeps + 1));
+  if (!B || !A || !ev || !count)
+    return ppx_set_err(ctx, PPX_ENOMEM, "sym_eig_topk needs %lld bytes of workspace",
+                       (long long)(16LL * n * n + 8LL * n + 4096));
+  PPX_CUDA(ctx, cudaMemsetAsync(count, 0, sizeof(int) * (max_sweeps + 1), ctx->stream));
+  sym_copy_kernel<<<ppx_cdiv((int64_t)n * n, 256), 256, 0, ctx->stream>>>(MTM, n, A);
   PPX_CHECK_LAUNCH(ctx);
-  int max_sweeps = 40;
-  int nn = n;
-  int blocks_per_sm = 0;
-  PPX_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, jacobi_global_kernel, 256, 0));
-  if (blocks_per_sm < 1) return ppx_set_err(ctx, PPX_ECUDA, "jacobi kernel cannot be resident");
-  int grid = ctx->sm_count * (blocks_per_sm > 2 ? 2 : blocks_per_sm);
-  // small problems: fewer CTAs make the grid barrier cheaper
-  int64_t work = (int64_t)(n / 2) * n;
-  int need = (int)((work + 255) / 256);
-  if (need < 1) need = 1;
-  if (grid > need) grid = need;
-  void *args[] = {&A, &Q, &cs, &norms, &nn, &max_sweeps};
-  PPX_CUDA(ctx, cudaLaunchCooperativeKernel((void *)jacobi_global_kernel, dim3(grid), dim3(256), args, 0, ctx->stream));
-  ctx->launches++;
-  eig_select_kernel<<<n, 256, 0, ctx->stream>>>(A, Q, n, (int)s, r, U, evals_out);
+  if (warm) {  // B = A V0 (DMMA GEMM of the first-contraction kernel: rows l = i, contracted mode x, "rank" = n columns)
+    const int rc = ppx_ttm_impl(ctx, A, n, n, 1, basis, n, n, B, 0, 0, true, false);
+    if (rc) return rc;
+  }
+  if (n > 1) {
+    int blocks_per_sm = 0;
+    PPX_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, jacobi_onesided_kernel, JT, 0));
+    if (blocks_per_sm < 1) return ppx_set_err(ctx, PPX_ECUDA, "jacobi kernel cannot be resident");
+    int grid = ctx->sm_count * blocks_per_sm;
+    if (grid > seats / 2) grid = seats / 2;  // one CTA per pair of a round; fewer CTAs make the grid barrier cheaper
+    int nn = n, ss = seats, ms = max_sweeps;
+    int *sweeps_done = count + max_sweeps;
+    void *args[] = {&B, &nn, &ss, &ms, &count, &ev, &sweeps_done, &basis};
+    PPX_CUDA(ctx, cudaLaunchCooperativeKernel((void *)jacobi_onesided_kernel, dim3(grid), dim3(JT), args, 0, ctx->stream));
+    ctx->launches++;
+  } else {
+    PPX_CUDA(ctx, cudaMemcpyAsync(ev, B, sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+  }
+  eig_select_kernel<<<n, 256, 0, ctx->stream>>>(B, ev, n, r, U, evals_out);
   PPX_CHECK_LAUNCH(ctx);
+  if (getenv("PPX_EIG_VERBOSE")) {  // development aid: rotations applied per sweep
+    int h[64];
+    cudaStreamSynchronize(ctx->stream);
+    cudaMemcpy(h, count, sizeof(int) * (max_sweeps + 1), cudaMemcpyDeviceToHost);
+    fprintf(stderr, "sym_eig_topk n=%d%s: %d sweeps, rotations:", n, warm ? " (warm)" : "", h[max_sweeps]);
+    for (int i = 0; i < h[max_sweeps] && i < max_sweeps; i++) fprintf(stderr, " %d", h[i]);
+    fprintf(stderr, "\n");
+  }
   return PPX_OK;
+}
+
+int ppx_sym_eig_topk(ppx_ctx *ctx, double *MTM, int64_t s, int r, double *U, double *evals_out) {
+  return ppx_sym_eig_topk_warm(ctx, MTM, s, r, U, evals_out, nullptr, 0);
 }
 
 int ppx_sign_align(ppx_ctx *ctx, double *U, const double *Uref, int64_t s, int r) {

@@ -64,6 +64,8 @@ public:
   ~World() {
     if (ctx) {
       ppx_sync(ctx);
+      for (auto &kv : eig_basis) dev_free(kv.second.data, kv.second.n * kv.second.n);
+      eig_basis.clear();
       trim();
       if (scal_dev) ppx_free(ctx, scal_dev);
       if (scal_host) ppx_host_free(ctx, scal_host);
@@ -120,6 +122,23 @@ public:
     memcpy(host, scal_host, sizeof(double) * n);
   }
   void sync() { PPXCK(*this, ppx_sync(ctx)); }
+  // Warm-start state of the Tucker factor update: all eigenvectors of the last Gram matrix of a mode
+  // (ppx_sym_eig_topk_warm).  `valid` is false until the first solve of that mode with that size has run.
+  struct EigBasis {
+    double *data = nullptr;
+    int64_t n = 0;
+    bool valid = false;
+  };
+  EigBasis &eig_basis_for(int mode, int64_t n) {
+    EigBasis &b = eig_basis[mode];
+    if (b.n != n) {
+      if (b.data) dev_free(b.data, b.n * b.n);
+      b.data = dev_alloc(n * n);
+      b.n = n;
+      b.valid = false;
+    }
+    return b;
+  }
   // sum over ranks (no-op on one GPU)
   void allreduce(double *dev, int64_t n) {
     if (np == 1) return;
@@ -129,6 +148,7 @@ public:
   }
 
 private:
+  std::map<int, EigBasis> eig_basis;
   std::multimap<size_t, void *> pool;
   size_t pooled_bytes = 0;
   void init(int device, size_t ws) {
