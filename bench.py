@@ -119,17 +119,20 @@ def run_reference(args):
 # clocks
 # ---------------------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """nvidia-smi polled every 20 ms from before the warm-up; stop() keeps the samples taken inside the timed window
+    (mark_begin .. mark_end) -- nvidia-smi needs a few hundred ms to start, longer than a short timed region."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, device):
         self.device, self.lines, self.proc = device, [], None
+        self.t_begin = self.t_end = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "20"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -138,33 +141,54 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def wait_first_sample(self, timeout=5.0):
+        t0 = time.perf_counter()
+        while self.proc and not self.lines and time.perf_counter() - t0 < timeout:
+            time.sleep(0.01)
+
+    def mark_begin(self):
+        self.t_begin = time.perf_counter()
+
+    def mark_end(self):
+        self.t_end = time.perf_counter()
 
     def stop(self):
         if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1]))
-                mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
+
+        def parse(rows):
+            sm, mx, reasons = [], [], set()
+            for ln in rows:
+                f = [x.strip() for x in ln.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1]))
+                    mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"],
+                                   f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            return sm, mx, reasons
+
+        inside = [ln for t, ln in self.lines if self.t_begin is not None and self.t_begin <= t <= (self.t_end or 1e300)]
+        sm, mx, reasons = parse(inside)
+        window = "timed region"
+        if not sm:  # a very short timed region: fall back to every sample since the warm-up began
+            sm, mx, reasons = parse([ln for _, ln in self.lines])
+            window = "warm-up + timed region"
         sm.sort()
-        load = [x for x in sm if x >= 0.5 * (mx[0] if mx else 1)] or sm
-        return {"sm_mhz": load[len(load) // 2] if load else None, "sm_max_mhz": mx[0] if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx[0] if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -247,11 +271,13 @@ def main():
         lib.ppx_event_create(world.ctx_handle(), C.byref(ev))
 
     # ---- device-resident sweeps: value ---------------------------------------------------------------------------
-    H.cp_dt_sweeps(world, V, W, G, max(args.warmup, 3))
-    barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+        sampler.wait_first_sample()
+    H.cp_dt_sweeps(world, V, W, G, max(args.warmup, 3))
+    barrier()
+    sampler.mark_begin()
     launches0 = world.launch_count()
     lib.ppx_event_record(world.ctx_handle(), evs[0])
     H.cp_dt_sweeps(world, V, W, G, args.steps)
@@ -259,6 +285,7 @@ def main():
     ms = C.c_float(0)
     lib.ppx_event_elapsed_ms(world.ctx_handle(), evs[0], evs[1], C.byref(ms))
     barrier()
+    sampler.mark_end()
     launches = world.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
     ms_total = max_over_ranks(float(ms.value))
@@ -278,7 +305,7 @@ def main():
     world.trim()  # the level-1 tensors of the build go back to the driver
     pp = {"operator_build_ms": ms_build, "approx_sweep_ms": ms_pp / args.pp_sweeps,
           "approx_sweeps_per_s": 1e3 * args.pp_sweeps / ms_pp, "sweeps_timed": args.pp_sweeps,
-          "note": "one CUDA graph per sweep (N x [correct, Gram-Hadamard, Cholesky solve+grad+dW, Gram] + Normalize + norms)"
+          "note": "one CUDA graph per sweep (N x [correct, Gram-Hadamard, LDL^T inverse + solve+grad+dW, Gram] + Normalize + norms)"
                   if nranks == 1 else "eager launches + NCCL all-reduce per mode (latency bound, does not scale)"}
 
     # ---- roofline of the dominant kernel: the first dimension-tree contraction (K1) ------------------------------
@@ -325,7 +352,7 @@ def main():
     except Exception:
         pass
     achieved = k1_flops / (k1_ms * 1e-3) / 1e12
-    roofline = {"kernel": "ttm_first_kernel via ppx_ttm_multi (K1, first dimension-tree contraction, modes %d..%d at once, "
+    roofline = {"kernel": "ttm_tma_kernel via ppx_ttm_multi (K1, first dimension-tree contraction, TMA-staged, modes %d..%d at once, "
                           "R=%d)" % (x_first, N - 1, R),
                 "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
                 "traffic": traffic, "algorithmic_flops": k1_flops, "algorithmic_bytes": k1_bytes, "ms": k1_ms,

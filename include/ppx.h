@@ -58,6 +58,10 @@ int ppx_host_free(ppx_ctx *ctx, void *hptr);
 int ppx_memcpy_h2d(ppx_ctx *ctx, void *dst, const void *src, size_t bytes); /* async on the stream */
 int ppx_memcpy_d2h(ppx_ctx *ctx, void *dst, const void *src, size_t bytes); /* async; ppx_sync before reading */
 int ppx_memcpy_d2d(ppx_ctx *ctx, void *dst, const void *src, size_t bytes);
+/* `height` columns of `width_bytes` each, column j at dst + j*dst_pitch / src + j*src_pitch (bytes): the row range of a
+ * column-major matrix -- how the rows of a sharded factor are cut out of / pasted into the replicated one. */
+int ppx_memcpy2d_d2d(ppx_ctx *ctx, void *dst, size_t dst_pitch, const void *src, size_t src_pitch, size_t width_bytes,
+                     size_t height);
 int ppx_memset_zero(ppx_ctx *ctx, void *dst, size_t bytes);
 int ppx_mem_info(ppx_ctx *ctx, size_t *free_bytes, size_t *total_bytes);
 

@@ -43,6 +43,7 @@ SIGNATURES = {
     "ppx_memcpy_h2d": (C.c_int, [_vp, _dp, _vp, C.c_size_t]),
     "ppx_memcpy_d2h": (C.c_int, [_vp, _vp, _dp, C.c_size_t]),
     "ppx_memcpy_d2d": (C.c_int, [_vp, _dp, _dp, C.c_size_t]),
+    "ppx_memcpy2d_d2d": (C.c_int, [_vp, _dp, C.c_size_t, _dp, C.c_size_t, C.c_size_t, C.c_size_t]),
     "ppx_memset_zero": (C.c_int, [_vp, _dp, C.c_size_t]),
     "ppx_mem_info": (C.c_int, [_vp, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "ppx_event_create": (C.c_int, [_vp, C.POINTER(_vp)]),

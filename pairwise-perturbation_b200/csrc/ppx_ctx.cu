@@ -149,6 +149,13 @@ int ppx_memcpy_d2d(ppx_ctx *ctx, void *dst, const void *src, size_t bytes) {
   PPX_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
   return PPX_OK;
 }
+int ppx_memcpy2d_d2d(ppx_ctx *ctx, void *dst, size_t dst_pitch, const void *src, size_t src_pitch, size_t width_bytes,
+                     size_t height) {
+  if (width_bytes == 0 || height == 0) return PPX_OK;
+  PPX_CUDA(ctx, cudaMemcpy2DAsync(dst, dst_pitch, src, src_pitch, width_bytes, height, cudaMemcpyDeviceToDevice,
+                                  ctx->stream));
+  return PPX_OK;
+}
 int ppx_memset_zero(ppx_ctx *ctx, void *dst, size_t bytes) {
   PPX_CUDA(ctx, cudaMemsetAsync(dst, 0, bytes, ctx->stream));
   return PPX_OK;

@@ -22,22 +22,50 @@ string without(const string &s, int i, int j = -1) {
     if (k != i && k != j) o.push_back(s[k]);
   return o;
 }
-void single_gpu_only(World &dw, const char *who) {
-  if (dw.np > 1) throw std::runtime_error(string(who) + ": the Tucker drivers run on one GPU in this round");
+// ---- multi-GPU: V is sharded along mode 0, rows [row_begin, row_end) of it per rank; every factor is
+// REPLICATED in full (the factor update is an eigenproblem every rank solves redundantly).  A tensor that still
+// carries mode 0 holds the local rows and is complete; contracting mode 0 uses the local rows of W_0 and leaves a
+// partial sum that stays partial down the chain (every later TTM is linear) until it is all-reduced.
+bool sharded(World &dw) { return dw.np > 1; }
+int64_t rows0(World &dw) { return dw.row_end - dw.row_begin; }
+
+// all-gather along mode 0 (the fastest index): local rows pasted into a zeroed full-size tensor, then summed over ranks
+Tensor<> gather_mode0(Tensor<> &Yloc, World &dw) {
+  int64_t lens[16];
+  for (int i = 0; i < Yloc.order; i++) lens[i] = Yloc.lens[i];
+  lens[0] = dw.shard_global;
+  Tensor<> full(Yloc.order, lens, dw);  // zero-initialised
+  const int64_t cols = Yloc.size / Yloc.lens[0];
+  PPXCK(dw, ppx_memcpy2d_d2d(dw.ctx, full.data + dw.row_begin, sizeof(double) * lens[0], Yloc.data,
+                             sizeof(double) * Yloc.lens[0], sizeof(double) * Yloc.lens[0], (size_t)cols));
+  dw.allreduce(full.data, full.size);
+  return full;
 }
 
-// Y[.., q, ..] = sum_x T[.., x, ..] Wx[x, q]: the rank replaces mode x in place (als_Tucker.cxx:102,224,464-465)
+// Y[.., q, ..] = sum_x T[.., x, ..] Wx[x, q]: the rank replaces mode x in place (als_Tucker.cxx:102,224,464-465).
+// Multi-GPU: a contraction of mode 0 sums over the local rows only (partial result).
 Tensor<> ttm_mode(Tensor<> &T, int x, Matrix<> &Wx, World &dw) {
   int64_t lens[16];
   for (int i = 0; i < T.order; i++) lens[i] = T.lens[i];
   lens[x] = Wx.ncol;
   Tensor<> out(T.order, lens, dw, false);
-  PPXCK(dw, ppx_ttm(dw.ctx, T.data, T.lens, T.order, x, Wx.data, Wx.nrow, (int)Wx.ncol, out.data));
+  if (sharded(dw) && x == 0) {
+    if (T.lens[0] != rows0(dw)) throw std::runtime_error("ttm_mode: mode 0 of a sharded tensor must hold the local rows");
+    PPXCK(dw, ppx_ttm(dw.ctx, T.data, T.lens, T.order, 0, Wx.data + dw.row_begin, Wx.nrow, (int)Wx.ncol, out.data));
+  } else {
+    PPXCK(dw, ppx_ttm(dw.ctx, T.data, T.lens, T.order, x, Wx.data, Wx.nrow, (int)Wx.ncol, out.data));
+  }
   return out;
 }
 
-// W_i <- leading r eigenvectors of Gram(Y_(i))  == MTM.svd(U,S,VT,r); W[i]=U  (als_Tucker.cxx:399-406)
-void factor_from_unfolding(Tensor<> &Y, int i, int r, Matrix<> &Wi, World &dw) {
+// W_i <- leading r eigenvectors of Gram(Y_(i))  == MTM.svd(U,S,VT,r); W[i]=U  (als_Tucker.cxx:399-406).
+// Multi-GPU: Y arrives as computed from the local slab -- for i != 0 a partial sum (all-reduced here), for i == 0 the
+// local rows (gathered here); the Gram and the eigenproblem are then replicated.  `complete`: Y is already global.
+void factor_from_unfolding(Tensor<> &Y, int i, int r, Matrix<> &Wi, World &dw, bool complete = false) {
+  if (sharded(dw) && !complete) {
+    if (i != 0) dw.allreduce(Y.data, Y.size);
+    else Y = gather_mode0(Y, dw);
+  }
   Matrix<> MTM = unroll_tensor_contraction(Y, i);
   Matrix<> U(Y.lens[i], r, dw);
   // warm start from the eigenvectors this mode had one sweep earlier (same result, fewer Jacobi sweeps)
@@ -60,9 +88,24 @@ double tucker_residual(Tensor<> &V, Tensor<> &core, Matrix<> *W, World &dw) {
     W_T.emplace_back(W[i].ncol, W[i].nrow, dw);
     PPXCK(dw, ppx_transpose(dw.ctx, W[i].data, W[i].nrow, W[i].ncol, W_T[i].data));
   }
-  Tensor<> V_check;
-  TTMc(V_check, core, W_T.data(), -1, dw);
-  PPXCK(dw, ppx_diff_sqnorm(dw.ctx, V_check.data, V.data, V.size, dw.scal_dev));
+  // multi-GPU: only the local rows of mode 0 are reconstructed (W_0^T restricted to the columns row_begin..row_end,
+  // a contiguous block of the R x s transposed factor) and the squared difference is summed over ranks
+  Tensor<> cur;
+  Tensor<> *src = &core;
+  for (int i = 0; i < N; i++) {
+    int64_t lens[16];
+    for (int k = 0; k < N; k++) lens[k] = src->lens[k];
+    const bool loc = sharded(dw) && i == 0;
+    const int64_t ncol = loc ? rows0(dw) : W_T[i].ncol;
+    const double *wt = loc ? W_T[i].data + W_T[i].nrow * dw.row_begin : W_T[i].data;
+    lens[i] = ncol;
+    Tensor<> nxt(N, lens, dw, false);
+    PPXCK(dw, ppx_ttm(dw.ctx, src->data, src->lens, N, i, wt, W_T[i].nrow, (int)ncol, nxt.data));
+    cur = std::move(nxt);
+    src = &cur;
+  }
+  PPXCK(dw, ppx_diff_sqnorm(dw.ctx, cur.data, V.data, V.size, dw.scal_dev));
+  dw.allreduce(dw.scal_dev, 1);
   double v;
   dw.fetch(dw.scal_dev, &v, 1);
   return std::sqrt(v);
@@ -104,6 +147,51 @@ void log_row_t(Tensor<> &V, int iter, double diffnorm, double tol, int pp_update
 
 }  // namespace
 
+namespace {
+// HOSVD factors of a tensor sharded along mode 0 (als_Tucker.cxx:12-40 on every rank's slab).  Modes i != 0: the Gram
+// of the mode-i unfolding sums over mode 0, so the local Grams are all-reduced.  Mode 0: MTM_0[p,q] pairs rows that
+// live on different ranks; the slab is gathered panel by panel along the last mode (zero-padded all-reduce, at most
+// ~1 GB per panel), the panels are dealt round-robin to the ranks for the Gram, and the partial Grams are all-reduced.
+void hosvd_sharded(Tensor<> &T, Matrix<> *factor_matrices, int *ranks, World &dw) {
+  const int N = T.order;
+  for (int i = 0; i < N; i++) {
+    Matrix<> MTM;
+    if (i != 0) {
+      MTM = unroll_tensor_contraction(T, i);
+      dw.allreduce(MTM.data, MTM.size);
+    } else {
+      const int64_t s0 = dw.shard_global, r0 = rows0(dw);
+      const int64_t last = T.lens[N - 1];
+      const int64_t cols_per_t = T.size / r0 / last;           // product of the middle modes
+      int64_t chunk = ((int64_t)1 << 27) / (s0 * cols_per_t);  // panel of <= 2^27 doubles
+      if (chunk < 1) chunk = 1;
+      if (chunk > last) chunk = last;
+      MTM = Matrix<>(s0, s0, dw);
+      int64_t lens_p[16];
+      for (int k = 0; k < N; k++) lens_p[k] = T.lens[k];
+      int panel_id = 0;
+      for (int64_t t0 = 0; t0 < last; t0 += chunk, panel_id++) {
+        const int64_t ct = std::min(chunk, last - t0);
+        lens_p[0] = r0;
+        lens_p[N - 1] = ct;
+        Tensor<> loc(N, lens_p, dw, false);
+        PPXCK(dw, ppx_memcpy_d2d(dw.ctx, loc.data, T.data + r0 * cols_per_t * t0, sizeof(double) * loc.size));
+        Tensor<> full = gather_mode0(loc, dw);
+        if (panel_id % dw.np != dw.rank) continue;
+        Matrix<> part = unroll_tensor_contraction(full, 0);
+        PPXCK(dw, ppx_axpby(dw.ctx, 1.0, part.data, 1.0, MTM.data, MTM.size));
+      }
+      dw.allreduce(MTM.data, MTM.size);
+    }
+    Matrix<> U(MTM.nrow, ranks[i], dw);
+    World::EigBasis &eb = dw.eig_basis_for(i, MTM.nrow);
+    PPXCK(dw, ppx_sym_eig_topk_warm(dw.ctx, MTM.data, MTM.nrow, ranks[i], U.data, nullptr, eb.data, eb.valid ? 1 : 0));
+    eb.valid = true;
+    factor_matrices[i] = std::move(U);
+  }
+}
+}  // namespace
+
 void get_factor_matrices(Tensor<> &T, Matrix<> *factor_matrices, int ranks[], World &dw) {
   for (int i = 0; i < T.order; i++) factor_from_unfolding(T, i, ranks[i], factor_matrices[i], dw);
 }
@@ -116,8 +204,11 @@ Tensor<> get_core_tensor(Tensor<> &T, Matrix<> *factor_matrices, int ranks[], Wo
 }
 
 void hosvd(Tensor<> &T, Tensor<> &core, Matrix<> *factor_matrices, int *ranks, World &dw) {
-  single_gpu_only(dw, "hosvd");
-  get_factor_matrices(T, factor_matrices, ranks, dw);
+  if (sharded(dw)) {
+    hosvd_sharded(T, factor_matrices, ranks, dw);
+  } else {
+    get_factor_matrices(T, factor_matrices, ranks, dw);
+  }
   core = get_core_tensor(T, factor_matrices, ranks, dw);
 }
 
@@ -134,11 +225,13 @@ void TTMc(Tensor<> &Y, Tensor<> &V, Matrix<> *W, int i, World &dw) {
   }
   if (any) Y = std::move(cur);
   else Y = V;
+  // multi-GPU: the core (i == -1) is summed over ranks here; for i >= 0 the caller gets the contribution of the
+  // local slab (partial sum for i != 0, local rows for i == 0), which factor_from_unfolding completes
+  if (sharded(dw) && i < 0 && V.lens[0] == rows0(dw)) dw.allreduce(Y.data, Y.size);
 }
 
 bool alsTucker(Tensor<> &V, Tensor<> &core, Matrix<> *W, double tol, double timelimit, int maxiter, World &dw) {
   // als_Tucker.cxx:120-176: no dimension tree, a full TTMc per mode
-  single_gpu_only(dw, "alsTucker");
   double st_time = synced_time(dw);
   int iter;
   Tensor<> core_prev(core);
@@ -190,7 +283,6 @@ void ttmc_map_DT(map<string, Tensor<>> &ttmc_map, map<string, string> &parent, m
 bool alsTucker_DT(Tensor<> &V, Tensor<> &core, Matrix<> *W, double tol, double timelimit, int maxiter,
                   ofstream &Plot_File, int resprint, bool bench, World &dw) {
   // als_Tucker.cxx:240-424
-  single_gpu_only(dw, "alsTucker_DT");
   cout.precision(13);
   const int N = V.order;
   if (!bench && Plot_File.is_open()) Plot_File << kCsvHeaderT << "\n";
@@ -267,16 +359,28 @@ void build_tucker_pp_operators(map<string, Tensor<>> &ttmc_map, Tensor<> &V, Mat
     if ((int)it->first.size() < N - 2) it = ttmc_map.erase(it);
     else ++it;
   }
+  // multi-GPU: an operator that contracted mode 0 is a partial sum over the local slab
+  if (sharded(dw))
+    for (auto &kv : ttmc_map)
+      if (kv.first.find('a') != string::npos) dw.allreduce(kv.second.data, kv.second.size);
 }
 
 // Y_i = Y_i(W_init) + sum_{j != i} T^(i,j) x_j dW_j   (als_Tucker.cxx:828-860)
 Tensor<> tucker_pp_corrected(map<string, Tensor<>> &ttmc_map, Matrix<> *dW, int i, int N, World &dw) {
   const string seq = all_modes(N);
+  // multi-GPU: for i != 0 everything is replicated except the j == 0 term, whose operator keeps the local rows of
+  // mode 0 -- that term is a partial sum and is all-reduced on its own; for i == 0 all terms act on the local rows
   Tensor<> Y = ttmc_map[without(seq, i)];
   for (int j = 0; j < N; j++) {
     if (j == i) continue;
     Tensor<> &T = ttmc_map[without(seq, std::min(i, j), std::max(i, j))];
-    PPXCK(dw, ppx_ttm_acc(dw.ctx, T.data, T.lens, N, j, dW[j].data, dW[j].nrow, (int)dW[j].ncol, Y.data));
+    if (sharded(dw) && j == 0) {
+      Tensor<> term = ttm_mode(T, 0, dW[0], dw);
+      dw.allreduce(term.data, term.size);
+      PPXCK(dw, ppx_axpby(dw.ctx, 1.0, term.data, 1.0, Y.data, Y.size));
+    } else {
+      PPXCK(dw, ppx_ttm_acc(dw.ctx, T.data, T.lens, N, j, dW[j].data, dW[j].nrow, (int)dW[j].ncol, Y.data));
+    }
   }
   return Y;
 }
@@ -407,7 +511,7 @@ void alsTucker_PP_sub(Tensor<> &V, Tensor<> &core, Tensor<> &core_prev, Matrix<>
     }
     for (int i = 0; i < N; i++) {  // :824-890
       Tensor<> Y = tucker_pp_corrected(ttmc_map, dW, i, N, dw);
-      factor_from_unfolding(Y, i, (int)core.lens[i], W[i], dw);
+      factor_from_unfolding(Y, i, (int)core.lens[i], W[i], dw, /*complete=*/i != 0);
       sign_align(W[i], W_init[i], dw);  // :874-885
       PPXCK(dw, ppx_memcpy_d2d(dw.ctx, dW[i].data, W[i].data, sizeof(double) * W[i].size));
       PPXCK(dw, ppx_axpby(dw.ctx, -1.0, W_init[i].data, 1.0, dW[i].data, dW[i].size));  // dW = W - W_init (:887)
@@ -422,7 +526,6 @@ void alsTucker_PP_sub(Tensor<> &V, Tensor<> &core, Tensor<> &core_prev, Matrix<>
 bool alsTucker_PP(Tensor<> &V, Tensor<> &core, Matrix<> *W, double tol, double tol_init, double timelimit,
                   int maxiter, ofstream &Plot_File, int resprint, bool bench, World &dw) {
   // als_Tucker.cxx:906-962
-  single_gpu_only(dw, "alsTucker_PP");
   cout.precision(13);
   const int N = V.order;
   if (!bench && dw.rank == 0 && Plot_File.is_open()) Plot_File << kCsvHeaderT << "\n";

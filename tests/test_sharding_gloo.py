@@ -96,3 +96,94 @@ def test_mode0_sharded_sweep_equals_unsharded(tmp_path, lens, R):
     # N-1 MTTKRP all-reduces + 1 Gram all-reduce per sweep (+1 initial Gram)
     assert int(parts[0]["n_allreduce"]) == 1 + 2 * N
     assert sum(int(p["e"]) - int(p["b"]) for p in parts) == lens[0]
+
+
+# ---- Tucker: V sharded along mode 0, factors replicated -------------------------------------------
+def _sharded_tucker(rank, nranks, port, lens, R, out_dir):
+    sys.path.insert(0, ROOT)
+    from oracle import pp_oracle as o
+
+    ppx = importlib.import_module("pairwise-perturbation_b200")
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=nranks)
+    N = len(lens)
+    V = o.make_tensor_r2(lens)
+    b, e = ppx.shard_range(lens[0], nranks, rank)
+    Vl = V[b:e]
+    n_allreduce = 0
+
+    def allreduce(x):
+        nonlocal n_allreduce
+        n_allreduce += 1
+        t = torch.from_numpy(np.ascontiguousarray(x))
+        dist.all_reduce(t)
+        return t.numpy()
+
+    def gather_mode0(Yl):     # zero-padded all-reduce, exactly what the host code does
+        full = np.zeros((lens[0],) + Yl.shape[1:])
+        full[b:e] = Yl
+        return allreduce(full)
+
+    ttm_saved = o.ttm
+
+    def local_ttm(T, x, Wx):  # a contraction of mode 0 sums over the local rows only
+        return ttm_saved(T, x, Wx[b:e] if x == 0 else Wx)
+
+    # HOSVD: modes != 0 all-reduce the local Gram; mode 0 gathers the slab panel by panel along the last mode
+    W = []
+    for i in range(N):
+        if i != 0:
+            MTM = allreduce(o.unroll_tensor_contraction(Vl, i))
+        else:
+            MTM = np.zeros((lens[0], lens[0]))
+            for pid, t0 in enumerate(range(0, lens[-1], 2)):
+                full = gather_mode0(Vl[..., t0:t0 + 2])
+                if pid % nranks == rank:
+                    MTM += o.unroll_tensor_contraction(full, 0)
+            MTM = allreduce(MTM)
+        W.append(o.top_left_singular(MTM, R))
+    # two HOOI sweeps with the dimension tree
+    parent, sibling = {}, {}
+    o.construct_dimension_tree(parent, sibling, 0, N - 1)
+    o.ttm = local_ttm         # the tree code calls o.ttm for every edge
+    try:
+        for sweep in range(2):
+            tm = {}
+            for i in range(N):
+                Y = o._tucker_leaf_Y(tm, parent, sibling, Vl, W, i)
+                Y = allreduce(Y) if i != 0 else gather_mode0(Y)
+                W[i] = o.top_left_singular(o.unroll_tensor_contraction(Y, i), R)
+    finally:
+        o.ttm = ttm_saved
+    np.savez(os.path.join(out_dir, "trank%d.npz" % rank), n_allreduce=n_allreduce,
+             **{"W%d" % i: w for i, w in enumerate(W)})
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("lens,R", [((8, 7, 6), 2), ((6, 5, 4, 5), 2)])
+def test_mode0_sharded_hooi_equals_unsharded(tmp_path, lens, R):
+    sys.path.insert(0, ROOT)
+    from oracle import pp_oracle as o
+
+    nranks = 2
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_sharded_tucker, args=(nranks, port, lens, R, str(tmp_path)), nprocs=nranks, join=True)
+    N = len(lens)
+    V = o.make_tensor_r2(lens)
+    _, W = o.hosvd(V, [R] * N)
+    parent, sibling = {}, {}
+    o.construct_dimension_tree(parent, sibling, 0, N - 1)
+    for sweep in range(2):
+        tm = {}
+        for i in range(N):
+            Y = o._tucker_leaf_Y(tm, parent, sibling, V, W, i)
+            W[i] = o.top_left_singular(o.unroll_tensor_contraction(Y, i), R)
+    parts = [np.load(os.path.join(str(tmp_path), "trank%d.npz" % r)) for r in range(nranks)]
+    for i in range(N):
+        for p in parts:       # replicated factors: same subspace on every rank as the unsharded run
+            A, B = p["W%d" % i], W[i]
+            assert np.abs(A @ A.T - B @ B.T).max() < 1e-9
+    # HOSVD: N-1 Gram all-reduces + (panels + 1) for mode 0; HOOI: one exchange per mode update
+    panels = (lens[-1] + 1) // 2
+    assert int(parts[0]["n_allreduce"]) == (N - 1) + panels + 1 + 2 * N

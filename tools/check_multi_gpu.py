@@ -1,6 +1,7 @@
 """Multi-GPU parity check (run under torch.distributed.run on a box with >= 2 GPUs; not part of the single-GPU
 `-m gpu` suite):  the tensor is sharded along mode 0, alsCP_DT and alsCP_PP run through the C++ drivers with the NCCL
-all-reduces, and every rank compares its rows of W_0 / the replicated W_j and the logged fitness with the CPU oracle.
+all-reduces, and every rank compares its rows of W_0 / the replicated W_j and the logged fitness with the CPU oracle;
+then hosvd + alsTucker_DT / alsTucker_PP on a sharded tensor (replicated factors) against the oracle.
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tools/check_multi_gpu.py
 """
@@ -71,6 +72,59 @@ for lens, R, maxiter, tol_init in [((13, 12, 11, 10), 4, 40, 0.1), ((9, 10, 11),
         ok_all &= ok
         for x in [Vd] + Wd + Gd + Fd:
             x.free()
+# ---- Tucker: hosvd + alsTucker_DT / alsTucker_PP on the sharded tensor (factors replicated) -------------
+def proj_err(A, B):
+    return float(np.abs(A @ A.T - B @ B.T).max())
+
+
+for lens, R, tol_init in [((12, 13, 14), 3, 0.3), ((9, 10, 8, 7), 3, 0.3)]:
+    N = len(lens)
+    b, e = ppx.shard_range(lens[0], nranks, rank)
+    world.set_shard(0, lens[0], b, e)
+    V = o.make_tensor_r2(lens)
+    vnorm = np.linalg.norm(V)
+    core_ref, W_ref = o.hosvd(V, [R] * N)
+    Vd = H.Tensor.from_numpy(world, np.ascontiguousarray(V[b:e]))
+    Wd = [H.Matrix(world, lens[i], R) for i in range(N)]
+    cored = H.Tensor(world, (R,) * N)
+    H.hosvd(world, Vd, cored, Wd, [R] * N)
+    ok = all(proj_err(Wd[i].numpy(), W_ref[i]) < 1e-8 for i in range(N))
+    ok &= abs(np.linalg.norm(cored.numpy()) - np.linalg.norm(core_ref)) < 1e-10 * vnorm
+    W2 = [w.copy() for w in W_ref]
+    ok_ref, rows_ref, _ = o.alsTucker_DT(V, core_ref, W2, 1e-10 * vnorm, 12, resprint=4)
+    with H.Trace(quiet=True) as t:
+        okd = H.alsTucker_DT(world, Vd, cored, Wd, 1e-10 * vnorm, 12, resprint=4)
+    ok &= okd == ok_ref and len(t.rows) == len(rows_ref)
+    worst = 0.0
+    for rg, rr in zip(t.rows, rows_ref):
+        ok &= int(rg[0]) == rr[0] and abs(rg[1] - rr[1]) <= 1e-9 * vnorm and abs(rg[3] - rr[2]) <= 1e-10 * vnorm
+        worst = max(worst, abs(rg[3] - rr[2]) / vnorm)
+    ok &= all(proj_err(Wd[i].numpy(), W2[i]) < 1e-7 for i in range(N))
+    print(f"rank {rank} Tucker lens {lens} R {R} hosvd+DT: {'OK' if ok else 'MISMATCH'} rows {len(t.rows)} "
+          f"fit_err {worst:.2e}", flush=True)
+    ok_all &= ok
+    for x in Wd + [cored]:
+        x.free()
+    # PP from the oracle's HOSVD factors (column signs agree from the first sweep on)
+    Wd = [H.Tensor.from_numpy(world, w, matrix=True) for w in W_ref]
+    cored = H.Tensor.from_numpy(world, core_ref)
+    W2 = [w.copy() for w in W_ref]
+    ok_ref, rows_ref, ev_ref, _, _ = o.alsTucker_PP(V, core_ref, W2, 1e-10 * vnorm, tol_init, 30, resprint=5)
+    with H.Trace(quiet=True) as t:
+        okp = H.alsTucker_PP(world, Vd, cored, Wd, 1e-10 * vnorm, tol_init, 30, resprint=5)
+    ok = okp == ok_ref and t.events == [(0 if k == "DT" else 1, it) for k, it in ev_ref] and len(t.rows) == len(rows_ref)
+    worst = 0.0
+    for rg, rr in zip(t.rows, rows_ref):
+        ok &= int(rg[0]) == rr[0] and int(rg[2]) == rr[2] and abs(rg[1] - rr[1]) <= 1e-9 * vnorm
+        ok &= abs(rg[3] - rr[3]) <= 1e-10 * vnorm
+        worst = max(worst, abs(rg[3] - rr[3]) / vnorm)
+    ok &= all(proj_err(Wd[i].numpy(), W2[i]) < 1e-7 for i in range(N))
+    print(f"rank {rank} Tucker lens {lens} R {R} PP: {'OK' if ok else 'MISMATCH'} rows {len(t.rows)} fit_err {worst:.2e} "
+          f"events {t.events}", flush=True)
+    ok_all &= ok
+    for x in [Vd] + Wd + [cored]:
+        x.free()
+
 flag = torch.tensor([1 if ok_all else 0], device="cuda")
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:
