@@ -449,7 +449,7 @@ int ppx_ttm_impl(ppx_ctx *ctx, const double *V, int64_t L, int64_t X, int64_t Rt
     };
     int best = 1;
     double best_eff = eff(1);
-    for (int S = 2; S <= 32 && p.nk / S >= 16; S++) {
+    for (int S = 2; S <= 512 && p.nk / S >= 16; S++) {
       const double e = eff(S);
       if (e > best_eff + 0.02) {
         best_eff = e;

@@ -16,7 +16,9 @@
 //   * B is packed once per call (krp_pack_kernel) into per-chunk slabs [chunk][8*NT + TAIL columns][20] with the same k
 //     permutation, zero padded in k and in the columns, so a stage's slab is ONE contiguous bulk copy.
 // Layouts:  KMAJOR (L == 1): tensor map 2-D {K, M}, one 16 x 128 box per stage;
-//           M-major (L > 1): tensor map 3-D {L, K, Rt}, eight 16(l) x 16(k) boxes per stage, row tiles do not straddle t.
+//           M-major (L > 1): 128 l of one t per row tile -- one 4-D box of a {16, K, L/16, Rt} view when L % 16 == 0,
+//                            else eight 16(l) x 16(k) boxes of the 3-D map {L, K, Rt};
+//           M-major, short L (128-row tiles would idle > 6 %): 16 l x 8 consecutive t per row tile, one 3-D box.
 // ppx_ttm_tma_try returns 1 (caller falls back to the cp.async kernel) when the shape is not TMA-friendly: odd
 // extents (TMA needs 16-byte global strides), unaligned base, R > 64, or an L that would waste > 6 % of a row tile.
 #include <cuda.h>
@@ -43,6 +45,7 @@ struct TmaParams {
   int nk, ksplit, cps;
   int inplace, accumulate;
   int onebox;  // M-major with L % 16 == 0: the eight 16 x 16 boxes of a stage are one 4-D box (see ppx_ttm_tma_try)
+  int tmulti;  // M-major with a short L: a row tile is 16 l x 8 consecutive t (one 3-D box); tiles_per_t = l groups
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -246,7 +249,9 @@ __global__ void __launch_bounds__(TTHREADS, 2) ttm_tma_kernel(const __grid_const
     } else {
       const int t = ld.tile / p.tiles_per_t;
       const int l0 = (ld.tile - t * p.tiles_per_t) * TBM;
-      if (p.onebox) {
+      if (p.tmulti) {
+        tma_load_3d(As, &tmap, &full[stage], (ld.tile - t * p.tiles_per_t) * 16, chunk * TBK, t * 8);
+      } else if (p.onebox) {
         tma_load_4d(As, &tmap, &full[stage], 0, chunk * TBK, l0 >> 4, t);
       } else {
 #pragma unroll
@@ -348,9 +353,16 @@ __global__ void __launch_bounds__(TTHREADS, 2) ttm_tma_kernel(const __grid_const
 #pragma unroll
       for (int i = 0; i < 4; i++) {
         const int rl = 32 * warp + 8 * i + g;
-        const bool rv = rl < rows_valid;
+        bool rv = rl < rows_valid;
         int64_t basei, cstride;
-        if (p.inplace) {
+        if (!KMAJOR && p.tmulti) {
+          // row rl of the tile = (l, t) = (16 * group + rl % 16, 8 * tt + rl / 16)
+          const int64_t l = (int64_t)(tile - tt * p.tiles_per_t) * 16 + (rl & 15);
+          const int64_t t = tt * 8 + (rl >> 4);
+          rv = l < p.L && t < p.Rt;
+          basei = p.inplace ? l + p.L * (int64_t)p.R * t : l + p.L * t;
+          cstride = p.inplace ? p.L : p.Mtot;
+        } else if (p.inplace) {
           // out[l + L*(col + R*t)]
           basei = KMAJOR ? (row0 + rl) * (int64_t)p.R : (row0 + rl) + p.L * (int64_t)p.R * tt;
           cstride = KMAJOR ? 1 : p.L;
@@ -488,12 +500,20 @@ int ppx_ttm_tma_try(ppx_ctx *ctx, const double *V, int64_t L, int64_t K, int64_t
   if (kmajor ? (K % 2 != 0) : (L % 2 != 0)) return 1;                   // 16-byte global strides
   if (K >= ((int64_t)1 << 31) || Rt >= ((int64_t)1 << 31) || L >= ((int64_t)1 << 31)) return 1;
   int64_t tiles_per_t = 1, num_tiles;
+  bool tmulti = false;
   if (kmajor) {
     num_tiles = (Mtot + TBM - 1) / TBM;
   } else {
     tiles_per_t = (L + TBM - 1) / TBM;
-    if ((double)(tiles_per_t * TBM - L) > 0.06 * (double)L) return 1;   // short L: too many idle rows per tile
     num_tiles = tiles_per_t * Rt;
+    if ((double)(tiles_per_t * TBM - L) > 0.06 * (double)L) {
+      // short L: too many idle rows in a 128 l x 1 t tile; try 16 l x 8 t tiles (e.g. L = 300: 19 groups, 1.3 % idle)
+      const int64_t lg = (L + 15) / 16, tb = (Rt + 7) / 8;
+      if ((double)(lg * 16 * tb * 8) > 1.06 * (double)Mtot) return 1;
+      tmulti = true;
+      tiles_per_t = lg;
+      num_tiles = lg * tb;
+    }
   }
   if (num_tiles > 0x7fffffff / 64) return 1;
   const int64_t nk64 = (K + TBK - 1) / TBK;
@@ -514,7 +534,8 @@ int ppx_ttm_tma_try(ppx_ctx *ctx, const double *V, int64_t L, int64_t K, int64_t
   p.split_stride = 0;
   p.inplace = inplace;
   p.accumulate = accumulate;
-  p.onebox = (!kmajor && L % 16 == 0) ? 1 : 0;
+  p.tmulti = tmulti ? 1 : 0;
+  p.onebox = (!kmajor && !tmulti && L % 16 == 0) ? 1 : 0;
   int nt, tail;
   tma_split_rank(R, &nt, &tail);
   const int ncols = 8 * nt + tail;
@@ -534,7 +555,7 @@ int ppx_ttm_tma_try(ppx_ctx *ctx, const double *V, int64_t L, int64_t K, int64_t
     };
     int best = 1;
     double best_eff = eff(1);
-    for (int S = 2; S <= 32 && p.nk / S >= 16; S++) {
+    for (int S = 2; S <= 512 && p.nk / S >= 16; S++) {
       const double e = eff(S);
       if (e > best_eff + 0.02) {
         best_eff = e;
@@ -578,7 +599,7 @@ int ppx_ttm_tma_try(ppx_ctx *ctx, const double *V, int64_t L, int64_t K, int64_t
   } else {
     cuuint64_t dims[3] = {(cuuint64_t)L, (cuuint64_t)K, (cuuint64_t)Rt};
     cuuint64_t strides[2] = {(cuuint64_t)L * 8, (cuuint64_t)L * (cuuint64_t)K * 8};
-    cuuint32_t box[3] = {16, TBK, 1};
+    cuuint32_t box[3] = {16, TBK, (cuuint32_t)(tmulti ? 8 : 1)};
     cuuint32_t es[3] = {1, 1, 1};
     if (strides[1] >= ((cuuint64_t)1 << 40)) return 1;
     cr = g_encode(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void *)V, dims, strides, box, es,

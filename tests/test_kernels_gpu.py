@@ -43,6 +43,8 @@ TTM_CASES = [
     ((128, 21, 3), 1, 41), ((640, 7, 2), 1, 58), ((256, 12, 3), 1, 59),
     # M-major with L % 16 != 0: eight 16 x 16 boxes per stage instead of the single 4-D box
     ((250, 12, 3), 1, 50), ((378, 9, 2), 1, 33), ((122, 40, 2), 1, 26),
+    # M-major with a short L: 16 l x 8 t row tiles (one 3-D box per stage)
+    ((300, 20, 16), 1, 50), ((46, 17, 40), 1, 27), ((300, 7, 4, 6), 1, 35), ((94, 33, 8), 1, 64), ((16, 40, 24), 1, 25),
 ]
 
 
@@ -246,7 +248,8 @@ def test_cp_residual_and_reconstruct(ctx, lens, R):
 @pytest.mark.parametrize("lens,x,Q", [((13, 9, 11), 0, 4), ((13, 9, 11), 1, 4), ((13, 9, 11), 2, 4),
                                       ((12, 10, 8, 6), 1, 3), ((40, 7, 40), 2, 40), ((5, 1, 6), 1, 2),
                                       # TMA path with the rank written in place (+ DFMA tail columns)
-                                      ((256, 14, 5), 1, 26), ((22, 130), 0, 27), ((128, 9, 3, 2), 1, 35)])
+                                      ((256, 14, 5), 1, 26), ((22, 130), 0, 27), ((128, 9, 3, 2), 1, 35),
+                                      ((300, 14, 8), 1, 26), ((46, 9, 16), 1, 40)])
 def test_tucker_ttm_and_acc(ctx, lens, x, Q):
     T = rnd(lens, 120)
     W = rnd((lens[x], Q), 121)
@@ -314,6 +317,7 @@ MULTI_CASES = [
     ((9, 7, 5), 0, 3, 2),       # everything contracted: a single row
     ((256, 6, 5, 3), 1, 2, 4), ((128, 30, 40), 1, 2, 50), ((10, 12, 130, 3), 0, 2, 50),  # TMA-eligible fused cases
     ((640, 4, 5, 6), 1, 3, 10), ((128, 9, 11), 1, 2, 26), ((12, 14, 140), 0, 2, 11), ((256, 5, 4, 3), 1, 3, 43),
+    ((46, 6, 5, 16), 1, 2, 26),
 ]
 
 
