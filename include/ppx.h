@@ -79,6 +79,9 @@ int ppx_graph_destroy(ppx_ctx *ctx, void *graph);
 /* out[i] = lo + (hi-lo) * u(seed, tensor_id, start+i), u = SplitMix64 finaliser of the counter (53 bits). */
 int ppx_fill_uniform(ppx_ctx *ctx, double *out, int64_t n, uint64_t seed, uint64_t tensor_id, int64_t start,
                      double lo, double hi);
+/* out (s^(2d) doubles) = the Laplacian tensor of order 2d, V[a1,b1,..,ad,bd] = sum_k D[a_k,b_k] prod_{m!=k} delta(a_m,b_m),
+ * D = tridiag(-1,2,-1): what laplacian_tensor builds from identity tensors (common.cxx:575-642; generators 'p','p2'). */
+int ppx_fill_laplacian(ppx_ctx *ctx, double *out, int d, int64_t s);
 
 /* ---- K1: first tensor-times-matrix contraction of the dimension tree ---------------------------------------
  * out[rest, r] = sum_x V[.., x, ..] * Wx[x, r]      (remaining modes in order, rank last)

@@ -954,6 +954,90 @@ def make_tensor_r2(lens, seed=1, lo=0.5, hi=1.0):
     return fill_uniform(tuple(lens), seed, 100, lo, hi)
 
 
+def identity_tensor(N, s):
+    """common.cxx:462-498  I[a,b,c,d,..] = delta(a,b) delta(c,d) ... (order N even), built pair by pair."""
+    ident = np.eye(s)
+    I = ident
+    for _ in range(1, N // 2):
+        I = np.multiply.outer(ident, I)  # I_temp[ab c..] = ident[ab] * I_temp2[c..]
+    return I
+
+
+def laplacian_tensor(N, s):
+    """common.cxx:575-642  V = D x I x .. x I + I x D x I .. + ... over the d = N/2 index pairs, D = tridiag(-1,2,-1)."""
+    d = N // 2
+    D = 2.0 * np.eye(s) - np.eye(s, k=1) - np.eye(s, k=-1)
+    V = np.zeros((s,) * N)
+    letters_ = "abcdefghijklmnop"[:N]
+    for k in range(d):
+        ops, subs = [], []
+        for m in range(d):
+            ops.append(D if m == k else np.eye(s))
+            subs.append(letters_[2 * m:2 * m + 2])
+        V += np.einsum(",".join(subs) + "->" + letters_, *ops)
+    return np.asfortranarray(V)
+
+
+def make_tensor_p(dim, s, folded=True):
+    """tensor 'p2' (order dim) / 'p' (the same entries as dim/2 modes of size s*s; fold_unfold, common.cxx:870-882)."""
+    V = laplacian_tensor(dim, s)
+    if not folded:
+        return V
+    return np.asfortranarray(V.reshape((s * s,) * (dim // 2), order="F"))
+
+
+def collinearity(v1, v2):
+    """common.cxx:297-302"""
+    ip = n1 = n2 = 0.0
+    for a, b in zip(v1.tolist(), v2.tolist()):  # same summation order as the host loop
+        ip += a * b
+        n1 += a * a
+        n2 += b * b
+    return ip / (np.sqrt(n1) * np.sqrt(n2))
+
+
+def gen_collinearity(lens, R, col_min, col_max, seed=1):
+    """common.cxx:361-423.  Draw k of the run is u(seed, id = 1000 + k, .); vectors are redrawn until their
+    collinearity with every earlier vector of the mode lies in [col_min, col_max]; lambda_i = 0.2 + 0.6 (i+1)/R."""
+    dim = len(lens)
+    draw = [1000]
+
+    def fill(n):
+        v = u01(seed, draw[0], n)
+        draw[0] += 1
+        return v
+
+    vec = [[fill(lens[j]) for j in range(dim)] for _ in range(R)]
+    for j in range(dim):
+        for i in range(1, R):
+            while True:
+                ok = True
+                for k in range(i):
+                    col = collinearity(vec[i][j], vec[k][j])
+                    if col < col_min or col > col_max:
+                        ok = False
+                        break
+                if ok:
+                    break
+                vec[i][j] = fill(lens[j])
+    W = []
+    for j in range(dim):
+        Wj = np.zeros((lens[j], R))
+        for i in range(R):
+            lam = 0.2 + 0.6 / R * (i + 1) if j == 0 else 1.0
+            Wj[:, i] = lam * vec[i][j]
+        W.append(Wj)
+    return np.asfortranarray(build_V(W)), vec
+
+
+def make_tensor_c(lens, R, col_min=0.5, col_max=0.9, ratio_noise=0.01, seed=1):
+    """tensor 'c' (test_ALS.cxx:245-261): collinearity-constrained rank-R tensor + uniform(-1,1) noise of norm
+    ratio_noise * ||V||."""
+    V, _ = gen_collinearity(lens, R, col_min, col_max, seed)
+    noise = fill_uniform(tuple(lens), seed, 101, -1.0, 1.0)
+    return np.asfortranarray(V + ratio_noise * np.linalg.norm(V) / np.linalg.norm(noise) * noise)
+
+
 def init_factors(lens, R, seed=2):
     """W0[i] = u(seed, id=i) in [0,1) (test_ALS.cxx:337)."""
     return [fill_uniform((lens[i], R), seed, i) for i in range(len(lens))]

@@ -55,6 +55,7 @@ SIGNATURES = {
     "ppx_graph_launch": (C.c_int, [_vp, _vp]),
     "ppx_graph_destroy": (C.c_int, [_vp, _vp]),
     "ppx_fill_uniform": (C.c_int, [_vp, _dp, _i64, C.c_uint64, C.c_uint64, _i64, C.c_double, C.c_double]),
+    "ppx_fill_laplacian": (C.c_int, [_vp, _dp, C.c_int, _i64]),
     "ppx_ttm_first": (C.c_int, [_vp, _dp, C.POINTER(_i64), C.c_int, C.c_int, _dp, _i64, C.c_int, _dp]),
     "ppx_ttm_multi": (C.c_int, [_vp, _dp, C.POINTER(_i64), C.c_int, C.c_int, C.c_int, C.POINTER(_dp), C.POINTER(_i64),
                                 C.c_int, _dp]),
@@ -282,6 +283,9 @@ class Ctx:
 
     def cp_reconstruct(self, lens, Ws, R, V_out):
         self._ck(self.lib.ppx_cp_reconstruct(self.h, _lens(lens), len(lens), _ptrs(Ws), R, _ptr(V_out)))
+
+    def fill_laplacian(self, out, d, s):
+        self._ck(self.lib.ppx_fill_laplacian(self.h, _ptr(out), d, s))
 
     def ttm(self, T, lens, x, W, Q, out, acc=False, ldw=None):
         fn = self.lib.ppx_ttm_acc if acc else self.lib.ppx_ttm

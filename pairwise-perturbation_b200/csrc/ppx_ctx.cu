@@ -209,6 +209,31 @@ int ppx_graph_destroy(ppx_ctx *ctx, void *graph) {
 
 }  // extern "C"
 
+// ---- Laplacian (Poisson) tensor of the reference's generator 'p' / 'p2' (common.cxx:575-642) --------------------
+// Order 2d, extents s: V[a1,b1,...,ad,bd] = sum_k D[a_k,b_k] prod_{m != k} delta(a_m,b_m), D = tridiag(-1, 2, -1).
+// Closed form per element: no pair off the diagonal -> 2d; exactly one pair (a,b) off the diagonal -> D[a,b]
+// (-1 if |a-b| == 1 else 0); two or more -> 0.
+__global__ void fill_laplacian_kernel(double *out, int64_t n, int d, int64_t s) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    int64_t r = i;
+    int off = 0;
+    double v = 0.0;
+    for (int m = 0; m < d; m++) {
+      const int64_t a = r % s;
+      r /= s;
+      const int64_t b = r % s;
+      r /= s;
+      if (a != b) {
+        off++;
+        v = (a - b == 1 || b - a == 1) ? -1.0 : 0.0;
+      }
+    }
+    out[i] = off == 0 ? 2.0 * d : (off == 1 ? v : 0.0);
+  }
+}
+
 // ---- generator ----------------------------------------------------------------------------------------------
 __global__ void fill_uniform_kernel(double *out, int64_t n, uint64_t base, int64_t start, double lo, double span) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -320,6 +345,19 @@ int ppx_fill_uniform(ppx_ctx *ctx, double *out, int64_t n, uint64_t seed, uint64
   int blocks = (int)((n + 255) / 256);
   if (blocks > ctx->sm_count * 16) blocks = ctx->sm_count * 16;
   fill_uniform_kernel<<<blocks, 256, 0, ctx->stream>>>(out, n, base, start, lo, hi - lo);
+  PPX_CHECK_LAUNCH(ctx);
+  return PPX_OK;
+}
+
+int ppx_fill_laplacian(ppx_ctx *ctx, double *out, int d, int64_t s) {
+  PPX_REQUIRE(ctx, out && d >= 1 && d <= 8 && s >= 1, "out != NULL, 1 <= d <= 8, s >= 1");
+  int64_t n = 1;
+  for (int m = 0; m < 2 * d; m++) {
+    if (n > ((int64_t)1 << 62) / s) return ppx_set_err(ctx, PPX_EINVAL, "fill_laplacian: s^(2d) overflows");
+    n *= s;
+  }
+  int blocks = (int)((n + 255) / 256 > (int64_t)ctx->sm_count * 16 ? (int64_t)ctx->sm_count * 16 : (n + 255) / 256);
+  fill_laplacian_kernel<<<blocks, 256, 0, ctx->stream>>>(out, n, d, s);
   PPX_CHECK_LAUNCH(ctx);
   return PPX_OK;
 }

@@ -140,8 +140,8 @@ inline World *make_world(const CliOptions &o) {
   return dw;
 }
 
-// Builds the input tensor the way test_ALS.cxx:222-326 does.  Generators outside the hot-path scope ('p','p2','c':
-// Laplacian / collinearity tensors, common.cxx:361-642) are not rebuilt here; see DESIGN.md.
+// Builds the input tensor the way test_ALS.cxx:222-326 does: p / p2 (Poisson operator), c (constrained collinearity +
+// noise), r, r2, o1 / o2 (raw files).
 inline bool build_input_tensor(const CliOptions &o, Tensor<> &V, World &dw, bool bench_ranges) {
   std::vector<int64_t> lens;
   if (!o.lens.empty()) {
@@ -159,6 +159,34 @@ inline bool build_input_tensor(const CliOptions &o, Tensor<> &V, World &dw, bool
   const char t0 = o.tensor[0];
   const bool second = o.tensor.size() > 1 && o.tensor[1] == '2';
   const bool first = o.tensor.size() > 1 && o.tensor[1] == '1';
+  if (t0 == 'p') {
+    // p2: Poisson operator as an order-dim tensor; p: the same entries folded to dim/2 modes of size s*s
+    // (test_ALS.cxx:222-244)
+    if (!o.lens.empty() || o.dim % 2) {
+      if (dw.rank == 0) fprintf(stderr, "tensor 'p'/'p2' needs an even -dim and a cubic -size\n");
+      return false;
+    }
+    Tensor<> V0;
+    laplacian_tensor(V0, o.dim, o.s, o.issparse != 0, dw);
+    if (second) {
+      V = std::move(V0);
+    } else {
+      std::vector<int64_t> l2(o.dim / 2, (int64_t)o.s * o.s);
+      V = Tensor<>(o.dim / 2, l2.data(), dw, false);
+      fold_unfold(V0, V);
+    }
+    return true;
+  }
+  if (t0 == 'c') {
+    // c: rank-R tensor with constrained collinearity plus uniform noise scaled to ratio_noise * ||V|| (test_ALS.cxx:245-261)
+    std::vector<int> li(lens.begin(), lens.end());
+    V = Gen_collinearity(li.data(), dim, o.R, o.col_min, o.col_max, dw);
+    Tensor<> V_noise(dim, lens.data(), dw, false);
+    V_noise.fill_random(-1, 1, o.seed, 101);
+    const double noise_norm = V_noise.norm2(), V_norm = V.norm2();
+    PPXCK(dw, ppx_axpby(dw.ctx, o.ratio_noise * V_norm / noise_norm, V_noise.data, 1.0, V.data, V.size));
+    return true;
+  }
   if (t0 == 'r' && second) {
     // r2: random tensor, uniform in [0.5,1) (test_ALS.cxx:266-273); pp_bench uses [-1,1) (pp_bench.cxx:249)
     V = Tensor<>(dim, lens.data(), dw);
@@ -188,7 +216,7 @@ inline bool build_input_tensor(const CliOptions &o, Tensor<> &V, World &dw, bool
     return true;
   }
   if (dw.rank == 0)
-    fprintf(stderr, "tensor '%s' is not available in this build (supported: r, r2, o1, o2 and -tensorfile)\n",
+    fprintf(stderr, "tensor '%s' is not known (p, p2, c, r, r2, o1, o2)\n",
             o.tensor.c_str());
   return false;
 }

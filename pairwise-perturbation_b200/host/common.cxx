@@ -131,6 +131,92 @@ void build_V(Tensor<> &V, Matrix<> *W, int order, World &dw) {
   V = std::move(out);
 }
 
+// ---- input generators ------------------------------------------------------------------------------------------
+void laplacian_tensor(Tensor<> &V, int N, int s, bool sparse_V, World &dw) {
+  // common.cxx:575-642: sum over the d = N/2 index pairs of D on one pair and identities on the others.  The
+  // reference assembles it from identity tensors with d+1 contractions; the closed form is filled in place.
+  if (sparse_V) throw std::runtime_error("sparse tensors are not supported (never exercised by the reference)");
+  if (N < 2 || N % 2) throw std::runtime_error("laplacian_tensor: the order must be even");
+  int64_t lens[16];
+  for (int i = 0; i < N; i++) lens[i] = s;
+  V = Tensor<>(N, lens, dw, false);
+  PPXCK(dw, ppx_fill_laplacian(dw.ctx, V.data, N / 2, s));
+}
+
+void fold_unfold(Tensor<> &X, Tensor<> &Y) {
+  // common.cxx:870-882: same global (first-index-fastest) order, different mode grouping -- a plain copy
+  if (X.size != Y.size) throw std::runtime_error("fold_unfold: sizes differ");
+  PPXCK(*X.wrld, ppx_memcpy_d2d(X.wrld->ctx, Y.data, X.data, sizeof(double) * X.size));
+}
+
+double host_u01(uint64_t seed, uint64_t tensor_id, uint64_t index) {
+  uint64_t z = index + seed * 0x9E3779B97F4A7C15ULL + tensor_id * 0xD1B54A32D192ED03ULL;
+  z += 0x9E3779B97F4A7C15ULL;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+  z ^= z >> 31;
+  return (double)(z >> 11) * (1.0 / 9007199254740992.0);
+}
+
+double collinearity(const std::vector<double> &v1, const std::vector<double> &v2) {
+  // common.cxx:297-302
+  double ip = 0, n1 = 0, n2 = 0;
+  for (size_t i = 0; i < v1.size(); i++) {
+    ip += v1[i] * v2[i];
+    n1 += v1[i] * v1[i];
+    n2 += v2[i] * v2[i];
+  }
+  return ip / (std::sqrt(n1) * std::sqrt(n2));
+}
+
+Tensor<> Gen_collinearity(int *lens, int dim, int R, double col_min, double col_max, World &dw) {
+  // common.cxx:361-423: R rank-one terms whose mode-j vectors have pairwise collinearity in [col_min, col_max]
+  // (redrawn until they do), weights lambda_i = 0.2 + 0.6 (i+1)/R.  The vectors are short, so the rejection loop runs
+  // on the host with the counter-based generator (draw k of the run uses tensor id 1000 + k); the sum of the R outer
+  // products is one fused reconstruction on the device.
+  vector<vector<vector<double>>> vec(R, vector<vector<double>>(dim));
+  uint64_t draw = 1000;
+  auto fill = [&](vector<double> &v, int n) {
+    v.resize(n);
+    for (int t = 0; t < n; t++) v[t] = host_u01(dw.seed, draw, (uint64_t)t);
+    draw++;
+  };
+  for (int i = 0; i < R; i++)
+    for (int j = 0; j < dim; j++) fill(vec[i][j], lens[j]);
+  for (int j = 0; j < dim; j++)
+    for (int i = 1; i < R; i++) {
+      bool ok = false;
+      int tries = 0;
+      while (!ok) {
+        int k = 0;
+        for (; k < i; k++) {
+          const double col = collinearity(vec[i][j], vec[k][j]);
+          if (col < col_min || col > col_max) break;
+        }
+        if (k == i) {
+          ok = true;
+        } else {
+          if (++tries > 100000) throw std::runtime_error("Gen_collinearity: no vector within the collinearity range");
+          fill(vec[i][j], lens[j]);
+        }
+      }
+    }
+  vector<Matrix<>> W;
+  vector<double> host;
+  for (int j = 0; j < dim; j++) {
+    W.emplace_back((int64_t)lens[j], (int64_t)R, dw, false);
+    host.assign((size_t)lens[j] * R, 0.0);
+    for (int i = 0; i < R; i++) {
+      const double lambda_ = (j == 0) ? 0.2 + 0.6 / R * (i + 1) : 1.0;  // :409
+      for (int t = 0; t < lens[j]; t++) host[(size_t)t + (size_t)lens[j] * i] = lambda_ * vec[i][j][t];
+    }
+    W[j].write_all(host.data());
+  }
+  Tensor<> X;
+  build_V(X, W.data(), dim, dw);
+  return X;
+}
+
 double cp_residual_norm(Tensor<> &V, Matrix<> *W, int order, World &dw) {
   const double *ptrs[16];
   for (int i = 0; i < order; i++) ptrs[i] = W[i].data;

@@ -32,6 +32,14 @@ void KhatriRao_contract(Matrix<> &M, Tensor<> &V, Matrix<> *W, int *index, int *
 void gradsubprob(Matrix<> &M, Matrix<> &S, Matrix<> &W, Matrix<> &grad_W);         // common.cxx:1002-1004
 void gradient_CP(Tensor<> &V, Matrix<> *W, Matrix<> *grad_W, World &dw);           // common.cxx:1009-1052
 
+// input generators of test_ALS / pp_bench / run (test_ALS.cxx:222-286)
+void laplacian_tensor(Tensor<> &V, int N, int s, bool sparse_V, World &dw);        // common.cxx:575-642
+void fold_unfold(Tensor<> &X, Tensor<> &Y);                                        // common.cxx:870-882
+double collinearity(const std::vector<double> &v1, const std::vector<double> &v2); // common.cxx:297-302
+Tensor<> Gen_collinearity(int *lens, int dim, int R, double col_min, double col_max, World &dw);  // common.cxx:361-423
+// u(seed, tensor_id, index) in [0,1) on the host: bit-identical to ppx_fill_uniform
+double host_u01(uint64_t seed, uint64_t tensor_id, uint64_t index);
+
 // ---- what the drivers use on top of it ------------------------------------------------------------------------
 double wall_time();  // MPI_Wtime stand-in
 

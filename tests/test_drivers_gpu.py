@@ -370,3 +370,44 @@ def test_full_size_properties(H, world, s, R):
     x, y = x / np.linalg.norm(x), y / np.linalg.norm(y)
     assert np.abs(x - y).max() <= 1e-9
     free_all(V, Wt, W, G, F, Wa, Ga)
+
+
+# ---- the command line with the reference's other input generators ------------------------------------------------
+import subprocess  # noqa: E402
+
+PKG = os.path.join(os.path.dirname(GOLD), "..", "pairwise-perturbation_b200")
+
+
+def _run_cli(args, tmp_path):
+    csv = os.path.join(str(tmp_path), "out.csv")
+    exe = os.path.join(PKG, "test_ALS")
+    subprocess.run([exe] + args + ["-filename", csv], check=True, stdout=subprocess.DEVNULL, timeout=300)
+    rows = []
+    for line in open(csv):
+        f = line.strip().split(",")
+        if len(f) == 7 and not f[0].startswith("["):
+            rows.append([float(x) for x in f])
+    return rows
+
+
+@pytest.mark.parametrize("tensor,dim,size,R", [("p", 6, 3, 3), ("p2", 4, 5, 4), ("c", 3, 12, 3), ("c", 4, 8, 3)])
+def test_cli_generators_match_oracle(tmp_path, tensor, dim, size, R):
+    """test_ALS -tensor p|p2|c: the tensor built on the GPU side is the oracle's, so the logged gradient norms and
+    residuals of an ALS run from the same seeded start agree."""
+    if tensor == "p":
+        V = o.make_tensor_p(dim, size, folded=True)
+    elif tensor == "p2":
+        V = o.make_tensor_p(dim, size, folded=False)
+    else:
+        V = o.make_tensor_c((size,) * dim, R, 0.5, 0.9, 0.01, seed=1)
+    lens = V.shape
+    vnorm = np.linalg.norm(V)
+    W, G = o.init_factors(lens, R), o.init_grad(lens, R)
+    _, tr = o.alsCP_DT(V, W, G, 1e-10 * vnorm, 8, resprint=2, F=None)
+    rows = _run_cli(["-model", "CP", "-tensor", tensor, "-dim", str(dim), "-size", str(size), "-rank", str(R), "-pp", "0",
+                     "-maxiter", "8", "-resprint", "2"], tmp_path)
+    assert len(rows) == len(tr.rows)
+    for rg, rr in zip(rows, tr.rows):
+        assert int(rg[1]) == rr[0]
+        assert abs(rg[2] - rr[1]) <= 1e-5 * max(rr[1], 1e-6 * vnorm)   # CSV keeps 6 significant digits
+        assert abs(rg[5] - rr[3]) <= 1e-5 * max(rr[3], 1e-6 * vnorm)

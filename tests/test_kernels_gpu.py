@@ -364,3 +364,11 @@ def test_solve_update_g_fuses_hadamard(ctx, mode, s, R):
     assert rel_err(ctx.to_host(Wd, (s, R)), W_ref) < 1e-9
     assert rel_err(ctx.to_host(dW, (s, R)), dW_ref) < 1e-9
     assert rel_err(ctx.to_host(grad, (s, R)), -M + W_old @ S) < 1e-12
+
+
+@pytest.mark.parametrize("d,s", [(1, 7), (2, 5), (3, 4)])
+def test_fill_laplacian(ctx, d, s):
+    ref = o.laplacian_tensor(2 * d, s) if d > 1 else (2.0 * np.eye(s) - np.eye(s, k=1) - np.eye(s, k=-1))
+    out = ctx.empty(ref.size)
+    ctx.fill_laplacian(out, d, s)
+    assert np.array_equal(ctx.to_host(out, ref.shape), ref)

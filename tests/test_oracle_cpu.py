@@ -237,3 +237,43 @@ def test_host_library_loads_and_fails_loudly_without_gpu():
             ppx.Ctx(0)
         with pytest.raises(ppx.PpxError):
             H.World(0)
+
+
+# ---- input generators 'p' / 'p2' / 'c' (test_ALS.cxx:222-261) ----------------------------------------------------
+@pytest.mark.parametrize("N,s", [(4, 3), (6, 3), (4, 5)])
+def test_laplacian_tensor_closed_form(N, s):
+    """The identity-tensor construction of common.cxx:575-642 equals the closed form the CUDA generator fills:
+    no index pair off the diagonal -> 2d, exactly one pair (a,b) off -> D[a,b], more -> 0."""
+    V = o.laplacian_tensor(N, s)
+    d = N // 2
+    W = np.zeros((s,) * N)
+    for idx in np.ndindex(*W.shape):
+        off = [(idx[2 * m], idx[2 * m + 1]) for m in range(d) if idx[2 * m] != idx[2 * m + 1]]
+        if not off:
+            W[idx] = 2.0 * d
+        elif len(off) == 1:
+            W[idx] = -1.0 if abs(off[0][0] - off[0][1]) == 1 else 0.0
+    assert np.array_equal(V, W)
+    # as an operator on d-dimensional grids it is the 2d-point Laplacian: fold (a_m) -> row, (b_m) -> column
+    A = np.transpose(V, list(range(0, N, 2)) + list(range(1, N, 2))).reshape(s ** d, s ** d)
+    D = 2.0 * np.eye(s) - np.eye(s, k=1) - np.eye(s, k=-1)
+    L = sum(np.kron(np.kron(np.eye(s ** m), D), np.eye(s ** (d - 1 - m))) for m in range(d))
+    assert np.array_equal(np.sort(np.linalg.eigvalsh(A)), np.sort(np.linalg.eigvalsh(A.T)))
+    assert np.allclose(np.sort(np.linalg.eigvalsh(A)), np.sort(np.linalg.eigvalsh(L)))
+    # 'p' is the same buffer seen as d modes of size s*s
+    P = o.make_tensor_p(N, s, folded=True)
+    assert P.shape == (s * s,) * d and np.array_equal(P.ravel(order="F"), V.ravel(order="F"))
+
+
+def test_gen_collinearity_respects_the_range_and_noise_level():
+    lens, R = (9, 8, 7), 4
+    X, vec = o.gen_collinearity(lens, R, 0.6, 0.85, seed=1)
+    for j in range(len(lens)):
+        for i in range(1, R):
+            for k in range(i):
+                assert 0.6 <= o.collinearity(vec[i][j], vec[k][j]) <= 0.85
+    lam = [0.2 + 0.6 / R * (i + 1) for i in range(R)]
+    ref = sum(lam[i] * np.einsum("a,b,c->abc", vec[i][0], vec[i][1], vec[i][2]) for i in range(R))
+    assert np.allclose(X, ref, rtol=1e-13, atol=1e-14)
+    V = o.make_tensor_c(lens, R, 0.6, 0.85, ratio_noise=0.05, seed=1)
+    assert abs(np.linalg.norm(V - X) / np.linalg.norm(X) - 0.05) < 1e-12
