@@ -290,6 +290,11 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     ms_total = max_over_ranks(float(ms.value))
     ms_per_step = ms_total / args.steps
+    per_rank_ms = [float(ms.value) / args.steps]
+    if dist is not None:  # every rank's own device time per step (the collectives make them wait for the slowest)
+        t_all = [torch.zeros(1, dtype=torch.float64, device="cuda") for _ in range(nranks)]
+        dist.all_gather(t_all, torch.tensor([per_rank_ms[0]], dtype=torch.float64, device="cuda"))
+        per_rank_ms = [float(t.item()) for t in t_all]
     value = 1e3 / ms_per_step
 
     # ---- PP phase (pp_bench protocol): operator build + approximate sweeps ----------------------------------------
@@ -334,6 +339,12 @@ def main():
     lib.ppx_event_record(world.ctx_handle(), evs[1])
     lib.ppx_event_elapsed_ms(world.ctx_handle(), evs[0], evs[1], C.byref(ms))
     k1_ms = float(ms.value) / reps
+    k1_per_rank = [k1_ms]
+    if dist is not None:
+        t_all = [torch.zeros(1, dtype=torch.float64, device="cuda") for _ in range(nranks)]
+        dist.all_gather(t_all, torch.tensor([k1_ms], dtype=torch.float64, device="cuda"))
+        k1_per_rank = [float(t.item()) for t in t_all]
+        k1_ms = max(k1_per_rank)
     out1.free()
     P_local = float(np.prod(lens_local))
     Kc = float(np.prod(lens_local[x_first:]))
@@ -358,7 +369,7 @@ def main():
                 "traffic": traffic, "algorithmic_flops": k1_flops, "algorithmic_bytes": k1_bytes, "ms": k1_ms,
                 "hbm_gbs": k1_bytes / (k1_ms * 1e-3) / 1e9,
                 "peak_source": "FP64 peak is not in MEASURED_PEAKS.json (it holds HBM and bf16); " + peak_src,
-                "share_of_step": 2 * k1_ms / ms_per_step}
+                "share_of_step": 2 * k1_ms / ms_per_step, "ms_per_rank": k1_per_rank}
 
     # ---- e2e: the driver call with host buffers --------------------------------------------------------------------
     pin = [torch.from_numpy(h.ravel(order="F").copy()).pin_memory() for h in W_start]
@@ -413,7 +424,7 @@ def main():
                        "tensor_bytes_per_gpu": 8 * P_local, "l2": "inputs (%.1f GB) larger than L2; no flush" % (8 * P_local / 1e9),
                        "parallelism": "mode-0 shards x%d, NCCL all-reduce of s x R partial MTTKRPs" % nranks if nranks > 1
                        else "single GPU", "solver": "cholesky"},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "pp": pp,
+            "ms_per_step_per_rank": per_rank_ms, "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "pp": pp,
         }
         print(json.dumps(line), flush=True)
     world.close()

@@ -170,6 +170,11 @@ int ppx_normalize_norms(ppx_ctx *ctx, double *const *W, const double *const *dW,
                         double *const *G, double *sq_out_dev);
 /* out_dev[j] = sum of squares of X[j][0..n[j]) for j < count (norm2()^2; als_CP.cxx:176-178,598-600). */
 int ppx_sqnorms(ppx_ctx *ctx, const double *const *X, const int64_t *n, int count, double *out_dev);
+/* out_dev[i] = <X[i], Y[i]> for count <= 16 pairs of n[i] doubles (deterministic).  With M = the MTTKRP of the last
+ * mode, W its updated factor, S = Hadamard of the other Grams and G = W^T W, the residual follows without touching V:
+ * ||V - [[W]]||^2 = ||V||^2 - 2 <M, W> + <S, G>   (a monitor: it cancels near convergence). */
+int ppx_dots(ppx_ctx *ctx, const double *const *X, const double *const *Y, const int64_t *n, int count,
+             double *out_dev);
 /* dW = W - W_prev; W_prev = W; sq_out_dev = { ||dW||^2, ||W||^2 }  (als_CP.cxx:596-600). */
 int ppx_diff_update(ppx_ctx *ctx, const double *W, double *W_prev, double *dW, int64_t n, double *sq_out_dev);
 /* y = alpha*x + beta*y  (elementwise; M += F, als_CP.cxx:294). */

@@ -80,6 +80,7 @@ SIGNATURES = {
     "ppx_normalize": (C.c_int, [_vp, C.POINTER(_dp), C.POINTER(_i64), C.c_int, C.c_int, C.POINTER(_dp)]),
     "ppx_normalize_g": (C.c_int, [_vp, C.POINTER(_dp), C.POINTER(_i64), C.c_int, C.c_int, C.POINTER(_dp)]),
     "ppx_sqnorms": (C.c_int, [_vp, C.POINTER(_dp), C.POINTER(_i64), C.c_int, _dp]),
+    "ppx_dots": (C.c_int, [_vp, C.POINTER(_dp), C.POINTER(_dp), C.POINTER(_i64), C.c_int, _dp]),
     "ppx_diff_update": (C.c_int, [_vp, _dp, _dp, _dp, _i64, _dp]),
     "ppx_axpby": (C.c_int, [_vp, C.c_double, _dp, C.c_double, _dp, _i64]),
     "ppx_cp_residual": (C.c_int, [_vp, _dp, C.POINTER(_i64), C.c_int, C.POINTER(_dp), C.c_int, _dp]),
@@ -112,9 +113,10 @@ def load_library():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        raise PpxError(f"{LIB_PATH} is missing: build it with `make -C {_HERE}`; there is no CPU fallback")
-    lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+    path = os.environ.get("PPX_LIB", LIB_PATH)  # PPX_LIB: A/B timing of two builds of the library (tools/)
+    if not os.path.exists(path):
+        raise PpxError(f"{path} is missing: build it with `make -C {_HERE}`; there is no CPU fallback")
+    lib = C.CDLL(path, mode=C.RTLD_GLOBAL)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)  # raises AttributeError if the library does not export a declared symbol
         fn.restype = res

@@ -442,20 +442,7 @@ int ppx_ttm_impl(ppx_ctx *ctx, const double *V, int64_t L, int64_t X, int64_t Rt
   double *partial = nullptr;
   const int G = 2 * ctx->sm_count;
   if (!inplace && !accumulate && col_blocks == 1 && p.nk >= 64 && p.num_tiles < 8 * G) {
-    auto eff = [&](int S) {
-      const int64_t units = (int64_t)p.num_tiles * S;
-      const int64_t waves = (units + G - 1) / G;
-      return (double)units / (double)(waves * G);
-    };
-    int best = 1;
-    double best_eff = eff(1);
-    for (int S = 2; S <= 512 && p.nk / S >= 16; S++) {
-      const double e = eff(S);
-      if (e > best_eff + 0.02) {
-        best_eff = e;
-        best = S;
-      }
-    }
+    const int best = ppx_pick_ksplit(p.num_tiles, p.nk, G, p.Mtot * (int64_t)R, ctx->ws_bytes - ctx->ws_used);
     if (best > 1) {
       if (!ws_keep) ppx_ws_reset(ctx);
       partial = (double *)ppx_ws_alloc(ctx, sizeof(double) * (size_t)best * p.Mtot * R);

@@ -24,6 +24,11 @@
 #include <cuda.h>
 #include "ppx_internal.h"
 
+// which layouts spell the register double buffering of the operand fragments out (see the consumer loop)
+#ifndef PPX_K1_EXPLICIT_PREFETCH
+#define PPX_K1_EXPLICIT_PREFETCH(kmajor) (true)  // k-major: 24.0 ms with, 24.9 ms without; M-major: 24.1 / 24.9
+#endif
+
 namespace {
 
 constexpr int TBM = 128;          // rows per tile
@@ -71,6 +76,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         : "r"(smem_u32(bar)), "r"(parity)
         : "memory");
   }
+}
+__device__ __forceinline__ bool mbar_test(uint64_t *bar, uint32_t parity) {  // non-blocking
+  uint32_t done;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(done)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return done != 0;
 }
 __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1) {
   asm volatile(
@@ -224,20 +242,26 @@ __global__ void __launch_bounds__(TTHREADS, 2) ttm_tma_kernel(const __grid_const
   set_unit(ld, blockIdx.x);
   int ld_kc = 0, ld_n = 0;  // ld/ld_kc describe chunk ld_n
   auto issue_chunk = [&](int n) {
-    int d = n - ld_n;
-    ld_n = n;
-    while (true) {
+    if (KMAJOR) {
+      // single producer thread (tid 0), chunks in order: ld/ld_kc already describe chunk n
+      if (tid != 0) return;
       while (ld.count == 0) set_unit(ld, ld.u + gridDim.x);
-      const int rem = ld.count - ld_kc;
-      if (d < rem) {
-        ld_kc += d;
-        break;
+    } else {
+      int d = n - ld_n;
+      ld_n = n;
+      while (true) {
+        while (ld.count == 0) set_unit(ld, ld.u + gridDim.x);
+        const int rem = ld.count - ld_kc;
+        if (d < rem) {
+          ld_kc += d;
+          break;
+        }
+        d -= rem;
+        ld_kc = 0;
+        set_unit(ld, ld.u + gridDim.x);
       }
-      d -= rem;
-      ld_kc = 0;
-      set_unit(ld, ld.u + gridDim.x);
+      if (lane != 0) return;
     }
-    if (lane != 0) return;
     const int stage = n % TSTAGES;
     const int round = n / TSTAGES;
     if (round > 0) mbar_wait(&empty[stage], (round - 1) & 1);  // every warp has released the stage
@@ -259,12 +283,19 @@ __global__ void __launch_bounds__(TTHREADS, 2) ttm_tma_kernel(const __grid_const
       }
     }
     bulk_load(W_base + stage * W_STAGE_BYTES, p.Wpp + (int64_t)chunk * (NCOLS * TLDW), W_STAGE_BYTES, &full[stage]);
+    if (KMAJOR) {  // advance to the next chunk of the stream
+      if (++ld_kc == ld.count) {
+        ld_kc = 0;
+        set_unit(ld, ld.u + gridDim.x);
+      }
+    }
   };
   // (measured at order-4 s=300 R=50: rotation gains 3 % for the M-major layout, whose issue path is longer, and
-  // loses 3 % for the k-major one, so that one keeps warp 0 as its only producer)
+  // loses 4 % for the k-major one -- 25.06 vs 24.02 ms -- so that one keeps thread 0 as its only producer, walking
+  // the chunk stream in order)
   constexpr int ROT = KMAJOR ? 0 : 3;
   for (int n = 0; n < TSTAGES - 1 && n < total; n++)
-    if (warp == (n & ROT)) issue_chunk(n);
+    if (KMAJOR ? tid == 0 : warp == (n & ROT)) issue_chunk(n);
 
   // ===================================== consumer warps =====================================
   const int g = lane >> 2, t4 = lane & 3;
@@ -301,41 +332,73 @@ __global__ void __launch_bounds__(TTHREADS, 2) ttm_tma_kernel(const __grid_const
   Unit cu;
   set_unit(cu, blockIdx.x);
   int kc = 0;
-  for (int c = 0; c < total; c++) {
-    while (cu.count == 0) set_unit(cu, cu.u + gridDim.x);
-    const int stage = c % TSTAGES;
-    mbar_wait(&full[stage], (c / TSTAGES) & 1);
+  // Operand fragments are double buffered in registers: the shared loads of MMA step q+1 are issued BEFORE the DMMAs of
+  // step q, also across the chunk boundary (the next stage's full barrier is polled without blocking; its data is
+  // normally there, three chunks were requested ahead).  ptxas found this overlap on its own only in some variants
+  // (254 registers: 23.6 ms, 206 registers: 25.0 ms on the same k-major problem), so it is spelled out.
+  struct Frag {
+    double a[4], b[NT], bt[TAIL > 0 ? TAIL : 1];
+  };
+  auto load_frag = [&](Frag &f, int stage, int q) {
     const uint8_t *As = A_base + stage * A_STAGE_BYTES;
     const double *Ws = (const double *)(W_base + stage * W_STAGE_BYTES);
 #pragma unroll
-    for (int q = 0; q < 4; q++) {
-      double a[4], b[NT];
+    for (int i = 0; i < 4; i++) {
+      if (KMAJOR)
+        f.a[i] = *(const double *)(As + aoff[q] + i * 1024);
+      else
+        f.a[i] = *(const double *)(As + aoff[2 * i + (q & 1)] + (q >> 1) * 1024);
+    }
 #pragma unroll
-      for (int i = 0; i < 4; i++) {
-        if (KMAJOR)
-          a[i] = *(const double *)(As + aoff[q] + i * 1024);
-        else
-          a[i] = *(const double *)(As + aoff[2 * i + (q & 1)] + (q >> 1) * 1024);
+    for (int j = 0; j < NT; j++) f.b[j] = Ws[(8 * j + g) * TLDW + 4 * q + t4];
+#pragma unroll
+    for (int cc = 0; cc < TAIL; cc++) f.bt[cc] = Ws[(8 * NT + cc) * TLDW + 4 * q + t4];
+  };
+  auto compute = [&](const Frag &f) {
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+      for (int j = 0; j < NT; j++) ppx_dmma(acc[i][j][0], acc[i][j][1], f.a[i], f.b[j]);
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+      for (int cc = 0; cc < TAIL; cc++) tacc[i][cc] = fma(f.a[i], f.bt[cc], tacc[i][cc]);
+  };
+  Frag f0, f1;
+  bool have_f0 = false;  // f0 already holds step 0 of the chunk about to be processed
+  for (int c = 0; c < total; c++) {
+    while (cu.count == 0) set_unit(cu, cu.u + gridDim.x);
+    const int stage = c % TSTAGES;
+    if (PPX_K1_EXPLICIT_PREFETCH(KMAJOR)) {
+      if (!have_f0) {
+        mbar_wait(&full[stage], (c / TSTAGES) & 1);
+        load_frag(f0, stage, 0);
       }
+      load_frag(f1, stage, 1);
+      compute(f0);
+      load_frag(f0, stage, 2);
+      compute(f1);
+      load_frag(f1, stage, 3);
+      compute(f0);
+      have_f0 = false;
+      if (c + 1 < total) {
+        const int ns = (c + 1) % TSTAGES;
+        have_f0 = __all_sync(0xffffffffu, mbar_test(&full[ns], ((c + 1) / TSTAGES) & 1));  // warp-uniform
+        if (have_f0) load_frag(f0, ns, 0);
+      }
+      compute(f1);
+    } else {
+      mbar_wait(&full[stage], (c / TSTAGES) & 1);
 #pragma unroll
-      for (int j = 0; j < NT; j++) b[j] = Ws[(8 * j + g) * TLDW + 4 * q + t4];
-#pragma unroll
-      for (int i = 0; i < 4; i++)
-#pragma unroll
-        for (int j = 0; j < NT; j++) ppx_dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
-      if (TAIL > 0) {
-        double bt[TAIL > 0 ? TAIL : 1];
-#pragma unroll
-        for (int c = 0; c < TAIL; c++) bt[c] = Ws[(8 * NT + c) * TLDW + 4 * q + t4];
-#pragma unroll
-        for (int i = 0; i < 4; i++)
-#pragma unroll
-          for (int c = 0; c < TAIL; c++) tacc[i][c] = fma(a[i], bt[c], tacc[i][c]);
+      for (int q = 0; q < 4; q++) {
+        load_frag(f0, stage, q);
+        compute(f0);
       }
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[stage]);  // this warp is done reading the stage
-    if (warp == ((c + TSTAGES - 1) & ROT) && c + TSTAGES - 1 < total) issue_chunk(c + TSTAGES - 1);  // stage of c-1
+    if ((KMAJOR ? tid == 0 : warp == ((c + TSTAGES - 1) & ROT)) && c + TSTAGES - 1 < total)
+      issue_chunk(c + TSTAGES - 1);  // refills the stage of chunk c-1
     __syncwarp();
     if (++kc == cu.count) {
       const int tile = cu.tile, split = cu.split;
@@ -548,20 +611,7 @@ int ppx_ttm_tma_try(ppx_ctx *ctx, const double *V, int64_t L, int64_t K, int64_t
   double *partial = nullptr;
   const int G = 2 * ctx->sm_count;
   if (!inplace && !accumulate && p.nk >= 64 && p.num_tiles < 8 * G) {
-    auto eff = [&](int S) {
-      const int64_t units = (int64_t)p.num_tiles * S;
-      const int64_t waves = (units + G - 1) / G;
-      return (double)units / (double)(waves * G);
-    };
-    int best = 1;
-    double best_eff = eff(1);
-    for (int S = 2; S <= 512 && p.nk / S >= 16; S++) {
-      const double e = eff(S);
-      if (e > best_eff + 0.02) {
-        best_eff = e;
-        best = S;
-      }
-    }
+    const int best = ppx_pick_ksplit(p.num_tiles, p.nk, G, Mtot * (int64_t)R, ctx->ws_bytes - ctx->ws_used);
     if (best > 1) {
       partial = (double *)ppx_ws_alloc(ctx, sizeof(double) * (size_t)best * Mtot * R);
       if (partial) {

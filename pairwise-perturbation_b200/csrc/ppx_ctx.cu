@@ -268,6 +268,22 @@ __global__ void __launch_bounds__(1024) sqnorms_kernel(SqnormArgs a, double *out
   if (threadIdx.x == 0) out[blockIdx.x] = s;
 }
 
+// one block per pair of arrays: deterministic inner product
+struct DotArgs {
+  const double *x[16];
+  const double *y[16];
+  int64_t n[16];
+};
+__global__ void __launch_bounds__(1024) dots_kernel(DotArgs a, double *out) {
+  __shared__ double red[32];
+  const double *x = a.x[blockIdx.x], *y = a.y[blockIdx.x];
+  const int64_t n = a.n[blockIdx.x];
+  double s = 0;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) s = fma(x[i], y[i], s);
+  s = ppx_block_sum(s, red);
+  if (threadIdx.x == 0) out[blockIdx.x] = s;
+}
+
 __global__ void __launch_bounds__(1024) diff_update_kernel(const double *W, double *Wp, double *dW, int64_t n,
                                                            double *out) {
   __shared__ double red[32];
@@ -370,6 +386,20 @@ int ppx_sqnorms(ppx_ctx *ctx, const double *const *X, const int64_t *n, int coun
     a.n[i] = n[i];
   }
   sqnorms_kernel<<<count, 1024, 0, ctx->stream>>>(a, out_dev);
+  PPX_CHECK_LAUNCH(ctx);
+  return PPX_OK;
+}
+
+int ppx_dots(ppx_ctx *ctx, const double *const *X, const double *const *Y, const int64_t *n, int count,
+             double *out_dev) {
+  PPX_REQUIRE(ctx, X && Y && n && out_dev && count >= 1 && count <= 16, "1 <= count <= 16");
+  DotArgs a;
+  for (int i = 0; i < count; i++) {
+    a.x[i] = X[i];
+    a.y[i] = Y[i];
+    a.n[i] = n[i];
+  }
+  dots_kernel<<<count, 1024, 0, ctx->stream>>>(a, out_dev);
   PPX_CHECK_LAUNCH(ctx);
   return PPX_OK;
 }

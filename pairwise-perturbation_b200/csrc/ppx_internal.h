@@ -79,6 +79,31 @@ static inline void ppx_split3(const int64_t *lens, int k, int x, int64_t *L, int
 
 static inline int ppx_cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
+// Number of K splits for the first-contraction kernels: `num_tiles` row tiles of `nk` 16-deep chunks on a persistent
+// grid of G CTAs, output of `out_elems` doubles per split.  Cost model in units of one chunk step of a CTA (~1.75 us
+// with two CTAs per SM): rounds of the grid x chunks per split, plus writing and re-reading the partial outputs at
+// ~6 TB/s; a split must keep >= 16 chunks and its partial buffer must fit in the free workspace.  (A plain "best grid
+// efficiency" rule picked 296 splits for 87 tiles -- efficiency exactly 1 -- whose 1.3 GB of partials did not fit.)
+static inline int ppx_pick_ksplit(int num_tiles, int nk, int G, int64_t out_elems, size_t ws_free) {
+  if (const char *f = getenv("PPX_KSPLIT"))  // experiments only
+    if (atoi(f) > 0) return atoi(f);
+  int best = 1;
+  double best_cost = 1e300;
+  for (int S = 1; S <= 512 && (S == 1 || nk / S >= 16); S++) {
+    if (S > 1 && (double)S * (double)out_elems * 8.0 + 4096.0 > (double)ws_free) break;
+    const int64_t units = (int64_t)num_tiles * S;
+    const double rounds = (double)((units + G - 1) / G);
+    const double cps = (double)((nk + S - 1) / S);
+    const double traffic_us = S > 1 ? (double)S * (double)out_elems * 16.0 / 6.0e6 : 0.0;
+    const double cost = rounds * cps + traffic_us / 1.75 + (S > 1 ? 4.0 : 0.0);  // + the reduce kernel's launch
+    if (cost < best_cost * 0.995) {  // prefer the smaller split on near ties
+      best_cost = cost;
+      best = S;
+    }
+  }
+  return best;
+}
+
 // ---- device helpers -------------------------------------------------------------------------------------
 #ifdef __CUDACC__
 __device__ __forceinline__ double ppx_warp_sum(double v) {

@@ -127,8 +127,11 @@ Matrix<> leaf_mttkrp(map<string, Tensor<>> &mttkrp_map, map<string, string> &par
 }
 
 // one exact ALS sweep over all modes with the dimension tree
+// `fit_terms` (device, 3 doubles, optional): <M_N, W_N>, <S_N, G_N>, <F_N, W_N> of the LAST mode update, from which
+// the residual of the sweep's result follows without a pass over V (World::fast_residual).
 void dt_sweep(Tensor<> &V, Matrix<> *W, Matrix<> *grad_W, Matrix<> *F, double lambda, bool always_regul,
-              map<string, string> &parent, map<string, string> &sibling, GramCache &gc, Matrix<> &S, World &dw) {
+              map<string, string> &parent, map<string, string> &sibling, GramCache &gc, Matrix<> &S, World &dw,
+              double *fit_terms = nullptr) {
   const int N = V.order;
   map<string, Tensor<>> mttkrp_map;  // cleared every sweep (als_CP.cxx:215)
   for (int i = 0; i < N; i++) {
@@ -137,6 +140,13 @@ void dt_sweep(Tensor<> &V, Matrix<> *W, Matrix<> *grad_W, Matrix<> *F, double la
     // S = Hadamard of the cached Grams (+ lambda I) (:288-292 / :573-579), gradient and solve (:296-297), one call
     gc.solve(i, (always_regul || lambda != 0) ? lambda : 0.0, M, W[i], nullptr, 1.0, &grad_W[i], nullptr, dw.solver, dw);
     gc.refresh(W, i, dw);
+    if (fit_terms && i == N - 1) {
+      gc.hadamard(i, 0.0, S, dw);  // without lambda I: <S, G_N> = ||[[W]]||^2
+      const double *xs[3] = {M.data, S.data, F ? F[i].data : M.data};
+      const double *ys[3] = {W[i].data, gc.G[i].data, W[i].data};
+      int64_t ns[3] = {M.size, S.size, F ? M.size : 0};
+      PPXCK(dw, ppx_dots(dw.ctx, xs, ys, ns, 3, fit_terms));
+    }
   }
   normalize_with_grams(W, N, gc, dw);  // :303
 }
@@ -226,11 +236,32 @@ bool alsCP_DT(Tensor<> &V, Matrix<> *W, Matrix<> *grad_W, Matrix<> *F, double to
   Construct_Dimension_Tree(parent, sibling, 0, N - 1);
   GramCache gc;
   gc.init(W, N, dw);
+  // fast residual (World::fast_residual): ||V||^2 once, then three inner products per sweep instead of a pass over V.
+  // Needs the last mode replicated (it is: only mode 0 is ever sharded); the first print point (no sweep yet) is exact.
+  const bool fast = dw.fast_residual && N >= 2 && !(trace_sink() && trace_sink()->skip_residual);
+  double vnorm_sq = 0;
+  bool have_terms = false;
+  double *fit_terms = fast ? dw.scal_dev + 40 : nullptr;
+  if (fast) {
+    const double *xs[1] = {V.data};
+    int64_t ns[1] = {V.size};
+    PPXCK(dw, ppx_sqnorms(dw.ctx, xs, ns, 1, dw.scal_dev));
+    dw.allreduce(dw.scal_dev, 1);
+    dw.fetch(dw.scal_dev, &vnorm_sq, 1);
+  }
   for (iter = 0; iter <= maxiter; iter++) {
     if (iter % resprint == 0 || iter == maxiter) {  // :166-213
       const double st_time1 = synced_time(dw);
       projnorm = gradnorm_global(grad_W, N, dw);
-      diffnorm_V = residual_or_skip(V, W, dw);
+      if (fast && have_terms) {
+        double h[3];
+        dw.fetch(fit_terms, h, 3);
+        // M includes F (:294): <MTTKRP, W> = <M, W> - <F, W>
+        const double r2 = vnorm_sq - 2.0 * (h[0] - (F ? h[2] : 0.0)) + h[1];
+        diffnorm_V = std::sqrt(r2 > 0 ? r2 : 0.0);
+      } else {
+        diffnorm_V = residual_or_skip(V, W, dw);
+      }
       st_time += synced_time(dw) - st_time1;  // the residual evaluation is taken off the clock (:189)
       const double dtime = wall_time() - st_time;
       if (!bench) {
@@ -244,7 +275,8 @@ bool alsCP_DT(Tensor<> &V, Matrix<> *W, Matrix<> *grad_W, Matrix<> *F, double to
       }
       if (projnorm < tol || wall_time() - st_time > timelimit) break;
     }
-    dt_sweep(V, W, grad_W, F, lambda, true, parent, sibling, gc, S, dw);
+    dt_sweep(V, W, grad_W, F, lambda, true, parent, sibling, gc, S, dw, fit_terms);
+    have_terms = fast;
     if (trace_sink()) trace_sink()->sweeps.push_back({0, iter});
     if (iter % 10 == 0 && dw.rank == 0 && !trace_quiet()) printf(".");
   }

@@ -86,6 +86,10 @@ int ppxh_world_set(void *w, int solver, int use_graph) {
   ((World *)w)->use_graph = use_graph != 0;
   return 0;
 }
+int ppxh_world_set_fast_residual(void *w, int on) {
+  ((World *)w)->fast_residual = on != 0;
+  return 0;
+}
 // multi-GPU: NCCL communicator + the shard layout of mode `shard_mode`
 int ppxh_world_comm_init(void *w_, const void *id128, int nranks, int rank, int shard_mode, int64_t shard_global,
                          int64_t row_begin, int64_t row_end) {

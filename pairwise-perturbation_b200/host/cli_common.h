@@ -34,6 +34,7 @@ struct CliOptions {
   std::string solver = "chol";  // -solver chol|svd : R x R solve behind SVD_solve
   uint64_t seed = 1;            // -seed     : counter-based generator seed for the tensor; factors use seed+1
   int graph = 1;                // -graph 0|1: replay the PP approximate sweep as a CUDA graph
+  int fastres = 0;              // -fastres 0|1: alsCP_DT reports the residual from the MTTKRP identity (no pass over V)
   std::string lens;             // -lens a,b,c,.. : non-cubic synthetic tensor (overrides -dim/-size)
   int updaterank = 1, randomsvd = 0;  // run.cxx only
 };
@@ -111,6 +112,7 @@ inline CliOptions parse_cli(int argc, char **argv, int pp_max) {
   if (char *v = get("-solver")) o.solver = v;
   if (char *v = get("-seed")) o.seed = strtoull(v, nullptr, 10);
   if (char *v = get("-graph")) o.graph = atoi(v);
+  if (char *v = get("-fastres")) o.fastres = atoi(v);
   if (char *v = get("-lens")) o.lens = v;
   return o;
 }
@@ -136,6 +138,7 @@ inline World *make_world(const CliOptions &o) {
   World *dw = new World(device, (size_t)2 << 30);
   dw->solver = (o.solver == "svd") ? PPX_SOLVE_SVD_PINV : PPX_SOLVE_CHOL;
   dw->use_graph = o.graph != 0;
+  dw->fast_residual = o.fastres != 0;
   dw->seed = o.seed;
   return dw;
 }

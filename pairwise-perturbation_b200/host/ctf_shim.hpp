@@ -44,6 +44,9 @@ public:
   ppx_ctx *ctx = nullptr;
   int solver = PPX_SOLVE_CHOL;  // R x R solve used by SVD_solve/SVD_solve_mod (CHOL | SVD_PINV)
   bool use_graph = true;        // replay the PP approximate sweep as a CUDA graph
+  // alsCP_DT: report ||V - [[W]]|| at the print points from the identity ||V||^2 - 2<M_N,W_N> + <S_N,G_N> of the last
+  // mode update instead of a pass over V (a monitor, it cancels near convergence).  Default: exact.
+  bool fast_residual = false;
   uint64_t seed = 1;            // fill_random stream: u(seed, next_id++, index)
   uint64_t next_id = 0;
   // leading-mode sharding (multi-GPU): global size of the sharded mode and the local row range

@@ -73,6 +73,7 @@ def load_host_library():
     lib.ppxh_cpd_als.argtypes = [_vp, d, d, C.c_int, C.c_int, C.c_char_p, C.c_int, PI]
     lib.ppxh_cpd_read_W.argtypes = [_vp, C.c_int, _vp]
     lib.ppxh_cpd_read_grad.argtypes = [_vp, C.c_int, _vp]
+    lib.ppxh_world_set_fast_residual.argtypes = [_vp, C.c_int]
     lib.ppxh_hosvd.argtypes = [_vp, _vp, PV, C.c_int, PI, _vp]
     lib.ppxh_alsTucker_DT.argtypes = [_vp, _vp, PV, C.c_int, d, d, C.c_int, C.c_char_p, C.c_int, C.c_int, _vp, PI]
     lib.ppxh_alsTucker_PP.argtypes = [_vp, _vp, PV, C.c_int, d, d, d, C.c_int, C.c_char_p, C.c_int, C.c_int, _vp, PI]
@@ -98,6 +99,10 @@ class World:
 
     def set(self, solver=0, use_graph=True):
         self.lib.ppxh_world_set(self.h, solver, int(use_graph))
+
+    def set_fast_residual(self, on):
+        """alsCP_DT print points: residual from ||V||^2 - 2<M_N,W_N> + <S_N,G_N> instead of a pass over V."""
+        self.lib.ppxh_world_set_fast_residual(self.h, int(on))
 
     def comm_init(self, id_bytes, nranks, rank, shard_mode, shard_global, row_begin, row_end):
         buf = C.create_string_buffer(bytes(id_bytes), 128) if id_bytes is not None else None

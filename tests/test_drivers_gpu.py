@@ -411,3 +411,28 @@ def test_cli_generators_match_oracle(tmp_path, tensor, dim, size, R):
         assert int(rg[1]) == rr[0]
         assert abs(rg[2] - rr[1]) <= 1e-5 * max(rr[1], 1e-6 * vnorm)   # CSV keeps 6 significant digits
         assert abs(rg[5] - rr[3]) <= 1e-5 * max(rr[3], 1e-6 * vnorm)
+
+
+@pytest.mark.parametrize("lens,R", [((14, 13, 12, 11), 4), ((10, 11, 12), 3), ((6, 7, 6, 5, 6, 7), 3)])
+def test_fast_residual_identity_tracks_the_exact_residual(H, world, lens, R):
+    """World::fast_residual: ||V||^2 - 2<M_N,W_N> + <S_N,G_N> from the last mode update equals the exact residual of
+    the sweep's result; same iterates, so the gradient norms are identical."""
+    V, W, G = problem(lens, R)
+    vnorm = np.linalg.norm(V)
+    Vd, Wd, Gd, Fd = to_dev(H, world, V, W, G)
+    with H.Trace() as exact:
+        H.alsCP_DT(world, Vd, Wd, Gd, Fd, 1e-10 * vnorm, 9, resprint=3)
+    free_all(Vd, Wd, Gd, Fd)
+    Vd, Wd, Gd, Fd = to_dev(H, world, V, W, G)
+    world.set_fast_residual(True)
+    try:
+        with H.Trace() as fast:
+            H.alsCP_DT(world, Vd, Wd, Gd, Fd, 1e-10 * vnorm, 9, resprint=3)
+    finally:
+        world.set_fast_residual(False)
+    assert len(fast.rows) == len(exact.rows) >= 3
+    for rf, re_ in zip(fast.rows, exact.rows):
+        assert rf[0] == re_[0] and rf[1] == re_[1]
+        # res^2 is a difference of numbers of size ||V||^2: absolute accuracy ~1e-16 ||V||^2 / res
+        assert abs(rf[3] - re_[3]) <= 1e-13 * vnorm * vnorm / max(re_[3], 1e-12 * vnorm) + 1e-12 * vnorm
+    free_all(Vd, Wd, Gd, Fd)
