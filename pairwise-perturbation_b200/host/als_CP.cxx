@@ -672,7 +672,14 @@ double alsCP_PP_partupdate_sub(Tensor<> &V, Matrix<> *W, Matrix<> *grad_W, Matri
   (void)F;
   const int N = V.order;
   const int R = (int)W[0].ncol;
-  if (dw.np > 1) throw std::runtime_error("alsCP_PP_partupdate: multi-GPU not supported yet");
+  // multi-GPU: W_0, dW_0, M_0, dM_0 hold the local rows of the sharded mode; everything else is replicated.  The only
+  // exchange inside the sweep is the propagation of dW_0 to the other modes (a contraction over the sharded index).
+  Matrix<> dM_term;
+  if (dw.np > 1) {
+    int64_t smax = 0;
+    for (int i = 0; i < N; i++) smax = std::max(smax, W[i].nrow);
+    dM_term = Matrix<>(smax, R, dw);
+  }
   double dtime_first = 0;
   const int init_iter = iter;
   double diffnorm_V = 1000;
@@ -754,7 +761,16 @@ double alsCP_PP_partupdate_sub(Tensor<> &V, Matrix<> *W, Matrix<> *grad_W, Matri
         const double *ops[1] = {P.data}, *dws[1] = {dW[i].data};
         const int which[1] = {i < ii ? 0 : 1};  // contract the index that belongs to mode i
         const int64_t so[1] = {dW[i].nrow};
-        PPXCK(dw, ppx_pp_correct(dw.ctx, dM[ii].data, ops, which, dws, so, 1, W[ii].nrow, R, dM[ii].data));
+        if (dw.np > 1 && i == dw.shard_mode) {
+          // partial sum over the local rows of mode i: 0 + P x dW_i into a scratch matrix, summed over ranks, then added
+          const int64_t n = W[ii].nrow * (int64_t)R;
+          PPXCK(dw, ppx_memset_zero(dw.ctx, dM_term.data, sizeof(double) * n));
+          PPXCK(dw, ppx_pp_correct(dw.ctx, dM_term.data, ops, which, dws, so, 1, W[ii].nrow, R, dM_term.data));
+          dw.allreduce(dM_term.data, n);
+          PPXCK(dw, ppx_axpby(dw.ctx, 1.0, dM_term.data, 1.0, dM[ii].data, n));
+        } else {
+          PPXCK(dw, ppx_pp_correct(dw.ctx, dM[ii].data, ops, which, dws, so, 1, W[ii].nrow, R, dM[ii].data));
+        }
       }
     }
     {  // :1060-1064

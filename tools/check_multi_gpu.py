@@ -40,12 +40,15 @@ for lens, R, maxiter, tol_init in [((13, 12, 11, 10), 4, 40, 0.1), ((9, 10, 11),
     V, _ = o.make_tensor_r(lens, R)
     W, G = o.init_factors(lens, R), o.init_grad(lens, R)
     vnorm = np.linalg.norm(V)
-    for driver in ("DT", "PP"):
+    for driver in ("DT", "PP", "PPpart"):
         W_ref, G_ref = [w.copy() for w in W], [g.copy() for g in G]
         if driver == "DT":
             _, tr = o.alsCP_DT(V, W_ref, G_ref, 1e-10 * vnorm, 12, resprint=4, F=None)
-        else:
+        elif driver == "PP":
             _, tr = o.alsCP_PP(V, W_ref, G_ref, 1e-10 * vnorm, tol_init, maxiter, resprint=4)
+        else:
+            _, tr = o.alsCP_PP_partupdate(V, W_ref, G_ref, 1e-10 * vnorm, tol_init, maxiter, update_percentage=1.0,
+                                          resprint=4)
         Vd = H.Tensor.from_numpy(world, np.ascontiguousarray(V[b:e]))
         Wd = [H.Tensor.from_numpy(world, (w[b:e] if i == 0 else w), matrix=True) for i, w in enumerate(W)]
         Gd = [H.Tensor.from_numpy(world, (g[b:e] if i == 0 else g), matrix=True) for i, g in enumerate(G)]
@@ -53,14 +56,17 @@ for lens, R, maxiter, tol_init in [((13, 12, 11, 10), 4, 40, 0.1), ((9, 10, 11),
         with H.Trace(quiet=True) as t:
             if driver == "DT":
                 H.alsCP_DT(world, Vd, Wd, Gd, Fd, 1e-10 * vnorm, 12, resprint=4)
-            else:
+            elif driver == "PP":
                 H.alsCP_PP(world, Vd, Wd, Gd, Fd, 1e-10 * vnorm, tol_init, maxiter, resprint=4)
+            else:
+                H.alsCP_PP_partupdate(world, Vd, Wd, Gd, Fd, 1e-10 * vnorm, tol_init, maxiter, update_percentage=1.0,
+                                      resprint=4)
         ok = len(t.rows) == len(tr.rows)
         worst_fit = worst_fac = 0.0
         for rg, rr in zip(t.rows, tr.rows):
             ok &= int(rg[0]) == rr[0] and abs(rg[3] - rr[3]) <= 1e-10 * vnorm and abs(rg[1] - rr[1]) <= 1e-9 * max(rr[1], 1e-6 * vnorm)
             worst_fit = max(worst_fit, abs(rg[3] - rr[3]) / vnorm)
-        if driver == "PP":
+        if driver != "DT":
             ok &= t.events == [(0 if k == "DT" else 1, it) for k, it in tr.events]
         for i in range(N):
             ref = W_ref[i][b:e] if i == 0 else W_ref[i]
@@ -68,7 +74,7 @@ for lens, R, maxiter, tol_init in [((13, 12, 11, 10), 4, 40, 0.1), ((9, 10, 11),
             worst_fac = max(worst_fac, err)
             ok &= err <= 1e-8
         print(f"rank {rank} lens {lens} R {R} {driver}: {'OK' if ok else 'MISMATCH'} rows {len(t.rows)} "
-              f"fit_err {worst_fit:.2e} factor_err {worst_fac:.2e} events {t.events if driver == 'PP' else ''}", flush=True)
+              f"fit_err {worst_fit:.2e} factor_err {worst_fac:.2e} events {t.events if driver != 'DT' else ''}", flush=True)
         ok_all &= ok
         for x in [Vd] + Wd + Gd + Fd:
             x.free()
