@@ -150,6 +150,18 @@ int ppx_spd_inverse_g(ppx_ctx *ctx, const double *const *G, int nG, int skip, do
 /*   grad_out = -M + W_old*S ; W = M*Sinv ; dW_out = ratio_step*(W - W_init)  (S may be NULL iff grad_out is NULL)  */
 int ppx_solve_apply(ppx_ctx *ctx, const double *M, const double *S, const double *Sinv, double *W, int64_t s, int R,
                     const double *W_init, double ratio_step, double *grad_out, double *dW_out);
+/* Linv_out (R x R, lower triangular, column-major) = L^-1 with S = L L^T (S symmetric positive definite): what the
+ * solve_tri calls of get_rankR_update_cholesky apply from the right (common.cxx:774-785). */
+int ppx_spd_factor_inverse(ppx_ctx *ctx, const double *S, int R, double *Linv_out);
+/* C (m x n) = alpha op(A) op(B) + beta C, column-major, op = transpose when the flag is non-zero; for the small dense
+ * products of the low-rank-update optimizers (common.cxx:760-786). */
+int ppx_gemm_small(ppx_ctx *ctx, int transa, int transb, int m, int n, int k, double alpha, const double *A,
+                   int64_t lda, const double *B, int64_t ldb, double beta, double *C, int64_t ldc);
+/* out[m, c] += sum_q T[m, q] VT[q, c] for m < Mtot, c < R, q < r <= 16: the rank-r patch
+ * cached += V x (U s) x VT of a dimension-tree root tensor, after T = V x (U s) was formed by ppx_ttm_first with
+ * "rank" r (cp_dt_lr_optimizer.cxx:152-158, cp_msdt_lr_optimizer.cxx:142-146). */
+int ppx_rank_expand_acc(ppx_ctx *ctx, const double *T, int64_t Mtot, int r, const double *VT, int64_t ldvt, int R,
+                        double *out);
 /* Fork / join for work that may overlap the main stream; valid eagerly and inside ppx_graph_begin/end:
  *   ppx_side_begin: the side stream waits for everything enqueued so far; subsequent calls go to the side stream
  *   ppx_side_end  : subsequent calls go to the main stream again (the side work keeps running concurrently)

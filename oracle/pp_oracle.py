@@ -647,14 +647,199 @@ class CPMSDTOptimizer(CPDTOptimizer):
         return 1.0 * (N - 1) / N
 
 
+
+# ----------------------------------------------------------------------------------------------------------------
+# low-rank-update optimizers (src/optimizer/cp_dt_lr_optimizer.cxx, cp_msdt_lr_optimizer.cxx; run.cxx -pp 2 / 3)
+# ----------------------------------------------------------------------------------------------------------------
+def randomized_range(X, r, seed, draw_id):
+    """randomized_svd (common.cxx:691-708) with iter = 1, reduced to what its callers use: U s VT2 = B Q^T = X Q Q^T
+    with Q = orth(X^T X orth(Omega)).  span(X^T X orth(Omega)) = span(X^T X Omega), so Q = orth(X^T X Omega);
+    Omega = u(seed, draw_id) in [0,1), n x r."""
+    n = X.shape[1]
+    Omega = fill_uniform((n, r), seed, draw_id)
+    Q, _ = np.linalg.qr((X.T @ X) @ Omega)
+    return Q
+
+
+def get_rankR_update_cholesky(r, M, A, gamma, random=False, seed=1, draw_id=5000):
+    """common.cxx:768-786.  Returns (U s, VT): the rank-r update of A towards M gamma^-1 is (U s) @ VT.
+    (The reference returns U, s, VT separately; every caller only ever uses U diag(s) and VT.)"""
+    L = np.linalg.cholesky(gamma)
+    Z = np.linalg.inv(L)                  # lower triangular
+    rhs = M - A @ gamma
+    X = rhs @ Z.T                         # solve_tri(L, X, lower, from the right, transposed): X L^T = rhs
+    if random:
+        Q = randomized_range(X, r, seed, draw_id)
+    else:
+        _, _, VTfull = np.linalg.svd(X, full_matrices=False)
+        Q = VTfull[:r].T                  # leading r right singular vectors
+    Us = X @ Q                            # = U diag(s)
+    VT = Q.T @ Z                          # xVT.solve_tri(L, xVT, lower, from the right): xVT_new L = xVT
+    return Us, VT
+
+
+class CPDTLROptimizer(CPDTOptimizer):
+    """cp_dt_lr_optimizer.cxx: dimension tree whose two root contractions are refreshed by rank-`update_rank`
+    patches  cached += V x (U s) x VT  for num_subiteration - 2 of every num_subiteration sweeps."""
+
+    def __init__(self, order, r, update_rank, randomsvd=0, seed=1):
+        super().__init__(order, r)
+        self.randomsvd = randomsvd > 0
+        self.num_subiteration = 5
+        self.lr_rank = update_rank
+        self.cached = {True: None, False: None}  # first_subtree -> cached root tensor
+        self.seed, self.draw = seed, 5000
+        self.initialize_low_rank_param()
+
+    def initialize_low_rank_param(self):
+        self.count_subiteration = 0
+        self.low_rank_decomp = False
+
+    def _root_modes(self, left_index):
+        return "".join(chr(97 + i) for i in self._rot(left_index)) + "*"
+
+    def mttkrp_map_init(self, left_index):
+        """:39-99."""
+        N = self.order
+        top = vec2str(list(range(N - 1)))
+        if self.low_rank_decomp and self.count_subiteration > 1:
+            self.update_cached_tensor(left_index)
+            self.mttkrp_map[top] = self.cached[self.first_subtree].copy()
+        else:
+            self.mttkrp_map[top] = contract(self._root_modes(left_index), self.V, letters(N), self.W[left_index],
+                                            chr(97 + left_index) + "*")
+            self.cached[self.first_subtree] = self.mttkrp_map[top].copy()
+
+    def update_cached_tensor(self, left_index):
+        """:127-159  cached += V x_left (U s) x VT."""
+        N = self.order
+        patch = contract(self._root_modes(left_index), self.V, letters(N), self.Us, chr(97 + left_index) + "&",
+                         self.VT, "&*")
+        self.cached[self.first_subtree] = self.cached[self.first_subtree] + patch
+
+    def step(self):
+        """:161-236."""
+        N = self.order
+        if self.first_subtree:
+            self.indexes, self.left_index = self.indexes1, self.left_index1
+        else:
+            self.indexes, self.left_index = self.indexes2, self.left_index2
+        self.mttkrp_map = {}
+        self.mttkrp_map_init(self.left_index)
+        n = len(self.indexes)
+        for i in range(n):
+            if self.first_subtree and i < self.special_index:
+                continue
+            if (not self.first_subtree) and i > self.special_index:
+                break
+            key = vec2str([i])
+            if key not in self.mttkrp_map:
+                self.mttkrp_map_DT(key)
+            M = self.mttkrp_map[key]
+            m = self.indexes[i]
+            S = self.update_S(m)
+            self.grad_W[m] = -M + self.W[m] @ S
+            lr_slot = (self.first_subtree and i == n - 1) or ((not self.first_subtree) and i == 0)
+            if lr_slot and self.count_subiteration >= 1:
+                self.Us, self.VT = get_rankR_update_cholesky(self.lr_rank, M, self.W[m], S, self.randomsvd, self.seed,
+                                                             self.draw)
+                self.draw += 1
+                self.W[m] = self.W[m] + self.Us @ self.VT
+                self.low_rank_decomp = True
+            else:
+                self.W[m] = cholesky_solve(M, S)
+        if not self.first_subtree:
+            self.count_subiteration += 1
+        if self.count_subiteration == self.num_subiteration and not self.first_subtree:
+            self.special_index = (self.special_index + 1) % (N - 1)
+            self.initialize_low_rank_param()
+            if self.special_index != 0:
+                self.left_index1 = (self.left_index1 + N - 1) % N
+                self.left_index2 = (self.left_index2 + N - 1) % N
+            else:
+                self.left_index = N - 1
+                self.left_index1 = self.left_index
+                self.left_index2 = (self.left_index + N - 1) % N
+            self.indexes1 = self._rot(self.left_index1)
+            self.indexes2 = self._rot(self.left_index2)
+        self.first_subtree = not self.first_subtree
+        return 0.5
+
+
+class CPMSDTLROptimizer(CPMSDTOptimizer):
+    """cp_msdt_lr_optimizer.cxx: multi-sweep dimension tree with one cached root tensor per mode, refreshed by a
+    rank-`update_rank` patch when that mode comes round as the root again."""
+
+    def __init__(self, order, r, update_rank, randomsvd=0, seed=1):
+        super().__init__(order, r)
+        self.randomsvd = randomsvd > 0
+        self.lr_rank = update_rank
+        self.low_rank_decomp = False
+        self.is_cached = [False] * order
+        self.cached_tensors = [None] * order
+        self.old_W = [None] * order
+        self.seed, self.draw = seed, 5000
+
+    def _root_modes(self, left_index):
+        return "".join(chr(97 + i) for i in self._rot(left_index)) + "*"
+
+    def mttkrp_map_init(self, left_index):
+        """:35-80."""
+        N = self.order
+        top = vec2str(list(range(N - 1)))
+        if self.low_rank_decomp and self.is_cached[left_index]:
+            self.update_cached_tensor(left_index)
+            self.mttkrp_map[top] = self.cached_tensors[left_index].copy()
+        else:
+            self.mttkrp_map[top] = contract(self._root_modes(left_index), self.V, letters(N), self.W[left_index],
+                                            chr(97 + left_index) + "*")
+            self.cached_tensors[left_index] = self.mttkrp_map[top].copy()
+            self.old_W[left_index] = self.W[left_index].copy()
+            self.is_cached[left_index] = True
+
+    def update_cached_tensor(self, left_index):
+        """:108-151."""
+        N = self.order
+        patch = contract(self._root_modes(left_index), self.V, letters(N), self.Us, chr(97 + left_index) + "&",
+                         self.VT, "&*")
+        self.cached_tensors[left_index] = self.cached_tensors[left_index] + patch
+        self.old_W[left_index] = self.W[left_index].copy()
+        self.is_cached[left_index] = True
+
+    def step(self):
+        """:153-205."""
+        N = self.order
+        self.mttkrp_map = {}
+        self.left_index = (self.left_index + N - 1) % N
+        self.indexes = self._rot(self.left_index)
+        self.mttkrp_map_init(self.left_index)
+        n = len(self.indexes)
+        for i in range(n):
+            key = vec2str([i])
+            if key not in self.mttkrp_map:
+                self.mttkrp_map_DT(key)
+            M = self.mttkrp_map[key]
+            m = self.indexes[i]
+            S = self.update_S(m)
+            self.grad_W[m] = -M + self.W[m] @ S
+            if (not self.is_cached[m]) or i != n - 1:
+                self.W[m] = cholesky_solve(M, S)
+            else:
+                self.Us, self.VT = get_rankR_update_cholesky(self.lr_rank, M, self.old_W[m], S, self.randomsvd,
+                                                             self.seed, self.draw)
+                self.draw += 1
+                self.W[m] = self.old_W[m] + self.Us @ self.VT
+                self.low_rank_decomp = True
+        return 1.0 * (N - 1) / N
+
 class CPD:
     """src/decomposition.{h,cxx} + src/CP.{h,cxx}."""
 
-    def __init__(self, order, size, r, optimizer_cls):
+    def __init__(self, order, size, r, optimizer_cls, *opt_args):
         self.order = order
         self.size = [size] * order if np.isscalar(size) else list(size)
         self.rank = [r] * order if np.isscalar(r) else list(r)
-        self.optimizer = optimizer_cls(order, self.rank[0])
+        self.optimizer = optimizer_cls(order, self.rank[0], *opt_args)  # (update_rank, randomsvd) for the LR ones
         self.V = self.W = self.grad_W = None
         self.gradnorm = 0.0
 

@@ -72,6 +72,10 @@ SIGNATURES = {
                                      C.c_double, C.c_int, _dp, _dp, _dp]),
     "ppx_spd_inverse_g": (C.c_int, [_vp, C.POINTER(_dp), C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, _dp, _dp]),
     "ppx_solve_apply": (C.c_int, [_vp, _dp, _dp, _dp, _dp, _i64, C.c_int, _dp, C.c_double, _dp, _dp]),
+    "ppx_spd_factor_inverse": (C.c_int, [_vp, _dp, C.c_int, _dp]),
+    "ppx_gemm_small": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, _dp, _i64, _dp, _i64,
+                                 C.c_double, _dp, _i64]),
+    "ppx_rank_expand_acc": (C.c_int, [_vp, _dp, _i64, C.c_int, _dp, _i64, C.c_int, _dp]),
     "ppx_side_begin": (C.c_int, [_vp]),
     "ppx_side_end": (C.c_int, [_vp]),
     "ppx_side_join": (C.c_int, [_vp]),
@@ -285,6 +289,16 @@ class Ctx:
 
     def cp_reconstruct(self, lens, Ws, R, V_out):
         self._ck(self.lib.ppx_cp_reconstruct(self.h, _lens(lens), len(lens), _ptrs(Ws), R, _ptr(V_out)))
+
+    def spd_factor_inverse(self, S, R, Linv):
+        self._ck(self.lib.ppx_spd_factor_inverse(self.h, _ptr(S), R, _ptr(Linv)))
+
+    def gemm_small(self, ta, tb, m, n, k, alpha, A, lda, B, ldb, beta, Cm, ldc):
+        self._ck(self.lib.ppx_gemm_small(self.h, int(ta), int(tb), m, n, k, alpha, _ptr(A), lda, _ptr(B), ldb, beta,
+                                         _ptr(Cm), ldc))
+
+    def rank_expand_acc(self, T, Mtot, r, VT, ldvt, R, out):
+        self._ck(self.lib.ppx_rank_expand_acc(self.h, _ptr(T), Mtot, r, _ptr(VT), ldvt, R, _ptr(out)))
 
     def fill_laplacian(self, out, d, s):
         self._ck(self.lib.ppx_fill_laplacian(self.h, _ptr(out), d, s))

@@ -97,7 +97,8 @@ __device__ __forceinline__ double inv_pivot(double d) {
 template <int T>
 __global__ void __launch_bounds__(INV_B *INV_B) spd_inverse_ldl_kernel(HadArgs h, int R, double lambda,
                                                                        double *__restrict__ S_out,
-                                                                       double *__restrict__ Sinv) {
+                                                                       double *__restrict__ Sinv,
+                                                                       double *__restrict__ Linv_out) {
   constexpr int B = INV_B;
   constexpr int NTH = B * B;
   constexpr int RP = B * T;   // padded order
@@ -189,6 +190,11 @@ __global__ void __launch_bounds__(INV_B *INV_B) spd_inverse_ldl_kernel(HadArgs h
         }
       }
       __syncthreads();
+      if (Linv_out) {
+        // row k of L^-1 (S = L L^T): sqrt(1/d_k) * (row k of Y, unit diagonal); columns past k are zero
+        const double sc = sqrt(inv);
+        for (int j = threadIdx.x; j < R; j += NTH) Linv_out[k + R * j] = j <= k ? p[j] * sc : 0.0;
+      }
       double t[T], pj[T], pjy[T];
 #pragma unroll
       for (int ii = 0; ii < T; ii++) t[ii] = p[ty + B * ii] * inv;
@@ -222,7 +228,7 @@ __global__ void __launch_bounds__(INV_B *INV_B) spd_inverse_ldl_kernel(HadArgs h
 #pragma unroll
     for (int jj = 0; jj < T; jj++) {
       const int i = ty + B * ii, j = tx + B * jj;
-      if (i < R && j < R) Sinv[i + R * j] = acc[ii][jj];
+      if (Sinv && i < R && j < R) Sinv[i + R * j] = acc[ii][jj];
     }
   PPX_PROF(4);
 }
@@ -518,13 +524,14 @@ __global__ void __launch_bounds__(1024) normalize_norms_kernel(NormNormsArgs a, 
   }
 }
 
-int inverse_launch(ppx_ctx *ctx, const HadArgs &h, int R, double lambda, int mode, double *S_out, double *Sinv) {
+int inverse_launch(ppx_ctx *ctx, const HadArgs &h, int R, double lambda, int mode, double *S_out, double *Sinv,
+                   double *Linv = nullptr) {
   if (mode == PPX_SOLVE_CHOL) {
     if (R > 112) return ppx_set_err(ctx, PPX_EUNSUPPORTED, "solve: R=%d too large for the one-CTA inverse (max 112)", R);
     const int T = (R + INV_B - 1) / INV_B;
     const size_t smem = sizeof(double) * (2 * ((size_t)INV_B * T + 2) + (size_t)R * (R + 1));
 #define PPX_INV_LAUNCH(T) \
-  spd_inverse_ldl_kernel<T><<<1, INV_B * INV_B, smem, ctx->stream>>>(h, R, lambda, S_out, Sinv)
+  spd_inverse_ldl_kernel<T><<<1, INV_B * INV_B, smem, ctx->stream>>>(h, R, lambda, S_out, Sinv, Linv)
     switch (T) {
       case 1: PPX_INV_LAUNCH(1); break;
       case 2: PPX_INV_LAUNCH(2); break;
@@ -569,6 +576,49 @@ int solve_impl(ppx_ctx *ctx, const double *M, const HadArgs &h, double lambda, c
     return ppx_sqnorms(ctx, xs, ns, 3, sq_norms_out);
   }
   return PPX_OK;
+}
+
+// ---- small dense products of the low-rank-update optimizers (operands of a few hundred x R; latency-size work) -----
+// C = alpha op(A) op(B) + beta C, column-major, one thread per element of C
+__global__ void __launch_bounds__(256) gemm_small_kernel(int ta, int tb, int m, int n, int k, double alpha,
+                                                         const double *__restrict__ A, int64_t lda,
+                                                         const double *__restrict__ B, int64_t ldb, double beta,
+                                                         double *__restrict__ C, int64_t ldc) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)m * n) return;
+  const int i = (int)(idx % m), j = (int)(idx / m);
+  double acc = 0.0;
+  for (int q = 0; q < k; q++) {
+    const double a = ta ? A[q + lda * i] : A[i + lda * q];
+    const double b = tb ? B[j + ldb * q] : B[q + ldb * j];
+    acc = fma(a, b, acc);
+  }
+  double *c = C + i + ldc * j;
+  *c = beta == 0.0 ? alpha * acc : alpha * acc + beta * *c;
+}
+
+// out[m, c] += sum_q T[m, q] VT[q, c]:  the rank-r patch of a cached root tensor expanded to R columns
+// (cp_dt_lr_optimizer.cxx:152-158).  HBM-bound read-modify-write of the Mtot x R tensor; VT lives in shared memory.
+constexpr int RX_MAX_r = 16;
+__global__ void __launch_bounds__(256) rank_expand_acc_kernel(const double *__restrict__ T, int64_t Mtot, int r,
+                                                              const double *__restrict__ VT, int64_t ldvt, int R,
+                                                              double *__restrict__ out) {
+  extern __shared__ double vt[];  // [r][R]
+  for (int i = threadIdx.x; i < r * R; i += blockDim.x) vt[i] = VT[(i / R) + ldvt * (i % R)];
+  __syncthreads();
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; m < Mtot; m += stride) {
+    double t[RX_MAX_r];
+#pragma unroll
+    for (int q = 0; q < RX_MAX_r; q++) t[q] = q < r ? T[m + Mtot * q] : 0.0;
+    for (int c = 0; c < R; c++) {
+      double acc = out[m + Mtot * c];
+#pragma unroll
+      for (int q = 0; q < RX_MAX_r; q++)
+        if (q < r) acc = fma(t[q], vt[q * R + c], acc);
+      out[m + Mtot * c] = acc;
+    }
+  }
 }
 
 }  // namespace
@@ -707,6 +757,36 @@ int ppx_normalize(ppx_ctx *ctx, double *const *W, const int64_t *s, int N, int R
 int ppx_normalize_g(ppx_ctx *ctx, double *const *W, const int64_t *s, int N, int R, double *const *G) {
   PPX_REQUIRE(ctx, G != nullptr, "G != NULL");
   return normalize_impl(ctx, W, s, N, R, G, true);
+}
+
+int ppx_spd_factor_inverse(ppx_ctx *ctx, const double *S, int R, double *Linv_out) {
+  PPX_REQUIRE(ctx, S && Linv_out && R >= 1, "S, Linv_out non-null; R >= 1");
+  HadArgs h;
+  h.n = 1;
+  h.g[0] = S;
+  return inverse_launch(ctx, h, R, 0.0, PPX_SOLVE_CHOL, nullptr, nullptr, Linv_out);
+}
+
+int ppx_gemm_small(ppx_ctx *ctx, int transa, int transb, int m, int n, int k, double alpha, const double *A,
+                   int64_t lda, const double *B, int64_t ldb, double beta, double *C, int64_t ldc) {
+  PPX_REQUIRE(ctx, C && (k == 0 || (A && B)) && m >= 0 && n >= 0 && k >= 0, "non-null operands, non-negative sizes");
+  if (m == 0 || n == 0) return PPX_OK;
+  gemm_small_kernel<<<ppx_cdiv((int64_t)m * n, 256), 256, 0, ctx->stream>>>(transa, transb, m, n, k, alpha, A, lda, B,
+                                                                         ldb, beta, C, ldc);
+  PPX_CHECK_LAUNCH(ctx);
+  return PPX_OK;
+}
+
+int ppx_rank_expand_acc(ppx_ctx *ctx, const double *T, int64_t Mtot, int r, const double *VT, int64_t ldvt, int R,
+                        double *out) {
+  PPX_REQUIRE(ctx, T && VT && out && Mtot >= 0 && R >= 1, "non-null operands");
+  PPX_REQUIRE(ctx, r >= 1 && r <= RX_MAX_r, "1 <= r <= 16");
+  if (Mtot == 0) return PPX_OK;
+  int64_t blocks = (Mtot + 255) / 256;
+  if (blocks > (int64_t)ctx->sm_count * 16) blocks = (int64_t)ctx->sm_count * 16;
+  rank_expand_acc_kernel<<<(int)blocks, 256, sizeof(double) * (size_t)r * R, ctx->stream>>>(T, Mtot, r, VT, ldvt, R, out);
+  PPX_CHECK_LAUNCH(ctx);
+  return PPX_OK;
 }
 
 }  // extern "C"

@@ -8,6 +8,8 @@
 #include "src/CP.h"
 #include "src/optimizer/cp_dt_optimizer.h"
 #include "src/optimizer/cp_msdt_optimizer.h"
+#include "src/optimizer/cp_dt_lr_optimizer.h"
+#include "src/optimizer/cp_msdt_lr_optimizer.h"
 #include "src/optimizer/cp_simple_optimizer.h"
 
 namespace {
@@ -52,6 +54,8 @@ template <class Opt>
 struct CpdHolder : CpdBase {
   CPD<double, Opt> cpd;
   CpdHolder(int order, int size, int r, World &dw) : cpd(order, size, r, dw) {}
+  CpdHolder(int order, int size, int r, int update_rank, int randomsvd, World &dw)
+      : cpd(order, size, r, update_rank, randomsvd, dw) {}
   void init(Tensor<> *V, Matrix<> *W, double lambda, uint64_t grad_seed) override {
     cpd.Init(V, W, lambda);
     for (int i = 0; i < cpd.order; i++) cpd.grad_W[i].fill_random(0, 1, grad_seed, (uint64_t)i);
@@ -262,6 +266,18 @@ int ppxh_cp_pp_phase_timed(void *V, void **W, void **grad_W, int N, int n_sweeps
 }
 
 // ---- OO path (src/CP.h + src/optimizer) ---------------------------------------------------------------------
+// kind: 3 = CPDTLROptimizer, 4 = CPMSDTLROptimizer  (run.cxx -pp 2 / 3)
+void *ppxh_cpd_create_lr(int kind, int order, int size, int r, int update_rank, int randomsvd, void *w) {
+  CpdBase *c = nullptr;
+  if (guarded([&] {
+        World &dw = *(World *)w;
+        if (kind == 3) c = new CpdHolder<CPDTLROptimizer<double>>(order, size, r, update_rank, randomsvd, dw);
+        else if (kind == 4) c = new CpdHolder<CPMSDTLROptimizer<double>>(order, size, r, update_rank, randomsvd, dw);
+        else throw std::runtime_error("unknown low-rank optimizer kind");
+      }))
+    return nullptr;
+  return c;
+}
 // kind: 0 = CPSimpleOptimizer, 1 = CPDTOptimizer, 2 = CPMSDTOptimizer  (run.cxx -pp 4 / 0 / 1)
 void *ppxh_cpd_create(int kind, int order, int size, int r, void *w) {
   CpdBase *c = nullptr;

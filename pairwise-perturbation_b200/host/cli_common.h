@@ -36,7 +36,7 @@ struct CliOptions {
   int graph = 1;                // -graph 0|1: replay the PP approximate sweep as a CUDA graph
   int fastres = 0;              // -fastres 0|1: alsCP_DT reports the residual from the MTTKRP identity (no pass over V)
   std::string lens;             // -lens a,b,c,.. : non-cubic synthetic tensor (overrides -dim/-size)
-  int updaterank = 1, randomsvd = 0;  // run.cxx only
+  int updaterank = 1, randomsvd = 0;  // run.cxx -pp 2 / 3: rank of the low-rank update, randomized range finder
 };
 
 inline CliOptions parse_cli(int argc, char **argv, int pp_max) {

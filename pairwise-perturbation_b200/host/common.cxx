@@ -131,6 +131,54 @@ void build_V(Tensor<> &V, Matrix<> *W, int order, World &dw) {
   V = std::move(out);
 }
 
+// ---- low-rank update (common.cxx:760-786) -----------------------------------------------------------------------
+void matrixDot(Matrix<> &result, Matrix<> &matrix1, Matrix<> &matrix2) {
+  World &dw = *matrix1.wrld;
+  result = Matrix<>(matrix1.nrow, matrix2.ncol, dw, false);
+  PPXCK(dw, ppx_gemm_small(dw.ctx, 0, 0, (int)matrix1.nrow, (int)matrix2.ncol, (int)matrix1.ncol, 1.0, matrix1.data,
+                           matrix1.nrow, matrix2.data, matrix2.nrow, 0.0, result.data, result.nrow));
+}
+
+void get_rankR_update_cholesky(int R, Matrix<> &xU, Vector<> &xS, Matrix<> &xVT, Matrix<> &M, Matrix<> &A,
+                               Matrix<> &gamma, bool random, uint64_t draw_id) {
+  World &dw = *M.wrld;
+  const int s = (int)M.nrow, n = (int)M.ncol, r = R;
+  // Z = L^-1, gamma = L L^T  (:772-773)
+  Matrix<> Z(n, n, dw, false);
+  PPXCK(dw, ppx_spd_factor_inverse(dw.ctx, gamma.data, n, Z.data));
+  // rhs = M - A gamma  (:774-776)
+  Matrix<> rhs(M);
+  PPXCK(dw, ppx_gemm_small(dw.ctx, 0, 0, s, n, n, -1.0, A.data, A.nrow, gamma.data, n, 1.0, rhs.data, s));
+  // X = rhs L^-T  (solve_tri from the right with L transposed, :777)
+  Matrix<> X(s, n, dw, false);
+  PPXCK(dw, ppx_gemm_small(dw.ctx, 0, 1, s, n, n, 1.0, rhs.data, s, Z.data, n, 0.0, X.data, s));
+  // Q (n x r): leading right singular vectors of X = leading eigenvectors of X^T X (:782), or the randomized range
+  Matrix<> G(n, n, dw, false), Q(n, r, dw, false);
+  PPXCK(dw, ppx_gram(dw.ctx, X.data, s, s, n, G.data));
+  if (!random) {
+    PPXCK(dw, ppx_sym_eig_topk(dw.ctx, G.data, n, r, Q.data, nullptr));
+  } else {
+    // Q = orth(X^T X Omega) by Cholesky QR: Y = G Omega, Y^T Y = C C^T, Q = Y C^-T  (:691-708 reduced, see the oracle)
+    Matrix<> Omega(n, r, dw, false), Y(n, r, dw, false), YtY(r, r, dw, false), Ci(r, r, dw, false);
+    Omega.fill_random(0, 1, dw.seed, draw_id);
+    PPXCK(dw, ppx_gemm_small(dw.ctx, 0, 0, n, r, n, 1.0, G.data, n, Omega.data, n, 0.0, Y.data, n));
+    for (int pass = 0; pass < 2; pass++) {  // twice: Cholesky QR loses orthogonality with the square of the condition
+      PPXCK(dw, ppx_gram(dw.ctx, Y.data, n, n, r, YtY.data));
+      PPXCK(dw, ppx_spd_factor_inverse(dw.ctx, YtY.data, r, Ci.data));
+      PPXCK(dw, ppx_gemm_small(dw.ctx, 0, 1, n, r, r, 1.0, Y.data, n, Ci.data, r, 0.0, Q.data, n));
+      if (pass == 0) PPXCK(dw, ppx_memcpy_d2d(dw.ctx, Y.data, Q.data, sizeof(double) * Q.size));
+    }
+  }
+  // xU = X Q (= U diag(s)), xS = 1, xVT = Q^T L^-1  (:785)
+  xU = Matrix<>(s, r, dw, false);
+  PPXCK(dw, ppx_gemm_small(dw.ctx, 0, 0, s, r, n, 1.0, X.data, s, Q.data, n, 0.0, xU.data, s));
+  xVT = Matrix<>(r, n, dw, false);
+  PPXCK(dw, ppx_gemm_small(dw.ctx, 1, 0, r, n, n, 1.0, Q.data, n, Z.data, n, 0.0, xVT.data, r));
+  xS = Vector<>(r, dw);
+  std::vector<double> ones((size_t)r, 1.0);
+  xS.write_all(ones.data());
+}
+
 // ---- input generators ------------------------------------------------------------------------------------------
 void laplacian_tensor(Tensor<> &V, int N, int s, bool sparse_V, World &dw) {
   // common.cxx:575-642: sum over the d = N/2 index pairs of D on one pair and identities on the others.  The

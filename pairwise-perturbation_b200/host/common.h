@@ -32,6 +32,14 @@ void KhatriRao_contract(Matrix<> &M, Tensor<> &V, Matrix<> *W, int *index, int *
 void gradsubprob(Matrix<> &M, Matrix<> &S, Matrix<> &W, Matrix<> &grad_W);         // common.cxx:1002-1004
 void gradient_CP(Tensor<> &V, Matrix<> *W, Matrix<> *grad_W, World &dw);           // common.cxx:1009-1052
 
+// rank-R update of A towards M gamma^-1 (common.cxx:768-786): A_new ~ A + xU diag(xS) xVT.  Here xU already carries the
+// singular values (xU = U diag(s), xS = ones): every caller only uses the products U diag(s) and VT.
+// `random`: range finder of randomized_svd (common.cxx:691-708, one power iteration) instead of the exact
+// truncated SVD; its test matrix is u(dw.seed, draw_id, .).
+void get_rankR_update_cholesky(int R, Matrix<> &xU, Vector<> &xS, Matrix<> &xVT, Matrix<> &M, Matrix<> &A,
+                               Matrix<> &gamma, bool random, uint64_t draw_id = 5000);
+void matrixDot(Matrix<> &result, Matrix<> &matrix1, Matrix<> &matrix2);             // common.cxx:760-763
+
 // input generators of test_ALS / pp_bench / run (test_ALS.cxx:222-286)
 void laplacian_tensor(Tensor<> &V, int N, int s, bool sparse_V, World &dw);        // common.cxx:575-642
 void fold_unfold(Tensor<> &X, Tensor<> &Y);                                        // common.cxx:870-882

@@ -1,15 +1,24 @@
 // run -- driver for the class-based path: CPD<double, Optimizer>::als with -pp selecting the optimizer
-// (reference: run.cxx:387-414).  -pp 0: CPDTOptimizer, 1: CPMSDTOptimizer, 4: CPSimpleOptimizer.
-// The low-rank-update optimizers (-pp 2, 3) are outside the hot-path scope.
+// (reference: run.cxx:387-414).  -pp 0: CPDTOptimizer, 1: CPMSDTOptimizer, 2: CPDTLROptimizer, 3: CPMSDTLROptimizer
+// (-updaterank, -randomsvd), 4: CPSimpleOptimizer.
 #include "cli_common.h"
 #include "src/CP.h"
 #include "src/optimizer/cp_dt_optimizer.h"
 #include "src/optimizer/cp_msdt_optimizer.h"
+#include "src/optimizer/cp_dt_lr_optimizer.h"
+#include "src/optimizer/cp_msdt_lr_optimizer.h"
 #include "src/optimizer/cp_simple_optimizer.h"
 
 template <class Opt>
 static void run_with(const CliOptions &o, Tensor<> *V, Matrix<> *W, double Vnorm, ofstream &Plot_File, World &dw) {
   CPD<double, Opt> decom(V->order, (int)V->lens[0], o.R, dw);
+  decom.Init(V, W, o.lambda_);
+  decom.als(o.tol * Vnorm, o.timelimit, o.maxiter, o.resprint, Plot_File);
+}
+
+template <class Opt>
+static void run_with_lr(const CliOptions &o, Tensor<> *V, Matrix<> *W, double Vnorm, ofstream &Plot_File, World &dw) {
+  CPD<double, Opt> decom(V->order, (int)V->lens[0], o.R, o.updaterank, o.randomsvd, dw);  // run.cxx:400-409
   decom.Init(V, W, o.lambda_);
   decom.als(o.tol * Vnorm, o.timelimit, o.maxiter, o.resprint, Plot_File);
 }
@@ -44,11 +53,9 @@ int main(int argc, char **argv) {
     }
     if (o.pp == 0) run_with<CPDTOptimizer<double>>(o, V, W, Vnorm, Plot_File, dw);
     else if (o.pp == 1) run_with<CPMSDTOptimizer<double>>(o, V, W, Vnorm, Plot_File, dw);
-    else if (o.pp == 4) run_with<CPSimpleOptimizer<double>>(o, V, W, Vnorm, Plot_File, dw);
-    else {
-      fprintf(stderr, "run: -pp %d (low-rank-update optimizers) is not part of this build\n", o.pp);
-      rc = 3;
-    }
+    else if (o.pp == 2) run_with_lr<CPDTLROptimizer<double>>(o, V, W, Vnorm, Plot_File, dw);
+    else if (o.pp == 3) run_with_lr<CPMSDTLROptimizer<double>>(o, V, W, Vnorm, Plot_File, dw);
+    else run_with<CPSimpleOptimizer<double>>(o, V, W, Vnorm, Plot_File, dw);
     if (dw.rank == 0) printf("experiment took %lf seconds\n", wall_time() - start_time);
     delete V;
   } catch (const std::exception &e) {

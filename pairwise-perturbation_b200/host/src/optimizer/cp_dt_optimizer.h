@@ -130,11 +130,15 @@ protected:
     parent[c] = t;
     contract_index[c] = m;
   }
-  void update_leaf(int i) {
+  // MTTKRP of local index i from the tree (a copy: the solve kernels may overwrite it)
+  Matrix<dtype> leaf(int i) {
     string key;
     vec2str(vector<int>{i}, key);
     if (mttkrp_map.find(key) == mttkrp_map.end()) mttkrp_map_DT(key);
-    Matrix<dtype> M = mttkrp_map[key];
+    return Matrix<dtype>(mttkrp_map[key]);
+  }
+  void update_leaf(int i) {
+    Matrix<dtype> M = leaf(i);
     this->solve_mode(indexes[i], M);
   }
 };

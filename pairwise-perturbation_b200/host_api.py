@@ -24,7 +24,7 @@ def load_host_library():
     lib = C.CDLL(HOST_LIB_PATH, mode=C.RTLD_GLOBAL)
     lib.ppxh_last_error.restype = C.c_char_p
     for name in ("ppxh_world_create", "ppxh_world_ctx", "ppxh_tensor_create", "ppxh_matrix_create", "ppxh_tensor_data",
-                 "ppxh_cpd_create"):
+                 "ppxh_cpd_create", "ppxh_cpd_create_lr"):
         getattr(lib, name).restype = _vp
     lib.ppxh_world_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_size_t]
     lib.ppxh_world_destroy.argtypes = [_vp]
@@ -67,6 +67,7 @@ def load_host_library():
     lib.ppxh_cp_pp_phase_timed.argtypes = [_vp, PV, PV, C.c_int, C.c_int, d, d, _vp, C.POINTER(C.c_float),
                                            C.POINTER(C.c_float)]
     lib.ppxh_cpd_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, _vp]
+    lib.ppxh_cpd_create_lr.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp]
     lib.ppxh_cpd_destroy.argtypes = [_vp]
     lib.ppxh_cpd_init.argtypes = [_vp, _vp, PV, C.c_int, d, C.c_uint64]
     lib.ppxh_cpd_step.argtypes = [_vp, C.POINTER(d)]
@@ -269,13 +270,17 @@ def cp_pp_phase_timed(world, V, W, grad_W, n_sweeps, lam=0.0, ratio_step=1.0):
 
 
 class CPD:
-    """CPD<double, Optimizer> (src/CP.h); kind: 'simple' | 'dt' | 'msdt'."""
+    """CPD<double, Optimizer> (src/CP.h); kind: 'simple' | 'dt' | 'msdt' | 'dtlr' | 'msdtlr' (the last two take
+    update_rank and randomsvd, run.cxx -pp 2 / 3)."""
 
-    KINDS = {"simple": 0, "dt": 1, "msdt": 2}
+    KINDS = {"simple": 0, "dt": 1, "msdt": 2, "dtlr": 3, "msdtlr": 4}
 
-    def __init__(self, world, kind, order, size, r):
+    def __init__(self, world, kind, order, size, r, update_rank=1, randomsvd=0):
         self.world, self.lib, self.order = world, world.lib, order
-        self.h = self.lib.ppxh_cpd_create(self.KINDS[kind], order, size, r, world.h)
+        if self.KINDS[kind] >= 3:
+            self.h = self.lib.ppxh_cpd_create_lr(self.KINDS[kind], order, size, r, update_rank, randomsvd, world.h)
+        else:
+            self.h = self.lib.ppxh_cpd_create(self.KINDS[kind], order, size, r, world.h)
         if not self.h:
             raise PpxError(self.lib.ppxh_last_error().decode())
 

@@ -436,3 +436,31 @@ def test_fast_residual_identity_tracks_the_exact_residual(H, world, lens, R):
         # res^2 is a difference of numbers of size ||V||^2: absolute accuracy ~1e-16 ||V||^2 / res
         assert abs(rf[3] - re_[3]) <= 1e-13 * vnorm * vnorm / max(re_[3], 1e-12 * vnorm) + 1e-12 * vnorm
     free_all(Vd, Wd, Gd, Fd)
+
+
+@pytest.mark.parametrize("kind,cls", [("dtlr", "CPDTLROptimizer"), ("msdtlr", "CPMSDTLROptimizer")])
+@pytest.mark.parametrize("order,size,R,update_rank,randomsvd", [(4, 7, 3, 1, 0), (4, 7, 4, 2, 0), (3, 9, 3, 2, 1),
+                                                                (5, 5, 3, 3, 0)])
+def test_low_rank_update_optimizers(H, world, kind, cls, order, size, R, update_rank, randomsvd):
+    """run -pp 2 / 3: CPD<double, CPDTLROptimizer / CPMSDTLROptimizer> against the oracle, step by step: cached root
+    tensors patched by V x (U s) x VT (first contraction with rank update_rank + rank expansion), the rank-r update
+    from get_rankR_update_cholesky (exact truncated SVD or the randomized range finder)."""
+    lens = (size,) * order
+    V, W, _ = problem(lens, R)
+    ref = o.CPD(order, size, R, getattr(o, cls), update_rank, randomsvd)
+    ref.Init(V, [w.copy() for w in W], grad_W=[o.fill_uniform(w.shape, 3, i) for i, w in enumerate(W)])
+    Vd = H.Tensor.from_numpy(world, V)
+    Wd = [H.Tensor.from_numpy(world, w, matrix=True) for w in W]
+    c = H.CPD(world, kind, order, size, R, update_rank=update_rank, randomsvd=randomsvd)
+    c.Init(Vd, Wd, grad_seed=3)
+    nsteps = 26 if kind == "dtlr" else 3 * order + 2   # past a full num_subiteration cycle / every mode cached and patched
+    for step in range(nsteps):
+        fa, fb = c.step(), ref.optimizer.step()
+        assert fa == fb
+        for i in range(order):
+            wr = ref.W[i]
+            assert np.abs(c.W(i) - wr).max() <= 1e-8 * max(1.0, np.abs(wr).max()), (step, i)
+            gr = ref.grad_W[i]
+            assert np.abs(c.grad(i) - gr).max() <= 1e-7 * max(1.0, np.abs(gr).max()), (step, i)
+    c.free()
+    Vd.free()

@@ -372,3 +372,38 @@ def test_fill_laplacian(ctx, d, s):
     out = ctx.empty(ref.size)
     ctx.fill_laplacian(out, d, s)
     assert np.array_equal(ctx.to_host(out, ref.shape), ref)
+
+
+@pytest.mark.parametrize("R", [1, 5, 16, 17, 50, 70])
+def test_spd_factor_inverse(ctx, R):
+    rng = np.random.default_rng(R)
+    B = rng.random((3 * R + 4, R))
+    S = np.asfortranarray(B.T @ B + 0.1 * np.eye(R))
+    Z = ctx.empty(R * R)
+    ctx.spd_factor_inverse(ctx.to_device(S), R, Z)
+    ref = np.linalg.inv(np.linalg.cholesky(S))
+    got = ctx.to_host(Z, (R, R))
+    assert np.abs(np.triu(got, 1)).max() == 0.0
+    assert rel_err(got, ref) < 1e-9
+
+
+@pytest.mark.parametrize("ta,tb,m,n,k", [(0, 0, 13, 7, 5), (1, 0, 4, 9, 11), (0, 1, 300, 50, 50), (1, 1, 6, 6, 6),
+                                         (0, 0, 5, 3, 0)])
+def test_gemm_small(ctx, ta, tb, m, n, k):
+    A = rnd((k, m) if ta else (m, k), 500)
+    B = rnd((n, k) if tb else (k, n), 501)
+    Cm = rnd((m, n), 502)
+    ref = 0.75 * (A.T if ta else A) @ (B.T if tb else B) - 0.5 * Cm
+    Cd = ctx.to_device(Cm)
+    ctx.gemm_small(ta, tb, m, n, k, 0.75, ctx.to_device(A), max(1, A.shape[0]), ctx.to_device(B), max(1, B.shape[0]),
+                   -0.5, Cd, m)
+    assert rel_err(ctx.to_host(Cd, (m, n)), ref) < 1e-13
+
+
+@pytest.mark.parametrize("Mtot,r,R", [(1000, 1, 7), (333, 3, 50), (70000, 5, 10), (17, 16, 3)])
+def test_rank_expand_acc(ctx, Mtot, r, R):
+    T, VT, out = rnd((Mtot, r), 510), rnd((r, R), 511), rnd((Mtot, R), 512)
+    ref = out + T @ VT
+    od = ctx.to_device(out)
+    ctx.rank_expand_acc(ctx.to_device(T), Mtot, r, ctx.to_device(VT), r, R, od)
+    assert rel_err(ctx.to_host(od, (Mtot, R)), ref) < 1e-13

@@ -277,3 +277,46 @@ def test_gen_collinearity_respects_the_range_and_noise_level():
     assert np.allclose(X, ref, rtol=1e-13, atol=1e-14)
     V = o.make_tensor_c(lens, R, 0.6, 0.85, ratio_noise=0.05, seed=1)
     assert abs(np.linalg.norm(V - X) / np.linalg.norm(X) - 0.05) < 1e-12
+
+
+# ---- low-rank-update optimizers (run.cxx -pp 2 / 3) -----------------------------------------------------------------
+def _run_opt(cls, lens, R, steps, *opt_args):
+    V, _ = o.make_tensor_r(lens, R)
+    W, G = o.init_factors(lens, R), o.init_grad(lens, R)
+    opt = cls(len(lens), R, *opt_args)
+    opt.configure(V, W, G, 0.0)
+    for _ in range(steps):
+        opt.step()
+    return V, opt
+
+
+@pytest.mark.parametrize("lens,R", [((7, 6, 5, 6), 3), ((6, 5, 7), 2)])
+def test_lr_optimizers_with_full_update_rank_are_the_exact_ones(lens, R):
+    """A rank-R 'low-rank' update is the whole update M S^-1 - W, and the patched root tensors are then the exact
+    first contractions: CPDTLROptimizer == CPDTOptimizer and CPMSDTLROptimizer == CPMSDTOptimizer step for step."""
+    for exact, lr in ((o.CPDTOptimizer, o.CPDTLROptimizer), (o.CPMSDTOptimizer, o.CPMSDTLROptimizer)):
+        _, a = _run_opt(exact, lens, R, 14)
+        _, b = _run_opt(lr, lens, R, 14, R, 0)
+        for wa, wb in zip(a.W, b.W):
+            assert np.abs(wa - wb).max() < 1e-11 * max(1.0, np.abs(wa).max())
+
+
+def test_rank_update_is_the_best_rank_r_correction_in_the_S_norm():
+    """get_rankR_update_cholesky: U s VT is the rank-r truncation of (M - A S) L^-T mapped back by L^-1, so
+    A + U s VT -> M S^-1 as r -> R, and the patched root equals V x (A + U s VT)."""
+    rng = np.random.default_rng(3)
+    s_, R = 11, 5
+    A, M = rng.random((s_, R)), rng.random((s_, R))
+    B = rng.random((20, R))
+    S = B.T @ B
+    exact = M @ np.linalg.inv(S)
+    errs = []
+    for r in range(1, R + 1):
+        Us, VT = o.get_rankR_update_cholesky(r, M, A, S)
+        assert Us.shape == (s_, r) and VT.shape == (r, R)
+        L = np.linalg.cholesky(S)
+        errs.append(np.linalg.norm((A + Us @ VT - exact) @ L))   # error in the S-weighted norm
+    assert all(errs[i + 1] <= errs[i] + 1e-12 for i in range(R - 1)) and errs[-1] < 1e-10
+    # randomized range finder: exact when r = R (the range is everything)
+    Us, VT = o.get_rankR_update_cholesky(R, M, A, S, random=True)
+    assert np.abs(A + Us @ VT - exact).max() < 1e-9

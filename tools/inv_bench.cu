@@ -40,11 +40,11 @@ int main(int argc, char **argv) {
   for (int rep = 0; rep < 5; rep++) {
     cudaEventRecord(e0);
     switch (T) {
-      case 1: spd_inverse_ldl_kernel<1><<<1, 256, smem>>>(h, R, 0.0, dS, dSi); break;
-      case 2: spd_inverse_ldl_kernel<2><<<1, 256, smem>>>(h, R, 0.0, dS, dSi); break;
-      case 3: spd_inverse_ldl_kernel<3><<<1, 256, smem>>>(h, R, 0.0, dS, dSi); break;
-      case 4: spd_inverse_ldl_kernel<4><<<1, 256, smem>>>(h, R, 0.0, dS, dSi); break;
-      default: spd_inverse_ldl_kernel<7><<<1, 256, smem>>>(h, R, 0.0, dS, dSi); break;
+      case 1: spd_inverse_ldl_kernel<1><<<1, 256, smem>>>(h, R, 0.0, dS, dSi, nullptr); break;
+      case 2: spd_inverse_ldl_kernel<2><<<1, 256, smem>>>(h, R, 0.0, dS, dSi, nullptr); break;
+      case 3: spd_inverse_ldl_kernel<3><<<1, 256, smem>>>(h, R, 0.0, dS, dSi, nullptr); break;
+      case 4: spd_inverse_ldl_kernel<4><<<1, 256, smem>>>(h, R, 0.0, dS, dSi, nullptr); break;
+      default: spd_inverse_ldl_kernel<7><<<1, 256, smem>>>(h, R, 0.0, dS, dSi, nullptr); break;
     }
     cudaEventRecord(e1);
     cudaEventSynchronize(e1);
