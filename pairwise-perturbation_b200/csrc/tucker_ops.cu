@@ -105,22 +105,29 @@ __global__ void unfold_gram_reduce_kernel(const double *__restrict__ parts, int6
 // mode in the previous HOOI sweep) the columns start almost orthogonal and few sweeps remain.  `Vout` (optional)
 // receives all n normalised columns for that purpose.
 // `count`: one int per sweep (zeroed by the launcher), rotations applied in that sweep (integer atomics: exact).
-constexpr int JT = 128;   // threads per CTA
+constexpr int JT = 128;   // threads per column pair
+constexpr int JG = 1;     // pairs per CTA (4 pairs per 512-thread CTA was measured: 3.65 us per round instead of 3.2)
 constexpr int JE = 8;     // column elements per thread held in registers per pass (n <= JT*JE in one pass)
-__global__ void __launch_bounds__(JT) jacobi_onesided_kernel(double *__restrict__ B, int n, int ncols, int max_sweeps,
-                                                             int *__restrict__ count, double *__restrict__ evals,
-                                                             int *__restrict__ sweeps_done, double *__restrict__ Vout) {
+__device__ __forceinline__ void group_bar(int g) { asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "r"(JT) : "memory"); }
+// `count`: [0, max_sweeps) rotations per sweep, [max_sweeps] sweeps done; `maxrot`: largest |sin| applied per sweep
+// (positive doubles compared as integers).  Jacobi converges quadratically: after a sweep whose largest rotation is
+// below 1e-8 what is left is of order 1e-16, so that sweep is the last -- no extra sweep just to see zero rotations.
+__global__ void __launch_bounds__(JT *JG) jacobi_onesided_kernel(double *__restrict__ B, int n, int ncols,
+                                                                 int max_sweeps, int *__restrict__ count,
+                                                                 unsigned long long *__restrict__ maxrot,
+                                                                 double *__restrict__ evals,
+                                                                 double *__restrict__ Vout) {
   cg::grid_group grid = cg::this_grid();
-  __shared__ double red[3][JT / 32];
-  __shared__ double bc[3];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  __shared__ double red[2][JG][3][JT / 32];
+  const int grp = threadIdx.x / JT, tid = threadIdx.x % JT, lane = tid & 31, warp = tid >> 5;
   const int m = ncols;            // even number of seats; seat index >= number of real columns: idle
   const double tol = 2.3e-16 * sqrt((double)n);
   const int half = m / 2;
-  int sweep = 0;
+  const bool onepass = n <= JT * JE;
+  int sweep = 0, buf = 0;
   for (; sweep < max_sweeps; sweep++) {
     for (int round = 0; round < m - 1; round++) {
-      for (int pr = blockIdx.x; pr < half; pr += gridDim.x) {
+      for (int pr = blockIdx.x * JG + grp; pr < half; pr += gridDim.x * JG) {
         int p, q;
         if (pr == 0) {
           p = m - 1;
@@ -138,7 +145,6 @@ __global__ void __launch_bounds__(JT) jacobi_onesided_kernel(double *__restrict_
         double *bp = B + (int64_t)n * p, *bq = B + (int64_t)n * q;
         double a = 0.0, b = 0.0, g = 0.0;
         double xp[JE], xq[JE];
-        const bool onepass = n <= JT * JE;
         if (onepass) {
 #pragma unroll
           for (int u = 0; u < JE; u++) {
@@ -163,35 +169,32 @@ __global__ void __launch_bounds__(JT) jacobi_onesided_kernel(double *__restrict_
         a = ppx_warp_sum(a);
         b = ppx_warp_sum(b);
         g = ppx_warp_sum(g);
-        __syncthreads();  // previous pair's broadcast has been read
+        // one barrier per pair: partial sums go to alternating buffers, every thread adds them up in the same order
+        buf ^= 1;
         if (lane == 0) {
-          red[0][warp] = a;
-          red[1][warp] = b;
-          red[2][warp] = g;
+          red[buf][grp][0][warp] = a;
+          red[buf][grp][1][warp] = b;
+          red[buf][grp][2][warp] = g;
         }
-        __syncthreads();
-        if (tid < 3) {
-          double v = 0.0;
+        group_bar(grp);
+        a = b = g = 0.0;
 #pragma unroll
-          for (int w = 0; w < JT / 32; w++) v += red[tid][w];
-          bc[tid] = v;
+        for (int w = 0; w < JT / 32; w++) {
+          a += red[buf][grp][0][w];
+          b += red[buf][grp][1][w];
+          g += red[buf][grp][2][w];
         }
-        __syncthreads();
-        a = bc[0];
-        b = bc[1];
-        g = bc[2];
         // rotate when the columns are not orthogonal to working precision
         // (threshold sqrt(n) eps, as LAPACK's dgesvj: a recomputed inner product of orthogonal columns is that large)
-        const bool rot = fabs(g) > tol * sqrt(a * b) && fabs(g) > 1e-300;
-        double c = 1.0, sn = 0.0;
-        if (rot) {
-          const double zeta = (b - a) / (2.0 * g);
-          const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-          c = 1.0 / sqrt(1.0 + t * t);
-          sn = c * t;
-          if (tid == 0) atomicAdd(&count[sweep], 1);
+        if (!(fabs(g) > tol * sqrt(a * b) && fabs(g) > 1e-300)) continue;
+        const double zeta = (b - a) / (2.0 * g);
+        const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+        const double c = 1.0 / sqrt(1.0 + t * t);
+        const double sn = c * t;
+        if (tid == 0) {
+          atomicAdd(&count[sweep], 1);
+          atomicMax(&maxrot[sweep], (unsigned long long)__double_as_longlong(fabs(sn)));
         }
-        if (!rot) continue;
         if (onepass) {
 #pragma unroll
           for (int u = 0; u < JE; u++) {
@@ -211,31 +214,27 @@ __global__ void __launch_bounds__(JT) jacobi_onesided_kernel(double *__restrict_
       }
       grid.sync();
     }
-    if (count[sweep] == 0) {
+    if (count[sweep] == 0 || __longlong_as_double((long long)maxrot[sweep]) < 1e-8) {
       sweep++;
       break;
     }
   }
-  if (blockIdx.x == 0 && tid == 0 && sweeps_done) *sweeps_done = sweep;
-  // eigenvalue estimates: column norms
-  for (int j = blockIdx.x; j < n; j += gridDim.x) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) count[max_sweeps] = sweep;
+  // eigenvalue estimates: column norms (one column per group)
+  for (int j = blockIdx.x * JG + grp; j < n; j += gridDim.x * JG) {
     const double *bj = B + (int64_t)n * j;
     double a = 0.0;
     for (int i = tid; i < n; i += JT) a = fma(bj[i], bj[i], a);
     a = ppx_warp_sum(a);
-    __syncthreads();
-    if (lane == 0) red[0][warp] = a;
-    __syncthreads();
-    if (tid == 0) {
-      double v = 0.0;
+    buf ^= 1;
+    if (lane == 0) red[buf][grp][0][warp] = a;
+    group_bar(grp);
+    double v = 0.0;
 #pragma unroll
-      for (int w = 0; w < JT / 32; w++) v += red[0][w];
-      evals[j] = sqrt(v);
-      bc[0] = sqrt(v);
-    }
+    for (int w = 0; w < JT / 32; w++) v += red[buf][grp][0][w];
+    const double nrm = sqrt(v);
+    if (tid == 0) evals[j] = nrm;
     if (Vout) {
-      __syncthreads();
-      const double nrm = bc[0];
       double *vj = Vout + (int64_t)n * j;
       for (int i = tid; i < n; i += JT) vj[i] = nrm > 0.0 ? bj[i] / nrm : (i == j ? 1.0 : 0.0);
     }
@@ -358,11 +357,13 @@ int ppx_sym_eig_topk_warm(ppx_ctx *ctx, double *MTM, int64_t s, int r, double *U
   double *B = (double *)ppx_ws_alloc(ctx, sizeof(double) * (size_t)n * n);
   double *A = warm ? (double *)ppx_ws_alloc(ctx, sizeof(double) * (size_t)n * n) : B;
   double *ev = (double *)ppx_ws_alloc(ctx, sizeof(double) * (size_t)n);
-  int *count = (int *)ppx_ws_alloc(ctx, sizeof(int) * (max_sweeps + 1));
+  int *count = (int *)ppx_ws_alloc(ctx, sizeof(int) * (max_sweeps + 2) + sizeof(unsigned long long) * max_sweeps);
   if (!B || !A || !ev || !count)
     return ppx_set_err(ctx, PPX_ENOMEM, "sym_eig_topk needs %lld bytes of workspace",
                        (long long)(16LL * n * n + 8LL * n + 4096));
-  PPX_CUDA(ctx, cudaMemsetAsync(count, 0, sizeof(int) * (max_sweeps + 1), ctx->stream));
+  unsigned long long *maxrot = (unsigned long long *)(count + max_sweeps + 2);  // 8-byte aligned: ws blocks are 256-byte
+  PPX_CUDA(ctx, cudaMemsetAsync(count, 0, sizeof(int) * (max_sweeps + 2) + sizeof(unsigned long long) * max_sweeps,
+                                ctx->stream));
   sym_copy_kernel<<<ppx_cdiv((int64_t)n * n, 256), 256, 0, ctx->stream>>>(MTM, n, A);
   PPX_CHECK_LAUNCH(ctx);
   if (warm) {  // B = A V0 (DMMA GEMM of the first-contraction kernel: rows l = i, contracted mode x, "rank" = n columns)
@@ -371,14 +372,15 @@ int ppx_sym_eig_topk_warm(ppx_ctx *ctx, double *MTM, int64_t s, int r, double *U
   }
   if (n > 1) {
     int blocks_per_sm = 0;
-    PPX_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, jacobi_onesided_kernel, JT, 0));
+    PPX_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, jacobi_onesided_kernel, JT * JG, 0));
     if (blocks_per_sm < 1) return ppx_set_err(ctx, PPX_ECUDA, "jacobi kernel cannot be resident");
     int grid = ctx->sm_count * blocks_per_sm;
-    if (grid > seats / 2) grid = seats / 2;  // one CTA per pair of a round; fewer CTAs make the grid barrier cheaper
+    const int need = (seats / 2 + JG - 1) / JG;  // JG pairs of a round per CTA
+    if (grid > need) grid = need;
     int nn = n, ss = seats, ms = max_sweeps;
-    int *sweeps_done = count + max_sweeps;
-    void *args[] = {&B, &nn, &ss, &ms, &count, &ev, &sweeps_done, &basis};
-    PPX_CUDA(ctx, cudaLaunchCooperativeKernel((void *)jacobi_onesided_kernel, dim3(grid), dim3(JT), args, 0, ctx->stream));
+    void *args[] = {&B, &nn, &ss, &ms, &count, &maxrot, &ev, &basis};
+    PPX_CUDA(ctx, cudaLaunchCooperativeKernel((void *)jacobi_onesided_kernel, dim3(grid), dim3(JT * JG), args, 0,
+                                              ctx->stream));
     ctx->launches++;
   } else {
     PPX_CUDA(ctx, cudaMemcpyAsync(ev, B, sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
