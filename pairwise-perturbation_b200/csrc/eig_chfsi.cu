@@ -1,0 +1,405 @@
+// Leading eigenvectors of a large symmetric positive semi-definite matrix by Chebyshev-filtered subspace iteration
+// with Rayleigh-Ritz and Hotelling deflation -- the GEMM-shaped alternative to the cooperative Jacobi of tucker_ops.cu
+// for the Tucker factor update (MTM.svd(U,S,VT,r), als_Tucker.cxx:20,402,627,868) when r << s.
+//
+//   X (n x p, p = r + guard) orthonormal; repeat:
+//     Rayleigh-Ritz:  H = X^T A X,  H = Z Theta Z^T (one-CTA one-sided Jacobi in shared memory),  X <- X Z
+//     residuals  ||A x_j - theta_j x_j||: a leading run of converged Ritz pairs is LOCKED and removed from the matrix,
+//       A <- A - theta_j x_j x_j^T  (their eigenvalue becomes 0, i.e. part of the damped interval: no projections, and
+//       a dominant outlier -- the mean component of a positive tensor is 10^6 x the rest -- stops polluting the
+//       products of the remaining block in floating point);
+//     filter:  X_active <- T_d((A - c)/e) X_active,  [0, b] = [0, smallest Ritz value of the block] the damped
+//       interval, degree d chosen so that the block's condition number stays below 5e6;
+//     orthonormalise X_active by Cholesky QR (twice).
+// Every step is a product with the n x n matrix (a small DFMA GEMM with the three-term recurrence fused into its
+// epilogue) or p x p work: ~60 products of 80 MFLOP instead of the ~10^4 grid-synchronised rounds of the Jacobi sweep.
+// Not converged within the iteration budget (or n too small to pay off) -> the caller falls back to Jacobi.
+#include <algorithm>
+#include <vector>
+#include "ppx_internal.h"
+
+namespace {
+
+// ---- Y = alpha A X + beta X + gamma Z  (A symmetric n x n; X, Z, Y n x pa with leading dimension ld) -----------------
+// CTA: 16 rows x 64 columns, 128 threads (2 rows x 4 columns each), K in chunks of 32 through shared memory.
+constexpr int CG_ROWS = 16, CG_COLS = 64, CG_K = 32;
+__global__ void __launch_bounds__(128) chfsi_gemm_kernel(const double *__restrict__ A, int n,
+                                                         const double *__restrict__ X, int64_t ld, int pa,
+                                                         double alpha, double beta, const double *__restrict__ Z,
+                                                         double gamma, double *__restrict__ Y) {
+  __shared__ double As[CG_K][CG_ROWS + 1];
+  __shared__ double Xs[CG_K][CG_COLS + 1];
+  const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
+  const int i0 = blockIdx.x * CG_ROWS, j0 = blockIdx.y * CG_COLS;
+  double acc[2][4];
+#pragma unroll
+  for (int a = 0; a < 2; a++)
+#pragma unroll
+    for (int b = 0; b < 4; b++) acc[a][b] = 0.0;
+  for (int k0 = 0; k0 < n; k0 += CG_K) {
+    // A is symmetric: rows i0.. are read as columns (contiguous along k)
+    for (int idx = tid; idx < CG_K * CG_ROWS; idx += 128) {
+      const int kk = idx % CG_K, ii = idx / CG_K;
+      const int k = k0 + kk, i = i0 + ii;
+      As[kk][ii] = (k < n && i < n) ? A[k + (int64_t)n * i] : 0.0;
+    }
+    for (int idx = tid; idx < CG_K * CG_COLS; idx += 128) {
+      const int kk = idx % CG_K, jj = idx / CG_K;
+      const int k = k0 + kk, j = j0 + jj;
+      Xs[kk][jj] = (k < n && j < pa) ? X[k + ld * j] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int kk = 0; kk < CG_K; kk++) {
+      const double a0 = As[kk][2 * ty], a1 = As[kk][2 * ty + 1];
+#pragma unroll
+      for (int b = 0; b < 4; b++) {
+        const double x = Xs[kk][4 * tx + b];
+        acc[0][b] = fma(a0, x, acc[0][b]);
+        acc[1][b] = fma(a1, x, acc[1][b]);
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int a = 0; a < 2; a++) {
+    const int i = i0 + 2 * ty + a;
+    if (i >= n) continue;
+#pragma unroll
+    for (int b = 0; b < 4; b++) {
+      const int j = j0 + 4 * tx + b;
+      if (j >= pa) continue;
+      double v = alpha * acc[a][b];
+      if (beta != 0.0) v = fma(beta, X[i + ld * j], v);
+      if (gamma != 0.0) v = fma(gamma, Z[i + ld * j], v);
+      Y[i + ld * j] = v;
+    }
+  }
+}
+
+// A -= sum_j theta[j] x_j x_j^T over k newly locked Ritz pairs (Hotelling deflation)
+__global__ void __launch_bounds__(256) chfsi_deflate_kernel(double *__restrict__ A, int n,
+                                                            const double *__restrict__ X, int64_t ld,
+                                                            const double *__restrict__ theta, int k) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)n * n) return;
+  const int i = (int)(idx % n), j = (int)(idx / n);
+  double s = 0.0;
+  for (int q = 0; q < k; q++) s = fma(theta[q] * X[i + ld * q], X[j + ld * q], s);
+  A[idx] -= s;
+}
+
+// res[j] = || AX_j - theta_j X_j ||, one CTA per column
+__global__ void __launch_bounds__(256) chfsi_resid_kernel(const double *__restrict__ AX, const double *__restrict__ X,
+                                                          int n, int64_t ld, const double *__restrict__ theta,
+                                                          double *__restrict__ res) {
+  __shared__ double red[32];
+  const int j = blockIdx.x;
+  const double th = theta[j];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const double d = AX[i + ld * j] - th * X[i + ld * j];
+    s = fma(d, d, s);
+  }
+  s = ppx_block_sum(s, red);
+  if (threadIdx.x == 0) res[j] = sqrt(s);
+}
+
+// ---- one-sided Jacobi of a p x p symmetric PSD matrix in shared memory, one CTA of 32 warps ----------------------------
+// B = 0.5 (H + H^T); plane rotations of column pairs until a sweep applies none above sqrt(p) eps (or the largest was
+// below 1e-8); column j converges to lambda_j z_j.  Output: Z (p x p, unit columns, DECREASING eigenvalue) and theta.
+__global__ void __launch_bounds__(1024) chfsi_jacobi_smem_kernel(const double *__restrict__ H, int p,
+                                                                 double *__restrict__ Zout,
+                                                                 double *__restrict__ theta_out) {
+  extern __shared__ double sm[];
+  const int ld = p + 1;
+  double *B = sm;                    // [p][ld], column c at B + c*ld
+  double *nrm = sm + (size_t)p * ld; // [p]
+  __shared__ int nrot;
+  __shared__ double maxrot;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+  for (int idx = tid; idx < p * p; idx += blockDim.x) {
+    const int i = idx % p, j = idx / p;
+    B[j * ld + i] = 0.5 * (H[i + (int64_t)p * j] + H[j + (int64_t)p * i]);
+  }
+  const int m = (p + 1) & ~1, half = m / 2;
+  const double tol = 2.3e-16 * sqrt((double)p);
+  __syncthreads();
+  for (int sweep = 0; sweep < 40; sweep++) {
+    if (tid == 0) {
+      nrot = 0;
+      maxrot = 0.0;
+    }
+    __syncthreads();
+    for (int round = 0; round < m - 1; round++) {
+      for (int pr = warp; pr < half; pr += nw) {
+        int a, b;
+        if (pr == 0) {
+          a = m - 1;
+          b = round % (m - 1);
+        } else {
+          a = (round + pr) % (m - 1);
+          b = (round + m - 1 - pr) % (m - 1);
+        }
+        if (a > b) {
+          const int t = a;
+          a = b;
+          b = t;
+        }
+        if (b >= p) continue;
+        double *ca = B + a * ld, *cb = B + b * ld;
+        double xa[4], xb[4];  // p <= 128
+        double saa = 0.0, sbb = 0.0, sab = 0.0;
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int i = lane + 32 * u;
+          xa[u] = i < p ? ca[i] : 0.0;
+          xb[u] = i < p ? cb[i] : 0.0;
+          saa = fma(xa[u], xa[u], saa);
+          sbb = fma(xb[u], xb[u], sbb);
+          sab = fma(xa[u], xb[u], sab);
+        }
+        saa = ppx_warp_sum(saa);
+        sbb = ppx_warp_sum(sbb);
+        sab = ppx_warp_sum(sab);
+        if (!(fabs(sab) > tol * sqrt(saa * sbb) && fabs(sab) > 1e-300)) continue;
+        const double zeta = (sbb - saa) / (2.0 * sab);
+        const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+        const double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int i = lane + 32 * u;
+          if (i < p) {
+            ca[i] = c * xa[u] - s * xb[u];
+            cb[i] = s * xa[u] + c * xb[u];
+          }
+        }
+        if (lane == 0) {
+          atomicAdd(&nrot, 1);
+          // positive doubles order like their bit patterns
+          atomicMax((unsigned long long *)&maxrot, (unsigned long long)__double_as_longlong(fabs(s)));
+        }
+      }
+      __syncthreads();
+    }
+    const bool done = nrot == 0 || maxrot < 1e-8;
+    __syncthreads();
+    if (done) break;
+  }
+  // column norms = eigenvalues
+  for (int c = warp; c < p; c += nw) {
+    double s = 0.0;
+    for (int i = lane; i < p; i += 32) s = fma(B[c * ld + i], B[c * ld + i], s);
+    s = ppx_warp_sum(s);
+    if (lane == 0) nrm[c] = sqrt(s);
+  }
+  __syncthreads();
+  // rank by counting (ties broken by index), write normalised columns in decreasing order
+  for (int c = warp; c < p; c += nw) {
+    const double lc = nrm[c];
+    int cnt = 0;
+    for (int j = lane; j < p; j += 32) {
+      const double lj = nrm[j];
+      if (j != c && (lj > lc || (lj == lc && j < c))) cnt++;
+    }
+    cnt = (int)ppx_warp_sum((double)cnt);  // exact: small integers
+    const double inv = lc > 0.0 ? 1.0 / lc : 0.0;
+    for (int i = lane; i < p; i += 32) Zout[i + (int64_t)p * cnt] = lc > 0.0 ? B[c * ld + i] * inv : (i == c ? 1.0 : 0.0);
+    if (lane == 0) theta_out[cnt] = lc;
+  }
+}
+
+// U[:, k] = sign * X[:, src[k]], largest-magnitude component positive (the convention of eig_select_kernel)
+__global__ void __launch_bounds__(256) chfsi_extract_kernel(const double *__restrict__ X, int n, int64_t ld,
+                                                            const int *__restrict__ src, double *__restrict__ U) {
+  __shared__ double red_v[256];
+  __shared__ int red_i[256];
+  const int k = blockIdx.x;
+  const double *x = X + ld * src[k];
+  double best = -1.0;
+  int bi = 0;
+  for (int j = threadIdx.x; j < n; j += blockDim.x) {
+    const double v = fabs(x[j]);
+    if (v > best) {
+      best = v;
+      bi = j;
+    }
+  }
+  red_v[threadIdx.x] = best;
+  red_i[threadIdx.x] = bi;
+  __syncthreads();
+  for (int st = 128; st > 0; st >>= 1) {
+    if (threadIdx.x < st) {
+      if (red_v[threadIdx.x + st] > red_v[threadIdx.x] ||
+          (red_v[threadIdx.x + st] == red_v[threadIdx.x] && red_i[threadIdx.x + st] < red_i[threadIdx.x])) {
+        red_v[threadIdx.x] = red_v[threadIdx.x + st];
+        red_i[threadIdx.x] = red_i[threadIdx.x + st];
+      }
+    }
+    __syncthreads();
+  }
+  const double sgn = x[red_i[0]] < 0.0 ? -1.0 : 1.0;
+  for (int j = threadIdx.x; j < n; j += blockDim.x) U[j + (int64_t)n * k] = sgn * x[j];
+}
+
+int gemm_cheb(ppx_ctx *ctx, const double *A, int n, const double *X, int64_t ld, int pa, double alpha, double beta,
+              const double *Z, double gamma, double *Y) {
+  dim3 grid(ppx_cdiv(n, CG_ROWS), ppx_cdiv(pa, CG_COLS));
+  chfsi_gemm_kernel<<<grid, 128, 0, ctx->stream>>>(A, n, X, ld, pa, alpha, beta, Z, gamma, Y);
+  PPX_CHECK_LAUNCH(ctx);
+  return PPX_OK;
+}
+
+#define CHK(x)            \
+  do {                    \
+    const int rc_ = (x);  \
+    if (rc_) return rc_;  \
+  } while (0)
+
+// X (n x pa, leading dimension ld) <- orthonormal basis of its columns by Cholesky QR, twice; T is scratch of the same
+// shape, G / Zi are pa x pa.  The result ends up in X.
+int cholqr2(ppx_ctx *ctx, double *X, double *T, int n, int64_t ld, int pa, double *G, double *Zi) {
+  for (int pass = 0; pass < 2; pass++) {
+    CHK(ppx_gram(ctx, X, n, ld, pa, G));
+    CHK(ppx_spd_factor_inverse(ctx, G, pa, Zi));
+    CHK(ppx_gemm_small(ctx, 0, 1, n, pa, pa, 1.0, X, ld, Zi, pa, 0.0, T, ld));
+    PPX_CUDA(ctx, cudaMemcpyAsync(X, T, sizeof(double) * (size_t)ld * pa, cudaMemcpyDeviceToDevice, ctx->stream));
+  }
+  return PPX_OK;
+}
+
+}  // namespace
+
+bool ppx_eig_chfsi_applicable(int64_t n, int r) {
+  if (getenv("PPX_EIG_JACOBI")) return false;
+  // p = r + 24 columns: the Cholesky-QR factor kernel takes p <= 112, the shared-memory Jacobi p <= 128
+  return n >= 384 && r >= 1 && r + 24 <= 112 && 4 * (int64_t)r <= n;
+}
+
+// Returns PPX_OK with U / evals_out filled, 1 if the iteration did not converge (nothing usable was written: the caller
+// falls back to the Jacobi solver), a negative code on errors.  `A` (n x n, symmetric) is destroyed.  `state`
+// (>= n*(r+24) doubles, optional) holds the final block for the next call on a nearby matrix.
+int ppx_eig_chfsi(ppx_ctx *ctx, double *A, int n, int r, double *U, double *evals_out, double *state, int state_valid) {
+  const int p = r + 24;
+  const int64_t ld = n;
+  const size_t np = (size_t)n * p;
+  double *X = (double *)ppx_ws_alloc(ctx, sizeof(double) * np);
+  double *Y0 = (double *)ppx_ws_alloc(ctx, sizeof(double) * np);
+  double *Y1 = (double *)ppx_ws_alloc(ctx, sizeof(double) * np);
+  double *AX = (double *)ppx_ws_alloc(ctx, sizeof(double) * np);
+  double *T = (double *)ppx_ws_alloc(ctx, sizeof(double) * np);
+  double *H = (double *)ppx_ws_alloc(ctx, sizeof(double) * p * p);
+  double *Zr = (double *)ppx_ws_alloc(ctx, sizeof(double) * p * p);
+  double *G = (double *)ppx_ws_alloc(ctx, sizeof(double) * p * p);
+  double *Zi = (double *)ppx_ws_alloc(ctx, sizeof(double) * p * p);
+  double *theta = (double *)ppx_ws_alloc(ctx, sizeof(double) * 2 * p);
+  int *src = (int *)ppx_ws_alloc(ctx, sizeof(int) * p);
+  if (!X || !Y0 || !Y1 || !AX || !T || !H || !Zr || !G || !Zi || !theta || !src) return 1;
+  double *res = theta + p;
+  const bool verbose = getenv("PPX_EIG_VERBOSE") != nullptr;
+
+  // start block: the previous call's block, or random
+  if (state && state_valid) {
+    PPX_CUDA(ctx, cudaMemcpyAsync(X, state, sizeof(double) * np, cudaMemcpyDeviceToDevice, ctx->stream));
+  } else {
+    CHK(ppx_fill_uniform(ctx, X, (int64_t)np, 0x5eedULL, 77, 0, -0.5, 0.5));
+  }
+  CHK(cholqr2(ctx, X, T, n, ld, p, G, Zi));
+
+  std::vector<double> h(2 * (size_t)p), lam_locked;
+  std::vector<int> order;
+  int nlock = 0;  // columns [0, nlock) of X are locked (final), in the order they were locked
+  double lam_max = -1.0;  // largest Ritz value of the first Rayleigh-Ritz step: the scale "numerically zero" refers to
+  const size_t jac_smem = sizeof(double) * ((size_t)p * (p + 1) + p);
+  static bool attr_set = false;
+  if (!attr_set) {
+    PPX_CUDA(ctx, cudaFuncSetAttribute(chfsi_jacobi_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    attr_set = true;
+  }
+  int iters = 0, products = 0;
+  for (int outer = 0; outer < 24; outer++, iters++) {
+    const int pa = p - nlock;
+    double *Xa = X + ld * nlock;
+    // Rayleigh-Ritz on the active block
+    CHK(gemm_cheb(ctx, A, n, Xa, ld, pa, 1.0, 0.0, nullptr, 0.0, AX));
+    products++;
+    CHK(ppx_gemm_small(ctx, 1, 0, pa, pa, n, 1.0, Xa, ld, AX, ld, 0.0, H, pa));
+    chfsi_jacobi_smem_kernel<<<1, 1024, jac_smem, ctx->stream>>>(H, pa, Zr, theta);
+    PPX_CHECK_LAUNCH(ctx);
+    CHK(ppx_gemm_small(ctx, 0, 0, n, pa, pa, 1.0, Xa, ld, Zr, pa, 0.0, T, ld));
+    PPX_CUDA(ctx, cudaMemcpyAsync(Xa, T, sizeof(double) * (size_t)ld * pa, cudaMemcpyDeviceToDevice, ctx->stream));
+    CHK(ppx_gemm_small(ctx, 0, 0, n, pa, pa, 1.0, AX, ld, Zr, pa, 0.0, T, ld));
+    chfsi_resid_kernel<<<pa, 256, 0, ctx->stream>>>(T, Xa, n, ld, theta, res);
+    PPX_CHECK_LAUNCH(ctx);
+    PPX_CUDA(ctx, cudaMemcpyAsync(h.data(), theta, sizeof(double) * 2 * p, cudaMemcpyDeviceToHost, ctx->stream));
+    PPX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const double *th = h.data(), *rs = h.data() + p;
+    for (int j = 0; j < pa; j++)
+      if (!(th[j] == th[j]) || !(rs[j] == rs[j])) return 1;  // NaN: the block lost rank somewhere
+    if (lam_max < 0.0) lam_max = th[0];
+    // lock the leading run of converged Ritz pairs (Ritz values are in decreasing order); below 1e-13 of the largest
+    // eigenvalue the matrix is numerically rank deficient and any orthonormal vectors of the block serve
+    int nconv = 0;
+    while (nconv < pa && nlock + nconv < r &&
+           (rs[nconv] <= 1e-12 * th[nconv] + 1e-300 || th[nconv] <= 1e-13 * lam_max))
+      nconv++;
+    if (verbose)
+      fprintf(stderr, "chfsi n=%d r=%d it %d: locked %d (+%d), theta[0]=%.6e theta[last]=%.6e res[first unconv]=%.3e\n", n,
+              r, outer, nlock, nconv, th[0], th[pa - 1], nconv < pa ? rs[nconv] : 0.0);
+    if (nconv > 0) {
+      for (int j = 0; j < nconv; j++) lam_locked.push_back(th[j]);
+      chfsi_deflate_kernel<<<ppx_cdiv((int64_t)n * n, 256), 256, 0, ctx->stream>>>(A, n, Xa, ld, theta, nconv);
+      PPX_CHECK_LAUNCH(ctx);
+      nlock += nconv;
+    }
+    if (nlock >= r) break;
+    if (outer == 23) return 1;
+    // Chebyshev filter of the remaining block on the deflated matrix: damp [0, b]
+    const int pa2 = p - nlock;
+    double *Xb = X + ld * nlock;
+    const double top = th[nconv];               // largest Ritz value still wanted
+    double b = th[pa - 1];                       // smallest Ritz value of the block: upper end of the unwanted part
+    if (!(b > 1e-8 * top)) b = 1e-8 * top;       // (rank-deficient matrices: everything below is zero)
+    if (!(top > 0.0)) return 1;
+    const double c = 0.5 * b, e = 0.5 * b;
+    const double xmax = (top - c) / e;
+    int d = 24;
+    if (xmax > 1.0) {
+      const double per = log(xmax + sqrt(xmax * xmax - 1.0));  // acosh
+      const int cap = (int)(log(5e6) / per);  // Cholesky QR twice copes with a block condition number up to ~1e7
+      if (cap < d) d = cap;
+    }
+    if (d < 2) d = 2;
+    // T_0 = X, T_1 = (A - c) X / e, T_{k+1} = 2 (A - c) T_k / e - T_{k-1}
+    // three buffers rotate: the one holding T_{k-1} is free once T_{k+1} has been formed
+    double *Tprev = Xb, *Tcur = Y0, *Tnext = Y1;
+    CHK(gemm_cheb(ctx, A, n, Tprev, ld, pa2, 1.0 / e, -c / e, nullptr, 0.0, Tcur));
+    for (int k = 2; k <= d; k++) {
+      CHK(gemm_cheb(ctx, A, n, Tcur, ld, pa2, 2.0 / e, -2.0 * c / e, Tprev, -1.0, Tnext));
+      double *freed = Tprev;
+      Tprev = Tcur;
+      Tcur = Tnext;
+      Tnext = freed;
+    }
+    products += d;
+    if (Tcur != Xb)
+      PPX_CUDA(ctx, cudaMemcpyAsync(Xb, Tcur, sizeof(double) * (size_t)ld * pa2, cudaMemcpyDeviceToDevice, ctx->stream));
+    CHK(cholqr2(ctx, Xb, T, n, ld, pa2, G, Zi));
+  }
+  if (verbose) fprintf(stderr, "chfsi n=%d r=%d: converged after %d iterations, %d products with A\n", n, r, iters + 1, products);
+  // order the locked vectors by decreasing eigenvalue and write U
+  order.resize(r);
+  for (int k = 0; k < r; k++) order[k] = k;
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return lam_locked[a] > lam_locked[b]; });
+  PPX_CUDA(ctx, cudaMemcpyAsync(src, order.data(), sizeof(int) * r, cudaMemcpyHostToDevice, ctx->stream));
+  chfsi_extract_kernel<<<r, 256, 0, ctx->stream>>>(X, n, ld, src, U);
+  PPX_CHECK_LAUNCH(ctx);
+  if (evals_out) {
+    std::vector<double> ev(r);
+    for (int k = 0; k < r; k++) ev[k] = lam_locked[order[k]];
+    PPX_CUDA(ctx, cudaMemcpyAsync(evals_out, ev.data(), sizeof(double) * r, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  if (state) PPX_CUDA(ctx, cudaMemcpyAsync(state, X, sizeof(double) * np, cudaMemcpyDeviceToDevice, ctx->stream));
+  PPX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // `order`, `ev` are host temporaries of the copies above
+  return PPX_OK;
+}

@@ -36,6 +36,9 @@ int ppx_ttm_tma_try(ppx_ctx *ctx, const double *V, int64_t L, int64_t K, int64_t
 // out[l,t,r] = sum_x V[l,x,t] W[x,r] (rank last, or in place of mode x); shared by the CP and Tucker entry points
 int ppx_ttm_impl(ppx_ctx *ctx, const double *V, int64_t L, int64_t X, int64_t Rt, const double *Wx, int64_t ldw, int R,
                  double *out, int inplace, int accumulate, bool ws_keep, bool try_tma);
+// Chebyshev-filtered subspace iteration for the leading eigenvectors (eig_chfsi.cu); see there for the contract
+bool ppx_eig_chfsi_applicable(int64_t n, int r);
+int ppx_eig_chfsi(ppx_ctx *ctx, double *A, int n, int r, double *U, double *evals_out, double *state, int state_valid);
 int ppx_k45_init(ppx_ctx *ctx);
 int ppx_k7_init(ppx_ctx *ctx);
 void ppx_comm_destroy_internal(ppx_ctx *ctx);

@@ -352,6 +352,20 @@ int ppx_sym_eig_topk_warm(ppx_ctx *ctx, double *MTM, int64_t s, int r, double *U
   const int n = (int)s;
   const int seats = (n + 1) & ~1;
   const int max_sweeps = 40;
+  // r << s: Chebyshev-filtered subspace iteration (GEMM-shaped, eig_chfsi.cu); `basis` then carries its block of
+  // r + 24 vectors.  Not converged -> the Jacobi solver below, started cold.
+  if (ppx_eig_chfsi_applicable(s, r)) {
+    ppx_ws_reset(ctx);
+    double *Ac = (double *)ppx_ws_alloc(ctx, sizeof(double) * (size_t)n * n);
+    if (Ac) {
+      sym_copy_kernel<<<ppx_cdiv((int64_t)n * n, 256), 256, 0, ctx->stream>>>(MTM, n, Ac);
+      PPX_CHECK_LAUNCH(ctx);
+      const int rc = ppx_eig_chfsi(ctx, Ac, n, r, U, evals_out, basis, basis_valid);
+      if (rc <= 0) return rc;
+      if (getenv("PPX_EIG_VERBOSE")) fprintf(stderr, "sym_eig_topk n=%d r=%d: subspace iteration gave up, Jacobi\n", n, r);
+    }
+    basis_valid = 0;
+  }
   const bool warm = basis && basis_valid && n > 1;
   ppx_ws_reset(ctx);
   double *B = (double *)ppx_ws_alloc(ctx, sizeof(double) * (size_t)n * n);

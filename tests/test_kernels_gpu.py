@@ -407,3 +407,47 @@ def test_rank_expand_acc(ctx, Mtot, r, R):
     od = ctx.to_device(out)
     ctx.rank_expand_acc(ctx.to_device(T), Mtot, r, ctx.to_device(VT), r, R, od)
     assert rel_err(ctx.to_host(od, (Mtot, R)), ref) < 1e-13
+
+
+# ---- leading eigenvectors at sizes where the Chebyshev-filtered subspace iteration takes over (n >= 384, r <= n/4) ----
+def _spectrum_case(kind, n, rng):
+    if kind == "noise+outlier":      # Gram of a positive random matrix: one eigenvalue 10^5-10^6 x the bulk
+        Y = 0.5 + 0.5 * rng.random((n, 2 * n))
+        return Y @ Y.T
+    if kind == "noise":              # Gram of a centred random matrix: Marchenko-Pastur bulk, gaps of a fraction of a %
+        Y = rng.standard_normal((n, 2 * n))
+        return Y @ Y.T
+    Q, _ = np.linalg.qr(rng.standard_normal((n, n)))
+    if kind == "decay":              # geometric decay over 8 orders of magnitude
+        lam = 10.0 ** (-8.0 * np.arange(n) / n)
+    elif kind == "lowrank":          # exact rank 12 (fewer non-zero eigenvalues than asked for when r > 12)
+        lam = np.r_[np.linspace(5.0, 1.0, 12), np.zeros(n - 12)]
+    else:                            # clusters of equal eigenvalues straddling nothing: subspaces well defined as a whole
+        lam = np.r_[np.repeat([9.0, 7.0, 5.0], 4), np.linspace(1.0, 0.1, n - 12)]
+    return (Q * lam) @ Q.T
+
+
+@pytest.mark.parametrize("kind,n,r", [("noise+outlier", 400, 8), ("noise+outlier", 800, 40), ("noise", 512, 24),
+                                      ("decay", 448, 16), ("lowrank", 400, 10), ("lowrank", 400, 20),
+                                      ("clusters", 384, 12), ("noise", 390, 88)])
+def test_sym_eig_topk_large(ctx, kind, n, r):
+    rng = np.random.default_rng(7)
+    A = _spectrum_case(kind, n, rng)
+    A = np.asfortranarray(0.5 * (A + A.T))
+    U, ev = ctx.empty(n * r), ctx.empty(r)
+    basis = ctx.empty(n * n)
+    w, Q = np.linalg.eigh(A)
+    w, Q = w[::-1], Q[:, ::-1]
+    for warm in (False, True):   # cold, then warm started from its own block (must give the same answer)
+        ctx.sym_eig_topk(ctx.to_device(A), n, r, U, ev, basis=basis, basis_valid=warm)
+        Uh, evh = ctx.to_host(U, (n, r)), ctx.to_host(ev, (r,))
+        assert np.abs(Uh.T @ Uh - np.eye(r)).max() < 1e-11
+        assert np.abs(evh - w[:r]).max() <= 1e-11 * w[0]
+        # invariant-subspace test that is meaningful with repeated / zero eigenvalues: A U = U (U^T A U)
+        resid = A @ Uh - Uh @ (Uh.T @ A @ Uh)
+        assert np.abs(resid).max() <= 1e-10 * w[0]
+        k = int(np.sum(w[:r] > 1e-9 * w[0]))
+        if kind in ("noise+outlier", "noise", "decay"):   # simple eigenvalues: the projector is unique
+            gap = np.min(w[:k] - w[1:k + 1]) if k < n else 1.0
+            P, Pr = Uh[:, :k] @ Uh[:, :k].T, Q[:, :k] @ Q[:, :k].T
+            assert np.abs(P - Pr).max() <= 1e-9 * w[0] / max(gap, 1e-300) * 1e-3 + 1e-9
