@@ -21,59 +21,142 @@
 namespace {
 
 // ---- Y = alpha A X + beta X + gamma Z  (A symmetric n x n; X, Z, Y n x pa with leading dimension ld) -----------------
-// CTA: 16 rows x 64 columns, 128 threads (2 rows x 4 columns each), K in chunks of 32 through shared memory.
-constexpr int CG_ROWS = 16, CG_COLS = 64, CG_K = 32;
-__global__ void __launch_bounds__(128) chfsi_gemm_kernel(const double *__restrict__ A, int n,
-                                                         const double *__restrict__ X, int64_t ld, int pa,
-                                                         double alpha, double beta, const double *__restrict__ Z,
-                                                         double gamma, double *__restrict__ Y) {
+// Two launches: partial products over CG_S slices of K (16 rows x 64 columns per CTA, 128 threads, two rows x four
+// columns each; the next 32-deep chunk is fetched into registers while the current one is multiplied), then the sum of
+// the slices fused with the three-term recurrence.  (A first version without the K split and the register prefetch
+// ran 50 CTAs at one exposed global-load latency per chunk: 129 us per product instead of ~12.)
+constexpr int CG_ROWS = 16, CG_COLS = 64, CG_K = 32, CG_S = 4;
+__global__ void __launch_bounds__(128) chfsi_gemm_part_kernel(const double *__restrict__ A, int n,
+                                                              const double *__restrict__ X, int64_t ld, int pa,
+                                                              int kslice, double *__restrict__ P) {
   __shared__ double As[CG_K][CG_ROWS + 1];
   __shared__ double Xs[CG_K][CG_COLS + 1];
+  // thread (tx, ty): rows ty, ty + 8; columns tx, tx + 16, tx + 32, tx + 48 (consecutive lanes -> consecutive banks)
   const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
   const int i0 = blockIdx.x * CG_ROWS, j0 = blockIdx.y * CG_COLS;
+  const int kbeg = blockIdx.z * kslice;
+  const int kend = min(n, kbeg + kslice);
   double acc[2][4];
 #pragma unroll
   for (int a = 0; a < 2; a++)
 #pragma unroll
     for (int b = 0; b < 4; b++) acc[a][b] = 0.0;
-  for (int k0 = 0; k0 < n; k0 += CG_K) {
-    // A is symmetric: rows i0.. are read as columns (contiguous along k)
-    for (int idx = tid; idx < CG_K * CG_ROWS; idx += 128) {
-      const int kk = idx % CG_K, ii = idx / CG_K;
+  double ra[4], rx[16];
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int u = 0; u < 4; u++) {  // A is symmetric: rows i0.. are read as columns (contiguous along k)
+      const int idx = tid + 128 * u, kk = idx % CG_K, ii = idx / CG_K;
       const int k = k0 + kk, i = i0 + ii;
-      As[kk][ii] = (k < n && i < n) ? A[k + (int64_t)n * i] : 0.0;
+      ra[u] = (k < kend && i < n) ? A[k + (int64_t)n * i] : 0.0;
     }
-    for (int idx = tid; idx < CG_K * CG_COLS; idx += 128) {
-      const int kk = idx % CG_K, jj = idx / CG_K;
+#pragma unroll
+    for (int u = 0; u < 16; u++) {
+      const int idx = tid + 128 * u, kk = idx % CG_K, jj = idx / CG_K;
       const int k = k0 + kk, j = j0 + jj;
-      Xs[kk][jj] = (k < n && j < pa) ? X[k + ld * j] : 0.0;
+      rx[u] = (k < kend && j < pa) ? X[k + ld * j] : 0.0;
+    }
+  };
+  fetch(kbeg);
+  for (int k0 = kbeg; k0 < kend; k0 += CG_K) {
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int idx = tid + 128 * u;
+      As[idx % CG_K][idx / CG_K] = ra[u];
+    }
+#pragma unroll
+    for (int u = 0; u < 16; u++) {
+      const int idx = tid + 128 * u;
+      Xs[idx % CG_K][idx / CG_K] = rx[u];
     }
     __syncthreads();
+    if (k0 + CG_K < kend) fetch(k0 + CG_K);
 #pragma unroll 8
     for (int kk = 0; kk < CG_K; kk++) {
-      const double a0 = As[kk][2 * ty], a1 = As[kk][2 * ty + 1];
+      const double a0 = As[kk][ty], a1 = As[kk][ty + 8];
 #pragma unroll
       for (int b = 0; b < 4; b++) {
-        const double x = Xs[kk][4 * tx + b];
+        const double x = Xs[kk][tx + 16 * b];
         acc[0][b] = fma(a0, x, acc[0][b]);
         acc[1][b] = fma(a1, x, acc[1][b]);
       }
     }
     __syncthreads();
   }
+  double *o = P + (size_t)blockIdx.z * n * pa;
 #pragma unroll
   for (int a = 0; a < 2; a++) {
-    const int i = i0 + 2 * ty + a;
+    const int i = i0 + ty + 8 * a;
     if (i >= n) continue;
 #pragma unroll
     for (int b = 0; b < 4; b++) {
-      const int j = j0 + 4 * tx + b;
-      if (j >= pa) continue;
-      double v = alpha * acc[a][b];
-      if (beta != 0.0) v = fma(beta, X[i + ld * j], v);
-      if (gamma != 0.0) v = fma(gamma, Z[i + ld * j], v);
-      Y[i + ld * j] = v;
+      const int j = j0 + tx + 16 * b;
+      if (j < pa) o[i + (size_t)n * j] = acc[a][b];
     }
+  }
+}
+__global__ void __launch_bounds__(256) chfsi_gemm_fin_kernel(const double *__restrict__ P, int n, int pa, int S,
+                                                             const double *__restrict__ X, int64_t ld, double alpha,
+                                                             double beta, const double *__restrict__ Z, double gamma,
+                                                             double *__restrict__ Y) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)n * pa) return;
+  const int i = (int)(idx % n), j = (int)(idx / n);
+  double s = 0.0;
+  for (int q = 0; q < S; q++) s += P[(size_t)q * n * pa + idx];  // fixed order: deterministic
+  double v = alpha * s;
+  if (beta != 0.0) v = fma(beta, X[i + ld * j], v);
+  if (gamma != 0.0) v = fma(gamma, Z[i + ld * j], v);
+  Y[i + ld * j] = v;
+}
+
+// H[a, b] = <X[:, a], Y[:, b]>  (pa x pa), one warp per element
+__global__ void __launch_bounds__(256) chfsi_cross_gram_kernel(const double *__restrict__ X,
+                                                               const double *__restrict__ Y, int n, int64_t ld, int pa,
+                                                               double *__restrict__ H) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= pa * pa) return;
+  const int a = w % pa, b = w / pa;
+  const double *x = X + ld * a, *y = Y + ld * b;
+  double s0 = 0.0, s1 = 0.0;
+  int i = lane;
+  for (; i + 32 < n; i += 64) {
+    s0 = fma(x[i], y[i], s0);
+    s1 = fma(x[i + 32], y[i + 32], s1);
+  }
+  if (i < n) s0 = fma(x[i], y[i], s0);
+  const double v = ppx_warp_sum(s0 + s1);
+  if (lane == 0) H[a + (int64_t)pa * b] = v;
+}
+
+// C (n x pa) = X (n x pa) op(Z), Z pa x pa (op = transpose when tz): 32 rows per CTA, Z and the row tile in shared memory
+__global__ void __launch_bounds__(256) chfsi_right_mult_kernel(const double *__restrict__ X, int n, int64_t ld, int pa,
+                                                               const double *__restrict__ Z, int tz,
+                                                               double *__restrict__ C) {
+  extern __shared__ double sm[];
+  double *Zs = sm;                       // Zs[q * pa + j] = op(Z)[q, j]
+  double *Xs = sm + (size_t)pa * pa;     // Xs[q * 33 + r] = X[i0 + r, q]
+  const int tid = threadIdx.x, i0 = blockIdx.x * 32;
+  for (int idx = tid; idx < pa * pa; idx += 256) {
+    const int q = idx % pa, j = idx / pa;  // Z[q + pa*j]
+    if (tz) Zs[j * pa + q] = Z[idx];       // op(Z)[j, q] = Z[q, j]
+    else Zs[q * pa + j] = Z[idx];
+  }
+  for (int idx = tid; idx < 32 * pa; idx += 256) {
+    const int r = idx % 32, q = idx / 32;
+    Xs[q * 33 + r] = (i0 + r < n) ? X[i0 + r + ld * q] : 0.0;
+  }
+  __syncthreads();
+  const int r = tid % 32;
+  if (i0 + r >= n) return;
+  for (int j = tid / 32; j < pa; j += 8) {
+    double s0 = 0.0, s1 = 0.0;
+    int q = 0;
+    for (; q + 1 < pa; q += 2) {
+      s0 = fma(Xs[q * 33 + r], Zs[q * pa + j], s0);
+      s1 = fma(Xs[(q + 1) * 33 + r], Zs[(q + 1) * pa + j], s1);
+    }
+    if (q < pa) s0 = fma(Xs[q * 33 + r], Zs[q * pa + j], s0);
+    C[i0 + r + ld * j] = s0 + s1;
   }
 }
 
@@ -103,6 +186,28 @@ __global__ void __launch_bounds__(256) chfsi_resid_kernel(const double *__restri
   }
   s = ppx_block_sum(s, red);
   if (threadIdx.x == 0) res[j] = sqrt(s);
+}
+
+// reciprocal square root / reciprocal from a float seed and three Newton steps (full double precision for arguments
+// inside the float range, IEEE fallback outside): the rotation parameters are the dependent latency of a Jacobi round
+__device__ __forceinline__ double fast_rsqrt(double w) {
+  const float f = (float)w;
+  if (!(f > 1e-30f && f < 1e30f)) return rsqrt(w);
+  double y = (double)rsqrtf(f);
+  const double hw = 0.5 * w;
+  y = y * fma(-hw * y, y, 1.5);
+  y = y * fma(-hw * y, y, 1.5);
+  y = y * fma(-hw * y, y, 1.5);
+  return y;
+}
+__device__ __forceinline__ double fast_rcp(double d) {
+  const float f = (float)d;
+  if (!(fabsf(f) > 1e-30f && fabsf(f) < 1e30f)) return 1.0 / d;
+  double x = (double)__fdividef(1.0f, f);
+  x = fma(x, fma(-d, x, 1.0), x);
+  x = fma(x, fma(-d, x, 1.0), x);
+  x = fma(x, fma(-d, x, 1.0), x);
+  return x;
 }
 
 // ---- one-sided Jacobi of a p x p symmetric PSD matrix in shared memory, one CTA of 32 warps ----------------------------
@@ -163,9 +268,13 @@ __global__ void __launch_bounds__(1024) chfsi_jacobi_smem_kernel(const double *_
         sbb = ppx_warp_sum(sbb);
         sab = ppx_warp_sum(sab);
         if (!(fabs(sab) > tol * sqrt(saa * sbb) && fabs(sab) > 1e-300)) continue;
-        const double zeta = (sbb - saa) / (2.0 * sab);
-        const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-        const double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
+        // t = sign(zeta) / (|zeta| + sqrt(1 + zeta^2)), zeta = (b - a) / (2 g), written with one sqrt, one division and
+        // one rsqrt (these are the dependent latencies of the round): t = 2 g / (h + sign(h) sqrt(h^2 + 4 g^2))
+        const double hh = sbb - saa, g2 = 2.0 * sab;
+        const double ww = fma(hh, hh, g2 * g2);
+        const double rad = ww * fast_rsqrt(ww);
+        const double t = g2 * fast_rcp(hh >= 0.0 ? hh + rad : hh - rad);
+        const double c = fast_rsqrt(fma(t, t, 1.0)), s = c * t;
 #pragma unroll
         for (int u = 0; u < 4; u++) {
           const int i = lane + 32 * u;
@@ -242,10 +351,27 @@ __global__ void __launch_bounds__(256) chfsi_extract_kernel(const double *__rest
   for (int j = threadIdx.x; j < n; j += blockDim.x) U[j + (int64_t)n * k] = sgn * x[j];
 }
 
+// P: scratch of CG_S * n * pa doubles
 int gemm_cheb(ppx_ctx *ctx, const double *A, int n, const double *X, int64_t ld, int pa, double alpha, double beta,
-              const double *Z, double gamma, double *Y) {
-  dim3 grid(ppx_cdiv(n, CG_ROWS), ppx_cdiv(pa, CG_COLS));
-  chfsi_gemm_kernel<<<grid, 128, 0, ctx->stream>>>(A, n, X, ld, pa, alpha, beta, Z, gamma, Y);
+              const double *Z, double gamma, double *Y, double *P) {
+  const int kslice = ppx_cdiv(ppx_cdiv(n, CG_S), CG_K) * CG_K;
+  const int S = ppx_cdiv(n, kslice);
+  dim3 grid(ppx_cdiv(n, CG_ROWS), ppx_cdiv(pa, CG_COLS), S);
+  chfsi_gemm_part_kernel<<<grid, 128, 0, ctx->stream>>>(A, n, X, ld, pa, kslice, P);
+  PPX_CHECK_LAUNCH(ctx);
+  chfsi_gemm_fin_kernel<<<ppx_cdiv((int64_t)n * pa, 256), 256, 0, ctx->stream>>>(P, n, pa, S, X, ld, alpha, beta, Z, gamma, Y);
+  PPX_CHECK_LAUNCH(ctx);
+  return PPX_OK;
+}
+
+int right_mult(ppx_ctx *ctx, const double *X, int n, int64_t ld, int pa, const double *Z, int tz, double *C) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    PPX_CUDA(ctx, cudaFuncSetAttribute(chfsi_right_mult_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    attr_set = true;
+  }
+  const size_t smem = sizeof(double) * ((size_t)pa * pa + 33 * (size_t)pa);
+  chfsi_right_mult_kernel<<<ppx_cdiv(n, 32), 256, smem, ctx->stream>>>(X, n, ld, pa, Z, tz, C);
   PPX_CHECK_LAUNCH(ctx);
   return PPX_OK;
 }
@@ -262,7 +388,7 @@ int cholqr2(ppx_ctx *ctx, double *X, double *T, int n, int64_t ld, int pa, doubl
   for (int pass = 0; pass < 2; pass++) {
     CHK(ppx_gram(ctx, X, n, ld, pa, G));
     CHK(ppx_spd_factor_inverse(ctx, G, pa, Zi));
-    CHK(ppx_gemm_small(ctx, 0, 1, n, pa, pa, 1.0, X, ld, Zi, pa, 0.0, T, ld));
+    CHK(right_mult(ctx, X, n, ld, pa, Zi, 1, T));
     PPX_CUDA(ctx, cudaMemcpyAsync(X, T, sizeof(double) * (size_t)ld * pa, cudaMemcpyDeviceToDevice, ctx->stream));
   }
   return PPX_OK;
@@ -294,7 +420,8 @@ int ppx_eig_chfsi(ppx_ctx *ctx, double *A, int n, int r, double *U, double *eval
   double *Zi = (double *)ppx_ws_alloc(ctx, sizeof(double) * p * p);
   double *theta = (double *)ppx_ws_alloc(ctx, sizeof(double) * 2 * p);
   int *src = (int *)ppx_ws_alloc(ctx, sizeof(int) * p);
-  if (!X || !Y0 || !Y1 || !AX || !T || !H || !Zr || !G || !Zi || !theta || !src) return 1;
+  double *P = (double *)ppx_ws_alloc(ctx, sizeof(double) * CG_S * np);
+  if (!X || !Y0 || !Y1 || !AX || !T || !H || !Zr || !G || !Zi || !theta || !src || !P) return 1;
   double *res = theta + p;
   const bool verbose = getenv("PPX_EIG_VERBOSE") != nullptr;
 
@@ -321,14 +448,15 @@ int ppx_eig_chfsi(ppx_ctx *ctx, double *A, int n, int r, double *U, double *eval
     const int pa = p - nlock;
     double *Xa = X + ld * nlock;
     // Rayleigh-Ritz on the active block
-    CHK(gemm_cheb(ctx, A, n, Xa, ld, pa, 1.0, 0.0, nullptr, 0.0, AX));
+    CHK(gemm_cheb(ctx, A, n, Xa, ld, pa, 1.0, 0.0, nullptr, 0.0, AX, P));
     products++;
-    CHK(ppx_gemm_small(ctx, 1, 0, pa, pa, n, 1.0, Xa, ld, AX, ld, 0.0, H, pa));
+    chfsi_cross_gram_kernel<<<ppx_cdiv((int64_t)pa * pa * 32, 256), 256, 0, ctx->stream>>>(Xa, AX, n, ld, pa, H);
+    PPX_CHECK_LAUNCH(ctx);
     chfsi_jacobi_smem_kernel<<<1, 1024, jac_smem, ctx->stream>>>(H, pa, Zr, theta);
     PPX_CHECK_LAUNCH(ctx);
-    CHK(ppx_gemm_small(ctx, 0, 0, n, pa, pa, 1.0, Xa, ld, Zr, pa, 0.0, T, ld));
+    CHK(right_mult(ctx, Xa, n, ld, pa, Zr, 0, T));
     PPX_CUDA(ctx, cudaMemcpyAsync(Xa, T, sizeof(double) * (size_t)ld * pa, cudaMemcpyDeviceToDevice, ctx->stream));
-    CHK(ppx_gemm_small(ctx, 0, 0, n, pa, pa, 1.0, AX, ld, Zr, pa, 0.0, T, ld));
+    CHK(right_mult(ctx, AX, n, ld, pa, Zr, 0, T));
     chfsi_resid_kernel<<<pa, 256, 0, ctx->stream>>>(T, Xa, n, ld, theta, res);
     PPX_CHECK_LAUNCH(ctx);
     PPX_CUDA(ctx, cudaMemcpyAsync(h.data(), theta, sizeof(double) * 2 * p, cudaMemcpyDeviceToHost, ctx->stream));
@@ -373,9 +501,9 @@ int ppx_eig_chfsi(ppx_ctx *ctx, double *A, int n, int r, double *U, double *eval
     // T_0 = X, T_1 = (A - c) X / e, T_{k+1} = 2 (A - c) T_k / e - T_{k-1}
     // three buffers rotate: the one holding T_{k-1} is free once T_{k+1} has been formed
     double *Tprev = Xb, *Tcur = Y0, *Tnext = Y1;
-    CHK(gemm_cheb(ctx, A, n, Tprev, ld, pa2, 1.0 / e, -c / e, nullptr, 0.0, Tcur));
+    CHK(gemm_cheb(ctx, A, n, Tprev, ld, pa2, 1.0 / e, -c / e, nullptr, 0.0, Tcur, P));
     for (int k = 2; k <= d; k++) {
-      CHK(gemm_cheb(ctx, A, n, Tcur, ld, pa2, 2.0 / e, -2.0 * c / e, Tprev, -1.0, Tnext));
+      CHK(gemm_cheb(ctx, A, n, Tcur, ld, pa2, 2.0 / e, -2.0 * c / e, Tprev, -1.0, Tnext, P));
       double *freed = Tprev;
       Tprev = Tcur;
       Tcur = Tnext;
