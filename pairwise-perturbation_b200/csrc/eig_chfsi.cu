@@ -220,8 +220,8 @@ __global__ void __launch_bounds__(1024) chfsi_jacobi_smem_kernel(const double *_
   const int ld = p + 1;
   double *B = sm;                    // [p][ld], column c at B + c*ld
   double *nrm = sm + (size_t)p * ld; // [p]
-  __shared__ int nrot;
-  __shared__ double maxrot;
+  __shared__ int nrot_w[32];       // per warp, written once per sweep (shared atomics from 32 warps per round cost
+  __shared__ double maxrot_w[32];  // more than the rotations themselves)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
   for (int idx = tid; idx < p * p; idx += blockDim.x) {
     const int i = idx % p, j = idx / p;
@@ -231,11 +231,8 @@ __global__ void __launch_bounds__(1024) chfsi_jacobi_smem_kernel(const double *_
   const double tol = 2.3e-16 * sqrt((double)p);
   __syncthreads();
   for (int sweep = 0; sweep < 40; sweep++) {
-    if (tid == 0) {
-      nrot = 0;
-      maxrot = 0.0;
-    }
-    __syncthreads();
+    int my_rot = 0;
+    double my_max = 0.0;
     for (int round = 0; round < m - 1; round++) {
       for (int pr = warp; pr < half; pr += nw) {
         int a, b;
@@ -283,17 +280,24 @@ __global__ void __launch_bounds__(1024) chfsi_jacobi_smem_kernel(const double *_
             cb[i] = s * xa[u] + c * xb[u];
           }
         }
-        if (lane == 0) {
-          atomicAdd(&nrot, 1);
-          // positive doubles order like their bit patterns
-          atomicMax((unsigned long long *)&maxrot, (unsigned long long)__double_as_longlong(fabs(s)));
-        }
+        my_rot++;
+        my_max = fmax(my_max, fabs(s));
       }
       __syncthreads();
     }
-    const bool done = nrot == 0 || maxrot < 1e-8;
+    if (lane == 0) {
+      nrot_w[warp] = my_rot;
+      maxrot_w[warp] = my_max;
+    }
     __syncthreads();
-    if (done) break;
+    int nrot = 0;
+    double maxrot = 0.0;
+    for (int w = 0; w < nw; w++) {
+      nrot += nrot_w[w];
+      maxrot = fmax(maxrot, maxrot_w[w]);
+    }
+    __syncthreads();
+    if (nrot == 0 || maxrot < 1e-8) break;
   }
   // column norms = eigenvalues
   for (int c = warp; c < p; c += nw) {
@@ -499,20 +503,39 @@ int ppx_eig_chfsi(ppx_ctx *ctx, double *A, int n, int r, double *U, double *eval
     }
     if (d < 2) d = 2;
     // T_0 = X, T_1 = (A - c) X / e, T_{k+1} = 2 (A - c) T_k / e - T_{k-1}
-    // three buffers rotate: the one holding T_{k-1} is free once T_{k+1} has been formed
-    double *Tprev = Xb, *Tcur = Y0, *Tnext = Y1;
-    CHK(gemm_cheb(ctx, A, n, Tprev, ld, pa2, 1.0 / e, -c / e, nullptr, 0.0, Tcur, P));
-    for (int k = 2; k <= d; k++) {
-      CHK(gemm_cheb(ctx, A, n, Tcur, ld, pa2, 2.0 / e, -2.0 * c / e, Tprev, -1.0, Tnext, P));
-      double *freed = Tprev;
-      Tprev = Tcur;
-      Tcur = Tnext;
-      Tnext = freed;
+    // The Rayleigh-Ritz step (a p x p eigenproblem) costs as much as ~30 products: when the slowest wanted pair is
+    // still far from converged, run several filter + orthonormalise passes before the next one.  A pass improves it by
+    // about T_d(x_w), x_w the position of the smallest wanted Ritz value.
+    int passes = 1;
+    {
+      const int rw = r - nlock;                        // wanted pairs still open
+      const int jw = nconv + (rw < pa2 ? rw : pa2) - 1;  // slowest of them, in the pre-lock numbering
+      const double xw = (th[jw] - c) / e;
+      double worst = 0.0;
+      for (int j = nconv; j <= jw; j++) worst = fmax(worst, rs[j] / th[j]);
+      if (xw > 1.0 && worst > 1e-12) {
+        const double gain = d * log(xw + sqrt(xw * xw - 1.0));  // log of T_d(x_w)
+        if (gain > 0.1) passes = (int)ceil(log(worst / 1e-12) / gain);
+      }
+      if (passes < 1) passes = 1;
+      if (passes > 3) passes = 3;
     }
-    products += d;
-    if (Tcur != Xb)
-      PPX_CUDA(ctx, cudaMemcpyAsync(Xb, Tcur, sizeof(double) * (size_t)ld * pa2, cudaMemcpyDeviceToDevice, ctx->stream));
-    CHK(cholqr2(ctx, Xb, T, n, ld, pa2, G, Zi));
+    for (int pass = 0; pass < passes; pass++) {
+      // three buffers rotate: the one holding T_{k-1} is free once T_{k+1} has been formed
+      double *Tprev = Xb, *Tcur = Y0, *Tnext = Y1;
+      CHK(gemm_cheb(ctx, A, n, Tprev, ld, pa2, 1.0 / e, -c / e, nullptr, 0.0, Tcur, P));
+      for (int k = 2; k <= d; k++) {
+        CHK(gemm_cheb(ctx, A, n, Tcur, ld, pa2, 2.0 / e, -2.0 * c / e, Tprev, -1.0, Tnext, P));
+        double *freed = Tprev;
+        Tprev = Tcur;
+        Tcur = Tnext;
+        Tnext = freed;
+      }
+      products += d;
+      if (Tcur != Xb)
+        PPX_CUDA(ctx, cudaMemcpyAsync(Xb, Tcur, sizeof(double) * (size_t)ld * pa2, cudaMemcpyDeviceToDevice, ctx->stream));
+      CHK(cholqr2(ctx, Xb, T, n, ld, pa2, G, Zi));
+    }
   }
   if (verbose) fprintf(stderr, "chfsi n=%d r=%d: converged after %d iterations, %d products with A\n", n, r, iters + 1, products);
   // order the locked vectors by decreasing eigenvalue and write U
