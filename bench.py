@@ -16,6 +16,8 @@ A "step" is ONE exact ALS sweep with the dimension tree over all four modes (2 f
             resident; h2d/d2h bytes are counted from the matrices copied.
 `pp`      : the PP phase with the reference's pp_bench protocol: operator build, then the approximate sweep.
 `roofline`: the first dimension-tree contraction (K1), timed alone with CUDA events; FP64 tensor pipe roofline.
+`tucker`  : side measurement, not part of `value`: hosvd + alsTucker_DT sweeps at BASELINE configs[2] (order-3 s=800
+            ranks 40, tensor 'r2'), ms per HOOI sweep through the same C++ drivers.
 `cpu_baseline`: oracle/pp_oracle.py (NumPy/OpenBLAS restatement of the reference, all host cores) on a bounded
             mode-0 slab of the same tensor, scaled to the full tensor.  The reference itself (Cyclops CTF + MPI)
             cannot be built in this image.
@@ -50,6 +52,7 @@ def parse_args():
     ap.add_argument("--pp-sweeps", type=int, default=10)
     ap.add_argument("--cpu-slab", type=int, default=4, help="mode-0 rows of the tensor used for the CPU baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-tucker", action="store_true", help="skip the Tucker HOOI side measurement (BASELINE configs[2])")
     return ap.parse_args()
 
 
@@ -414,6 +417,52 @@ def main():
                          "of %d/%d rows: %.2f s per sweep, scaled x%.1f; the reference itself (Cyclops CTF + MPI) cannot "
                          "be built in this image" % (cores, slab, s, sec, s / slab)}
 
+    # ---- side measurement: Tucker HOOI at BASELINE configs[2] (order-3 s=800 ranks 40, tensor 'r2') ---------------
+    # Not part of `value`; reported so that the Tucker half of the path has a number in the same file.  Never allowed
+    # to take the headline down: any failure is recorded in the object instead.
+    tucker = None
+    if not args.no_tucker:
+        try:
+            for t_ in [V] + W + G + F:
+                t_.free()
+            world.trim()
+            ts, tr, tn = 800, 40, 3
+            tb, te = ppx.shard_range(ts, nranks, rank)
+            if nranks > 1:
+                world.set_shard(0, ts, tb, te)
+            full = H.Tensor(world, (ts,) * tn)
+            full.fill(1, 100, 0.5, 1.0)
+            if nranks > 1:  # local rows of mode 0 (the fastest index): a strided device copy
+                Vt = H.Tensor(world, (te - tb,) + (ts,) * (tn - 1))
+                rc = lib.ppx_memcpy2d_d2d(world.ctx_handle(), C.c_void_p(Vt.data_ptr()), C.c_size_t(8 * (te - tb)),
+                                          C.c_void_p(full.data_ptr() + 8 * tb), C.c_size_t(8 * ts),
+                                          C.c_size_t(8 * (te - tb)), C.c_size_t(ts ** (tn - 1)))
+                assert rc == 0
+                world.sync()
+                full.free()
+            else:
+                Vt = full
+            Wt_ = [H.Matrix(world, ts, tr) for _ in range(tn)]
+            core = H.Tensor(world, (tr,) * tn)
+            barrier()
+            t0 = time.perf_counter()
+            H.hosvd(world, Vt, core, Wt_, [tr] * tn)
+            barrier()
+            t_hosvd = max_over_ranks(time.perf_counter() - t0)
+            nsw = 6
+            with H.Trace(quiet=True, skip_residual=True):
+                H.alsTucker_DT(world, Vt, core, Wt_, 0.0, 1, resprint=1 << 30)  # warm-up: 2 sweeps
+                barrier()
+                t0 = time.perf_counter()
+                H.alsTucker_DT(world, Vt, core, Wt_, 0.0, nsw - 1, resprint=1 << 30)
+                barrier()
+                t_sw = max_over_ranks(time.perf_counter() - t0)
+            tucker = {"workload": "Tucker HOOI (alsTucker_DT) order-3 s=800 ranks 40, tensor 'r2' (BASELINE configs[2])",
+                      "hosvd_ms": 1e3 * t_hosvd, "ms_per_sweep": 1e3 * t_sw / nsw, "sweeps_per_s": nsw / t_sw,
+                      "sweeps_timed": nsw, "timing": "wall clock around the driver call, synchronised on both sides"}
+        except Exception as exc:  # noqa: BLE001
+            tucker = {"error": "%s: %s" % (type(exc).__name__, exc)}
+
     if rank == 0:
         line = {
             "metric": "ALS-DT sweeps/s (CP order-%d s=%d R=%d FP64)" % (N, s, R), "value": value, "unit": "sweeps/s",
@@ -425,6 +474,7 @@ def main():
                        "parallelism": "mode-0 shards x%d, NCCL all-reduce of s x R partial MTTKRPs" % nranks if nranks > 1
                        else "single GPU", "solver": "cholesky"},
             "ms_per_step_per_rank": per_rank_ms, "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "pp": pp,
+            "tucker": tucker,
         }
         print(json.dumps(line), flush=True)
     world.close()
