@@ -402,15 +402,15 @@ int cholqr2(ppx_ctx *ctx, double *X, double *T, int n, int64_t ld, int pa, doubl
 
 bool ppx_eig_chfsi_applicable(int64_t n, int r) {
   if (getenv("PPX_EIG_JACOBI")) return false;
-  // p = r + 24 columns: the Cholesky-QR factor kernel takes p <= 112, the shared-memory Jacobi p <= 128
-  return n >= 384 && r >= 1 && r + 24 <= 112 && 4 * (int64_t)r <= n;
+  // p = r + guard columns (guard 24, down to 8 for large r): the Cholesky-QR factor kernel takes p <= 112
+  return n >= 384 && r >= 1 && r + 8 <= 112 && 4 * (int64_t)r <= n;
 }
 
 // Returns PPX_OK with U / evals_out filled, 1 if the iteration did not converge (nothing usable was written: the caller
 // falls back to the Jacobi solver), a negative code on errors.  `A` (n x n, symmetric) is destroyed.  `state`
-// (>= n*(r+24) doubles, optional) holds the final block for the next call on a nearby matrix.
+// (>= n*(r+24) doubles, optional) holds the final block for the next call on a nearby matrix (same n and r).
 int ppx_eig_chfsi(ppx_ctx *ctx, double *A, int n, int r, double *U, double *evals_out, double *state, int state_valid) {
-  const int p = r + 24;
+  const int p = r + (112 - r < 24 ? 112 - r : 24);
   const int64_t ld = n;
   const size_t np = (size_t)n * p;
   double *X = (double *)ppx_ws_alloc(ctx, sizeof(double) * np);

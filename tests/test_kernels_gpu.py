@@ -429,7 +429,7 @@ def _spectrum_case(kind, n, rng):
 
 @pytest.mark.parametrize("kind,n,r", [("noise+outlier", 400, 8), ("noise+outlier", 800, 40), ("noise", 512, 24),
                                       ("decay", 448, 16), ("lowrank", 400, 10), ("lowrank", 400, 20),
-                                      ("clusters", 384, 12), ("noise", 390, 88)])
+                                      ("clusters", 384, 12), ("noise", 390, 88), ("noise+outlier", 448, 100)])
 def test_sym_eig_topk_large(ctx, kind, n, r):
     rng = np.random.default_rng(7)
     A = _spectrum_case(kind, n, rng)
