@@ -76,14 +76,112 @@ __global__ void __launch_bounds__(256) unfold_gram_kernel(const double *__restri
     }
 }
 
-__global__ void unfold_gram_reduce_kernel(const double *__restrict__ parts, int64_t X, int nz,
+// ---- the same for large unfoldings (HOSVD: X x prod(other modes)): 128 x 128 tile, 8 x 8 per thread (4 FMA per shared
+// load instead of 2), the next chunk fetched into registers while the current one is multiplied, no division per element
+constexpr int UH_T = 128, UH_K = 16;
+__global__ void __launch_bounds__(256) unfold_gram128_kernel(const double *__restrict__ T, int64_t L, int64_t X,
+                                                             int64_t Rt, int64_t C, int64_t c_per_z,
+                                                             double *__restrict__ out_z) {
+  __shared__ double Ap[UH_K][UH_T + 1];
+  __shared__ double Aq[UH_K][UH_T + 1];
+  const int tid = threadIdx.x;
+  const int64_t p0 = (int64_t)blockIdx.x * UH_T, q0 = (int64_t)blockIdx.y * UH_T;
+  if (q0 > p0) return;  // lower triangle of tiles only; mirrored by the reduction kernel
+  const bool diag = (p0 == q0);
+  const int64_t cb = (int64_t)blockIdx.z * c_per_z;
+  int64_t ce = cb + c_per_z;
+  if (ce > C) ce = C;
+  const int tx = tid % 16, ty = tid / 16;  // rows p0 + tx + 16 i, columns q0 + ty + 16 j
+  double acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; i++)
+#pragma unroll
+    for (int j = 0; j < 8; j++) acc[i][j] = 0.0;
+  // element (c, p) lives at l + L*(p + X*t), c = l + L*t.  L == 1: p is the fastest index -> threads run along p;
+  // L > 1: c is -> threads run along c (16 consecutive c per p)
+  const bool pfast = (L == 1);
+  const int my_cc = pfast ? tid / 128 : tid % 16;  // + 2u (pfast) per load u
+  const int my_pp = pfast ? tid % 128 : tid / 16;  // + 16u (!pfast)
+  int64_t lt_l = 0, lt_t = 0;                       // (l, t) of c = chunk start + my_cc, kept incrementally
+  if (!pfast) {
+    const int64_t c = cb + my_cc;
+    lt_t = c / L;
+    lt_l = c - lt_t * L;
+  }
+  double rp[8], rq[8];
+  auto fetch = [&](int64_t c0) {
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      const int cc = pfast ? my_cc + 2 * u : my_cc;
+      const int pp = pfast ? my_pp : my_pp + 16 * u;
+      const int64_t c = c0 + cc;
+      double vp = 0.0, vq = 0.0;
+      if (c < ce) {
+        const int64_t base = pfast ? X * c : lt_l + L * X * lt_t;
+        const int64_t st = pfast ? 1 : L;
+        if (p0 + pp < X) vp = T[base + st * (p0 + pp)];
+        if (!diag && q0 + pp < X) vq = T[base + st * (q0 + pp)];
+      }
+      rp[u] = vp;
+      rq[u] = vq;
+    }
+  };
+  auto advance = [&]() {  // (l, t) += UH_K along c
+    if (!pfast) {
+      lt_l += UH_K;
+      while (lt_l >= L) {
+        lt_l -= L;
+        lt_t++;
+      }
+    }
+  };
+  fetch(cb);
+  for (int64_t c0 = cb; c0 < ce; c0 += UH_K) {
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      const int cc = pfast ? my_cc + 2 * u : my_cc;
+      const int pp = pfast ? my_pp : my_pp + 16 * u;
+      Ap[cc][pp] = rp[u];
+      if (!diag) Aq[cc][pp] = rq[u];
+    }
+    __syncthreads();
+    if (c0 + UH_K < ce) {
+      advance();
+      fetch(c0 + UH_K);
+    }
+    const double(*Bq)[UH_T + 1] = diag ? Ap : Aq;
+#pragma unroll 4
+    for (int cc = 0; cc < UH_K; cc++) {
+      double a[8], b[8];
+#pragma unroll
+      for (int i = 0; i < 8; i++) a[i] = Ap[cc][tx + 16 * i];
+#pragma unroll
+      for (int j = 0; j < 8; j++) b[j] = Bq[cc][ty + 16 * j];
+#pragma unroll
+      for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int j = 0; j < 8; j++) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  double *o = out_z + (int64_t)blockIdx.z * X * X;
+#pragma unroll
+  for (int i = 0; i < 8; i++)
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const int64_t p = p0 + tx + 16 * i, q = q0 + ty + 16 * j;
+      if (p < X && q < X) o[p + X * q] = acc[i][j];
+    }
+}
+
+__global__ void unfold_gram_reduce_kernel(const double *__restrict__ parts, int64_t X, int nz, int tile,
                                           double *__restrict__ MTM) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= X * X) return;
   int64_t p = idx % X, q = idx / X;
   // tiles with q0 > p0 were skipped: read the mirrored element
   int64_t pp = p, qq = q;
-  if ((q / UG_T) > (p / UG_T)) {
+  if ((q / tile) > (p / tile)) {
     pp = q;
     qq = p;
   }
@@ -325,7 +423,10 @@ int ppx_unfold_gram(ppx_ctx *ctx, const double *T, const int64_t *lens, int k, i
   int64_t L, X, Rt;
   ppx_split3(lens, k, i, &L, &X, &Rt);
   const int64_t C = L * Rt;
-  const int tiles = ppx_cdiv(X, UG_T);
+  // large unfoldings (HOSVD) take the 128 x 128 tile kernel
+  const bool big = X >= 192 && C >= 4096;
+  const int tile = big ? UH_T : UG_T;
+  const int tiles = ppx_cdiv(X, tile);
   const int ntile_ctas = tiles * (tiles + 1) / 2;
   int nz = ppx_cdiv(4 * ctx->sm_count, ntile_ctas);
   if (nz > 32) nz = 32;
@@ -338,9 +439,12 @@ int ppx_unfold_gram(ppx_ctx *ctx, const double *T, const int64_t *lens, int k, i
   if (!parts) return ppx_set_err(ctx, PPX_ENOMEM, "unfold_gram needs %lld bytes of workspace", (long long)(8 * X * X));
   int64_t c_per_z = (C + nz - 1) / nz;
   c_per_z = ((c_per_z + UG_K - 1) / UG_K) * UG_K;
-  unfold_gram_kernel<<<dim3(tiles, tiles, nz), 256, 0, ctx->stream>>>(T, L, X, Rt, C, c_per_z, parts);
+  if (big)
+    unfold_gram128_kernel<<<dim3(tiles, tiles, nz), 256, 0, ctx->stream>>>(T, L, X, Rt, C, c_per_z, parts);
+  else
+    unfold_gram_kernel<<<dim3(tiles, tiles, nz), 256, 0, ctx->stream>>>(T, L, X, Rt, C, c_per_z, parts);
   PPX_CHECK_LAUNCH(ctx);
-  unfold_gram_reduce_kernel<<<ppx_cdiv(X * X, 256), 256, 0, ctx->stream>>>(parts, X, nz, MTM);
+  unfold_gram_reduce_kernel<<<ppx_cdiv(X * X, 256), 256, 0, ctx->stream>>>(parts, X, nz, tile, MTM);
   PPX_CHECK_LAUNCH(ctx);
   return PPX_OK;
 }

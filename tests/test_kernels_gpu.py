@@ -262,7 +262,10 @@ def test_tucker_ttm_and_acc(ctx, lens, x, Q):
 
 
 @pytest.mark.parametrize("lens,i", [((13, 9, 11), 0), ((13, 9, 11), 1), ((13, 9, 11), 2), ((70, 5, 66), 2),
-                                    ((130, 40, 3), 0), ((4, 150, 5, 3), 1)])
+                                    ((130, 40, 3), 0), ((4, 150, 5, 3), 1),
+                                    # 128 x 128 tile kernel (X >= 192 and >= 4096 columns): mode first / middle / last,
+                                    # ragged tiles, columns not a multiple of the chunk
+                                    ((200, 70, 61), 0), ((67, 257, 63), 1), ((90, 47, 193), 2), ((384, 4100), 0)])
 def test_unfold_gram(ctx, lens, i):
     T = rnd(lens, 130)
     ref = o.unroll_tensor_contraction(T, i)
