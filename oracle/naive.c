@@ -1,7 +1,7 @@
 /* Independent loop-based CPU restatement of the contractions on the ALS / pairwise-perturbation hot path.
  *
- * TEST INFRASTRUCTURE ONLY (see oracle/pp_oracle.py header).  PARITY UNPINNED: the reference cannot be built here
- * (needs Cyclops CTF + MPI + ScaLAPACK) and ships no golden vectors.  This file shares no code with pp_oracle.py:
+ * TEST INFRASTRUCTURE ONLY (see oracle/pp_oracle.py header: the oracle is pinned against the reference's own sources
+ * built on a CTF stand-in, oracle/_ref/; CTF's own arithmetic stays unpinned).  This file shares no code with pp_oracle.py:
  * plain loops over the first-index-fastest buffers with long double accumulators; tests/test_oracle_cpu.py checks
  * the two against each other and against tests/golden/.  Links nothing but libm.
  *

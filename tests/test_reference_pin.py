@@ -1,0 +1,245 @@
+"""Pins oracle/pp_oracle.py against THE REFERENCE'S OWN CODE: oracle/_ref/ holds the reference's unmodified sources
+(common.cxx, als_CP.cxx, als_Tucker.cxx, test_ALS.cxx, run.cxx, src/**, tests/test_decomposition.cxx) compiled against
+oracle/ctf_standin/ctf.hpp, a dense single-process stand-in for the CTF/MPI API they use (`make -C oracle ref`).
+
+Same bytes in (tensor, initial factors, initial gradient), then: per-print gradient norm and residual within 1e-10
+relative to ||V||, factors within 1e-8, identical DT<->PP switching iterations -- the bar BASELINE.json sets.
+What this pins: control flow, contraction strings and layouts, the quirks listed in DESIGN.md section 2, solves,
+normalisation, the switching logic.  What it cannot pin: CTF's own arithmetic (summation order, ScaLAPACK's SVD).
+
+CPU only; needs the prebuilt oracle/_ref/ (it travels with the repo), never /root/reference at run time."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import pp_oracle as o  # noqa: E402
+from oracle import ref_harness as rh  # noqa: E402
+
+pytestmark = pytest.mark.skipif(not rh.available(), reason="oracle/_ref not built (needs /root/reference once)")
+
+FIT_RTOL, FACTOR_TOL = 1e-10, 1e-8
+
+
+def problem(lens, R, seed=1):
+    V, _ = o.make_tensor_r(lens, R, seed=seed)
+    return V, o.init_factors(lens, R, seed=seed + 1), o.init_grad(lens, R, seed=seed + 2)
+
+
+def check_rows(ref_rows, rows, vnorm):
+    assert len(ref_rows) == len(rows) and len(rows) > 0
+    a, b = np.array(ref_rows, dtype=float), np.array([(r[0], r[1], r[2], r[3]) for r in rows], dtype=float)
+    assert np.array_equal(a[:, 0], b[:, 0]) and np.array_equal(a[:, 2], b[:, 2])  # iterations, pp_update flags
+    assert np.allclose(a[:, 3], b[:, 3], rtol=0, atol=FIT_RTOL * vnorm)  # residual ("fitness")
+    assert np.allclose(a[:, 1], b[:, 1], rtol=1e-9, atol=1e-9 * vnorm)  # gradient norm
+
+
+def check_factors(Wref, W):
+    for a, b in zip(Wref, W):
+        assert np.abs(a - b).max() < FACTOR_TOL
+
+
+# ---- the pieces (one call each of the reference's functions) ----------------------------------------------------
+@pytest.mark.parametrize("lens,R", [((7, 6, 5, 4), 3), ((6, 6, 6, 6), 3), ((4, 3, 5, 3, 4, 3), 2),
+                                    ((5, 4, 3, 4, 3, 2, 3), 2)])
+def test_reference_pieces_match_oracle(lens, R):
+    """mttkrp_map_DT, Build_mttkrp_map, KhatriRao_contract, unroll_tensor_contraction, TTMc, build_V, Normalize,
+    SVD_solve, cholesky_solve of the reference against the restatement (orders 4, 6, 7)."""
+    N = len(lens)
+    V = o.fill_uniform(lens, 7, 0, -1.0, 1.0)
+    W = [o.fill_uniform((lens[i], R), 8, i) for i in range(N)]
+    ref = rh.run_driver("kernels", V, W)
+    f = ref["files"]
+    parent, sibling = {}, {}
+    o.construct_dimension_tree(parent, sibling, 0, N - 1)
+    mp = {}
+    n_tree = 0
+    for name in parent:
+        if len(name) == N or len(name) < 2:
+            continue
+        o.mttkrp_map_DT(mp, parent, sibling, V, W, name)
+    for name, T in mp.items():
+        assert np.allclose(f["tree_" + name], T.ravel(order="F"), rtol=1e-12, atol=1e-12), name
+        n_tree += 1
+    assert n_tree == len([k for k in f if k.startswith("tree_")]) and n_tree >= 2
+    ops = o.build_pp_operators(V, W)
+    n_pp = 0
+    for name, T in ops.items():
+        assert np.allclose(f["pp_" + name], T.ravel(order="F"), rtol=1e-12, atol=1e-12), name
+        n_pp += 1
+    assert n_pp == len([k for k in f if k.startswith("pp_")])
+    for i in range(N):
+        assert np.allclose(f["gram_%d" % i], o.unroll_tensor_contraction(V, i).ravel(order="F"), rtol=1e-12)
+        assert np.allclose(f["ttmc_%d" % i], o.TTMc(V, W, i).ravel(order="F"), rtol=1e-12, atol=1e-12)
+        if "krc_%d" % i in f:  # uniform extents only: the reference's callers mis-size lens_H otherwise
+            index = [m for m in range(N) if m != i] + [i]
+            assert np.allclose(f["krc_%d" % i], o.KhatriRao_contract(V, W, index).ravel(order="F"), rtol=1e-12,
+                               atol=1e-12)
+    assert np.allclose(f["build_V"], o.build_V(W).ravel(order="F"), rtol=1e-13)
+    S = o.gram_hadamard(W, 0)
+    assert np.allclose(f["S"], S.ravel(order="F"), rtol=1e-13)
+    assert np.allclose(f["svd_solve"], o.SVD_solve(W[0], S).ravel(order="F"), rtol=1e-8)
+    assert np.allclose(f["cholesky_solve"], o.cholesky_solve(W[0], S).ravel(order="F"), rtol=1e-8)
+    Wn = [w.copy() for w in W]
+    o.normalize(Wn)
+    check_factors(ref["normalized"], Wn)
+
+
+# ---- the drivers ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("lens,R,lam,maxiter", [((9, 8, 7, 6), 3, 0.0, 25), ((6, 5, 4, 5, 4, 3), 2, 1e-3, 15)])
+def test_reference_alsCP_DT(lens, R, lam, maxiter):
+    V, W, G = problem(lens, R)
+    vnorm = np.linalg.norm(V)
+    ref = rh.run_driver("alsCP_DT", V, W, G, tol=1e-10 * vnorm, maxiter=maxiter, lambda_=lam, resprint=5)
+    tr = o.Trace()
+    o.alsCP_DT(V, W, G, 1e-10 * vnorm, maxiter, lam=lam, resprint=5, trace=tr)
+    check_rows(ref["rows"], tr.rows, vnorm)
+    check_factors(ref["W"], W)
+    check_factors(ref["grad"], G)
+
+
+@pytest.mark.parametrize("lens,R,tol_init,ratio,lam,maxiter",
+                         [((10, 10, 10, 10), 3, 0.1, 1.0, 0.0, 60), ((9, 14, 5, 11), 4, 0.05, 1.0, 0.0, 40),
+                          ((8, 7, 9, 6), 3, 0.2, 0.8, 1e-4, 40), ((5, 4, 5, 4, 5, 4), 2, 0.1, 1.0, 0.0, 30)])
+def test_reference_alsCP_PP(lens, R, tol_init, ratio, lam, maxiter):
+    """The switching driver: identical `DT starts from` / `pairwise perturbation starts from` iterations."""
+    V, W, G = problem(lens, R)
+    vnorm = np.linalg.norm(V)
+    ref = rh.run_driver("alsCP_PP", V, W, G, tol=1e-10 * vnorm, tol_init=tol_init, maxiter=maxiter, lambda_=lam,
+                        ratio_step=ratio, resprint=5)
+    _, tr = o.alsCP_PP(V, W, G, 1e-10 * vnorm, tol_init, maxiter, lam=lam, ratio_step=ratio, resprint=5)
+    assert ref["events"] == tr.events and any(k == "PP" for k, _ in tr.events)
+    check_rows(ref["rows"], tr.rows, vnorm)
+    check_factors(ref["W"], W)
+
+
+@pytest.mark.parametrize("lens,R,pct", [((9, 8, 10, 7), 3, 1.0), ((9, 8, 10, 7), 3, 0.5), ((5, 4, 5, 4, 5, 4), 2, 0.7)])
+def test_reference_alsCP_PP_partupdate(lens, R, pct):
+    V, W, G = problem(lens, R)
+    vnorm = np.linalg.norm(V)
+    ref = rh.run_driver("alsCP_PP_partupdate", V, W, G, tol=1e-10 * vnorm, tol_init=0.1, maxiter=30, update_pct=pct,
+                        resprint=5)
+    _, tr = o.alsCP_PP_partupdate(V, W, G, 1e-10 * vnorm, 0.1, 30, update_percentage=pct, resprint=5)
+    assert ref["events"] == tr.events
+    check_rows(ref["rows"], tr.rows, vnorm)
+    check_factors(ref["W"], W)
+
+
+def projector_err(A, B):
+    return np.abs(A @ A.T - B @ B.T).max()
+
+
+@pytest.mark.parametrize("lens,ranks", [((9, 8, 7, 6), (3, 3, 3, 3)), ((8, 9, 6, 7), (2, 3, 2, 4))])
+def test_reference_tucker(lens, ranks):
+    """hosvd, alsTucker_DT, alsTucker_PP.  Singular vectors carry an arbitrary sign, so factors are compared through
+    their projectors W W^T and the printed core-norm differences / residuals directly."""
+    V = o.make_tensor_r2(lens, seed=1)
+    vnorm = np.linalg.norm(V)
+    ref = rh.run_driver("hosvd", V, ranks=ranks)
+    core, W = o.hosvd(V, list(ranks))
+    for a, b in zip(ref["W"], W):
+        assert projector_err(a, b) < 1e-9
+    assert abs(np.linalg.norm(ref["core"]) - np.linalg.norm(core)) < 1e-10 * vnorm
+
+    ref = rh.run_driver("alsTucker_DT", V, ranks=ranks, tol=1e-10 * vnorm, maxiter=12, resprint=4)
+    core, W = o.hosvd(V, list(ranks))
+    _, rows, core = o.alsTucker_DT(V, core, W, 1e-10 * vnorm, 12, resprint=4)
+    assert [r[0] for r in ref["rows"]] == [r[0] for r in rows]
+    assert np.allclose([r[3] for r in ref["rows"]], [r[2] for r in rows], rtol=0, atol=FIT_RTOL * vnorm)
+    assert np.allclose([r[1] for r in ref["rows"]], [r[1] for r in rows], rtol=0, atol=1e-9 * vnorm)
+    for a, b in zip(ref["W"], W):
+        assert projector_err(a, b) < 1e-7
+
+    ref = rh.run_driver("alsTucker_PP", V, ranks=ranks, tol=1e-10 * vnorm, tol_init=0.3, maxiter=16, resprint=4)
+    core, W = o.hosvd(V, list(ranks))
+    _, rows, events, sweeps, core = o.alsTucker_PP(V, core, W, 1e-10 * vnorm, 0.3, 16, resprint=4)
+    assert ref["events"] == events and any(k == "PP" for k, _ in events)
+    assert [r[0] for r in ref["rows"]] == [r[0] for r in rows]
+    assert np.allclose([r[3] for r in ref["rows"]], [r[-1] for r in rows], rtol=0, atol=FIT_RTOL * vnorm)
+    for a, b in zip(ref["W"], W):
+        assert projector_err(a, b) < 1e-7
+
+
+# ---- the reference's own mains -----------------------------------------------------------------------------------
+def cli_fills(N, tensor="r"):
+    """fill_random calls of test_ALS.cxx in order: `r` -> W_true[0..N-1] (:279-282), `r2` -> V (:272); then W[i],
+    grad_W[i] interleaved (:337-338).  Mapped to the (seed, id) pairs our CLI and the oracle use."""
+    head = [(1, i) for i in range(N)] if tensor == "r" else [(1, 100)]
+    return head + [p for i in range(N) for p in ((2, i), (3, i))]
+
+
+@pytest.mark.parametrize("N,s,R,pp,maxiter", [(4, 10, 3, 1, 60), (4, 12, 4, 0, 20), (6, 5, 2, 1, 30), (4, 9, 3, 2, 30)])
+def test_reference_test_ALS_main_matches_oracle(N, s, R, pp, maxiter):
+    """The reference's test_ALS executable, flags as in BASELINE.json configs, against the restatement."""
+    lens = (s,) * N
+    ref = rh.run_cli("test_ALS", ["-model", "CP", "-tensor", "r", "-dim", N, "-size", s, "-rank", R, "-pp", pp,
+                                  "-maxiter", maxiter, "-pp_res_tol", 0.1, "-resprint", 5], fills=cli_fills(N))
+    V, W, G = problem(lens, R)
+    vnorm = np.linalg.norm(V)
+    if pp == 0:
+        tr = o.Trace()
+        o.alsCP_DT(V, W, G, 1e-10 * vnorm, maxiter, resprint=5, trace=tr)
+    elif pp == 1:
+        _, tr = o.alsCP_PP(V, W, G, 1e-10 * vnorm, 0.1, maxiter, resprint=5)
+    else:
+        _, tr = o.alsCP_PP_partupdate(V, W, G, 1e-10 * vnorm, 0.1, maxiter, update_percentage=1.0, resprint=5)
+    assert ref["events"] == tr.events
+    a = np.array(ref["rows"])
+    b = np.array([(r[0], r[1], r[2], r[3]) for r in tr.rows])
+    assert a.shape == b.shape
+    # the main prints 13 significant digits
+    assert np.array_equal(a[:, 0], b[:, 0]) and np.array_equal(a[:, 2], b[:, 2])
+    assert np.allclose(a[:, 3], b[:, 3], rtol=1e-9, atol=FIT_RTOL * vnorm)
+    assert np.allclose(a[:, 1], b[:, 1], rtol=1e-8, atol=1e-9 * vnorm)
+
+
+def test_reference_test_ALS_tucker_main_matches_oracle():
+    N, s, R = 4, 8, 3
+    ref = rh.run_cli("test_ALS", ["-model", "Tucker", "-tensor", "r2", "-dim", N, "-size", s, "-rank", R, "-pp", 1,
+                                  "-maxiter", 16, "-pp_res_tol", 0.3, "-resprint", 4], fills=cli_fills(N, "r2"))
+    V = o.make_tensor_r2((s,) * N, seed=1)
+    vnorm = np.linalg.norm(V)
+    core, W = o.hosvd(V, [R] * N)
+    _, rows, events, sweeps, core = o.alsTucker_PP(V, core, W, 1e-10 * vnorm, 0.3, 16, resprint=4)
+    assert ref["events"] == events
+    assert [r[0] for r in ref["rows"]] == [r[0] for r in rows]
+    assert np.allclose([r[3] for r in ref["rows"]], [r[-1] for r in rows], rtol=1e-9, atol=FIT_RTOL * vnorm)
+
+
+def test_reference_own_test_runs():
+    """tests/test_decomposition.cxx, the reference's single test (asserts on order / rank, then runs CPD::als with
+    each optimizer): must run to completion on the stand-in."""
+    out = rh.run_cli("test_decomposition", [])
+    assert "Iters" in out["stdout"] or "sweeps" in out["stdout"]
+
+
+# ---- the OO path: the reference's `run` main (src/CP.cxx + src/optimizer/**) --------------------------------------
+@pytest.mark.parametrize("N,s,R,pp,extra", [(4, 8, 3, 0, []), (3, 9, 3, 0, []), (4, 8, 3, 1, []), (5, 5, 2, 1, []),
+                                            (4, 7, 3, 4, []), (4, 8, 4, 2, ["-updaterank", 2]),
+                                            (4, 8, 4, 3, ["-updaterank", 2])])
+def test_reference_run_main_matches_oracle(N, s, R, pp, extra):
+    """run -pp 0/1/4/2/3 = CPD<double, CPDTOptimizer | CPMSDTOptimizer | CPSimpleOptimizer | CPDTLROptimizer |
+    CPMSDTLROptimizer>::als (run.cxx:387-414).  fill_random calls: W_true[i] (run.cxx:313), W[i] (:374), then
+    grad_W[i] in CPD::Init (src/CP.cxx:78)."""
+    fills = [(1, i) for i in range(N)] + [(2, i) for i in range(N)] + [(3, i) for i in range(N)]
+    maxiter = 12
+    ref = rh.run_cli("run", ["-model", "CP", "-tensor", "r", "-dim", N, "-size", s, "-rank", R, "-pp", pp,
+                             "-maxiter", maxiter, "-resprint", 3] + extra, fills=fills)
+    lens = (s,) * N
+    V, _ = o.make_tensor_r(lens, R, seed=1)
+    W = o.init_factors(lens, R, seed=2)
+    vnorm = np.linalg.norm(V)
+    cls = {0: o.CPDTOptimizer, 1: o.CPMSDTOptimizer, 4: o.CPSimpleOptimizer, 2: o.CPDTLROptimizer,
+           3: o.CPMSDTLROptimizer}[pp]
+    args = (2, 0) if pp in (2, 3) else ()
+    d = o.CPD(N, s, R, cls, *args)
+    d.Init(V, W, grad_W=o.init_grad(lens, R, seed=3))
+    _, rows = d.als(1e-10 * vnorm, maxiter, 3)
+    a, b = np.array(ref["rows"])[:, [0, 1, 3]], np.array(rows)
+    assert a.shape == b.shape and len(rows) >= 3
+    assert np.allclose(a[:, 0], b[:, 0])  # sweep counts (fractions: 0.5 / (N-1)/N / 1 per step)
+    assert np.allclose(a[:, 2], b[:, 2], rtol=1e-9, atol=FIT_RTOL * vnorm)
+    assert np.allclose(a[:, 1], b[:, 1], rtol=1e-8, atol=1e-9 * vnorm)
