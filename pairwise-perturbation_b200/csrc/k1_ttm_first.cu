@@ -417,6 +417,10 @@ int ppx_ttm_impl(ppx_ctx *ctx, const double *V, int64_t L, int64_t X, int64_t Rt
   p.ksplit = 1;
   p.split_stride = 0;
   if (p.Mtot == 0 || R == 0) return PPX_OK;
+  {  // small X and R: bandwidth problem with a large output -> streaming DFMA kernel
+    const int rc = ppx_ttm_stream_try(ctx, V, L, X, Rt, Wx, ldw, R, out, inplace, accumulate);
+    if (rc != 1) return rc;
+  }
   if (try_tma) {  // TMA-staged tiles when the shape allows it
     const double *fac[1] = {Wx};
     const int64_t ld1[1] = {ldw}, xs1[1] = {X};

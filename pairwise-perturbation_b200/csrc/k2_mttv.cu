@@ -142,6 +142,159 @@ __global__ void __launch_bounds__(256) mttv_small_kernel(const double *__restric
   }
 }
 
+
+// ---- small X (<= 64), many outputs: one thread per output (two when VEC == 2), no cross-warp reduction ---------
+// The block-per-(l tile, t, r) kernel below splits x over eight warps; with X = 40 that is five loads per warp and a
+// shared-memory reduction for 20 KB of traffic per CTA (order-6 PP build, BASELINE configs[3]: 400 000 such CTAs,
+// 0.34-0.54 of the HBM rate).  Here lanes run along the flat output index (l fastest, so loads for a fixed x are
+// coalesced), every thread loops over all x with eight independent loads in flight and writes its own output.
+template <int VEC>
+__global__ void __launch_bounds__(256) mttv_flat_m_kernel(const double *__restrict__ T, const double *__restrict__ W,
+                                                          double *__restrict__ out, int64_t L, int64_t X, int64_t Rt,
+                                                          int R, int64_t ldw) {
+  const int64_t n_out = L * Rt * (int64_t)R, nvec = n_out / VEC;
+  const int64_t LX = L * X;
+  for (int64_t ov = (int64_t)blockIdx.x * 256 + threadIdx.x; ov < nvec; ov += (int64_t)gridDim.x * 256) {
+    const int64_t o = ov * VEC;
+    const int64_t tr = o / L, l = o - tr * L;
+    const int64_t r = tr / Rt;
+    const double *tp = T + l + LX * tr;
+    const double *wp = W + r * ldw;
+    double acc[VEC];
+#pragma unroll
+    for (int e = 0; e < VEC; e++) acc[e] = 0.0;
+    for (int64_t x0 = 0; x0 < X; x0 += 8) {
+      double v[8][VEC], w[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        if (x0 + u < X) {
+          if (VEC == 2) {
+            const double2 q = *reinterpret_cast<const double2 *>(tp + L * (x0 + u));
+            v[u][0] = q.x;
+            v[u][VEC - 1] = q.y;
+          } else {
+            v[u][0] = tp[L * (x0 + u)];
+          }
+          w[u] = wp[x0 + u];
+        } else {
+#pragma unroll
+          for (int e = 0; e < VEC; e++) v[u][e] = 0.0;
+          w[u] = 0.0;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 8; u++)
+#pragma unroll
+        for (int e = 0; e < VEC; e++) acc[e] = fma(v[u][e], w[u], acc[e]);
+    }
+    if (VEC == 2)
+      *reinterpret_cast<double2 *>(out + o) = make_double2(acc[0], acc[VEC - 1]);
+    else
+      out[o] = acc[0];
+  }
+}
+
+// L == 1, small X: the rows o = (t, r) are X contiguous doubles each.  A CTA stages 128 consecutive rows (one
+// contiguous slab, coalesced) in shared memory with an odd pitch; every thread then forms the dot product of its row.
+constexpr int FK_ROWS = 128;
+__global__ void __launch_bounds__(FK_ROWS) mttv_flat_k_kernel(const double *__restrict__ T, const double *__restrict__ W,
+                                                              double *__restrict__ out, int64_t X, int64_t Rt, int R,
+                                                              int64_t ldw, int pitch) {
+  extern __shared__ __align__(16) double fk_slab[];  // [FK_ROWS][pitch]
+  const int tid = threadIdx.x;
+  const int64_t n_out = Rt * (int64_t)R;
+  const int Xi = (int)X;
+  const int step_row = FK_ROWS / Xi, step_x = FK_ROWS - step_row * Xi;
+  for (int64_t o0 = (int64_t)blockIdx.x * FK_ROWS; o0 < n_out; o0 += (int64_t)gridDim.x * FK_ROWS) {
+    const int nrows = (int)(n_out - o0 < FK_ROWS ? n_out - o0 : FK_ROWS);
+    const int n = nrows * Xi;
+    const double *src = T + o0 * X;
+    __syncthreads();
+    int row = tid / Xi, x = tid - row * Xi;
+    for (int i0 = tid; i0 < n; i0 += 4 * FK_ROWS) {
+      double v[4];
+      int rr[4], xx[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        rr[u] = row;
+        xx[u] = x;
+        v[u] = (i0 + u * FK_ROWS < n) ? src[i0 + u * FK_ROWS] : 0.0;
+        row += step_row;
+        x += step_x;
+        if (x >= Xi) {
+          x -= Xi;
+          row++;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++)
+        if (i0 + u * FK_ROWS < n) fk_slab[rr[u] * pitch + xx[u]] = v[u];
+    }
+    __syncthreads();
+    if (tid < nrows) {
+      const int64_t o = o0 + tid;
+      const double *wp = W + (o / Rt) * ldw;
+      const double *my = fk_slab + tid * pitch;
+      double a0 = 0.0, a1 = 0.0;
+      int xq = 0;
+      for (; xq + 1 < Xi; xq += 2) {
+        a0 = fma(my[xq], wp[xq], a0);
+        a1 = fma(my[xq + 1], wp[xq + 1], a1);
+      }
+      if (xq < Xi) a0 = fma(my[xq], wp[xq], a0);
+      out[o] = a0 + a1;
+    }
+  }
+}
+
+// ---- few outputs, long x (e.g. the leaf contraction over the 7200-image mode of the coil-shaped tensor): the x range
+// is split over gridDim.y CTAs and eight warps each; partial sums go to the workspace and are added in a fixed order.
+constexpr int SX_WY = 8;
+__global__ void __launch_bounds__(32 * SX_WY) mttv_splitx_kernel(const double *__restrict__ T,
+                                                                 const double *__restrict__ W,
+                                                                 double *__restrict__ part, int64_t L, int64_t X,
+                                                                 int64_t Rt, int R, int64_t ldw, int64_t xchunk) {
+  __shared__ double red[SX_WY][32];
+  const int lane = threadIdx.x, wy = threadIdx.y;
+  const int64_t n_out = L * Rt * (int64_t)R;
+  const int64_t o = (int64_t)blockIdx.x * 32 + lane;
+  double acc = 0.0;
+  if (o < n_out) {
+    const int64_t tr = o / L, l = o - tr * L;
+    const double *tp = T + l + L * X * tr;
+    const double *wp = W + (tr / Rt) * ldw;
+    const int64_t xb = (int64_t)blockIdx.y * xchunk;
+    const int64_t xe = xb + xchunk < X ? xb + xchunk : X;
+    for (int64_t x0 = xb + wy; x0 < xe; x0 += 4 * SX_WY) {
+      double v[4], w[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int64_t x = x0 + u * SX_WY;
+        v[u] = x < xe ? tp[L * x] : 0.0;
+        w[u] = x < xe ? wp[x] : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) acc = fma(v[u], w[u], acc);
+    }
+  }
+  red[wy][lane] = acc;
+  __syncthreads();
+  if (wy == 0 && o < n_out) {
+    double s = 0.0;
+#pragma unroll
+    for (int y = 0; y < SX_WY; y++) s += red[y][lane];
+    part[(int64_t)blockIdx.y * n_out + o] = s;
+  }
+}
+__global__ void __launch_bounds__(256) mttv_splitx_reduce_kernel(const double *__restrict__ part, int64_t n, int nsplit,
+                                                                 double *__restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  double s = part[i];
+  for (int k = 1; k < nsplit; k++) s += part[(int64_t)k * n + i];
+  out[i] = s;
+}
+
 // ---- K3 ------------------------------------------------------------------------------------------------------
 constexpr int PP_MAX_OPS = 15;
 struct PpArgs {
@@ -162,8 +315,12 @@ constexpr int PP_WY = 8;  // warps per CTA
 constexpr int PP_B = 8;   // loads in flight per thread and batch
 template <int VEC>
 __global__ void __launch_bounds__(32 * PP_WY, 4) pp_correct_kernel(const double *__restrict__ M0, PpArgs a,
-                                                                   int64_t s_i, int R, double *__restrict__ Mout) {
-  __shared__ double part[PP_WY][32];  // which==1 partial sums (per warp, per row)
+                                                                   int64_t s_i, int R, double *__restrict__ Mout,
+                                                                   double *__restrict__ part) {
+  // gridDim.z > 1: the contracted index q of every operator is split into gridDim.z (even-sized) ranges; each z writes
+  // its partial sums to part[z][s_i x R] and pp_correct_reduce_kernel adds them to M0 in a fixed order.  Used when
+  // s_i x R alone gives too few CTAs (the size-3 and size-128 modes of the coil-shaped tensor against s_j = 7200).
+  __shared__ double psum[PP_WY][32];  // which==1 partial sums (per warp, per row)
   __shared__ double dots[32];         // which==0 sums (per row; row rr is owned by warp rr % PP_WY)
   const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;
   const int64_t i0 = (int64_t)blockIdx.x * 32;
@@ -180,16 +337,22 @@ __global__ void __launch_bounds__(32 * PP_WY, 4) pp_correct_kernel(const double 
   for (int j = 0; j < a.n_ops; j++) {
     const int64_t sj = a.sj[j];
     const double *dw = a.dw[j] + sj * r;
+    int64_t qb = 0, qe = sj;
+    if (gridDim.z > 1) {
+      const int64_t chunk = (((sj + gridDim.z - 1) / gridDim.z) + 1) & ~(int64_t)1;
+      qb = (int64_t)blockIdx.z * chunk;
+      qe = qb + chunk < sj ? qb + chunk : sj;
+    }
     if (a.which[j]) {
       if (i0 + lrow < s_i) {
         const double *pp = a.op[j] + i0 + lrow + s_i * sj * (int64_t)r;
         constexpr int QSTEP = PP_WY * VEC;
-        for (int64_t q0 = wy * VEC + qlane; q0 < sj; q0 += PP_B * QSTEP) {
+        for (int64_t q0 = qb + wy * VEC + qlane; q0 < qe; q0 += PP_B * QSTEP) {
           double v[PP_B][VEC];
 #pragma unroll
           for (int u = 0; u < PP_B; u++) {
             const int64_t q = q0 + u * QSTEP;
-            if (q < sj) {
+            if (q < qe) {
               if (VEC == 2) {
                 const double2 t = *reinterpret_cast<const double2 *>(pp + s_i * q);
                 v[u][0] = t.x;
@@ -205,7 +368,7 @@ __global__ void __launch_bounds__(32 * PP_WY, 4) pp_correct_kernel(const double 
 #pragma unroll
           for (int u = 0; u < PP_B; u++) {
             const int64_t q = q0 + u * QSTEP;
-            const double w = q < sj ? dw[q] : 0.0;
+            const double w = q < qe ? dw[q] : 0.0;
 #pragma unroll
             for (int e = 0; e < VEC; e++) acc[e] = fma(v[u][e], w, acc[e]);
           }
@@ -218,12 +381,12 @@ __global__ void __launch_bounds__(32 * PP_WY, 4) pp_correct_kernel(const double 
         double d = 0.0;
         if (ii < s_i) {
           const double *pp = a.op[j] + sj * (ii + s_i * (int64_t)r);
-          for (int64_t q0 = lane * VEC; q0 < sj; q0 += 32 * VEC * PP_B) {
+          for (int64_t q0 = qb + lane * VEC; q0 < qe; q0 += 32 * VEC * PP_B) {
             double v[PP_B][VEC];
 #pragma unroll
             for (int u = 0; u < PP_B; u++) {
               const int64_t q = q0 + 32 * VEC * u;
-              if (q < sj) {
+              if (q < qe) {
                 if (VEC == 2) {
                   const double2 t = *reinterpret_cast<const double2 *>(pp + q);
                   v[u][0] = t.x;
@@ -239,7 +402,7 @@ __global__ void __launch_bounds__(32 * PP_WY, 4) pp_correct_kernel(const double 
 #pragma unroll
             for (int u = 0; u < PP_B; u++) {
               const int64_t q = q0 + 32 * VEC * u;
-              if (q < sj) {
+              if (q < qe) {
 #pragma unroll
                 for (int e = 0; e < VEC; e++) d = fma(v[u][e], dw[q + e], d);
               }
@@ -255,10 +418,10 @@ __global__ void __launch_bounds__(32 * PP_WY, 4) pp_correct_kernel(const double 
     for (int e = 0; e < VEC; e++) acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 16);
     if (lane < 16) {
 #pragma unroll
-      for (int e = 0; e < VEC; e++) part[wy][lrow + e] = acc[e];
+      for (int e = 0; e < VEC; e++) psum[wy][lrow + e] = acc[e];
     }
   } else {
-    part[wy][lane] = acc[0];
+    psum[wy][lane] = acc[0];
   }
   if (lane == 0) {
 #pragma unroll
@@ -266,21 +429,79 @@ __global__ void __launch_bounds__(32 * PP_WY, 4) pp_correct_kernel(const double 
   }
   __syncthreads();
   if (wy == 0 && i0 + lane < s_i) {
-    double s = M0[i0 + lane + s_i * r];
+    double s = gridDim.z > 1 ? 0.0 : M0[i0 + lane + s_i * r];
 #pragma unroll
-    for (int y = 0; y < PP_WY; y++) s += part[y][lane];
+    for (int y = 0; y < PP_WY; y++) s += psum[y][lane];
     s += dots[lane];
-    Mout[i0 + lane + s_i * r] = s;
+    if (gridDim.z > 1)
+      part[(int64_t)blockIdx.z * s_i * R + i0 + lane + s_i * r] = s;
+    else
+      Mout[i0 + lane + s_i * r] = s;
   }
+}
+
+__global__ void __launch_bounds__(256) pp_correct_reduce_kernel(const double *__restrict__ M0,
+                                                                const double *__restrict__ part, int64_t n, int nz,
+                                                                double *__restrict__ Mout) {
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  double s = M0[i];
+  for (int z = 0; z < nz; z++) s += part[(int64_t)z * n + i];
+  Mout[i] = s;
 }
 
 }  // namespace
 
 int ppx_mttv_impl(ppx_ctx *ctx, const double *T, int64_t L, int64_t X, int64_t Rt, const double *Wx, int64_t ldw,
                   int R, double *out) {
-  if (L * Rt * R == 0) return PPX_OK;
+  const int64_t n_out = L * Rt * (int64_t)R;
+  if (n_out == 0) return PPX_OK;
+  static const bool no_flat = getenv("PPX_NO_FLAT") != nullptr;  // experiments only
+  // few outputs and a long contracted mode: split x over CTAs (partials in the workspace, fixed-order sum)
+  if (!no_flat && X >= 512 && (n_out + 31) / 32 < ctx->sm_count) {
+    const int64_t ob = (n_out + 31) / 32;
+    int64_t nsplit = (4 * (int64_t)ctx->sm_count + ob - 1) / ob;
+    if (nsplit > (X + 63) / 64) nsplit = (X + 63) / 64;
+    const size_t mark = ctx->ws_used;
+    double *part = nsplit > 1 ? (double *)ppx_ws_alloc(ctx, sizeof(double) * (size_t)nsplit * n_out) : nullptr;
+    if (part) {
+      const int64_t xchunk = (X + nsplit - 1) / nsplit;
+      mttv_splitx_kernel<<<dim3((unsigned)ob, (unsigned)nsplit), dim3(32, SX_WY), 0, ctx->stream>>>(T, Wx, part, L, X, Rt,
+                                                                                                   R, ldw, xchunk);
+      PPX_CHECK_LAUNCH(ctx);
+      mttv_splitx_reduce_kernel<<<ppx_cdiv(n_out, 256), 256, 0, ctx->stream>>>(part, n_out, (int)nsplit, out);
+      PPX_CHECK_LAUNCH(ctx);
+      ctx->ws_used = mark;  // stream ordered: the next user of this scratch runs after the two kernels above
+      return PPX_OK;
+    }
+    ctx->ws_used = mark;
+  }
+  if (!no_flat && X <= 64 && n_out >= 512 && (L == 1 || L >= 16)) {
+    if (L == 1) {
+      const int pitch = (int)X | 1;
+      static bool optin = false;
+      if (!optin) {  // up to 128 x 65 doubles
+        PPX_CUDA(ctx, cudaFuncSetAttribute(mttv_flat_k_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+        optin = true;
+      }
+      int64_t blocks = (n_out + FK_ROWS - 1) / FK_ROWS;
+      if (blocks > (int64_t)ctx->sm_count * 16) blocks = (int64_t)ctx->sm_count * 16;
+      mttv_flat_k_kernel<<<(int)blocks, FK_ROWS, sizeof(double) * FK_ROWS * pitch, ctx->stream>>>(T, Wx, out, X, Rt, R,
+                                                                                                  ldw, pitch);
+    } else {
+      const bool vec = (L % 2 == 0) && ((((uintptr_t)T) | ((uintptr_t)out)) & 15) == 0;
+      const int64_t nvec = vec ? n_out / 2 : n_out;
+      int64_t blocks = (nvec + 255) / 256;
+      if (blocks > (int64_t)ctx->sm_count * 16) blocks = (int64_t)ctx->sm_count * 16;
+      if (vec)
+        mttv_flat_m_kernel<2><<<(int)blocks, 256, 0, ctx->stream>>>(T, Wx, out, L, X, Rt, R, ldw);
+      else
+        mttv_flat_m_kernel<1><<<(int)blocks, 256, 0, ctx->stream>>>(T, Wx, out, L, X, Rt, R, ldw);
+    }
+    PPX_CHECK_LAUNCH(ctx);
+    return PPX_OK;
+  }
   if (L == 1) {
-    const int64_t n_out = Rt * (int64_t)R;
     int G = 32;
     while (G > 4 && X < 2 * G) G >>= 1;
     int64_t blocks = (n_out * G + 255) / 256;
@@ -303,7 +524,6 @@ int ppx_mttv_impl(ppx_ctx *ctx, const double *T, int64_t L, int64_t X, int64_t R
       mttv_mid_kernel<1><<<(unsigned)blocks, dim3(32, MT_WY), 0, ctx->stream>>>(T, Wx, out, L, X, Rt, R, ldw, ltiles);
     PPX_CHECK_LAUNCH(ctx);
   } else {
-    const int64_t n_out = L * Rt * (int64_t)R;
     int64_t blocks = (n_out + 255) / 256;
     if (blocks > (int64_t)ctx->sm_count * 32) blocks = (int64_t)ctx->sm_count * 32;
     mttv_small_kernel<<<(int)blocks, 256, 0, ctx->stream>>>(T, Wx, out, L, X, Rt, R, ldw);
@@ -363,11 +583,33 @@ int ppx_pp_correct(ppx_ctx *ctx, const double *M0, const double *const *ops, con
   for (int j = 0; j < n_ops && vec; j++)
     vec = (s_other[j] % 2 == 0) && ((((uintptr_t)ops[j]) | ((uintptr_t)dW[j])) & 15) == 0;
   dim3 grid(ppx_cdiv(s_i, 32), R), block(32 * PP_WY);
+  // too few CTAs for the machine and long operators: split the contracted index over gridDim.z
+  int64_t max_sj = 0;
+  for (int j = 0; j < n_ops; j++) max_sj = s_other[j] > max_sj ? s_other[j] : max_sj;
+  const int64_t ctas = (int64_t)grid.x * grid.y;
+  double *part = nullptr;
+  int nz = 1;
+  static const bool no_split = getenv("PPX_NO_FLAT") != nullptr;  // experiments only
+  if (!no_split && ctas < 2 * ctx->sm_count && max_sj >= 256) {
+    nz = (int)((4 * (int64_t)ctx->sm_count + ctas - 1) / ctas);
+    if (nz > (max_sj + 63) / 64) nz = (int)((max_sj + 63) / 64);
+    if (nz > 64) nz = 64;
+    if (nz > 1) {
+      ppx_ws_reset(ctx);
+      part = (double *)ppx_ws_alloc(ctx, sizeof(double) * (size_t)nz * s_i * R);
+    }
+    if (!part) nz = 1;
+  }
+  grid.z = nz;
   if (vec)
-    pp_correct_kernel<2><<<grid, block, 0, ctx->stream>>>(M0, a, s_i, R, M_out);
+    pp_correct_kernel<2><<<grid, block, 0, ctx->stream>>>(M0, a, s_i, R, M_out, part);
   else
-    pp_correct_kernel<1><<<grid, block, 0, ctx->stream>>>(M0, a, s_i, R, M_out);
+    pp_correct_kernel<1><<<grid, block, 0, ctx->stream>>>(M0, a, s_i, R, M_out, part);
   PPX_CHECK_LAUNCH(ctx);
+  if (nz > 1) {
+    pp_correct_reduce_kernel<<<ppx_cdiv(s_i * R, 256), 256, 0, ctx->stream>>>(M0, part, s_i * (int64_t)R, nz, M_out);
+    PPX_CHECK_LAUNCH(ctx);
+  }
   return PPX_OK;
 }
 

@@ -33,6 +33,9 @@ int ppx_k1_tma_init(ppx_ctx *ctx);
 int ppx_ttm_tma_try(ppx_ctx *ctx, const double *V, int64_t L, int64_t K, int64_t Rt, const double *const *fac,
                     const int64_t *ld, const int64_t *xs, int n_fac, int R, double *out, int inplace, int accumulate,
                     bool ws_keep);
+// streaming variant of the first contraction for X <= 64, R <= 16 (k1_ttm_stream.cu); returns 1 when not eligible
+int ppx_ttm_stream_try(ppx_ctx *ctx, const double *V, int64_t L, int64_t X, int64_t Rt, const double *W, int64_t ldw,
+                       int R, double *out, int inplace, int accumulate);
 // out[l,t,r] = sum_x V[l,x,t] W[x,r] (rank last, or in place of mode x); shared by the CP and Tucker entry points
 int ppx_ttm_impl(ppx_ctx *ctx, const double *V, int64_t L, int64_t X, int64_t Rt, const double *Wx, int64_t ldw, int R,
                  double *out, int inplace, int accumulate, bool ws_keep, bool try_tma);

@@ -45,6 +45,11 @@ TTM_CASES = [
     ((250, 12, 3), 1, 50), ((378, 9, 2), 1, 33), ((122, 40, 2), 1, 26),
     # M-major with a short L: 16 l x 8 t row tiles (one 3-D box per stage)
     ((300, 20, 16), 1, 50), ((46, 17, 40), 1, 27), ((300, 7, 4, 6), 1, 35), ((94, 33, 8), 1, 64), ((16, 40, 24), 1, 25),
+    # streaming kernels (X <= 64 and R <= 16, k1_ttm_stream.cu): lanes along l with one or two rows per thread
+    # (L odd / even), the slab-staged kernel for L == 1, every register-block width, ragged last block
+    ((40, 40, 40), 1, 4), ((40, 40, 40), 2, 16), ((40, 24, 30), 1, 1), ((41, 17, 29), 1, 10), ((25, 64, 33), 1, 12),
+    ((1600, 40, 3), 1, 10), ((16, 3, 50), 1, 5), ((18, 1, 40), 1, 3),
+    ((40, 700), 0, 10), ((3, 5000), 0, 10), ((64, 150), 0, 16), ((7, 333, 3), 0, 8), ((1, 600), 0, 4), ((33, 1027), 0, 13),
 ]
 
 
@@ -78,7 +83,13 @@ def test_ttm_first_unaligned_and_ldw(ctx):
 
 
 MTTV_CASES = [((13, 9, 11), 0, 5), ((13, 9, 11), 1, 5), ((13, 9, 11), 2, 5), ((300, 300), 1, 50), ((300, 300), 0, 50),
-              ((40, 33), 0, 10), ((3, 50, 7), 1, 4), ((70, 5, 9, 4), 2, 3), ((6,), 0, 3), ((100, 64, 3), 1, 2)]
+              ((40, 33), 0, 10), ((3, 50, 7), 1, 4), ((70, 5, 9, 4), 2, 3), ((6,), 0, 3), ((100, 64, 3), 1, 2),
+              # one thread per output for X <= 64 (lanes along l, L even / odd; slab-staged for L == 1)
+              ((40, 40, 12), 1, 10), ((41, 17, 9), 1, 5), ((1600, 40), 1, 10), ((16, 64, 8), 1, 3), ((25, 3, 30), 1, 7),
+              ((40, 130), 0, 10), ((3, 999), 0, 4), ((64, 77), 0, 2), ((17, 40, 5), 0, 6),
+              # few outputs, long contracted mode: x split over CTAs (coil-shaped leaves)
+              ((3, 7200), 1, 10), ((128, 7200), 1, 10), ((5, 2, 1500), 2, 3), ((1000,), 0, 10), ((40, 600), 1, 2),
+              ((700, 6), 0, 5)]
 
 
 @pytest.mark.parametrize("lens,x,R", MTTV_CASES)
@@ -116,7 +127,9 @@ def test_ttm_first_mttv(ctx):
     assert rel_err(ctx.to_host(out, ref.shape), ref) < 1e-12
 
 
-@pytest.mark.parametrize("lens,R", [((12, 10, 8, 6), 4), ((33, 40, 35), 7), ((5, 6, 4, 5, 3, 4), 3)])
+@pytest.mark.parametrize("lens,R", [((12, 10, 8, 6), 4), ((33, 40, 35), 7), ((5, 6, 4, 5, 3, 4), 3),
+                                    # few rows against long operators: the contracted index is split over gridDim.z
+                                    ((3, 16, 600), 10), ((4, 301, 20, 6), 3), ((40, 3, 517), 5)])
 def test_pp_correct_matches_reference_formula(ctx, lens, R):
     N = len(lens)
     V = rnd(lens, 14)
@@ -249,7 +262,10 @@ def test_cp_residual_and_reconstruct(ctx, lens, R):
                                       ((12, 10, 8, 6), 1, 3), ((40, 7, 40), 2, 40), ((5, 1, 6), 1, 2),
                                       # TMA path with the rank written in place (+ DFMA tail columns)
                                       ((256, 14, 5), 1, 26), ((22, 130), 0, 27), ((128, 9, 3, 2), 1, 35),
-                                      ((300, 14, 8), 1, 26), ((46, 9, 16), 1, 40)])
+                                      ((300, 14, 8), 1, 26), ((46, 9, 16), 1, 40),
+                                      # streaming kernels with the rank written in place (+ accumulate)
+                                      ((40, 24, 30), 1, 10), ((41, 17, 29), 1, 3), ((40, 700), 0, 10), ((3, 900, 2), 0, 16),
+                                      ((64, 20, 5), 2, 12)])
 def test_tucker_ttm_and_acc(ctx, lens, x, Q):
     T = rnd(lens, 120)
     W = rnd((lens[x], Q), 121)

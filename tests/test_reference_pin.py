@@ -243,3 +243,54 @@ def test_reference_run_main_matches_oracle(N, s, R, pp, extra):
     assert np.allclose(a[:, 0], b[:, 0])  # sweep counts (fractions: 0.5 / (N-1)/N / 1 per step)
     assert np.allclose(a[:, 2], b[:, 2], rtol=1e-9, atol=FIT_RTOL * vnorm)
     assert np.allclose(a[:, 1], b[:, 1], rtol=1e-8, atol=1e-9 * vnorm)
+
+
+# ---- the input generators of test_ALS.cxx (-tensor p / p2 / c), through the reference's main ------------------------
+@pytest.mark.parametrize("tensor,dim,size,R", [("p2", 4, 5, 3), ("p", 8, 3, 3), ("c", 4, 7, 3)])
+def test_reference_generators_match_oracle(tensor, dim, size, R):
+    """laplacian_tensor + fold_unfold (common.cxx:575-642, 870-882), Gen_collinearity + noise (common.cxx:361-423,
+    test_ALS.cxx:245-261): the reference's main and the restatement must print the same ||V|| and the same ALS trace.
+    Gen_collinearity redraws vectors until their collinearity fits, so the number of fill_random calls is data
+    dependent: the restatement counts its draws and the schedule handed to the stand-in follows it."""
+    if tensor == "c":
+        lens = (size,) * dim
+        _, vec = o.gen_collinearity(lens, R, 0.5, 0.9, seed=1)
+        V = o.make_tensor_c(lens, R, 0.5, 0.9, 0.01, seed=1)
+        # count the draws the restatement made: rerun with a counting generator
+        n_draws = [0]
+        orig = o.u01
+
+        def counting(seed, tid, n, start=0):
+            if tid >= 1000:
+                n_draws[0] += 1
+            return orig(seed, tid, n, start)
+
+        o.u01 = counting
+        try:
+            o.gen_collinearity(lens, R, 0.5, 0.9, seed=1)
+        finally:
+            o.u01 = orig
+        head = [(1, 1000 + k) for k in range(n_draws[0])] + [(1, 101)]
+    elif tensor == "p2":
+        V = o.make_tensor_p(dim, size, folded=False)
+        head = []
+    else:
+        V = o.make_tensor_p(dim, size, folded=True)
+        head = []
+    N = V.ndim
+    lens = V.shape
+    fills = head + [p for i in range(N) for p in ((2, i), (3, i))]
+    ref = rh.run_cli("test_ALS", ["-model", "CP", "-tensor", tensor, "-dim", dim, "-size", size, "-rank", R, "-pp", 0,
+                                  "-maxiter", 10, "-resprint", 5], fills=fills)
+    vnorm = np.linalg.norm(V)
+    import re
+    printed = float(re.search(r"Vnorm= (\S+)", ref["stdout"]).group(1))
+    assert abs(printed - vnorm) < 1e-5 * vnorm  # the main prints 6 digits
+    W, G = o.init_factors(lens, R), o.init_grad(lens, R)
+    tr = o.Trace()
+    o.alsCP_DT(V, W, G, 1e-10 * vnorm, 10, resprint=5, trace=tr)
+    a = np.array(ref["rows"])
+    b = np.array([(r[0], r[1], r[2], r[3]) for r in tr.rows])
+    assert a.shape == b.shape
+    assert np.allclose(a[:, 3], b[:, 3], rtol=1e-9, atol=FIT_RTOL * vnorm)
+    assert np.allclose(a[:, 1], b[:, 1], rtol=1e-8, atol=1e-9 * vnorm)
