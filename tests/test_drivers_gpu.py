@@ -468,10 +468,13 @@ def test_low_rank_update_optimizers(H, world, kind, cls, order, size, R, update_
     Vd.free()
 
 
-# ---- edge shapes: rank 1, a mode of extent 1, a deep tree (order 7), rank above 64 (two column blocks in K1) ---------
+# ---- edge shapes: rank 1, a mode of extent 1, a deep tree (order 7), rank above 64 (two column blocks in K1), one long
+# ---- mode beside short ones (coil-like: x-split leaves, q-split PP correction inside the captured graph), order 6 with
+# ---- extents that take the streaming first contraction and the one-thread-per-output children
 @pytest.mark.parametrize("lens,R,sweeps,tol_init", [((9, 8, 7, 6), 1, 8, 0.1), ((7, 1, 6, 5), 2, 8, 0.1),
                                                     ((4, 3, 4, 3, 4, 3, 4), 2, 8, 0.1), ((70, 69, 68), 66, 4, 0.1),
-                                                    ((33, 2, 31), 2, 8, 0.1)])
+                                                    ((33, 2, 31), 2, 8, 0.1), ((3, 16, 12, 640), 3, 6, 0.2),
+                                                    ((16, 6, 16, 5, 6, 4), 3, 5, 0.2)])
 def test_cp_drivers_edge_shapes(H, world, lens, R, sweeps, tol_init):
     V, W, G = problem(lens, R)
     vnorm = np.linalg.norm(V)
