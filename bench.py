@@ -19,8 +19,9 @@ A "step" is ONE exact ALS sweep with the dimension tree over all four modes (2 f
 `tucker`  : side measurement, not part of `value`: hosvd + alsTucker_DT sweeps at BASELINE configs[2] (order-3 s=800
             ranks 40, tensor 'r2'), ms per HOOI sweep through the same C++ drivers.
 `cpu_baseline`: oracle/pp_oracle.py (NumPy/OpenBLAS restatement of the reference, all host cores) on a bounded
-            mode-0 slab of the same tensor, scaled to the full tensor.  The reference itself (Cyclops CTF + MPI)
-            cannot be built in this image.
+            mode-0 slab of the same tensor, scaled to the full tensor.  Cyclops CTF + MPI cannot be built in this
+            image; oracle/_ref (the reference's sources on a loop-based CTF stand-in) is a checker whose contraction
+            engine is ours and slow, so timing it would flatter the GPU: the OpenBLAS-backed port is the baseline.
 With N>1 the tensor is sharded along mode 0 (strong scaling: the problem is fixed); the only collectives are the
 NCCL all-reduces of the s x R partial MTTKRPs and the R x R Gram of the sharded factor.
 """
@@ -92,8 +93,9 @@ def cpu_sweep_time(s, R, N, slab, reps):
 
 
 def run_reference(args):
-    """The reference arm: the reference's own algorithm on the host cores (the oracle port -- CTF is not buildable
-    here), each step a bounded mode-0 slab of the same workload, scaled to the full tensor."""
+    """The reference arm: the reference's own algorithm on the host cores (the oracle port, NumPy + OpenBLAS on all
+    cores -- CTF is not buildable here and oracle/_ref's loop-based stand-in engine would be an unfairly slow
+    baseline), each step a bounded mode-0 slab of the same workload, scaled to the full tensor."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -414,8 +416,9 @@ def main():
         full = sec * (s / slab)
         cpu = {"value": 1.0 / full, "unit": "sweeps/s", "cores": cores, "kind": "port",
                "sample": "oracle/pp_oracle.py (NumPy + OpenBLAS restatement of als_CP.cxx, %d threads) on a mode-0 slab "
-                         "of %d/%d rows: %.2f s per sweep, scaled x%.1f; the reference itself (Cyclops CTF + MPI) cannot "
-                         "be built in this image" % (cores, slab, s, sec, s / slab)}
+                         "of %d/%d rows: %.2f s per sweep, scaled x%.1f; Cyclops CTF + MPI are not buildable in this "
+                         "image and oracle/_ref runs on a loop-based stand-in (a checker, not a fair baseline)"
+                         % (cores, slab, s, sec, s / slab)}
 
     # ---- side measurement: Tucker HOOI at BASELINE configs[2] (order-3 s=800 ranks 40, tensor 'r2') ---------------
     # Not part of `value`; reported so that the Tucker half of the path has a number in the same file.  Never allowed
