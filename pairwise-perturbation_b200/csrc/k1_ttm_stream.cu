@@ -211,8 +211,11 @@ int launch_stream(ppx_ctx *ctx, const double *V, int64_t L, int64_t X, int64_t R
 int ppx_ttm_stream_try(ppx_ctx *ctx, const double *V, int64_t L, int64_t X, int64_t Rt, const double *W, int64_t ldw,
                        int R, double *out, int inplace, int accumulate) {
   static const bool off = getenv("PPX_NO_STREAM") != nullptr;  // experiments only
-  if (off || R > 16 || X > 64 || X < 1) return 1;
-  if (L != 1 && L < 16) return 1;  // too short to coalesce along l
+  if (off || R > 16 || X < 1) return 1;
+  // 1 < L < 16 (a short mode in front of the contracted one, e.g. the colour mode of the coil-shaped tensor): the
+  // 128-row tiles of the DMMA kernels gather 8 L-byte pieces (0.41 of the HBM rate at L = 3, X = 128); here the three
+  // threads of a slab sweep it front to back and the L1 absorbs the partial sectors, so longer X is taken as well
+  if (X > (L > 1 && L < 16 ? 256 : 64)) return 1;
   // L == 1: the slab kernel wins for very short rows (X = 3: 0.92 of the HBM rate against 0.31); from X ~ 16 on the
   // per-row shared-memory pass costs more than the TMA tile kernel's 0.78 (measured at X = 40: 14.1 ms against 8.0 ms)
   if (L == 1 && X > 8) return 1;

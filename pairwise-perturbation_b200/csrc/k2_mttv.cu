@@ -8,43 +8,69 @@
 
 namespace {
 
-// ---- L == 1: contiguous dot products.  A group of G lanes owns one output. ---------------------------------
+// ---- L == 1: contiguous dot products.  A group of G lanes owns FR consecutive outputs per pass. ------------------
+// All FR x FU loads of a pass are issued before the first multiply (16 independent 8-byte loads per lane): the dot
+// products are short, so memory-level parallelism, not instruction count, decides (one output per pass measured
+// 0.48-0.77 of the HBM rate at X = 40 ... 300).  When the FR rows share one rank column (all but the rows straddling
+// a column boundary) the factor values are loaded once per pass.
+constexpr int FR = 4;  // rows per group and pass
+constexpr int FU = 4;  // loads per row, lane and x step
 template <int G>
 __global__ void __launch_bounds__(256) mttv_first_kernel(const double *__restrict__ T, const double *__restrict__ W,
                                                          double *__restrict__ out, int64_t X, int64_t Rt, int R,
                                                          int64_t ldw) {
   const int64_t n_out = Rt * (int64_t)R;
   const int lane_g = threadIdx.x % G;
-  int64_t o = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
-  const int64_t ostride = ((int64_t)gridDim.x * blockDim.x) / G;
+  int64_t o0 = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G) * FR;
+  const int64_t ostride = (((int64_t)gridDim.x * blockDim.x) / G) * FR;
   const int64_t niter = (n_out + ostride - 1) / ostride;  // same trip count for every lane (shuffles below)
-  for (int64_t it = 0; it < niter; ++it, o += ostride) {
-    double acc = 0.0;
-    if (o < n_out) {
-      const int64_t r = o / Rt;
-      const double *tp = T + o * X;
-      const double *wp = W + r * ldw;
-      // 8 independent loads in flight per lane (the dot products are short: latency, not bandwidth, limits them)
-      for (int64_t x0 = lane_g; x0 < X; x0 += 8 * G) {
-        double v[8];
+  for (int64_t it = 0; it < niter; ++it, o0 += ostride) {
+    double acc[FR];
 #pragma unroll
-        for (int u = 0; u < 8; u++) {
-          const int64_t x = x0 + (int64_t)u * G;
-          v[u] = x < X ? tp[x] : 0.0;
-        }
-        double a0 = 0.0, a1 = 0.0;
+    for (int j = 0; j < FR; j++) acc[j] = 0.0;
+    if (o0 < n_out) {
+      const int64_t r0 = o0 / Rt;
+      const bool full = o0 + FR <= n_out;
+      const bool same_r = full && (o0 + FR - 1) / Rt == r0;
+      const double *tp = T + o0 * X;
+      if (same_r) {
+        const double *wp = W + r0 * ldw;
+        for (int64_t x0 = lane_g; x0 < X; x0 += (int64_t)FU * G) {
+          double v[FR][FU], w[FU];
 #pragma unroll
-        for (int u = 0; u < 8; u += 2) {
-          const int64_t xa = x0 + (int64_t)u * G, xb = xa + G;
-          a0 += v[u] * (xa < X ? wp[xa] : 0.0);
-          a1 += v[u + 1] * (xb < X ? wp[xb] : 0.0);
+          for (int u = 0; u < FU; u++) {
+            const int64_t x = x0 + (int64_t)u * G;
+            const bool ok = x < X;
+            w[u] = ok ? wp[x] : 0.0;
+#pragma unroll
+            for (int j = 0; j < FR; j++) v[j][u] = ok ? tp[j * X + x] : 0.0;
+          }
+#pragma unroll
+          for (int u = 0; u < FU; u++)
+#pragma unroll
+            for (int j = 0; j < FR; j++) acc[j] = fma(v[j][u], w[u], acc[j]);
         }
-        acc += a0 + a1;
+      } else {
+#pragma unroll
+        for (int j = 0; j < FR; j++) {
+          const int64_t o = o0 + j;
+          if (o < n_out) {
+            const double *wp = W + (o / Rt) * ldw;
+            for (int64_t x = lane_g; x < X; x += G) acc[j] = fma(tp[j * X + x], wp[x], acc[j]);
+          }
+        }
       }
     }
 #pragma unroll
-    for (int s = G / 2; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
-    if (lane_g == 0 && o < n_out) out[o] = acc;
+    for (int j = 0; j < FR; j++) {
+#pragma unroll
+      for (int sft = G / 2; sft > 0; sft >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], sft);
+    }
+    if (lane_g == 0) {
+#pragma unroll
+      for (int j = 0; j < FR; j++)
+        if (o0 + j < n_out) out[o0 + j] = acc[j];
+    }
   }
 }
 
@@ -191,59 +217,6 @@ __global__ void __launch_bounds__(256) mttv_flat_m_kernel(const double *__restri
       *reinterpret_cast<double2 *>(out + o) = make_double2(acc[0], acc[VEC - 1]);
     else
       out[o] = acc[0];
-  }
-}
-
-// L == 1, small X: the rows o = (t, r) are X contiguous doubles each.  A CTA stages 128 consecutive rows (one
-// contiguous slab, coalesced) in shared memory with an odd pitch; every thread then forms the dot product of its row.
-constexpr int FK_ROWS = 128;
-__global__ void __launch_bounds__(FK_ROWS) mttv_flat_k_kernel(const double *__restrict__ T, const double *__restrict__ W,
-                                                              double *__restrict__ out, int64_t X, int64_t Rt, int R,
-                                                              int64_t ldw, int pitch) {
-  extern __shared__ __align__(16) double fk_slab[];  // [FK_ROWS][pitch]
-  const int tid = threadIdx.x;
-  const int64_t n_out = Rt * (int64_t)R;
-  const int Xi = (int)X;
-  const int step_row = FK_ROWS / Xi, step_x = FK_ROWS - step_row * Xi;
-  for (int64_t o0 = (int64_t)blockIdx.x * FK_ROWS; o0 < n_out; o0 += (int64_t)gridDim.x * FK_ROWS) {
-    const int nrows = (int)(n_out - o0 < FK_ROWS ? n_out - o0 : FK_ROWS);
-    const int n = nrows * Xi;
-    const double *src = T + o0 * X;
-    __syncthreads();
-    int row = tid / Xi, x = tid - row * Xi;
-    for (int i0 = tid; i0 < n; i0 += 4 * FK_ROWS) {
-      double v[4];
-      int rr[4], xx[4];
-#pragma unroll
-      for (int u = 0; u < 4; u++) {
-        rr[u] = row;
-        xx[u] = x;
-        v[u] = (i0 + u * FK_ROWS < n) ? src[i0 + u * FK_ROWS] : 0.0;
-        row += step_row;
-        x += step_x;
-        if (x >= Xi) {
-          x -= Xi;
-          row++;
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < 4; u++)
-        if (i0 + u * FK_ROWS < n) fk_slab[rr[u] * pitch + xx[u]] = v[u];
-    }
-    __syncthreads();
-    if (tid < nrows) {
-      const int64_t o = o0 + tid;
-      const double *wp = W + (o / Rt) * ldw;
-      const double *my = fk_slab + tid * pitch;
-      double a0 = 0.0, a1 = 0.0;
-      int xq = 0;
-      for (; xq + 1 < Xi; xq += 2) {
-        a0 = fma(my[xq], wp[xq], a0);
-        a1 = fma(my[xq + 1], wp[xq + 1], a1);
-      }
-      if (xq < Xi) a0 = fma(my[xq], wp[xq], a0);
-      out[o] = a0 + a1;
-    }
   }
 }
 
@@ -476,36 +449,25 @@ int ppx_mttv_impl(ppx_ctx *ctx, const double *T, int64_t L, int64_t X, int64_t R
     }
     ctx->ws_used = mark;
   }
-  if (!no_flat && X <= 64 && n_out >= 512 && (L == 1 || L >= 16)) {
-    if (L == 1) {
-      const int pitch = (int)X | 1;
-      static bool optin = false;
-      if (!optin) {  // up to 128 x 65 doubles
-        PPX_CUDA(ctx, cudaFuncSetAttribute(mttv_flat_k_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
-        optin = true;
-      }
-      int64_t blocks = (n_out + FK_ROWS - 1) / FK_ROWS;
-      if (blocks > (int64_t)ctx->sm_count * 16) blocks = (int64_t)ctx->sm_count * 16;
-      mttv_flat_k_kernel<<<(int)blocks, FK_ROWS, sizeof(double) * FK_ROWS * pitch, ctx->stream>>>(T, Wx, out, X, Rt, R,
-                                                                                                  ldw, pitch);
-    } else {
-      const bool vec = (L % 2 == 0) && ((((uintptr_t)T) | ((uintptr_t)out)) & 15) == 0;
-      const int64_t nvec = vec ? n_out / 2 : n_out;
-      int64_t blocks = (nvec + 255) / 256;
-      if (blocks > (int64_t)ctx->sm_count * 16) blocks = (int64_t)ctx->sm_count * 16;
-      if (vec)
-        mttv_flat_m_kernel<2><<<(int)blocks, 256, 0, ctx->stream>>>(T, Wx, out, L, X, Rt, R, ldw);
-      else
-        mttv_flat_m_kernel<1><<<(int)blocks, 256, 0, ctx->stream>>>(T, Wx, out, L, X, Rt, R, ldw);
-    }
+  if (!no_flat && X <= 64 && n_out >= 512 && L >= 16) {
+    const bool vec = (L % 2 == 0) && ((((uintptr_t)T) | ((uintptr_t)out)) & 15) == 0;
+    const int64_t nvec = vec ? n_out / 2 : n_out;
+    int64_t blocks = (nvec + 255) / 256;
+    if (blocks > (int64_t)ctx->sm_count * 16) blocks = (int64_t)ctx->sm_count * 16;
+    if (vec)
+      mttv_flat_m_kernel<2><<<(int)blocks, 256, 0, ctx->stream>>>(T, Wx, out, L, X, Rt, R, ldw);
+    else
+      mttv_flat_m_kernel<1><<<(int)blocks, 256, 0, ctx->stream>>>(T, Wx, out, L, X, Rt, R, ldw);
     PPX_CHECK_LAUNCH(ctx);
     return PPX_OK;
   }
   if (L == 1) {
+    // lanes per output: every lane should have about FU elements of a row (one x step), at least 4 lanes
     int G = 32;
-    while (G > 4 && X < 2 * G) G >>= 1;
-    int64_t blocks = (n_out * G + 255) / 256;
-    if (blocks > (int64_t)ctx->sm_count * 32) blocks = (int64_t)ctx->sm_count * 32;
+    while (G > 4 && X <= (int64_t)(G / 2) * FU + G / 4) G >>= 1;
+    const int64_t groups = (n_out + FR - 1) / FR;
+    int64_t blocks = (groups * G + 255) / 256;
+    if (blocks > (int64_t)ctx->sm_count * 16) blocks = (int64_t)ctx->sm_count * 16;
     switch (G) {
       case 32: mttv_first_kernel<32><<<(int)blocks, 256, 0, ctx->stream>>>(T, Wx, out, X, Rt, R, ldw); break;
       case 16: mttv_first_kernel<16><<<(int)blocks, 256, 0, ctx->stream>>>(T, Wx, out, X, Rt, R, ldw); break;

@@ -50,6 +50,7 @@ TTM_CASES = [
     ((40, 40, 40), 1, 4), ((40, 40, 40), 2, 16), ((40, 24, 30), 1, 1), ((41, 17, 29), 1, 10), ((25, 64, 33), 1, 12),
     ((1600, 40, 3), 1, 10), ((16, 3, 50), 1, 5), ((18, 1, 40), 1, 3),
     ((40, 700), 0, 10), ((3, 5000), 0, 10), ((64, 150), 0, 16), ((7, 333, 3), 0, 8), ((1, 600), 0, 4), ((33, 1027), 0, 13),
+    ((3, 128, 300), 1, 10), ((2, 200, 150), 1, 16), ((5, 256, 120), 1, 7), ((15, 70, 40), 1, 3),
 ]
 
 
