@@ -423,8 +423,22 @@ int ppx_unfold_gram(ppx_ctx *ctx, const double *T, const int64_t *lens, int k, i
   int64_t L, X, Rt;
   ppx_split3(lens, k, i, &L, &X, &Rt);
   const int64_t C = L * Rt;
-  // large unfoldings (HOSVD) take the 128 x 128 tile kernel
+  // large unfoldings (HOSVD): DMMA SYRK (gram_dmma.cu); PPX_NO_GRAM_DMMA=1 selects the DFMA tile kernel (experiments)
   const bool big = X >= 192 && C >= 4096;
+  static const bool no_dmma = getenv("PPX_NO_GRAM_DMMA") != nullptr;
+  if (big && !no_dmma) {
+    ppx_ws_reset(ctx);
+    int max_splits = 64;
+    double *parts = nullptr;
+    while (max_splits >= 1 && !(parts = (double *)ppx_ws_alloc(ctx, sizeof(double) * (size_t)max_splits * X * X)))
+      max_splits /= 2;
+    if (!parts) return ppx_set_err(ctx, PPX_ENOMEM, "unfold_gram needs %lld bytes of workspace", (long long)(8 * X * X));
+    const int nz = ppx_gram_dmma(ctx, T, L, X, Rt, parts, max_splits);
+    if (nz < 0) return nz;
+    unfold_gram_reduce_kernel<<<ppx_cdiv(X * X, 256), 256, 0, ctx->stream>>>(parts, X, nz, 128, MTM);
+    PPX_CHECK_LAUNCH(ctx);
+    return PPX_OK;
+  }
   const int tile = big ? UH_T : UG_T;
   const int tiles = ppx_cdiv(X, tile);
   const int ntile_ctas = tiles * (tiles + 1) / 2;
