@@ -233,6 +233,16 @@ __global__ void __launch_bounds__(1024) chfsi_jacobi_smem_kernel(const double *_
   for (int sweep = 0; sweep < 40; sweep++) {
     int my_rot = 0;
     double my_max = 0.0;
+    // squared column norms, exact at the start of every sweep; inside the sweep a rotation updates the two it touches
+    // (|a'|^2 = |a|^2 - t a.b, |b'|^2 = |b|^2 + t a.b), so a pair costs ONE inner product and one warp reduction
+    // instead of three -- the single SM this kernel runs on is bound by its FP64 rate
+    for (int c = warp; c < p; c += nw) {
+      double q = 0.0;
+      for (int i = lane; i < p; i += 32) q = fma(B[c * ld + i], B[c * ld + i], q);
+      q = ppx_warp_sum(q);
+      if (lane == 0) nrm[c] = q;
+    }
+    __syncthreads();
     for (int round = 0; round < m - 1; round++) {
       for (int pr = warp; pr < half; pr += nw) {
         int a, b;
@@ -251,18 +261,15 @@ __global__ void __launch_bounds__(1024) chfsi_jacobi_smem_kernel(const double *_
         if (b >= p) continue;
         double *ca = B + a * ld, *cb = B + b * ld;
         double xa[4], xb[4];  // p <= 128
-        double saa = 0.0, sbb = 0.0, sab = 0.0;
+        double sab = 0.0;
 #pragma unroll
         for (int u = 0; u < 4; u++) {
           const int i = lane + 32 * u;
           xa[u] = i < p ? ca[i] : 0.0;
           xb[u] = i < p ? cb[i] : 0.0;
-          saa = fma(xa[u], xa[u], saa);
-          sbb = fma(xb[u], xb[u], sbb);
           sab = fma(xa[u], xb[u], sab);
         }
-        saa = ppx_warp_sum(saa);
-        sbb = ppx_warp_sum(sbb);
+        const double saa = nrm[a], sbb = nrm[b];
         sab = ppx_warp_sum(sab);
         if (!(fabs(sab) > tol * sqrt(saa * sbb) && fabs(sab) > 1e-300)) continue;
         // t = sign(zeta) / (|zeta| + sqrt(1 + zeta^2)), zeta = (b - a) / (2 g), written with one sqrt, one division and
@@ -279,6 +286,11 @@ __global__ void __launch_bounds__(1024) chfsi_jacobi_smem_kernel(const double *_
             ca[i] = c * xa[u] - s * xb[u];
             cb[i] = s * xa[u] + c * xb[u];
           }
+        }
+        if (lane == 0) {
+          const double na = saa - t * sab, nb = sbb + t * sab;
+          nrm[a] = na > 0.0 ? na : 0.0;
+          nrm[b] = nb > 0.0 ? nb : 0.0;
         }
         my_rot++;
         my_max = fmax(my_max, fabs(s));
