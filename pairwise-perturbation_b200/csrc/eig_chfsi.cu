@@ -420,7 +420,7 @@ bool ppx_eig_chfsi_applicable(int64_t n, int r) {
 
 // Returns PPX_OK with U / evals_out filled, 1 if the iteration did not converge (nothing usable was written: the caller
 // falls back to the Jacobi solver), a negative code on errors.  `A` (n x n, symmetric) is destroyed.  `state`
-// (>= n*(r+24) doubles, optional) holds the final block for the next call on a nearby matrix (same n and r).
+// (>= n*(r+24) + 1 doubles, optional) holds the final block and a tag for the next call on a nearby matrix (same n and r).
 int ppx_eig_chfsi(ppx_ctx *ctx, double *A, int n, int r, double *U, double *evals_out, double *state, int state_valid) {
   const int p = r + (112 - r < 24 ? 112 - r : 24);
   const int64_t ld = n;
@@ -441,7 +441,18 @@ int ppx_eig_chfsi(ppx_ctx *ctx, double *A, int n, int r, double *U, double *eval
   double *res = theta + p;
   const bool verbose = getenv("PPX_EIG_VERBOSE") != nullptr;
 
-  // start block: the previous call's block, or random
+  // start block: the previous call's block, or random.  `state` is shared with the Jacobi solver (which stores an
+  // n x n basis there when this iteration gave up): a block left by THIS solver carries a tag behind its last column
+  // (np < n*n because 4 r <= n); anything else is not a block and a cold start is taken.  (Reading a Jacobi basis as
+  // a block started one mode of a 2-GPU HOOI run orthogonal to its dominant eigenvector: the filter then diverged,
+  // the fallback ran again, and the mode stayed on the 15 ms solver for the rest of the run.)
+  const double kStateTag = 0x1.c4f51b5ea7ap+77 * (double)p + (double)n;
+  if (state && state_valid) {
+    double tag = 0.0;
+    PPX_CUDA(ctx, cudaMemcpyAsync(&tag, state + np, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    PPX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (tag != kStateTag) state_valid = 0;
+  }
   if (state && state_valid) {
     PPX_CUDA(ctx, cudaMemcpyAsync(X, state, sizeof(double) * np, cudaMemcpyDeviceToDevice, ctx->stream));
   } else {
@@ -460,6 +471,13 @@ int ppx_eig_chfsi(ppx_ctx *ctx, double *A, int n, int r, double *U, double *eval
     attr_set = true;
   }
   int iters = 0, products = 0;
+  // Stagnation: the attainable residual sits near 1e-12 theta_j (deflation with a locked vector that is itself only
+  // converged to that level, orthonormality of the block after Cholesky QR); a pair can stall a few per cent above the
+  // threshold for ever (seen at 1.06e-12 on the all-reduced Gram of a 2-GPU run).  When the first open pair has not
+  // improved by a factor 2 since the previous step with nothing newly locked, 1e-10 theta_j is accepted: still two
+  // orders below the eps ||A|| / gap accuracy of a dense eigensolver on these matrices.
+  double prev_rel = -1.0;
+  int prev_nlock = -1;
   for (int outer = 0; outer < 24; outer++, iters++) {
     const int pa = p - nlock;
     double *Xa = X + ld * nlock;
@@ -483,10 +501,15 @@ int ppx_eig_chfsi(ppx_ctx *ctx, double *A, int n, int r, double *U, double *eval
     if (lam_max < 0.0) lam_max = th[0];
     // lock the leading run of converged Ritz pairs (Ritz values are in decreasing order); below 1e-13 of the largest
     // eigenvalue the matrix is numerically rank deficient and any orthonormal vectors of the block serve
+    const double rel0 = th[0] > 0.0 ? rs[0] / th[0] : 0.0;
+    const bool stagnated = outer >= 2 && prev_nlock == nlock && prev_rel > 0.0 && rel0 > 0.5 * prev_rel && rel0 <= 1e-10;
+    const double tolrel = stagnated ? 1e-10 : 1e-12;
     int nconv = 0;
     while (nconv < pa && nlock + nconv < r &&
-           (rs[nconv] <= 1e-12 * th[nconv] + 1e-300 || th[nconv] <= 1e-13 * lam_max))
+           (rs[nconv] <= tolrel * th[nconv] + 1e-300 || th[nconv] <= 1e-13 * lam_max))
       nconv++;
+    prev_rel = rel0;
+    prev_nlock = nlock;
     if (verbose)
       fprintf(stderr, "chfsi n=%d r=%d it %d: locked %d (+%d), theta[0]=%.6e theta[last]=%.6e res[first unconv]=%.3e\n", n,
               r, outer, nlock, nconv, th[0], th[pa - 1], nconv < pa ? rs[nconv] : 0.0);
@@ -562,7 +585,10 @@ int ppx_eig_chfsi(ppx_ctx *ctx, double *A, int n, int r, double *U, double *eval
     for (int k = 0; k < r; k++) ev[k] = lam_locked[order[k]];
     PPX_CUDA(ctx, cudaMemcpyAsync(evals_out, ev.data(), sizeof(double) * r, cudaMemcpyHostToDevice, ctx->stream));
   }
-  if (state) PPX_CUDA(ctx, cudaMemcpyAsync(state, X, sizeof(double) * np, cudaMemcpyDeviceToDevice, ctx->stream));
+  if (state) {
+    PPX_CUDA(ctx, cudaMemcpyAsync(state, X, sizeof(double) * np, cudaMemcpyDeviceToDevice, ctx->stream));
+    PPX_CUDA(ctx, cudaMemcpyAsync(state + np, &kStateTag, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  }
   PPX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // `order`, `ev` are host temporaries of the copies above
   return PPX_OK;
 }

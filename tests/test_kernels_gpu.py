@@ -471,3 +471,24 @@ def test_sym_eig_topk_large(ctx, kind, n, r):
             gap = np.min(w[:k] - w[1:k + 1]) if k < n else 1.0
             P, Pr = Uh[:, :k] @ Uh[:, :k].T, Q[:, :k] @ Q[:, :k].T
             assert np.abs(P - Pr).max() <= 1e-9 * w[0] / max(gap, 1e-300) * 1e-3 + 1e-9
+
+
+def test_sym_eig_topk_ignores_a_foreign_basis(ctx):
+    """The `basis` buffer is shared by the two solvers behind ppx_sym_eig_topk_warm: the subspace iteration keeps an
+    n x p block there, the Jacobi fallback an n x n matrix.  A buffer marked valid that was not written by the
+    subspace iteration -- here the eigenvectors in INCREASING order, whose first columns are orthogonal to everything
+    wanted, as a Jacobi run leaves them -- must be recognised (tag behind the block) and a cold start taken."""
+    n, r = 512, 16
+    rng = np.random.default_rng(7)
+    A = _spectrum_case("noise+outlier", n, rng)
+    A = np.asfortranarray(0.5 * (A + A.T))
+    w, Q = np.linalg.eigh(A)  # increasing
+    basis = ctx.to_device(np.asfortranarray(Q))
+    U, ev = ctx.empty(n * r), ctx.empty(r)
+    ctx.sym_eig_topk(ctx.to_device(A), n, r, U, ev, basis=basis, basis_valid=True)
+    evh, Uh = ctx.to_host(ev, (r,)), ctx.to_host(U, (n, r))
+    assert np.abs(evh - w[::-1][:r]).max() <= 1e-11 * w[-1]
+    assert np.abs(A @ Uh - Uh @ (Uh.T @ A @ Uh)).max() <= 1e-10 * w[-1]
+    # and the block it left is its own: a warm restart reproduces the answer
+    ctx.sym_eig_topk(ctx.to_device(A), n, r, U, ev, basis=basis, basis_valid=True)
+    assert np.abs(ctx.to_host(ev, (r,)) - w[::-1][:r]).max() <= 1e-11 * w[-1]
