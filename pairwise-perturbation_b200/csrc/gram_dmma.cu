@@ -180,19 +180,20 @@ __global__ void __launch_bounds__(GB_THREADS, 2) gram_dmma_kernel(GramParams p) 
 
 }  // namespace
 
+// Opt-in shared memory of the two kernels; per device, called from ppx_ctx_create.
+int ppx_gram_init(ppx_ctx *ctx) {
+  cudaError_t e = cudaFuncSetAttribute(gram_dmma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)(sizeof(double) * gram_stages<true>() * gram_stage_doubles<true>()));
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(gram_dmma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)(sizeof(double) * gram_stages<false>() * gram_stage_doubles<false>()));
+  if (e != cudaSuccess) return ppx_set_err(ctx, PPX_ECUDA, "gram_dmma init: %s", cudaGetErrorString(e));
+  return PPX_OK;
+}
+
 // Partial Grams into `parts` ([nz][X*X], only 128-blocks in or below the diagonal are written; the caller's reduction
 // mirrors the others with tile = 128).  Returns the number of K splits used, 0 when the shape is not taken, < 0 on error.
 int ppx_gram_dmma(ppx_ctx *ctx, const double *T, int64_t L, int64_t X, int64_t Rt, double *parts, int max_splits) {
-  static bool init = false;
-  if (!init) {
-    cudaError_t e = cudaFuncSetAttribute(gram_dmma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)(sizeof(double) * gram_stages<true>() * gram_stage_doubles<true>()));
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(gram_dmma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)(sizeof(double) * gram_stages<false>() * gram_stage_doubles<false>()));
-    if (e != cudaSuccess) return ppx_set_err(ctx, PPX_ECUDA, "gram_dmma: %s", cudaGetErrorString(e));
-    init = true;
-  }
   GramParams p;
   p.T = T;
   p.parts = parts;

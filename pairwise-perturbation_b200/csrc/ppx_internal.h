@@ -44,6 +44,7 @@ bool ppx_eig_chfsi_applicable(int64_t n, int r);
 int ppx_eig_chfsi(ppx_ctx *ctx, double *A, int n, int r, double *U, double *evals_out, double *state, int state_valid);
 // DMMA SYRK for large unfoldings (gram_dmma.cu): partial Grams, returns the number of K splits written (0: not taken)
 int ppx_gram_dmma(ppx_ctx *ctx, const double *T, int64_t L, int64_t X, int64_t Rt, double *parts, int max_splits);
+int ppx_gram_init(ppx_ctx *ctx);
 int ppx_k45_init(ppx_ctx *ctx);
 int ppx_k7_init(ppx_ctx *ctx);
 void ppx_comm_destroy_internal(ppx_ctx *ctx);

@@ -499,3 +499,55 @@ def test_cp_drivers_edge_shapes(H, world, lens, R, sweeps, tol_init):
         check_factors(Wd, W_ref)
         free_all(Wd, Gd)
     free_all(Vd, Fd)
+
+
+# ---- our command lines beside the reference's own mains (oracle/_ref, built from the unmodified sources) ----------------
+import re  # noqa: E402
+
+from oracle import ref_harness as rh  # noqa: E402
+
+
+def _stdout_numbers(text):
+    """what both mains print at a print point / at the end: (iteration, gradient norm, pp flag, residual), switching
+    markers, and the `Final ... norm` lines (6 digits)."""
+    rows, events = rh.parse_stdout(text)
+    finals = [float(x) for x in re.findall(r"Final (?:proj-)?grad norm (\S+)", text)]
+    return rows, events, finals
+
+
+@pytest.mark.skipif(not rh.available(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("exe,extra", [("test_ALS", ["-pp", "1", "-maxiter", "40", "-pp_res_tol", "0.1", "-resprint", "5"]),
+                                       ("test_ALS", ["-pp", "0", "-maxiter", "12", "-resprint", "3"]),
+                                       ("test_ALS", ["-pp", "2", "-maxiter", "30", "-pp_res_tol", "0.1", "-resprint", "5",
+                                                     "-update_percentage_pp", "0.5"]),
+                                       ("pp_bench", ["-maxiter", "2"]),
+                                       ("run", ["-pp", "0", "-maxiter", "10", "-resprint", "3"]),
+                                       ("run", ["-pp", "1", "-maxiter", "10", "-resprint", "3"]),
+                                       ("run", ["-pp", "4", "-maxiter", "6", "-resprint", "2"]),
+                                       ("run", ["-pp", "2", "-maxiter", "10", "-resprint", "3", "-updaterank", "2"]),
+                                       ("run", ["-pp", "3", "-maxiter", "10", "-resprint", "3", "-updaterank", "2"])])
+def test_cli_beside_the_reference_main(tmp_path, exe, extra):
+    """Same flags to pairwise-perturbation_b200/<exe> (CUDA) and oracle/_ref/<exe> (the reference's main on the CTF
+    stand-in); the stand-in's fill_random is scheduled to the (seed, id) pairs our CLI draws.  Printed traces must agree:
+    identical switching iterations, residuals and gradient norms to the printed precision."""
+    N, s, R = 4, 11, 3
+    args = ["-model", "CP", "-tensor", "r", "-dim", str(N), "-size", str(s), "-rank", str(R)] + extra
+    fills = [(1, i) for i in range(N)] + [p for i in range(N) for p in ((2, i), (3, i))]
+    if exe == "run":  # run.cxx: W_true, then W; CPD::Init then draws grad_W from the World's default stream (seed 1, ids 0..)
+        fills = [(1, i) for i in range(N)] + [(2, i) for i in range(N)] + [(1, i) for i in range(N)]
+    ref = rh.run_cli(exe, args + ["-filename", os.path.join(str(tmp_path), "ref.csv")], fills=fills)
+    ours = subprocess.run([os.path.join(PKG, exe)] + args + ["-filename", os.path.join(str(tmp_path), "ours.csv")],
+                          check=True, capture_output=True, text=True, timeout=300).stdout
+    rows_r, ev_r, fin_r = _stdout_numbers(ref["stdout"])
+    rows_o, ev_o, fin_o = _stdout_numbers(ours)
+    assert ev_o == ev_r
+    assert len(rows_o) == len(rows_r) and len(fin_o) == len(fin_r) and len(fin_r) >= 1
+    for a, b in zip(rows_o, rows_r):
+        assert a[0] == b[0] and a[2] == b[2]
+        assert abs(a[1] - b[1]) <= 1e-9 * max(abs(b[1]), 1.0) and abs(a[3] - b[3]) <= 1e-9 * max(abs(b[3]), 1.0)
+    for a, b in zip(fin_o, fin_r):
+        assert abs(a - b) <= 2e-6 * max(abs(b), 1e-30)
+    # the CSV files carry the same sequence of records (labels; the timings differ)
+    def labels(path):
+        return [ln.split(",")[0].strip() for ln in open(path) if ln.strip() and ln.split(",")[0].strip().startswith("[")]
+    assert labels(os.path.join(str(tmp_path), "ours.csv")) == labels(os.path.join(str(tmp_path), "ref.csv"))
