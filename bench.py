@@ -92,6 +92,31 @@ def cpu_sweep_time(s, R, N, slab, reps):
     return min(ts), os.cpu_count() or 1
 
 
+def ref_standin_sweep(s, R, N, small=28):
+    """For the record only: the reference's own alsCP_DT (oracle/_ref/pp_bench, the unmodified sources on the loop-based
+    CTF stand-in) on a size-`small` cube, scaled by (s/small)^N.  One scalar thread; never used as the baseline."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "pp_bench")
+    if not os.path.exists(exe):
+        return None
+    import re
+    import tempfile
+    try:
+        with tempfile.TemporaryDirectory() as td:
+            out = subprocess.run([exe, "-model", "CP", "-tensor", "r", "-dim", str(N), "-size", str(small), "-rank", str(R),
+                                  "-maxiter", "1", "-filename", os.path.join(td, "x.csv")], capture_output=True, text=True,
+                                 timeout=300, cwd=td).stdout
+        ts = [float(x) for x in re.findall(r"\[dimension tree step time\]\s+(\S+)", out)]
+        if not ts:
+            return None
+        sec = min(ts) * (s / small) ** N
+        return {"value": 1.0 / sec, "unit": "sweeps/s", "cores": 1, "kind": "reference",
+                "sample": "oracle/_ref/pp_bench (reference sources, loop-based CTF stand-in) at size %d, one DT sweep "
+                          "%.3f s, scaled x%.0f; NOT the baseline: the stand-in's contraction engine is ours and scalar"
+                          % (small, min(ts), (s / small) ** N)}
+    except Exception as exc:  # noqa: BLE001
+        return {"error": "%s: %s" % (type(exc).__name__, exc)}
+
+
 def run_reference(args):
     """The reference arm: the reference's own algorithm on the host cores (the oracle port, NumPy + OpenBLAS on all
     cores -- CTF is not buildable here and oracle/_ref's loop-based stand-in engine would be an unfairly slow
@@ -115,7 +140,7 @@ def run_reference(args):
                          "sample": "oracle/pp_oracle.py (NumPy + OpenBLAS, %d threads) on a mode-0 slab of %d/%d rows; "
                                    "seconds per sweep x %.1f" % (cores, slab, s, s / slab)},
         "e2e": {"value": val, "unit": "sweeps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0, "wall_s": time.perf_counter() - t0,
+        "gpu_launches": 0, "reference_sources_on_standin": ref_standin_sweep(s, R, N), "wall_s": time.perf_counter() - t0,
     }
     print(json.dumps(line), flush=True)
 
@@ -418,7 +443,8 @@ def main():
                "sample": "oracle/pp_oracle.py (NumPy + OpenBLAS restatement of als_CP.cxx, %d threads) on a mode-0 slab "
                          "of %d/%d rows: %.2f s per sweep, scaled x%.1f; Cyclops CTF + MPI are not buildable in this "
                          "image and oracle/_ref runs on a loop-based stand-in (a checker, not a fair baseline)"
-                         % (cores, slab, s, sec, s / slab)}
+                         % (cores, slab, s, sec, s / slab),
+               "reference_sources_on_standin": ref_standin_sweep(s, R, N)}
 
     # ---- side measurement: Tucker HOOI at BASELINE configs[2] (order-3 s=800 ranks 40, tensor 'r2') ---------------
     # Not part of `value`; reported so that the Tucker half of the path has a number in the same file.  Never allowed
