@@ -217,7 +217,8 @@ int ppx_ttm_stream_try(ppx_ctx *ctx, const double *V, int64_t L, int64_t X, int6
   // threads of a slab sweep it front to back and the L1 absorbs the partial sectors, so longer X is taken as well
   if (X > (L > 1 && L < 16 ? 256 : 64)) return 1;
   // L == 1: the slab kernel wins for very short rows (X = 3: 0.92 of the HBM rate against 0.31); from X ~ 16 on the
-  // per-row shared-memory pass costs more than the TMA tile kernel's 0.78 (measured at X = 40: 14.1 ms against 8.0 ms)
+  // per-row shared-memory pass costs more than the TMA tile kernel's 0.78 (measured at X = 40: 14.1 ms against 8.0 ms;
+  // one thread per row with 16-byte loads straight from global memory, relying on L1 for the half-used sectors: 11.8 ms)
   if (L == 1 && X > 8) return 1;
   if (L * Rt < 512) return 1;      // tiny problems: nothing to stream
   if (R <= 4) return launch_stream<4>(ctx, V, L, X, Rt, W, ldw, R, out, inplace, accumulate);
