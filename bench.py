@@ -343,6 +343,50 @@ def main():
           "note": "one CUDA graph per sweep (N x [correct, Gram-Hadamard, LDL^T inverse + solve+grad+dW, Gram] + Normalize + norms)"
                   if nranks == 1 else "eager launches + NCCL all-reduce per mode (latency bound, does not scale)"}
 
+    # ---- K3 (PP correction of one mode) and the solve kernels alone, as HBM GB/s ----------------------
+    if nranks == 1:
+        try:
+            i_mode = 1
+            s_i = lens_local[i_mode]
+            others = [j for j in range(N) if j != i_mode]
+            ops = [H.Tensor(world, (s_i, lens_local[j], R)) for j in others]
+            for k_, t_ in enumerate(ops):
+                t_.fill(4, k_)
+            M0, Mo = H.Matrix(world, s_i, R), H.Matrix(world, s_i, R)
+            n_ops = len(ops)
+            opp = (C.c_void_p * n_ops)(*[t_.data_ptr() for t_ in ops])
+            dwp = (C.c_void_p * n_ops)(*[W[j].data_ptr() for j in others])
+            which = (C.c_int * n_ops)(*[0 if j < i_mode else 1 for j in others])
+            so = (C.c_int64 * n_ops)(*[lens_local[j] for j in others])
+
+            def k3():
+                rc_ = lib.ppx_pp_correct(world.ctx_handle(), C.c_void_p(M0.data_ptr()), opp, which, dwp, so, n_ops, s_i, R,
+                                         C.c_void_p(Mo.data_ptr()))
+                assert rc_ == 0, lib.ppx_last_error(world.ctx_handle())
+
+            for _ in range(5):
+                k3()
+            lib.ppx_event_record(world.ctx_handle(), evs[0])
+            for _ in range(20):
+                k3()
+            lib.ppx_event_record(world.ctx_handle(), evs[1])
+            lib.ppx_event_elapsed_ms(world.ctx_handle(), evs[0], evs[1], C.byref(ms))
+            k3_ms = float(ms.value) / 20
+            k3_bytes = 8.0 * (sum(s_i * lens_local[j] * R + lens_local[j] * R for j in others) + 2 * s_i * R)
+            hbm = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] \
+                if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6543.1
+            pp["k3_pp_correct"] = {"us": 1e3 * k3_ms, "algorithmic_bytes": k3_bytes, "gbs": k3_bytes / k3_ms / 1e6,
+                                   "frac_hbm": k3_bytes / k3_ms / 1e6 / hbm,
+                                   "timing": "20 back-to-back launches, CUDA events (launch ramp included)"}
+            sweep_bytes = 8.0 * sum(lens_local[i] * lens_local[j] * R + lens_local[j] * R
+                                    for i in range(N) for j in range(N) if i != j) + 24.0 * sum(lens_local) * R
+            pp["approx_sweep_algorithmic_bytes"] = sweep_bytes
+            pp["approx_sweep_frac_hbm"] = sweep_bytes / (ms_pp / args.pp_sweeps) / 1e6 / hbm
+            for t_ in ops + [M0, Mo]:
+                t_.free()
+        except Exception as exc:  # noqa: BLE001
+            pp["k3_pp_correct"] = {"error": "%s: %s" % (type(exc).__name__, exc)}
+
     # ---- roofline of the dominant kernel: the first dimension-tree contraction (K1) ------------------------------
     # The sweep contracts the sibling modes of the first-level tree node in ONE launch (ppx_ttm_multi: DMMA GEMM against
     # the Khatri-Rao rows of their factors); that call is what is timed here.
