@@ -3,7 +3,7 @@
 all-reduces, and every rank compares its rows of W_0 / the replicated W_j and the logged fitness with the CPU oracle;
 then hosvd + alsTucker_DT / alsTucker_PP on a sharded tensor (replicated factors) against the oracle.
 
-    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tools/check_multi_gpu.py
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tests/check_multi_gpu.py
 """
 import importlib
 import os
