@@ -307,15 +307,46 @@ __global__ void __launch_bounds__(THREADS, 2) ttm_first_kernel(TtmParams p) {
   ppx_cp_async_wait<0>();
 }
 
-// out[i] = sum_s part[s][i], fixed order
+// out[i] = sum_s part[s][i] in a fixed order.  Few splits: one thread per output.  Many splits (a fused contraction with
+// few output rows, e.g. 200 x 10 outputs from 148 K slices at BASELINE configs[0]): the serial sum of one thread is a
+// chain of dependent loads (measured 101 us for 2000 outputs) -- eight groups of lanes take the splits round-robin with
+// four independent partial sums each and are combined through shared memory in a fixed order.
 __global__ void __launch_bounds__(256) split_reduce_kernel(const double *__restrict__ part, int64_t n, int nsplit,
-                                                           double *__restrict__ out) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (; i < n; i += stride) {
-    double s = part[i];
-    for (int k = 1; k < nsplit; k++) s += part[(int64_t)k * n + i];
-    out[i] = s;
+                                            double *__restrict__ out) {
+  if (nsplit < 16) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+      double s = part[i];
+      for (int k = 1; k < nsplit; k++) s += part[(int64_t)k * n + i];
+      out[i] = s;
+    }
+    return;
+  }
+  __shared__ double red[8][32];
+  const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
+  for (int64_t i0 = (int64_t)blockIdx.x * 32; i0 < n; i0 += (int64_t)gridDim.x * 32) {
+    const int64_t i = i0 + lane;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    if (i < n) {
+      int k = g;
+      for (; k + 24 < nsplit; k += 32) {
+        a0 += part[(int64_t)k * n + i];
+        a1 += part[(int64_t)(k + 8) * n + i];
+        a2 += part[(int64_t)(k + 16) * n + i];
+        a3 += part[(int64_t)(k + 24) * n + i];
+      }
+      for (; k < nsplit; k += 8) a0 += part[(int64_t)k * n + i];
+    }
+    red[g][lane] = (a0 + a1) + (a2 + a3);
+    __syncthreads();
+    if (g == 0 && i < n) {
+      double s = red[0][lane];
+#pragma unroll
+      for (int q = 1; q < 8; q++) s += red[q][lane];
+      out[i] = s;
+    }
+    __syncthreads();
   }
 }
 
@@ -462,7 +493,7 @@ int ppx_ttm_impl(ppx_ctx *ctx, const double *V, int64_t L, int64_t X, int64_t Rt
   if (rc) return rc;
   if (p.ksplit > 1) {
     const int64_t n = p.Mtot * (int64_t)R;
-    int blocks = ppx_cdiv(n, 256 * 4);
+    int blocks = p.ksplit < 16 ? ppx_cdiv(n, 256 * 4) : ppx_cdiv(n, 32);
     if (blocks > ctx->sm_count * 8) blocks = ctx->sm_count * 8;
     split_reduce_kernel<<<blocks, 256, 0, ctx->stream>>>(partial, n, p.ksplit, out);
     PPX_CHECK_LAUNCH(ctx);

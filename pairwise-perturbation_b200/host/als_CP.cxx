@@ -151,6 +151,61 @@ void dt_sweep(Tensor<> &V, Matrix<> *W, Matrix<> *grad_W, Matrix<> *F, double la
   normalize_with_grams(W, N, gc, dw);  // :303
 }
 
+// The exact sweep as a CUDA graph.  A sweep enqueues a fixed sequence of kernels on fixed buffers (the tree
+// intermediates come out of the World's pool at the same addresses every sweep, the workspace arena is reset per call,
+// nothing is read back to the host), so the FIRST sweep of a driver call runs eagerly -- it also fills the pool --, the
+// SECOND is captured and launched, and every later one is a single graph launch.  At BASELINE configs[0] (order 3,
+// s = 200, R = 10) a sweep is ~30 launches of a few microseconds of work each: launch-bound when enqueued one by one.
+// One GPU only (the NCCL all-reduces stay eager); any allocation that misses the pool during the capture abandons it.
+struct DtSweepGraph {
+  World &dw;
+  void *graph = nullptr;
+  bool disabled = false;
+  int eager_done = 0;
+  explicit DtSweepGraph(World &w) : dw(w) { disabled = !(w.use_graph && w.np == 1) || getenv("PPX_NO_DT_GRAPH"); }
+  DtSweepGraph(const DtSweepGraph &) = delete;
+  ~DtSweepGraph() {
+    if (graph) ppx_graph_destroy(dw.ctx, graph);
+  }
+  // `remaining`: sweeps still to come after this one (a capture pays off from the second replay on)
+  template <typename Sweep>
+  void run(Sweep &&sweep, int remaining) {
+    if (graph) {
+      PPXCK(dw, ppx_graph_launch(dw.ctx, graph));
+      return;
+    }
+    if (!disabled && eager_done >= 1 && remaining >= 2) {
+      bool ok = ppx_graph_begin(dw.ctx) == PPX_OK;
+      if (ok) {
+        dw.capturing = true;
+        try {
+          sweep();
+        } catch (const World::CaptureMiss &) {
+          ok = false;
+        } catch (...) {
+          dw.capturing = false;
+          void *g = nullptr;
+          ppx_graph_end(dw.ctx, &g);
+          if (g) ppx_graph_destroy(dw.ctx, g);
+          throw;
+        }
+        dw.capturing = false;
+        void *g = nullptr;
+        const int rc = ppx_graph_end(dw.ctx, &g);  // always ends the capture
+        if (ok && rc == PPX_OK && g) {
+          graph = g;
+          PPXCK(dw, ppx_graph_launch(dw.ctx, graph));
+          return;
+        }
+        if (g) ppx_graph_destroy(dw.ctx, g);
+      }
+      disabled = true;  // nothing was executed: run this sweep, and all later ones, eagerly
+    }
+    sweep();
+    eager_done++;
+  }
+};
+
 }  // namespace
 
 vector<int> sort_indexes(const vector<double> &v) {
@@ -249,6 +304,7 @@ bool alsCP_DT(Tensor<> &V, Matrix<> *W, Matrix<> *grad_W, Matrix<> *F, double to
     dw.allreduce(dw.scal_dev, 1);
     dw.fetch(dw.scal_dev, &vnorm_sq, 1);
   }
+  DtSweepGraph sweep_graph(dw);
   for (iter = 0; iter <= maxiter; iter++) {
     if (iter % resprint == 0 || iter == maxiter) {  // :166-213
       const double st_time1 = synced_time(dw);
@@ -275,7 +331,8 @@ bool alsCP_DT(Tensor<> &V, Matrix<> *W, Matrix<> *grad_W, Matrix<> *F, double to
       }
       if (projnorm < tol || wall_time() - st_time > timelimit) break;
     }
-    dt_sweep(V, W, grad_W, F, lambda, true, parent, sibling, gc, S, dw, fit_terms);
+    sweep_graph.run([&]() { dt_sweep(V, W, grad_W, F, lambda, true, parent, sibling, gc, S, dw, fit_terms); },
+                    maxiter - iter);
     have_terms = fast;
     if (trace_sink()) trace_sink()->sweeps.push_back({0, iter});
     if (iter % 10 == 0 && dw.rank == 0 && !trace_quiet()) printf(".");

@@ -87,6 +87,12 @@ public:
   // Stream-ordered caching allocator: every kernel of this World runs on ONE stream, so a freed buffer can be
   // handed to the next allocation of the same size without synchronising (the dimension-tree intermediates have
   // the same sizes every sweep; cudaMalloc/cudaFree of 10.8 GB blocks would cost milliseconds per sweep).
+  // Set while a sweep is being captured into a CUDA graph: an allocation the pool cannot serve would call cudaMalloc
+  // inside the capture, so it throws instead and the caller runs the sweep eagerly.
+  struct CaptureMiss : std::runtime_error {
+    CaptureMiss() : std::runtime_error("allocation during graph capture missed the pool") {}
+  };
+  bool capturing = false;
   double *dev_alloc(int64_t n) {
     const size_t bytes = sizeof(double) * (size_t)(n > 0 ? n : 1);
     auto it = pool.find(bytes);
@@ -96,6 +102,7 @@ public:
       pooled_bytes -= bytes;
       return p;
     }
+    if (capturing) throw CaptureMiss();
     void *p = nullptr;
     int rc = ppx_malloc(ctx, bytes, &p);
     if (rc != PPX_OK) {  // out of memory: drop the cache and retry once
