@@ -517,6 +517,7 @@ def main():
                 Vt = full
             Wt_ = [H.Matrix(world, ts, tr) for _ in range(tn)]
             core = H.Tensor(world, (tr,) * tn)
+            H.hosvd(world, Vt, core, Wt_, [tr] * tn)  # warm-up: first-use kernel loading and pool allocations
             barrier()
             t0 = time.perf_counter()
             H.hosvd(world, Vt, core, Wt_, [tr] * tn)

@@ -184,8 +184,10 @@ void hosvd_sharded(Tensor<> &T, Matrix<> *factor_matrices, int *ranks, World &dw
       dw.allreduce(MTM.data, MTM.size);
     }
     Matrix<> U(MTM.nrow, ranks[i], dw);
+    // HOSVD is an initialisation: always a cold solve (whatever an earlier decomposition left in this World is
+    // unrelated); the basis it leaves warm-starts the first HOOI sweep
     World::EigBasis &eb = dw.eig_basis_for(i, MTM.nrow);
-    PPXCK(dw, ppx_sym_eig_topk_warm(dw.ctx, MTM.data, MTM.nrow, ranks[i], U.data, nullptr, eb.data, eb.valid ? 1 : 0));
+    PPXCK(dw, ppx_sym_eig_topk_warm(dw.ctx, MTM.data, MTM.nrow, ranks[i], U.data, nullptr, eb.data, 0));
     eb.valid = true;
     factor_matrices[i] = std::move(U);
   }
