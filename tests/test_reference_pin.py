@@ -294,3 +294,58 @@ def test_reference_generators_match_oracle(tensor, dim, size, R):
     assert a.shape == b.shape
     assert np.allclose(a[:, 3], b[:, 3], rtol=1e-9, atol=FIT_RTOL * vnorm)
     assert np.allclose(a[:, 1], b[:, 1], rtol=1e-8, atol=1e-9 * vnorm)
+
+
+# ---- who checks the checker: the CTF stand-in on its own against NumPy ---------------------------------------------
+def test_ctf_standin_against_numpy(tmp_path):
+    """oracle/_ref/standin_selftest (oracle/standin_selftest.cxx) runs expressions of every kind the reference uses --
+    tensor-times-matrix, Hadamard-batched contraction, multi-term sums with += / -= and scalar factors, a right-hand
+    side that mentions the output, diagonal assignment / extraction, Transform, scalar conversion, the unfolding Gram with
+    the '^' '&' index characters, svd (tall and wide), qr, cholesky, solve_tri in its four variants -- through
+    oracle/ctf_standin/ctf.hpp alone; NumPy recomputes them from the same counter-based inputs."""
+    import subprocess
+    exe = os.path.join(rh.REF_DIR, "standin_selftest")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/standin_selftest not built")
+    pre = os.path.join(str(tmp_path), "st")
+    subprocess.run([exe, pre], check=True, env=dict(os.environ, CTF_STANDIN_SEED="11"), capture_output=True, timeout=60)
+
+    def ld(name, shape):
+        return np.fromfile(pre + "." + name + ".bin").reshape(shape, order="F")
+
+    V = o.fill_uniform((5, 4, 3, 6), 11, 0, -1.0, 1.0)
+    A, B, C, D = (o.fill_uniform(sh, 11, k) for k, sh in ((1, (5, 3)), (2, (4, 3)), (3, (3, 3)), (4, (6, 3))))
+    assert np.array_equal(ld("V", V.shape), V)
+    T1 = np.einsum("abcd,cr->abdr", V, C)
+    assert np.allclose(ld("ttm", T1.shape), T1, rtol=1e-13, atol=1e-14)
+    T2 = np.einsum("abdr,dr->abr", T1, D)
+    assert np.allclose(ld("mttv", T2.shape), T2, rtol=1e-13, atol=1e-14)
+    M = np.einsum("abr,br->ar", T2, B) + 2.0 * A
+    M = M - 0.5 * (A - M)
+    assert np.allclose(ld("chain", M.shape), M, rtol=1e-13)
+    S = (A.T @ A) * (B.T @ B) + 0.25 * np.eye(3)
+    assert np.allclose(ld("S", (3, 3)), S, rtol=1e-13)
+    dg = np.where(np.diag(S) > 2.0, 1.0, -1.0)
+    assert np.array_equal(ld("diag", (3, 3)), np.diag(dg))
+    sc = ld("scalars", (2,))
+    assert np.isclose(sc[0], np.sum(A * A), rtol=1e-14) and np.isclose(sc[1], np.linalg.norm(V), rtol=1e-14)
+    G = np.einsum("ipkl,iqkl->pq", V, V)
+    assert np.allclose(ld("unfold_gram", (4, 4)), G, rtol=1e-13)
+    for tag, shape in (("svd", (6, 4)), ("svdw", (3, 5))):
+        X = ld(tag + "_in", shape)
+        U, s, VT = ld(tag + "_U", (shape[0], 3)), ld(tag + "_s", (3,)), ld(tag + "_VT", (3, shape[1]))
+        sref = np.linalg.svd(X, compute_uv=False)[:3]
+        assert np.allclose(s, sref, rtol=1e-12)
+        assert np.abs(U.T @ U - np.eye(3)).max() < 1e-12 and np.abs(VT @ VT.T - np.eye(3)).max() < 1e-12
+        Ur, sr, VTr = np.linalg.svd(X, full_matrices=False)
+        assert np.allclose((U * s) @ VT, (Ur[:, :3] * sr[:3]) @ VTr[:3], atol=1e-12)  # best rank-3 approximation
+    Wd = ld("svd_in", (6, 4))
+    Q, R = ld("qr_Q", (6, 4)), ld("qr_R", (4, 4))
+    assert np.allclose(Q @ R, Wd, atol=1e-13) and np.abs(Q.T @ Q - np.eye(4)).max() < 1e-13
+    assert np.abs(np.tril(R, -1)).max() == 0.0
+    L = ld("chol_L", (3, 3))
+    assert np.allclose(L, np.linalg.cholesky(S), rtol=1e-13)
+    assert np.allclose(ld("tri_right_T", (5, 3)) @ L.T, A, atol=1e-13)
+    assert np.allclose(ld("tri_right_N", (5, 3)) @ L, A, atol=1e-13)
+    assert np.allclose(L @ ld("tri_left_N", (3, 5)), A.T, atol=1e-13)
+    assert np.allclose(L.T @ ld("tri_left_T", (3, 5)), A.T, atol=1e-13)
