@@ -349,3 +349,26 @@ def test_ctf_standin_against_numpy(tmp_path):
     assert np.allclose(ld("tri_right_N", (5, 3)) @ L, A, atol=1e-13)
     assert np.allclose(L @ ld("tri_left_N", (3, 5)), A.T, atol=1e-13)
     assert np.allclose(L.T @ ld("tri_left_T", (3, 5)), A.T, atol=1e-13)
+
+
+# ---- the plain (tree-less) drivers of the reference: same normal equations, so the same iterates as the DT drivers ----
+def test_reference_plain_alsCP_equals_dt_sweeps():
+    """alsCP (als_CP.cxx:20-115: one KhatriRao_contract per mode, SVD_solve, Normalize) produces the factors of the
+    dimension-tree sweeps.  Equal extents only: its callers mis-size lens_H for ragged tensors."""
+    lens, R = (9, 9, 9, 9), 3
+    V, W, G = problem(lens, R)
+    ref = rh.run_driver("alsCP", V, W, G, tol=0.0, maxiter=5)
+    o.alsCP_DT(V, W, G, 0.0, 5, resprint=100, want_residual=False)
+    check_factors(ref["W"], W)
+
+
+def test_reference_plain_alsTucker_equals_dt_sweeps():
+    """alsTucker (als_Tucker.cxx:112-172: TTMc per mode, no tree) against the restated alsTucker_DT: same subspaces."""
+    lens, ranks = (8, 9, 7, 6), (3, 3, 3, 3)
+    V = o.make_tensor_r2(lens, seed=1)
+    vnorm = np.linalg.norm(V)
+    ref = rh.run_driver("alsTucker", V, ranks=ranks, tol=1e-10 * vnorm, maxiter=6)
+    core, W = o.hosvd(V, list(ranks))
+    o.alsTucker_DT(V, core, W, 1e-10 * vnorm, 6, resprint=100, want_residual=False)
+    for a, b in zip(ref["W"], W):
+        assert projector_err(a, b) < 1e-7
