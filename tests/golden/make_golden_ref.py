@@ -33,6 +33,11 @@ CASES = {
                             resprint=5, update_pct=1.0),
     "cp_part_n4_half": dict(op="alsCP_PP_partupdate", lens=(12, 13, 14, 15), R=4, tol_init=0.1, maxiter=30,
                             resprint=5, update_pct=0.5),
+    # sizes at which the streaming first contraction (X <= 64, R <= 16), the one-thread-per-output children and the TMA
+    # tiles are the kernels that run on the CUDA side
+    "cp_pp_n4_s40_r10": dict(op="alsCP_PP", lens=(40, 40, 40, 40), R=10, tol_init=0.1, maxiter=30, resprint=5),
+    "cp_pp_n6_s12_r4": dict(op="alsCP_PP", lens=(12,) * 6, R=4, tol_init=0.1, maxiter=20, resprint=5),
+    "cp_dt_n4_ragged_r12": dict(op="alsCP_DT", lens=(48, 20, 36, 30), R=12, maxiter=10, resprint=5),
     "tucker_dt_n4": dict(op="alsTucker_DT", lens=(9, 10, 8, 7), R=3, maxiter=12, resprint=4),
     "tucker_pp_n4": dict(op="alsTucker_PP", lens=(9, 10, 8, 7), R=3, tol_init=0.3, maxiter=30, resprint=5),
 }
