@@ -38,6 +38,8 @@ CASES = {
     "cp_pp_n4_s40_r10": dict(op="alsCP_PP", lens=(40, 40, 40, 40), R=10, tol_init=0.1, maxiter=30, resprint=5),
     "cp_pp_n6_s12_r4": dict(op="alsCP_PP", lens=(12,) * 6, R=4, tol_init=0.1, maxiter=20, resprint=5),
     "cp_dt_n4_ragged_r12": dict(op="alsCP_DT", lens=(48, 20, 36, 30), R=12, maxiter=10, resprint=5),
+    # HOSVD with one long mode: on the CUDA side its Gram is solved by the subspace iteration (n >= 384)
+    "hosvd_n3_long_mode": dict(op="hosvd", lens=(400, 12, 10), R=4, ranks=(8, 4, 4)),
     "tucker_dt_n4": dict(op="alsTucker_DT", lens=(9, 10, 8, 7), R=3, maxiter=12, resprint=4),
     "tucker_pp_n4": dict(op="alsTucker_PP", lens=(9, 10, 8, 7), R=3, tol_init=0.3, maxiter=30, resprint=5),
 }
@@ -53,7 +55,15 @@ def main():
         out = dict(op=op, lens=np.array(lens), R=R, source="reference (oracle/_ref/ref_driver)")
         for k, v in c.items():
             out[k] = v
-        if op.startswith("alsTucker"):
+        if op == "hosvd":
+            ranks = c.pop("ranks")
+            V = o.make_tensor_r2(lens)
+            vnorm = np.linalg.norm(V)
+            ref = rh.run_driver(op, V, ranks=list(ranks))
+            out["ranks"] = np.array(ranks)
+            out["core_norm"] = float(np.linalg.norm(ref["core"]))
+            ref["rows"], ref["events"] = [(0.0, 0.0, 0, 0.0)], []
+        elif op.startswith("alsTucker"):
             V = o.make_tensor_r2(lens)
             vnorm = np.linalg.norm(V)
             _, W0 = o.hosvd(V, [R] * N)

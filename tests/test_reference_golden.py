@@ -44,7 +44,8 @@ def proj_err(A, B):
 
 def test_fixture_set_is_complete():
     ops = {load(n)["op"] for n in NAMES}
-    assert ops == {"alsCP_DT", "alsCP_PP", "alsCP_PP_partupdate", "alsTucker_DT", "alsTucker_PP"} and len(NAMES) >= 11
+    assert ops == {"alsCP_DT", "alsCP_PP", "alsCP_PP_partupdate", "alsTucker_DT", "alsTucker_PP", "hosvd"}
+    assert len(NAMES) >= 15
 
 
 @pytest.mark.parametrize("name", NAMES)
@@ -52,6 +53,13 @@ def test_oracle_reproduces_reference_fixture(name):
     c = load(name)
     lens, R, N, vnorm = c["lens"], c["R"], len(c["lens"]), c["vnorm"]
     kinds = {"DT": 0, "PP": 1}
+    if c["op"] == "hosvd":
+        V = o.make_tensor_r2(lens)
+        core, W = o.hosvd(V, [int(x) for x in c["g"]["ranks"]])
+        for a, b in zip(W, c["W"]):
+            assert proj_err(a, b) < 1e-9
+        assert abs(np.linalg.norm(core) - float(c["g"]["core_norm"])) < 1e-10 * vnorm
+        return
     if c["op"].startswith("alsTucker"):
         V = o.make_tensor_r2(lens)
         assert abs(np.linalg.norm(V) - vnorm) < 1e-12 * vnorm
@@ -110,6 +118,21 @@ def test_cuda_path_reproduces_reference_fixture(H, world, name, solver):
     c = load(name)
     lens, R, N, vnorm = c["lens"], c["R"], len(c["lens"]), c["vnorm"]
     world.set(solver=solver, use_graph=True)
+    if c["op"] == "hosvd":
+        if solver == 1:
+            pytest.skip("no R x R solve on the Tucker path")
+        ranks = [int(x) for x in c["g"]["ranks"]]
+        V = o.make_tensor_r2(lens)
+        Vd = H.Tensor.from_numpy(world, V)
+        Wd = [H.Matrix(world, lens[i], ranks[i]) for i in range(N)]
+        cored = H.Tensor(world, tuple(ranks))
+        H.hosvd(world, Vd, cored, Wd, ranks)
+        for i in range(N):
+            assert proj_err(Wd[i].numpy(), c["W"][i]) < 1e-8
+        assert abs(np.linalg.norm(cored.numpy()) - float(c["g"]["core_norm"])) < 1e-10 * vnorm
+        for x in [Vd, cored] + Wd:
+            x.free()
+        return
     if c["op"].startswith("alsTucker"):
         if solver == 1:
             pytest.skip("no R x R solve on the Tucker path")
