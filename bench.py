@@ -92,6 +92,19 @@ def cpu_sweep_time(s, R, N, slab, reps):
     return min(ts), os.cpu_count() or 1
 
 
+def cpu_full_sweep_estimate(s, R, N, slab, reps):
+    """Seconds per sweep of the full tensor from two mode-0 slabs (slab and 2*slab rows): the contractions that read V
+    scale with the slab, the ones that start from an intermediate that has lost mode 0 do not, so the time is
+    a + b*rows and is extrapolated linearly to s rows.  Returns (sec_full, sec_slab, sec_2slab, cores)."""
+    slab2 = min(2 * slab, s)
+    t1, cores = cpu_sweep_time(s, R, N, slab, reps)
+    if slab2 == slab:
+        return t1, t1, t1, cores
+    t2, _ = cpu_sweep_time(s, R, N, slab2, reps)
+    per_row = max((t2 - t1) / (slab2 - slab), 0.0)
+    return t1 + per_row * (s - slab), t1, t2, cores
+
+
 def ref_standin_sweep(s, R, N, small=28):
     """For the record only: the reference's own alsCP_DT (oracle/_ref/pp_bench, the unmodified sources on the loop-based
     CTF stand-in) on a size-`small` cube, scaled by (s/small)^N.  One scalar thread; never used as the baseline."""
@@ -126,8 +139,7 @@ def run_reference(args):
         return
     s, R, N, slab = args.size, args.rank, args.order, min(args.cpu_slab, args.size)
     t0 = time.perf_counter()
-    sec, cores = cpu_sweep_time(s, R, N, slab, max(1, min(args.steps, 3)))
-    full = sec * (s / slab)
+    full, sec, sec2, cores = cpu_full_sweep_estimate(s, R, N, slab, max(1, min(args.steps, 3)))
     val = 1.0 / full
     line = {
         "impl": "reference", "metric": "ALS-DT sweeps/s (CP order-%d s=%d R=%d FP64)" % (N, s, R), "value": val,
@@ -135,10 +147,11 @@ def run_reference(args):
         "ms_per_step": full * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": "CP-ALS dimension-tree sweep, order-%d s=%d R=%d, tensor 'r'" % (N, s, R),
-                   "sample": "mode-0 slab of %d/%d rows, time scaled x%.1f" % (slab, s, s / slab)},
+                   "sample": "mode-0 slabs of %d and %d of %d rows, linear extrapolation" % (slab, min(2 * slab, s), s)},
         "cpu_baseline": {"value": val, "unit": "sweeps/s", "cores": cores, "kind": "port",
-                         "sample": "oracle/pp_oracle.py (NumPy + OpenBLAS, %d threads) on a mode-0 slab of %d/%d rows; "
-                                   "seconds per sweep x %.1f" % (cores, slab, s, s / slab)},
+                         "sample": "oracle/pp_oracle.py (NumPy + OpenBLAS, %d threads) on mode-0 slabs of %d and %d of %d "
+                                   "rows: %.2f s and %.2f s per sweep, extrapolated linearly to %.1f s"
+                                   % (cores, slab, min(2 * slab, s), s, sec, sec2, full)},
         "e2e": {"value": val, "unit": "sweeps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "reference_sources_on_standin": ref_standin_sweep(s, R, N), "wall_s": time.perf_counter() - t0,
     }
@@ -481,13 +494,12 @@ def main():
     cpu = None
     if rank == 0 and nranks == 1 and not args.no_cpu_baseline:
         slab = min(args.cpu_slab, s)
-        sec, cores = cpu_sweep_time(s, R, N, slab, 2)
-        full = sec * (s / slab)
+        full, sec, sec2, cores = cpu_full_sweep_estimate(s, R, N, slab, 2)
         cpu = {"value": 1.0 / full, "unit": "sweeps/s", "cores": cores, "kind": "port",
-               "sample": "oracle/pp_oracle.py (NumPy + OpenBLAS restatement of als_CP.cxx, %d threads) on a mode-0 slab "
-                         "of %d/%d rows: %.2f s per sweep, scaled x%.1f; Cyclops CTF + MPI are not buildable in this "
-                         "image and oracle/_ref runs on a loop-based stand-in (a checker, not a fair baseline)"
-                         % (cores, slab, s, sec, s / slab),
+               "sample": "oracle/pp_oracle.py (NumPy + OpenBLAS restatement of als_CP.cxx, %d threads) on mode-0 slabs "
+                         "of %d and %d of %d rows: %.2f s and %.2f s per sweep, extrapolated linearly to %.1f s; Cyclops "
+                         "CTF + MPI are not buildable in this image and oracle/_ref runs on a loop-based stand-in (a "
+                         "checker, not a fair baseline)" % (cores, slab, min(2 * slab, s), s, sec, sec2, full),
                "reference_sources_on_standin": ref_standin_sweep(s, R, N)}
 
     # ---- side measurement: Tucker HOOI at BASELINE configs[2] (order-3 s=800 ranks 40, tensor 'r2') ---------------

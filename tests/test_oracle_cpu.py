@@ -320,3 +320,22 @@ def test_rank_update_is_the_best_rank_r_correction_in_the_S_norm():
     # randomized range finder: exact when r = R (the range is everything)
     Us, VT = o.get_rankR_update_cholesky(R, M, A, S, random=True)
     assert np.abs(A + Us @ VT - exact).max() < 1e-9
+
+
+# ---- the BLAS formulation the oracle switches to for large arrays (only bench.py's CPU baseline reaches that size) ----
+@pytest.mark.parametrize("shape,iT,x", [((4, 30, 20, 25), "abcd", "c"), ((4, 30, 20, 25), "abcd", "a"),
+                                        ((4, 30, 20, 25), "abcd", "d"), ((6, 17, 20, 9), "abd*", "d"),
+                                        ((6, 17, 20, 9), "abd*", "a"), ((6, 17, 20, 9), "abd*", "b"), ((40, 7), "a*", "a")])
+def test_contract_blas_path_equals_einsum(shape, iT, x, monkeypatch):
+    T = o.fill_uniform(shape, 21, 0, -1.0, 1.0)
+    batched = iT.endswith("*")
+    modes = iT[:-1] if batched else iT
+    R = shape[-1] if batched else 6
+    W = o.fill_uniform((shape[modes.index(x)], R), 21, 1, -1.0, 1.0)
+    out = modes.replace(x, "") + "*"
+    monkeypatch.setattr(o, "_FAST_MIN_ELEMS", 1)
+    fast = o.contract(out, T, iT, W, x + "*")
+    assert o._contract_big(out, T, iT, W, x + "*") is not None  # the pattern is recognised
+    monkeypatch.setattr(o, "_FAST_MIN_ELEMS", 10 ** 15)
+    ref = o.contract(out, T, iT, W, x + "*")
+    assert fast.shape == ref.shape and np.abs(fast - ref).max() <= 1e-13 * np.abs(ref).max()
