@@ -51,7 +51,8 @@ def parse_args():
     ap.add_argument("--rank", type=int, default=50)
     ap.add_argument("--order", type=int, default=4)
     ap.add_argument("--pp-sweeps", type=int, default=10)
-    ap.add_argument("--cpu-slab", type=int, default=4, help="mode-0 rows of the tensor used for the CPU baseline")
+    ap.add_argument("--cpu-slab", type=int, default=8,
+                    help="mode-0 rows of the smaller of the two slabs (the other has twice as many) timed for the CPU baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-tucker", action="store_true", help="skip the Tucker HOOI side measurement (BASELINE configs[2])")
     return ap.parse_args()
