@@ -372,3 +372,17 @@ def test_reference_plain_alsTucker_equals_dt_sweeps():
     o.alsTucker_DT(V, core, W, 1e-10 * vnorm, 6, resprint=100, want_residual=False)
     for a, b in zip(ref["W"], W):
         assert projector_err(a, b) < 1e-7
+
+
+def test_reference_tree_code_cannot_do_order_3(tmp_path):
+    """DESIGN.md section 2 / SURVEY 8a: for N = 3 the leaf `c` hangs off the root, mttkrp_map_DT asks for the root's
+    parent and recurses for ever (common.cxx:29,89-91) -- the reference's test_ALS overflows its stack, while its OO
+    path (run, CPDTOptimizer) handles order 3.  This is why the order-3 fixtures come from the oracle alone and why our
+    drivers treat a leaf whose parent is the root by the first-level rule."""
+    import subprocess
+    args = ["-model", "CP", "-tensor", "r", "-dim", "3", "-size", "6", "-rank", "2", "-pp", "0", "-maxiter", "2"]
+    bad = subprocess.run([os.path.join(rh.REF_DIR, "test_ALS")] + args, capture_output=True, timeout=120,
+                         cwd=str(tmp_path))
+    assert bad.returncode != 0  # SIGSEGV from the unbounded recursion
+    good = rh.run_cli("run", args)
+    assert "Iters" in good["stdout"]
