@@ -79,6 +79,11 @@ int ppx_graph_destroy(ppx_ctx *ctx, void *graph);
 /* out[i] = lo + (hi-lo) * u(seed, tensor_id, start+i), u = SplitMix64 finaliser of the counter (53 bits). */
 int ppx_fill_uniform(ppx_ctx *ctx, double *out, int64_t n, uint64_t seed, uint64_t tensor_id, int64_t start,
                      double lo, double hi);
+/* The local slab of a tensor whose leading mode (global extent L_global) is sharded: rows [row_begin, row_begin+L_local)
+ * of each of the n_cols columns, out[i + L_local*c] = lo + (hi-lo) * u(seed, tensor_id, row_begin + i + L_global*c) --
+ * the same values ppx_fill_uniform gives the whole tensor, so any rank generates its slice without communication. */
+int ppx_fill_uniform_rows(ppx_ctx *ctx, double *out, int64_t L_local, int64_t L_global, int64_t row_begin,
+                          int64_t n_cols, uint64_t seed, uint64_t tensor_id, double lo, double hi);
 /* out (s^(2d) doubles) = the Laplacian tensor of order 2d, V[a1,b1,..,ad,bd] = sum_k D[a_k,b_k] prod_{m!=k} delta(a_m,b_m),
  * D = tridiag(-1,2,-1): what laplacian_tensor builds from identity tensors (common.cxx:575-642; generators 'p','p2'). */
 int ppx_fill_laplacian(ppx_ctx *ctx, double *out, int d, int64_t s);
@@ -231,6 +236,11 @@ int ppx_transpose(ppx_ctx *ctx, const double *A, int64_t m, int64_t n, double *B
 int ppx_shard_range(int64_t s, int nranks, int rank, int64_t *begin, int64_t *end);
 int ppx_comm_unique_id(void *id128);                                  /* 128 bytes; rank 0 calls, others receive */
 int ppx_comm_init(ppx_ctx *ctx, const void *id128, int nranks, int rank);
+/* The same without a launcher-side broadcast, for the SPMD command lines (the reference's mains call MPI_Init and
+ * build World(argc, argv), test_ALS.cxx:58-60,200): rank 0 creates the id and hands it to the other nranks-1 processes
+ * over TCP on addr:port (it listens, they connect, retrying for up to timeout_s seconds), then every rank calls
+ * ppx_comm_init.  One node or several; nothing else ever goes over that socket. */
+int ppx_comm_bootstrap(ppx_ctx *ctx, int nranks, int rank, const char *addr, int port, int timeout_s);
 int ppx_comm_size(ppx_ctx *ctx);
 int ppx_comm_rank(ppx_ctx *ctx);
 /* in-place sum over ranks of n buffers as ONE NCCL group (bufs/sizes: HOST arrays; no-op when nranks == 1). */

@@ -55,6 +55,8 @@ SIGNATURES = {
     "ppx_graph_launch": (C.c_int, [_vp, _vp]),
     "ppx_graph_destroy": (C.c_int, [_vp, _vp]),
     "ppx_fill_uniform": (C.c_int, [_vp, _dp, _i64, C.c_uint64, C.c_uint64, _i64, C.c_double, C.c_double]),
+    "ppx_fill_uniform_rows": (C.c_int, [_vp, _dp, _i64, _i64, _i64, _i64, C.c_uint64, C.c_uint64, C.c_double,
+                                        C.c_double]),
     "ppx_fill_laplacian": (C.c_int, [_vp, _dp, C.c_int, _i64]),
     "ppx_ttm_first": (C.c_int, [_vp, _dp, C.POINTER(_i64), C.c_int, C.c_int, _dp, _i64, C.c_int, _dp]),
     "ppx_ttm_multi": (C.c_int, [_vp, _dp, C.POINTER(_i64), C.c_int, C.c_int, C.c_int, C.POINTER(_dp), C.POINTER(_i64),
@@ -100,6 +102,7 @@ SIGNATURES = {
     "ppx_shard_range": (C.c_int, [_i64, C.c_int, C.c_int, C.POINTER(_i64), C.POINTER(_i64)]),
     "ppx_comm_unique_id": (C.c_int, [_vp]),
     "ppx_comm_init": (C.c_int, [_vp, _vp, C.c_int, C.c_int]),
+    "ppx_comm_bootstrap": (C.c_int, [_vp, C.c_int, C.c_int, C.c_char_p, C.c_int, C.c_int]),
     "ppx_comm_size": (C.c_int, [_vp]),
     "ppx_comm_rank": (C.c_int, [_vp]),
     "ppx_allreduce_packed": (C.c_int, [_vp, C.POINTER(_dp), C.POINTER(_i64), C.c_int]),
@@ -274,6 +277,10 @@ class Ctx:
 
     def normalize_g(self, Ws, sizes, R, Gs):
         self._ck(self.lib.ppx_normalize_g(self.h, _ptrs(Ws), _lens(sizes), len(Ws), R, _ptrs(Gs)))
+
+    def normalize_norms(self, Ws, dWs, sizes, R, Gs, sq_out):
+        self._ck(self.lib.ppx_normalize_norms(self.h, _ptrs(Ws), _ptrs(dWs) if dWs is not None else None, _lens(sizes),
+                                              len(Ws), R, _ptrs(Gs), _ptr(sq_out)))
 
     def sqnorms(self, Xs, out):
         self._ck(self.lib.ppx_sqnorms(self.h, _ptrs(Xs), _lens([x.numel() for x in Xs]), len(Xs), _ptr(out)))

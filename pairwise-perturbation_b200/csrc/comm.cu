@@ -5,8 +5,14 @@
 //
 // NCCL is loaded lazily with dlopen so that the single-GPU path has no link-time dependency on it (inside a
 // Python process that already imported torch this resolves to torch's bundled libnccl.so.2).
+#include <arpa/inet.h>
 #include <dlfcn.h>
+#include <errno.h>
+#include <netinet/in.h>
+#include <poll.h>
 #include <string.h>
+#include <sys/socket.h>
+#include <unistd.h>
 #include "ppx_internal.h"
 
 namespace {
@@ -86,6 +92,86 @@ int ppx_comm_init(ppx_ctx *ctx, const void *id128, int nranks, int rank) {
     return ppx_set_err(ctx, PPX_ENCCL, "ncclCommInitRank failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
   ctx->comm = comm;
   return PPX_OK;
+}
+
+int ppx_comm_bootstrap(ppx_ctx *ctx, int nranks, int rank, const char *addr, int port, int timeout_s) {
+  PPX_REQUIRE(ctx, nranks >= 1 && rank >= 0 && rank < nranks, "0 <= rank < nranks");
+  if (nranks == 1) return ppx_comm_init(ctx, nullptr, 1, 0);
+  PPX_REQUIRE(ctx, addr && port > 0 && port < 65536, "addr != NULL, 0 < port < 65536");
+  if (timeout_s <= 0) timeout_s = 120;
+  unsigned char id[128];
+  struct sockaddr_in sa;
+  memset(&sa, 0, sizeof(sa));
+  sa.sin_family = AF_INET;
+  sa.sin_port = htons((uint16_t)port);
+  auto send_all = [](int fd, const void *buf, size_t n) {
+    const char *p = (const char *)buf;
+    while (n) {
+      ssize_t k = send(fd, p, n, MSG_NOSIGNAL);
+      if (k <= 0) return false;
+      p += k;
+      n -= (size_t)k;
+    }
+    return true;
+  };
+  auto recv_all = [](int fd, void *buf, size_t n) {
+    char *p = (char *)buf;
+    while (n) {
+      ssize_t k = recv(fd, p, n, 0);
+      if (k <= 0) return false;
+      p += k;
+      n -= (size_t)k;
+    }
+    return true;
+  };
+  if (rank == 0) {
+    int rc = ppx_comm_unique_id(id);
+    if (rc) return ppx_set_err(ctx, PPX_ENCCL, "ncclGetUniqueId failed");
+    int ls = socket(AF_INET, SOCK_STREAM, 0);
+    if (ls < 0) return ppx_set_err(ctx, PPX_ENCCL, "bootstrap: socket(): %s", strerror(errno));
+    int one = 1;
+    setsockopt(ls, SOL_SOCKET, SO_REUSEADDR, &one, sizeof(one));
+    sa.sin_addr.s_addr = htonl(INADDR_ANY);
+    if (bind(ls, (struct sockaddr *)&sa, sizeof(sa)) != 0 || listen(ls, nranks) != 0) {
+      const int e = errno;
+      close(ls);
+      return ppx_set_err(ctx, PPX_ENCCL, "bootstrap: cannot listen on port %d: %s (set PPX_BOOT_PORT)", port, strerror(e));
+    }
+    for (int got = 0; got < nranks - 1; got++) {
+      struct pollfd pf = {ls, POLLIN, 0};
+      if (poll(&pf, 1, timeout_s * 1000) <= 0) {
+        close(ls);
+        return ppx_set_err(ctx, PPX_ENCCL, "bootstrap: only %d of %d peers connected within %d s", got, nranks - 1, timeout_s);
+      }
+      int fd = accept(ls, nullptr, nullptr);
+      if (fd < 0) {
+        got--;
+        continue;
+      }
+      int peer = -1;
+      const bool ok = recv_all(fd, &peer, sizeof(peer)) && peer > 0 && peer < nranks && send_all(fd, id, sizeof(id));
+      close(fd);
+      if (!ok) {
+        close(ls);
+        return ppx_set_err(ctx, PPX_ENCCL, "bootstrap: exchange with a peer failed");
+      }
+    }
+    close(ls);
+  } else {
+    if (inet_pton(AF_INET, strcmp(addr, "localhost") == 0 ? "127.0.0.1" : addr, &sa.sin_addr) != 1)
+      return ppx_set_err(ctx, PPX_ENCCL, "bootstrap: '%s' is not an IPv4 address", addr);
+    bool ok = false;
+    for (int attempt = 0; attempt < timeout_s * 20 && !ok; attempt++) {
+      int fd = socket(AF_INET, SOCK_STREAM, 0);
+      if (fd < 0) break;
+      if (connect(fd, (struct sockaddr *)&sa, sizeof(sa)) == 0)
+        ok = send_all(fd, &rank, sizeof(rank)) && recv_all(fd, id, sizeof(id));
+      close(fd);
+      if (!ok) usleep(50000);
+    }
+    if (!ok) return ppx_set_err(ctx, PPX_ENCCL, "bootstrap: rank %d could not reach rank 0 at %s:%d", rank, addr, port);
+  }
+  return ppx_comm_init(ctx, id, nranks, rank);
 }
 
 int ppx_comm_size(ppx_ctx *ctx) { return ctx->nranks; }

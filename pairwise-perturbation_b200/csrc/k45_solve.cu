@@ -475,9 +475,10 @@ __global__ void __launch_bounds__(256) norm_scale_kernel(NormArgs a, const doubl
   }
 }
 
-// Normalize from the cached Grams + the squared norms the PP switching test needs, one launch, one block per mode:
-// ||W_j||^2 = trace(G_j) for all j (recomputed by every block), W_i and G_i rescaled, sq[2i] = ||dW_i||^2,
-// sq[2i+1] = ||W_i||^2 after the rescale.
+// Normalize from the cached Grams + the squared norms the PP switching test needs, one block per mode:
+// ||W_j||^2 = trace(G_j) for all j comes in through `tr` (filled by norm_sq_from_gram_kernel in a launch of its own:
+// block m rescales G_m in place, so reading the other Grams here would race with the blocks that own them), W_m and
+// G_m are rescaled, sq[2m] = ||dW_m||^2, sq[2m+1] = ||W_m||^2 after the rescale.
 struct NormNormsArgs {
   double *w[16];
   double *g[16];
@@ -486,18 +487,10 @@ struct NormNormsArgs {
   int N;
   int R;
 };
-__global__ void __launch_bounds__(1024) normalize_norms_kernel(NormNormsArgs a, double *__restrict__ sq_out) {
+__global__ void __launch_bounds__(1024) normalize_norms_kernel(NormNormsArgs a, const double *__restrict__ tr,
+                                                               double *__restrict__ sq_out) {
   __shared__ double red[32];
-  __shared__ double tr[16];
   const int m = blockIdx.x;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (warp < a.N) {
-    double s = 0.0;
-    for (int k = lane; k < a.R; k += 32) s += a.g[warp][k + (int64_t)a.R * k];
-    s = ppx_warp_sum(s);
-    if (lane == 0) tr[warp] = s;
-  }
-  __syncthreads();
   double prod = 1.0;
   for (int j = 0; j < a.N; j++) prod *= sqrt(tr[j]);
   const double f = pow(prod, 1.0 / a.N) / sqrt(tr[m]);
@@ -745,7 +738,16 @@ int ppx_normalize_norms(ppx_ctx *ctx, double *const *W, const double *const *dW,
     a.dw[i] = dW ? dW[i] : nullptr;
     a.n[i] = s[i] * R;
   }
-  normalize_norms_kernel<<<N, 1024, 0, ctx->stream>>>(a, sq_out_dev);
+  NormArgs t;
+  t.N = N;
+  t.R = R;
+  for (int i = 0; i < N; i++) t.g[i] = G[i];
+  ppx_ws_reset(ctx);
+  double *tr = (double *)ppx_ws_alloc(ctx, sizeof(double) * 16);
+  if (!tr) return ppx_set_err(ctx, PPX_ENOMEM, "workspace too small");
+  norm_sq_from_gram_kernel<<<N, 32, 0, ctx->stream>>>(t, tr);
+  PPX_CHECK_LAUNCH(ctx);
+  normalize_norms_kernel<<<N, 1024, 0, ctx->stream>>>(a, tr, sq_out_dev);
   PPX_CHECK_LAUNCH(ctx);
   return PPX_OK;
 }

@@ -249,6 +249,24 @@ __global__ void fill_uniform_kernel(double *out, int64_t n, uint64_t base, int64
   }
 }
 
+// rows [row_begin, row_begin + L_local) of every column of a (L_global x n_cols) first-index-fastest array: the local
+// slab of a tensor whose leading mode is sharded, drawn from the same global counter
+__global__ void fill_uniform_rows_kernel(double *out, int64_t L_local, int64_t L_global, int64_t row_begin,
+                                         int64_t n_cols, uint64_t base, double lo, double span) {
+  const int64_t n = L_local * n_cols;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    const int64_t c = i / L_local, r = i - c * L_local;
+    uint64_t z = (uint64_t)(row_begin + r + L_global * c) + base;
+    z += 0x9E3779B97F4A7C15ULL;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    z ^= z >> 31;
+    out[i] = lo + span * ((double)(z >> 11) * (1.0 / 9007199254740992.0));
+  }
+}
+
 // ---- small elementwise / reduction kernels --------------------------------------------------------------------
 struct SqnormArgs {
   const double *x[16];
@@ -362,6 +380,20 @@ int ppx_fill_uniform(ppx_ctx *ctx, double *out, int64_t n, uint64_t seed, uint64
   int blocks = (int)((n + 255) / 256);
   if (blocks > ctx->sm_count * 16) blocks = ctx->sm_count * 16;
   fill_uniform_kernel<<<blocks, 256, 0, ctx->stream>>>(out, n, base, start, lo, hi - lo);
+  PPX_CHECK_LAUNCH(ctx);
+  return PPX_OK;
+}
+
+int ppx_fill_uniform_rows(ppx_ctx *ctx, double *out, int64_t L_local, int64_t L_global, int64_t row_begin,
+                          int64_t n_cols, uint64_t seed, uint64_t tensor_id, double lo, double hi) {
+  PPX_REQUIRE(ctx, out && L_local >= 0 && n_cols >= 0 && row_begin >= 0 && row_begin + L_local <= L_global,
+              "out != NULL, 0 <= row_begin, row_begin + L_local <= L_global");
+  const int64_t n = L_local * n_cols;
+  if (n == 0) return PPX_OK;
+  uint64_t base = seed * 0x9E3779B97F4A7C15ULL + tensor_id * 0xD1B54A32D192ED03ULL;
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > ctx->sm_count * 16) blocks = ctx->sm_count * 16;
+  fill_uniform_rows_kernel<<<blocks, 256, 0, ctx->stream>>>(out, L_local, L_global, row_begin, n_cols, base, lo, hi - lo);
   PPX_CHECK_LAUNCH(ctx);
   return PPX_OK;
 }

@@ -200,6 +200,9 @@ struct DtSweepGraph {
         if (g) ppx_graph_destroy(dw.ctx, g);
       }
       disabled = true;  // nothing was executed: run this sweep, and all later ones, eagerly
+      if (dw.rank == 0)
+        fprintf(stderr, "ppx: the exact sweep could not be captured as a CUDA graph (%s); running it kernel by kernel\n",
+                ok ? ppx_last_error(dw.ctx) : "an allocation missed the pool or the capture could not start");
     }
     sweep();
     eager_done++;
@@ -518,7 +521,16 @@ struct PPPhase {
     // every approximate sweep of the phase -- including the first, the one pp_bench times -- is one graph launch.
     if (dw.use_graph && dw.np == 1 && !graph) {
       PPXCK(dw, ppx_graph_begin(dw.ctx));
-      enqueue_sweep();
+      try {
+        enqueue_sweep();
+      } catch (...) {
+        // leave the context usable: back on the main stream, capture ended, nothing instantiated
+        ppx_side_end(dw.ctx);
+        void *g = nullptr;
+        ppx_graph_end(dw.ctx, &g);
+        if (g) ppx_graph_destroy(dw.ctx, g);
+        throw;
+      }
       PPXCK(dw, ppx_graph_end(dw.ctx, &graph));
     }
   }

@@ -69,7 +69,7 @@ void factor_from_unfolding(Tensor<> &Y, int i, int r, Matrix<> &Wi, World &dw, b
   Matrix<> MTM = unroll_tensor_contraction(Y, i);
   Matrix<> U(Y.lens[i], r, dw);
   // warm start from the eigenvectors this mode had one sweep earlier (same result, fewer Jacobi sweeps)
-  World::EigBasis &eb = dw.eig_basis_for(i, Y.lens[i]);
+  World::EigBasis &eb = dw.eig_basis_for(i, Y.lens[i], r);
   PPXCK(dw, ppx_sym_eig_topk_warm(dw.ctx, MTM.data, Y.lens[i], r, U.data, nullptr, eb.data, eb.valid ? 1 : 0));
   eb.valid = true;
   Wi = std::move(U);
@@ -136,10 +136,10 @@ void log_row_t(Tensor<> &V, int iter, double diffnorm, double tol, int pp_update
   if (trace_sink()) trace_sink()->rows.push_back({(double)iter, diffnorm, pp_update, diffV, dtime});
   if (dw.rank != 0) return;
   if (!trace_quiet())
-    cout << "  [dim]=  " << V.lens[0] << "  [iter]=  " << iter << "  [diffnorm]  " << diffnorm << "  [tol]  " << tol
+    cout << "  [dim]=  " << (dw.np > 1 && dw.shard_mode == 0 ? dw.shard_global : V.lens[0]) << "  [iter]=  " << iter << "  [diffnorm]  " << diffnorm << "  [tol]  " << tol
          << "  [pp_update]  " << pp_update << "  [diffV]  " << diffV << "  [dtime]  " << dtime << "\n";
   if (Plot_File.is_open()) {
-    Plot_File << V.lens[0] << "," << iter << "," << diffnorm << "," << tol << "," << pp_update << "," << diffV << ","
+    Plot_File << (dw.np > 1 && dw.shard_mode == 0 ? dw.shard_global : V.lens[0]) << "," << iter << "," << diffnorm << "," << tol << "," << pp_update << "," << diffV << ","
               << dtime << "\n";
     if (iter % 100 == 0 && iter != 0) Plot_File << endl;
   }
@@ -186,7 +186,7 @@ void hosvd_sharded(Tensor<> &T, Matrix<> *factor_matrices, int *ranks, World &dw
     Matrix<> U(MTM.nrow, ranks[i], dw);
     // HOSVD is an initialisation: always a cold solve (whatever an earlier decomposition left in this World is
     // unrelated); the basis it leaves warm-starts the first HOOI sweep
-    World::EigBasis &eb = dw.eig_basis_for(i, MTM.nrow);
+    World::EigBasis &eb = dw.eig_basis_for(i, MTM.nrow, ranks[i]);
     PPXCK(dw, ppx_sym_eig_topk_warm(dw.ctx, MTM.data, MTM.nrow, ranks[i], U.data, nullptr, eb.data, 0));
     eb.valid = true;
     factor_matrices[i] = std::move(U);
@@ -244,7 +244,7 @@ bool alsTucker(Tensor<> &V, Tensor<> &core, Matrix<> *W, double tol, double time
       diffnorm = std::fabs(core.norm2() - core_prev.norm2());
       if (trace_sink()) trace_sink()->rows.push_back({(double)iter, diffnorm, 0, -1.0, 0.0});
       if (dw.rank == 0 && !trace_quiet())
-        cout << "  [dim]=  " << V.lens[0] << "  [iter]=  " << iter << "  [diffnorm]  " << diffnorm << "  [tol]  "
+        cout << "  [dim]=  " << (dw.np > 1 && dw.shard_mode == 0 ? dw.shard_global : V.lens[0]) << "  [iter]=  " << iter << "  [diffnorm]  " << diffnorm << "  [tol]  "
              << tol << "\n";
       if (diffnorm < tol || synced_time(dw) - st_time > timelimit) break;
       core_prev = core;

@@ -6,6 +6,7 @@
 #include "als_CP.h"
 #include "als_Tucker.h"
 #include "src/CP.h"
+#include "src/Tucker.h"
 #include "src/optimizer/cp_dt_optimizer.h"
 #include "src/optimizer/cp_msdt_optimizer.h"
 #include "src/optimizer/cp_dt_lr_optimizer.h"
@@ -353,6 +354,42 @@ int ppxh_alsTucker(void *V, void *core, void **W, int N, double tol, double time
     MatArray Wa(W, N);
     *stopped = alsTucker(*(Tensor<> *)V, *(Tensor<> *)core, Wa.ptr(), tol, timelimit, maxiter, *(World *)w);
   });
+}
+
+// ---- src/Tucker.h ------------------------------------------------------------------------------------------------
+void *ppxh_tucker_create(int order, const int *size, const int *ranks, void *w) {
+  Tucker<double> *t = nullptr;
+  if (guarded([&] {
+        std::vector<int> sz(size, size + order), rk(ranks, ranks + order);
+        t = new Tucker<double>(order, sz.data(), rk.data(), *(World *)w);
+      }))
+    return nullptr;
+  return t;
+}
+void ppxh_tucker_destroy(void *t) { delete (Tucker<double> *)t; }
+// V stays owned by the caller; the factor array is created here and adopted by the object
+int ppxh_tucker_init(void *t_, void *V) {
+  return guarded([&] {
+    Tucker<double> *t = (Tucker<double> *)t_;
+    Matrix<> *arr = new Matrix<>[t->order];
+    for (int i = 0; i < t->order; i++) arr[i] = Matrix<>(t->size[i], t->rank[i], *t->world);
+    t->Init((Tensor<> *)V, arr);
+  });
+}
+int ppxh_tucker_als(void *t, int pp, double tol, double tol_init, double timelimit, int maxiter, int resprint,
+                    const char *csv, int *stopped) {
+  return guarded([&] {
+    ofstream f;
+    if (csv && csv[0]) f.open(csv);
+    Tucker<double> *T = (Tucker<double> *)t;
+    *stopped = pp ? T->als_pp(tol, tol_init, timelimit, maxiter, resprint, f) : T->als(tol, timelimit, maxiter, resprint, f);
+  });
+}
+int ppxh_tucker_read_W(void *t, int i, double *host) {
+  return guarded([&] { ((Tucker<double> *)t)->W[i].read_all(host); });
+}
+int ppxh_tucker_read_core(void *t, double *host) {
+  return guarded([&] { ((Tucker<double> *)t)->core.read_all(host); });
 }
 
 }  // extern "C"

@@ -129,18 +129,36 @@ inline void print_options(const CliOptions &o, World &dw) {
   cout << "  solver=  " << o.solver << "  seed=  " << o.seed << "  graph=  " << o.graph << endl;
 }
 
-inline World *make_world(const CliOptions &o) {
-  int device = o.device;
-  if (device < 0) {
-    const char *lr = getenv("LOCAL_RANK");
-    device = lr ? atoi(lr) : 0;
-  }
-  World *dw = new World(device, (size_t)2 << 30);
+// One process per GPU, like the reference's mains under mpirun (test_ALS.cxx:58-60,200): rank, size and device come from
+// the launcher's environment and World(argc, argv) joins the NCCL communicator by itself.
+inline World *make_world(const CliOptions &o, int argc, char **argv) {
+  World *dw = new World(argc, argv, (size_t)2 << 30, o.device);
   dw->solver = (o.solver == "svd") ? PPX_SOLVE_SVD_PINV : PPX_SOLVE_CHOL;
   dw->use_graph = o.graph != 0;
   dw->fast_residual = o.fastres != 0;
   dw->seed = o.seed;
   return dw;
+}
+
+// rows [row_begin, row_end) of a full tensor whose leading mode is being sharded (generators that have no slab form)
+inline Tensor<> shard_leading(Tensor<> &full, World &dw) {
+  if (dw.np == 1) return std::move(full);
+  std::vector<int64_t> l(full.lens, full.lens + full.order);
+  const int64_t Lg = l[0], rows = dw.row_end - dw.row_begin;
+  l[0] = rows;
+  Tensor<> loc(full.order, l.data(), dw, false);
+  PPXCK(dw, ppx_memcpy2d_d2d(dw.ctx, loc.data, sizeof(double) * rows, full.data + dw.row_begin, sizeof(double) * Lg,
+                             sizeof(double) * rows, (size_t)(full.size / Lg)));
+  return loc;
+}
+
+// factor / gradient matrix of mode i filled like W[i].fill_random(0,1) of the reference (test_ALS.cxx:337-338); for the
+// sharded mode the local rows of the same global matrix
+inline Matrix<> seeded_factor(int64_t rows_local, int R, int mode, uint64_t seed, World &dw) {
+  Matrix<> m(rows_local, R, dw, false);
+  if (dw.np > 1 && mode == dw.shard_mode) m.fill_random_rows(0, 1, seed, (uint64_t)mode, dw.shard_global, dw.row_begin);
+  else m.fill_random(0, 1, seed, (uint64_t)mode);
+  return m;
 }
 
 // Builds the input tensor the way test_ALS.cxx:222-326 does: p / p2 (Poisson operator), c (constrained collinearity +
@@ -158,10 +176,27 @@ inline bool build_input_tensor(const CliOptions &o, Tensor<> &V, World &dw, bool
   } else {
     lens.assign(o.dim, o.s);
   }
-  const int dim = (int)lens.size();
   const char t0 = o.tensor[0];
   const bool second = o.tensor.size() > 1 && o.tensor[1] == '2';
   const bool first = o.tensor.size() > 1 && o.tensor[1] == '1';
+  if (t0 == 'o' && o.lens.empty()) {
+    // o1: coil-100 (3 x 128 x 128 x 7200), o2: time-lapse (33 x 1344 x 1024 x 9)  (test_ALS.cxx:294-297, :313-316)
+    const int64_t l1[4] = {3, 128, 128, 7200}, l2[4] = {33, 1344, 1024, 9};
+    lens.assign(second ? l2 : l1, (second ? l2 : l1) + 4);
+  }
+  const int dim = (int)lens.size();
+  // several GPUs: the tensor is sharded along its leading mode; every generator below produces this rank's
+  // rows of the same global tensor a single process would build
+  auto shard = [&](int64_t global_leading) {
+    if (dw.np == 1) return true;
+    if (global_leading < dw.np) {
+      if (dw.rank == 0) fprintf(stderr, "the leading mode (%lld) is shorter than the number of GPUs (%d)\n",
+                                (long long)global_leading, dw.np);
+      return false;
+    }
+    dw.set_shard(0, global_leading);
+    return true;
+  };
   if (t0 == 'p') {
     // p2: Poisson operator as an order-dim tensor; p: the same entries folded to dim/2 modes of size s*s
     // (test_ALS.cxx:222-244)
@@ -172,49 +207,51 @@ inline bool build_input_tensor(const CliOptions &o, Tensor<> &V, World &dw, bool
     Tensor<> V0;
     laplacian_tensor(V0, o.dim, o.s, o.issparse != 0, dw);
     if (second) {
-      V = std::move(V0);
+      if (!shard(o.s)) return false;
+      V = shard_leading(V0, dw);
     } else {
       std::vector<int64_t> l2(o.dim / 2, (int64_t)o.s * o.s);
-      V = Tensor<>(o.dim / 2, l2.data(), dw, false);
-      fold_unfold(V0, V);
+      Tensor<> Vf(o.dim / 2, l2.data(), dw, false);
+      fold_unfold(V0, Vf);
+      if (!shard((int64_t)o.s * o.s)) return false;
+      V = shard_leading(Vf, dw);
     }
     return true;
   }
+  if (!shard(lens[0])) return false;
+  std::vector<int64_t> lloc(lens);
+  if (dw.np > 1) lloc[0] = dw.row_end - dw.row_begin;
   if (t0 == 'c') {
     // c: rank-R tensor with constrained collinearity plus uniform noise scaled to ratio_noise * ||V|| (test_ALS.cxx:245-261)
     std::vector<int> li(lens.begin(), lens.end());
     V = Gen_collinearity(li.data(), dim, o.R, o.col_min, o.col_max, dw);
-    Tensor<> V_noise(dim, lens.data(), dw, false);
-    V_noise.fill_random(-1, 1, o.seed, 101);
-    const double noise_norm = V_noise.norm2(), V_norm = V.norm2();
+    Tensor<> V_noise(dim, lloc.data(), dw, false);
+    V_noise.fill_random_rows(-1, 1, o.seed, 101, lens[0], dw.np > 1 ? dw.row_begin : 0);
+    const double noise_norm = V_noise.norm2_sharded(), V_norm = V.norm2_sharded();
     PPXCK(dw, ppx_axpby(dw.ctx, o.ratio_noise * V_norm / noise_norm, V_noise.data, 1.0, V.data, V.size));
     return true;
   }
   if (t0 == 'r' && second) {
     // r2: random tensor, uniform in [0.5,1) (test_ALS.cxx:266-273); pp_bench uses [-1,1) (pp_bench.cxx:249)
-    V = Tensor<>(dim, lens.data(), dw);
-    if (bench_ranges) V.fill_random(-1, 1, o.seed, 100);
-    else V.fill_random(0.5, 1, o.seed, 100);
+    V = Tensor<>(dim, lloc.data(), dw, false);
+    V.fill_random_rows(bench_ranges ? -1 : 0.5, 1, o.seed, 100, lens[0], dw.np > 1 ? dw.row_begin : 0);
     return true;
   }
   if (t0 == 'r') {
     // r: tensor made by random matrices (test_ALS.cxx:274-286)
     std::vector<Matrix<>> Wt;
-    for (int i = 0; i < dim; i++) {
-      Wt.emplace_back(lens[i], o.R, dw);
-      Wt[i].fill_random(0, 1, o.seed, (uint64_t)i);
-    }
+    for (int i = 0; i < dim; i++) Wt.push_back(seeded_factor(lloc[i], o.R, i, o.seed, dw));
     build_V(V, Wt.data(), dim, dw);
     return true;
   }
   if (t0 == 'o') {
-    // o1: coil-100 (3 x 128 x 128 x 7200), o2: time-lapse (33 x 1344 x 1024 x 9); raw doubles, global order
-    int64_t l1[4] = {3, 128, 128, 7200}, l2[4] = {33, 1344, 1024, 9};
+    // raw little-endian doubles in global order (test_ALS.cxx:287-326); -lens overrides the extents for a file of
+    // another shape in the same format
     if (!first && !second) return false;
-    V = Tensor<>(4, first ? l1 : l2, dw);
+    V = Tensor<>(dim, lloc.data(), dw, false);
     std::string path = (o.tensorfile != "test") ? o.tensorfile : (first ? "coil-100.bin" : "time-lapse.bin");
     if (dw.rank == 0) cout << "Read the tensor from file " << path << " ...... " << endl;
-    V.read_dense_from_file(path.c_str());
+    V.read_dense_rows_from_file(path.c_str(), lens[0], dw.np > 1 ? dw.row_begin : 0);
     if (dw.rank == 0) cout << "Read dataset finished " << endl;
     return true;
   }

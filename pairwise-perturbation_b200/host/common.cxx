@@ -252,11 +252,15 @@ Tensor<> Gen_collinearity(int *lens, int dim, int R, double col_min, double col_
   vector<Matrix<>> W;
   vector<double> host;
   for (int j = 0; j < dim; j++) {
-    W.emplace_back((int64_t)lens[j], (int64_t)R, dw, false);
-    host.assign((size_t)lens[j] * R, 0.0);
+    // several GPUs: this rank's rows of the sharded mode (the vectors themselves are drawn identically everywhere)
+    const bool cut = dw.np > 1 && j == dw.shard_mode;
+    const int t0 = cut ? (int)dw.row_begin : 0, t1 = cut ? (int)dw.row_end : lens[j];
+    const int rows = t1 - t0;
+    W.emplace_back((int64_t)rows, (int64_t)R, dw, false);
+    host.assign((size_t)rows * R, 0.0);
     for (int i = 0; i < R; i++) {
       const double lambda_ = (j == 0) ? 0.2 + 0.6 / R * (i + 1) : 1.0;  // :409
-      for (int t = 0; t < lens[j]; t++) host[(size_t)t + (size_t)lens[j] * i] = lambda_ * vec[i][j][t];
+      for (int t = t0; t < t1; t++) host[(size_t)(t - t0) + (size_t)rows * i] = lambda_ * vec[i][j][t];
     }
     W[j].write_all(host.data());
   }
@@ -402,6 +406,8 @@ void gradient_CP(Tensor<> &V, Matrix<> *W, Matrix<> *grad_W, World &dw) {
     index[N - 1] = i;
     Matrix<> M(W[i].nrow, W[i].ncol, dw);
     KhatriRao_contract(M, V, W, index, lens_H, dw);
+    // a replicated mode's MTTKRP is a partial sum over the local slab of the sharded mode (as in alsCP's own sweep)
+    if (dw.np > 1 && i != dw.shard_mode) dw.allreduce(M.data, M.size);
     gc.hadamard(i, 0.0, S, dw);
     gradsubprob(M, S, W[i], grad_W[i]);
   }

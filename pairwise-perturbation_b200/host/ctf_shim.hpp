@@ -17,6 +17,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <stdexcept>
+#include <initializer_list>
 #include <map>
 #include <string>
 #include <utility>
@@ -56,11 +57,17 @@ public:
   double *scal_host = nullptr;  // pinned mirror
 
   explicit World(int device = 0, size_t workspace_bytes = (size_t)1 << 30) { init(device, workspace_bytes); }
-  World(int argc, char **argv) {
+  // The SPMD constructor of the reference's mains (test_ALS.cxx:58-60,200: MPI_Init + World dw(argc, argv)): one
+  // process per GPU, rank / size / device from the launcher's environment (torchrun --no-python, mpirun or srun all
+  // work: RANK | OMPI_COMM_WORLD_RANK | PMI_RANK | SLURM_PROCID, WORLD_SIZE | ..., LOCAL_RANK | ...), the NCCL
+  // communicator bootstrapped by the library itself over MASTER_ADDR : PPX_BOOT_PORT (default MASTER_PORT + 1; the
+  // launcher's own store listens on MASTER_PORT).
+  World(int argc, char **argv, size_t workspace_bytes = (size_t)1 << 30, int device = -1) {
     (void)argc;
     (void)argv;
-    const char *d = getenv("LOCAL_RANK");
-    init(d ? atoi(d) : 0, (size_t)1 << 30);
+    if (device < 0) device = env_int({"LOCAL_RANK", "OMPI_COMM_WORLD_LOCAL_RANK", "MPI_LOCALRANKID", "SLURM_LOCALID"}, 0);
+    init(device, workspace_bytes);
+    connect_from_env();
   }
   World(const World &) = delete;
   World &operator=(const World &) = delete;
@@ -137,9 +144,12 @@ public:
   struct EigBasis {
     double *data = nullptr;
     int64_t n = 0;
+    int r = -1;  // the rank the stored state was computed for: which solver wrote it is a function of (n, r)
     bool valid = false;
   };
-  EigBasis &eig_basis_for(int mode, int64_t n) {
+  // The stored state is only meaningful to the solver that wrote it (an n x (r+24) block + tag for the subspace
+  // iteration, an n x n orthogonal matrix for Jacobi), so a request with another n or r starts cold.
+  EigBasis &eig_basis_for(int mode, int64_t n, int r) {
     EigBasis &b = eig_basis[mode];
     if (b.n != n) {
       if (b.data) dev_free(b.data, b.n * b.n);
@@ -147,7 +157,31 @@ public:
       b.n = n;
       b.valid = false;
     }
+    if (b.r != r) b.valid = false;
+    b.r = r;
     return b;
+  }
+  static int env_int(std::initializer_list<const char *> names, int dflt) {
+    for (const char *n : names)
+      if (const char *v = getenv(n)) return atoi(v);
+    return dflt;
+  }
+  // joins the NCCL communicator the launcher's environment describes; a single process stays a one-rank world
+  void connect_from_env() {
+    const int nranks = env_int({"WORLD_SIZE", "OMPI_COMM_WORLD_SIZE", "PMI_SIZE", "SLURM_NTASKS"}, 1);
+    const int r = env_int({"RANK", "OMPI_COMM_WORLD_RANK", "PMI_RANK", "SLURM_PROCID"}, 0);
+    if (nranks <= 1) return;
+    const char *addr = getenv("MASTER_ADDR");
+    const int port = env_int({"PPX_BOOT_PORT"}, env_int({"MASTER_PORT"}, 29500) + 1);
+    PPXCK(*this, ppx_comm_bootstrap(ctx, nranks, r, addr ? addr : "127.0.0.1", port, 120));
+    np = nranks;
+    rank = r;
+  }
+  // rows [row_begin, row_end) of mode `mode` (global extent `global`) live on this rank
+  void set_shard(int mode, int64_t global) {
+    shard_mode = mode;
+    shard_global = global;
+    PPXCK(*this, ppx_shard_range(global, np, rank, &row_begin, &row_end));
   }
   // sum over ranks (no-op on one GPU)
   void allreduce(double *dev, int64_t n) {
@@ -227,6 +261,24 @@ public:
   void fill_random(double lo, double hi, uint64_t seed, uint64_t id) {
     PPXCK(*wrld, ppx_fill_uniform(wrld->ctx, data, size, seed, id, 0, lo, hi));
   }
+  // this tensor holds rows [row_begin, row_begin + lens[0]) of a leading mode of global extent L_global: the values the
+  // whole tensor would get from fill_random(lo, hi, seed, id)
+  void fill_random_rows(double lo, double hi, uint64_t seed, uint64_t id, int64_t L_global, int64_t row_begin) {
+    PPXCK(*wrld, ppx_fill_uniform_rows(wrld->ctx, data, lens[0], L_global, row_begin, lens[0] ? size / lens[0] : 0, seed,
+                                       id, lo, hi));
+  }
+  // Frobenius norm of a tensor whose leading mode is sharded over the ranks of its World (norm2() of the local slab
+  // otherwise): what CTF's norm2 returns for the distributed tensor
+  double norm2_sharded() const {
+    if (wrld->np == 1) return norm2();
+    const double *xs[1] = {data};
+    int64_t ns[1] = {size};
+    PPXCK(*wrld, ppx_sqnorms(wrld->ctx, xs, ns, 1, wrld->scal_dev));
+    wrld->allreduce(wrld->scal_dev, 1);
+    double v;
+    wrld->fetch(wrld->scal_dev, &v, 1);
+    return sqrt_(v);
+  }
   void set_zero() {
     if (size) PPXCK(*wrld, ppx_memset_zero(wrld->ctx, data, sizeof(double) * size));
   }
@@ -255,6 +307,27 @@ public:
     }
     fclose(f);
     if (done != size) throw std::runtime_error(std::string("short read from ") + path);
+  }
+  // The same file when this tensor holds only rows [row_begin, row_begin + lens[0]) of a leading mode of global
+  // extent L_global (one process per GPU, every rank streams the file and keeps its rows)
+  void read_dense_rows_from_file(const char *path, int64_t L_global, int64_t row_begin) {
+    if (L_global == lens[0] && row_begin == 0) return read_dense_from_file(path);
+    FILE *f = fopen(path, "rb");
+    if (!f) throw std::runtime_error(std::string("cannot open ") + path);
+    const int64_t L = lens[0], ncols = L ? size / L : 0;
+    const int64_t cols_per = std::max<int64_t>(1, ((int64_t)1 << 22) / std::max<int64_t>(L_global, 1));
+    std::vector<double> in((size_t)(cols_per * L_global)), keep((size_t)(cols_per * std::max<int64_t>(L, 1)));
+    for (int64_t c0 = 0; c0 < ncols; c0 += cols_per) {
+      const int64_t nc = std::min(cols_per, ncols - c0);
+      if (fread(in.data(), sizeof(double), (size_t)(nc * L_global), f) != (size_t)(nc * L_global)) {
+        fclose(f);
+        throw std::runtime_error(std::string("short read from ") + path);
+      }
+      for (int64_t c = 0; c < nc; c++) memcpy(&keep[(size_t)(c * L)], &in[(size_t)(c * L_global + row_begin)], sizeof(double) * L);
+      PPXCK(*wrld, ppx_memcpy_h2d(wrld->ctx, data + c0 * L, keep.data(), sizeof(double) * nc * L));
+      wrld->sync();
+    }
+    fclose(f);
   }
   void write_dense_to_file(const char *path) const {
     FILE *f = fopen(path, "wb");

@@ -9,7 +9,7 @@ int main(int argc, char **argv) {
   const double start_time = wall_time();
   World *dwp;
   try {
-    dwp = make_world(o);
+    dwp = make_world(o, argc, argv);
   } catch (const std::exception &e) {
     fprintf(stderr, "pp_bench: %s\n", e.what());
     return 2;
@@ -23,19 +23,26 @@ int main(int argc, char **argv) {
       delete dwp;
       return 3;
     }
-    const double Vnorm = V.norm2();
-    ofstream Plot_File(o.filename);
+    const double Vnorm = V.norm2_sharded();
+    ofstream Plot_File;
+    if (dw.rank == 0) Plot_File.open(o.filename);
     const int N = V.order;
     Matrix<> *W = new Matrix<>[N], *W_DT = new Matrix<>[N], *W_PP = new Matrix<>[N], *grad_W = new Matrix<>[N];
     Matrix<> *F = new Matrix<>[N];
     for (int i = 0; i < N; i++) {  // pp_bench.cxx:270-287
-      W[i] = Matrix<>(V.lens[i], o.R, dw);
-      W[i].fill_random(0, 1, o.seed + 1, (uint64_t)i);
+      if (o.model[0] == 'C') {
+        W[i] = seeded_factor(V.lens[i], o.R, i, o.seed + 1, dw);
+        grad_W[i] = seeded_factor(V.lens[i], o.R, i, o.seed + 2, dw);
+      } else {  // Tucker factors are replicated in full on every rank (multi-GPU)
+        const int64_t rows = (dw.np > 1 && i == dw.shard_mode) ? dw.shard_global : V.lens[i];
+        W[i] = Matrix<>(rows, o.R, dw, false);
+        W[i].fill_random(0, 1, o.seed + 1, (uint64_t)i);
+        grad_W[i] = Matrix<>(rows, o.R, dw, false);
+        grad_W[i].fill_random(0, 1, o.seed + 2, (uint64_t)i);
+      }
       W_DT[i] = W[i];
       W_PP[i] = W[i];
-      grad_W[i] = Matrix<>(V.lens[i], o.R, dw);
-      grad_W[i].fill_random(0, 1, o.seed + 2, (uint64_t)i);
-      F[i] = Matrix<>(V.lens[i], o.R, dw);
+      F[i] = Matrix<>(W[i].nrow, o.R, dw);
     }
     if (dw.rank == 0) Plot_File << "[timetype],[dtime]" << "\n";
     if (o.model[0] == 'C') {

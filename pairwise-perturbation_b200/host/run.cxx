@@ -28,7 +28,7 @@ int main(int argc, char **argv) {
   const double start_time = wall_time();
   World *dwp;
   try {
-    dwp = make_world(o);
+    dwp = make_world(o, argc, argv);
   } catch (const std::exception &e) {
     fprintf(stderr, "run: %s\n", e.what());
     return 2;
@@ -36,6 +36,7 @@ int main(int argc, char **argv) {
   World &dw = *dwp;
   int rc = 0;
   try {
+    if (dw.np > 1) throw std::runtime_error("run (the class-based optimizers of src/optimizer) is single-GPU; use test_ALS / pp_bench under a multi-process launcher");
     print_options(o, dw);
     Tensor<> *V = new Tensor<>();  // adopted by the decomposition and never freed, as in the reference
     if (!build_input_tensor(o, *V, dw, false)) {

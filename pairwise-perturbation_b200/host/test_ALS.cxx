@@ -8,7 +8,7 @@ int main(int argc, char **argv) {
   const double start_time = wall_time();
   World *dwp;
   try {
-    dwp = make_world(o);
+    dwp = make_world(o, argc, argv);
   } catch (const std::exception &e) {
     fprintf(stderr, "test_ALS: %s\n", e.what());
     return 2;
@@ -22,18 +22,17 @@ int main(int argc, char **argv) {
       delete dwp;
       return 3;
     }
-    const double Vnorm = V.norm2();
+    const double Vnorm = V.norm2_sharded();
     if (dw.rank == 0) cout << "Vnorm= " << Vnorm << endl;
-    ofstream Plot_File(o.filename);
+    ofstream Plot_File;
+    if (dw.rank == 0) Plot_File.open(o.filename);  // only rank 0 writes (als_CP.cxx:132,192)
     const int N = V.order;
     Matrix<> *W = new Matrix<>[N];
     Matrix<> *grad_W = new Matrix<>[N];
     Matrix<> *F = new Matrix<>[N];
     for (int i = 0; i < N; i++) {  // test_ALS.cxx:332-345
-      W[i] = Matrix<>(V.lens[i], o.R, dw);
-      grad_W[i] = Matrix<>(V.lens[i], o.R, dw);
-      W[i].fill_random(0, 1, o.seed + 1, (uint64_t)i);
-      grad_W[i].fill_random(0, 1, o.seed + 2, (uint64_t)i);
+      W[i] = seeded_factor(V.lens[i], o.R, i, o.seed + 1, dw);
+      grad_W[i] = seeded_factor(V.lens[i], o.R, i, o.seed + 2, dw);
       F[i] = Matrix<>(V.lens[i], o.R, dw);
     }
     if (o.model[0] == 'C') {

@@ -24,7 +24,7 @@ def load_host_library():
     lib = C.CDLL(HOST_LIB_PATH, mode=C.RTLD_GLOBAL)
     lib.ppxh_last_error.restype = C.c_char_p
     for name in ("ppxh_world_create", "ppxh_world_ctx", "ppxh_tensor_create", "ppxh_matrix_create", "ppxh_tensor_data",
-                 "ppxh_cpd_create", "ppxh_cpd_create_lr"):
+                 "ppxh_cpd_create", "ppxh_cpd_create_lr", "ppxh_tucker_create"):
         getattr(lib, name).restype = _vp
     lib.ppxh_world_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_size_t]
     lib.ppxh_world_destroy.argtypes = [_vp]
@@ -79,6 +79,12 @@ def load_host_library():
     lib.ppxh_alsTucker_DT.argtypes = [_vp, _vp, PV, C.c_int, d, d, C.c_int, C.c_char_p, C.c_int, C.c_int, _vp, PI]
     lib.ppxh_alsTucker_PP.argtypes = [_vp, _vp, PV, C.c_int, d, d, d, C.c_int, C.c_char_p, C.c_int, C.c_int, _vp, PI]
     lib.ppxh_alsTucker.argtypes = [_vp, _vp, PV, C.c_int, d, d, C.c_int, _vp, PI]
+    lib.ppxh_tucker_create.argtypes = [C.c_int, PI, PI, _vp]
+    lib.ppxh_tucker_destroy.argtypes = [_vp]
+    lib.ppxh_tucker_init.argtypes = [_vp, _vp]
+    lib.ppxh_tucker_als.argtypes = [_vp, C.c_int, d, d, d, C.c_int, C.c_int, C.c_char_p, PI]
+    lib.ppxh_tucker_read_W.argtypes = [_vp, C.c_int, _vp]
+    lib.ppxh_tucker_read_core.argtypes = [_vp, _vp]
     _hlib = lib
     return lib
 
@@ -337,3 +343,39 @@ def alsTucker(world, V, core, W, tol, maxiter, timelimit=5e3):
     st = C.c_int(0)
     _ck(world.lib.ppxh_alsTucker(V.h, core.h, _harr(W), len(W), tol, timelimit, maxiter, world.h, C.byref(st)))
     return bool(st.value)
+
+
+class Tucker:
+    """Tucker<double> (src/Tucker.h): HOSVD initialisation at Init, then als (alsTucker_DT) or als_pp (alsTucker_PP)."""
+
+    def __init__(self, world, sizes, ranks):
+        self.world, self.lib = world, world.lib
+        self.sizes, self.ranks = list(sizes), list(ranks)
+        n = len(self.sizes)
+        self.h = self.lib.ppxh_tucker_create(n, (C.c_int * n)(*self.sizes), (C.c_int * n)(*self.ranks), world.h)
+        if not self.h:
+            raise PpxError(self.lib.ppxh_last_error().decode())
+
+    def Init(self, V):
+        _ck(self.lib.ppxh_tucker_init(self.h, V.h))
+
+    def als(self, tol, maxiter, resprint=10, pp=False, tol_init=1e-2, csv=None, timelimit=5e3):
+        st = C.c_int(0)
+        _ck(self.lib.ppxh_tucker_als(self.h, int(pp), tol, tol_init, timelimit, maxiter, resprint,
+                                     csv.encode() if csv else None, C.byref(st)))
+        return bool(st.value)
+
+    def W(self, i):
+        out = np.empty(self.sizes[i] * self.ranks[i])
+        _ck(self.lib.ppxh_tucker_read_W(self.h, i, out.ctypes.data_as(_vp)))
+        return out.reshape((self.sizes[i], self.ranks[i]), order="F")
+
+    def core(self):
+        out = np.empty(int(np.prod(self.ranks)))
+        _ck(self.lib.ppxh_tucker_read_core(self.h, out.ctypes.data_as(_vp)))
+        return out.reshape(tuple(self.ranks), order="F")
+
+    def free(self):
+        if self.h:
+            self.lib.ppxh_tucker_destroy(self.h)
+            self.h = None

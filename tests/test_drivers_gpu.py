@@ -285,6 +285,46 @@ def test_hosvd_and_alsTucker_DT(H, world, lens, R):
     free_all(Vd, Wd, cored)
 
 
+@pytest.mark.parametrize("lens,ranks,pp", [((12, 13, 14), (3, 3, 3), False), ((9, 10, 8, 7), (3, 4, 2, 3), False),
+                                           ((9, 10, 8, 7), (3, 3, 3, 3), True)])
+def test_tucker_class(H, world, lens, ranks, pp):
+    """Tucker<double> (host/src/Tucker.h; the reference's src/Tucker.h is a non-compiling draft, its Tucker path is the
+    sequence of test_ALS.cxx:360-397): Init = HOSVD, als = alsTucker_DT, als_pp = alsTucker_PP -- against the oracle's
+    hosvd + drivers: projectors of the factors, core norm, the logged rows and the switching iterations (all of them
+    invariant under the sign of the HOSVD columns)."""
+    N = len(lens)
+    V = o.make_tensor_r2(lens)
+    vnorm = np.linalg.norm(V)
+    core_ref, W_ref = o.hosvd(V, list(ranks))
+    Vd = H.Tensor.from_numpy(world, V)
+    T = H.Tucker(world, lens, ranks)
+    T.Init(Vd)
+    for i in range(N):
+        assert proj_err(T.W(i), W_ref[i]) < 1e-8
+    assert abs(np.linalg.norm(T.core()) - np.linalg.norm(core_ref)) < 1e-10 * vnorm
+    W2 = [w.copy() for w in W_ref]
+    if not pp:
+        ok_ref, rows_ref, _ = o.alsTucker_DT(V, core_ref, W2, 1e-10 * vnorm, 10, resprint=3)
+        with H.Trace() as t:
+            ok = T.als(1e-10 * vnorm, 10, resprint=3)
+        assert ok == ok_ref and len(t.rows) == len(rows_ref)
+        for rg, rr in zip(t.rows, rows_ref):
+            assert int(rg[0]) == rr[0] and abs(rg[1] - rr[1]) <= 1e-9 * vnorm and abs(rg[3] - rr[2]) <= FIT_RTOL * vnorm
+    else:
+        ok_ref, rows_ref, ev_ref, _, _ = o.alsTucker_PP(V, core_ref, W2, 1e-10 * vnorm, 0.3, 24, resprint=4)
+        with H.Trace() as t:
+            ok = T.als(1e-10 * vnorm, 24, resprint=4, pp=True, tol_init=0.3)
+        assert ok == ok_ref and t.events == [(0 if k == "DT" else 1, it) for k, it in ev_ref]
+        assert len(t.rows) == len(rows_ref)
+        for rg, rr in zip(t.rows, rows_ref):
+            assert int(rg[0]) == rr[0] and int(rg[2]) == rr[2]
+            assert abs(rg[1] - rr[1]) <= 1e-9 * vnorm and abs(rg[3] - rr[3]) <= FIT_RTOL * vnorm
+    for i in range(N):
+        assert proj_err(T.W(i), W2[i]) < 1e-7
+    T.free()
+    Vd.free()
+
+
 @pytest.mark.parametrize("lens,R,tol_init", [((12, 13, 14), 3, 0.3), ((9, 10, 8, 7), 3, 0.3)])
 def test_alsTucker_PP(H, world, lens, R, tol_init):
     N = len(lens)
@@ -551,3 +591,100 @@ def test_cli_beside_the_reference_main(tmp_path, exe, extra):
     def labels(path):
         return [ln.split(",")[0].strip() for ln in open(path) if ln.strip() and ln.split(",")[0].strip().startswith("[")]
     assert labels(os.path.join(str(tmp_path), "ours.csv")) == labels(os.path.join(str(tmp_path), "ref.csv"))
+
+
+# ---- the SPMD command lines on several GPUs (the reference's mains run under mpirun: test_ALS.cxx:58-60,200,413) ---------
+def _free_port():
+    import socket
+
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        return sk.getsockname()[1]
+
+
+def _n_gpus():
+    import torch
+
+    return torch.cuda.device_count() if torch.cuda.is_available() else 0
+
+
+def _spmd(exe, args, nproc, timeout=600):
+    """torchrun --no-python: one process per GPU; the C++ main reads RANK / WORLD_SIZE / LOCAL_RANK / MASTER_* itself and
+    World(argc, argv) bootstraps the NCCL communicator (no Python in the worker processes)."""
+    import sys
+
+    env = dict(os.environ, PPX_BOOT_PORT=str(_free_port()))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--no-python", "--nnodes=1", "--nproc-per-node", str(nproc),
+           "--master-addr", "127.0.0.1", "--master-port", str(_free_port()), os.path.join(PKG, exe)] + args
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env)
+    assert res.returncode == 0, res.stderr[-3000:]
+    return res.stdout
+
+
+@pytest.mark.skipif(not rh.available(), reason="oracle/_ref not built")
+@pytest.mark.skipif(_n_gpus() < 2, reason="needs at least 2 GPUs")
+@pytest.mark.parametrize("exe,model,extra", [
+    ("test_ALS", "CP", ["-tensor", "r", "-pp", "1", "-maxiter", "40", "-pp_res_tol", "0.1", "-resprint", "5"]),
+    ("test_ALS", "CP", ["-tensor", "r", "-pp", "0", "-maxiter", "12", "-resprint", "3"]),
+    ("test_ALS", "CP", ["-tensor", "r", "-pp", "2", "-maxiter", "30", "-pp_res_tol", "0.1", "-resprint", "5"]),
+    ("pp_bench", "CP", ["-tensor", "r", "-maxiter", "2"]),
+    ("test_ALS", "Tucker", ["-tensor", "r2", "-pp", "0", "-maxiter", "8", "-resprint", "2"]),
+    ("test_ALS", "Tucker", ["-tensor", "r2", "-pp", "1", "-maxiter", "20", "-pp_res_tol", "0.3", "-resprint", "4"])])
+def test_cli_on_several_gpus_beside_the_reference_main(tmp_path, exe, model, extra):
+    """The same command line on min(#GPUs, 4) GPUs (torchrun --no-python) and the reference's single-process main on the
+    stand-in: every rank generates its mode-0 slab of the same tensor, rank 0 prints; traces must agree as on one GPU."""
+    N, s, R = 4, 11, 3
+    nproc = min(_n_gpus(), 4)
+    args = ["-model", model, "-dim", str(N), "-size", str(s), "-rank", str(R)] + extra
+    if model == "CP":
+        fills = [(1, i) for i in range(N)] + [p for i in range(N) for p in ((2, i), (3, i))]
+    else:
+        fills = [(1, 100)] + [p for i in range(N) for p in ((2, i), (3, i))]
+    ref = rh.run_cli(exe, args + ["-filename", os.path.join(str(tmp_path), "ref.csv")], fills=fills)
+    ours = _spmd(exe, args + ["-filename", os.path.join(str(tmp_path), "ours.csv")], nproc)
+    rows_r, ev_r, fin_r = _stdout_numbers(ref["stdout"])
+    rows_o, ev_o, fin_o = _stdout_numbers(ours)
+    assert ev_o == ev_r
+    assert len(rows_o) == len(rows_r)
+    scale = max(abs(b[3]) for b in rows_r) if rows_r else 1.0
+    for a, b in zip(rows_o, rows_r):
+        assert a[0] == b[0] and a[2] == b[2]
+        assert abs(a[1] - b[1]) <= 1e-9 * max(abs(b[1]), 1.0) and abs(a[3] - b[3]) <= 1e-9 * max(abs(b[3]), scale, 1.0)
+    if exe == "pp_bench":  # the three timing labels, once per repetition, from rank 0 only
+        for label in ("[dimension tree step time]", "[PP first time]", "[PP second time]"):
+            assert ours.count(label) == ref["stdout"].count(label) == 2
+
+
+# ---- raw-double tensor files: -tensor o1 -tensorfile (test_ALS.cxx:287-326, read_dense_from_file) -----------------------
+@pytest.mark.parametrize("pp", [0, 1])
+def test_cli_reads_a_raw_tensor_file(tmp_path, pp):
+    """A tensor written as raw little-endian doubles in global (first-index-fastest) order -- the format of coil-100.bin
+    that read_dense_from_file consumes -- goes through `test_ALS -tensor o1 -tensorfile F -lens ...`; the trace must be
+    the oracle's on the same array and the same seeded factors."""
+    lens, R = (3, 16, 12, 40), 4
+    Wt = [o.fill_uniform((l, 6), 7, i) for i, l in enumerate(lens)]
+    V = 255.0 * o.build_V(Wt) / 40.0 + 0.05 * (o.fill_uniform(lens, 7, 50) - 0.5)
+    path = os.path.join(str(tmp_path), "tensor.bin")
+    np.asarray(V).ravel(order="F").tofile(path)
+    vnorm = float(np.linalg.norm(V))
+    W, G = o.init_factors(lens, R), o.init_grad(lens, R)
+    maxiter, tol_init, resprint = 24, 0.1, 4
+    if pp == 0:
+        _, tr = o.alsCP_DT(V, W, G, 1e-10 * vnorm, maxiter, resprint=resprint, F=[np.zeros_like(w) for w in W])
+    else:
+        _, tr = o.alsCP_PP(V, W, G, 1e-10 * vnorm, tol_init, maxiter, resprint=resprint)
+    out = subprocess.run([os.path.join(PKG, "test_ALS"), "-model", "CP", "-tensor", "o1", "-tensorfile", path, "-lens",
+                          ",".join(str(x) for x in lens), "-rank", str(R), "-pp", str(pp), "-maxiter", str(maxiter),
+                          "-pp_res_tol", str(tol_init), "-resprint", str(resprint), "-filename",
+                          os.path.join(str(tmp_path), "o.csv")], check=True, capture_output=True, text=True,
+                         timeout=300).stdout
+    assert "Read the tensor from file" in out and "Read dataset finished" in out
+    m = re.search(r"Vnorm= (\S+)", out)
+    assert m and abs(float(m.group(1)) - vnorm) <= 1e-10 * vnorm
+    rows, events, _ = _stdout_numbers(out)
+    if pp:
+        assert events == list(tr.events)
+    assert len(rows) == len(tr.rows)
+    for a, b in zip(rows, tr.rows):
+        assert a[0] == b[0] and a[2] == b[2]
+        assert abs(a[1] - b[1]) <= 1e-9 * max(abs(b[1]), 1e-6 * vnorm) and abs(a[3] - b[3]) <= 1e-9 * vnorm

@@ -228,6 +228,34 @@ def test_normalize(ctx):
         assert rel_err(ctx.to_host(Gs[i], (R, R)), ref[i].T @ ref[i]) < 1e-12
 
 
+@pytest.mark.parametrize("sizes", [[4096, 8, 8], [13, 40, 7, 300], [3, 128, 128, 7200]])
+def test_normalize_norms_ragged(ctx, sizes):
+    """Normalize + switching norms in one call (als_CP.cxx:657-664, :825; common.cxx:680-688) with very unequal factor
+    sizes, repeated: the block of a small factor finishes (and rescales its Gram) long before the block of a large one
+    starts -- every block must still see the traces of the UNSCALED Grams (round-1 advisor finding)."""
+    R = 6
+    W = [rnd((s, R), 190 + i) * (i + 1) for i, s in enumerate(sizes)]
+    D = [rnd((s, R), 290 + i) for i, s in enumerate(sizes)]
+    ref = [w.copy() for w in W]
+    o.normalize(ref)
+    for rep in range(20):
+        dW = [ctx.to_device(w) for w in W]
+        dD = [ctx.to_device(d) for d in D]
+        Gs = []
+        for w, s in zip(dW, sizes):
+            G = ctx.empty(R * R)
+            ctx.gram(w, s, R, G)
+            Gs.append(G)
+        sq = ctx.empty(2 * len(sizes))
+        ctx.normalize_norms(dW, dD, sizes, R, Gs, sq)
+        h = ctx.to_host(sq, (2 * len(sizes),))
+        for i, s in enumerate(sizes):
+            assert rel_err(ctx.to_host(dW[i], (s, R)), ref[i]) < 1e-13
+            assert rel_err(ctx.to_host(Gs[i], (R, R)), ref[i].T @ ref[i]) < 1e-12
+            assert abs(h[2 * i] - np.sum(D[i] ** 2)) <= 1e-12 * np.sum(D[i] ** 2)
+            assert abs(h[2 * i + 1] - np.sum(ref[i] ** 2)) <= 1e-12 * np.sum(ref[i] ** 2)
+
+
 def test_sqnorms_and_diff_update(ctx):
     a, b = rnd((1234,), 95), rnd((1234,), 96)
     out = ctx.empty(2)
