@@ -287,6 +287,22 @@ __global__ void __launch_bounds__(1024) sqnorms_kernel(SqnormArgs a, double *out
   if (threadIdx.x == 0) out[blockIdx.x] = s;
 }
 
+// tensor-sized arrays: many blocks write partial sums (fixed grid, fixed order -> deterministic), sum_stage2 adds them
+__global__ void __launch_bounds__(256) sq_stage1(const double *__restrict__ x, int64_t n, double *partial) {
+  __shared__ double red[32];
+  double s0 = 0, s1 = 0;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i + stride < n; i += 2 * stride) {
+    const double a = x[i], b = x[i + stride];
+    s0 = fma(a, a, s0);
+    s1 = fma(b, b, s1);
+  }
+  if (i < n) s0 = fma(x[i], x[i], s0);
+  const double s = ppx_block_sum(s0 + s1, red);
+  if (threadIdx.x == 0) partial[blockIdx.x] = s;
+}
+
 // one block per pair of arrays: deterministic inner product
 struct DotArgs {
   const double *x[16];
@@ -418,8 +434,25 @@ int ppx_sqnorms(ppx_ctx *ctx, const double *const *X, const int64_t *n, int coun
     a.x[i] = X[i];
     a.n[i] = n[i];
   }
-  sqnorms_kernel<<<count, 1024, 0, ctx->stream>>>(a, out_dev);
-  PPX_CHECK_LAUNCH(ctx);
+  // factor-sized arrays: one block each, one launch.  An array of tensor size would run through a single SM (64.8 GB at
+  // BASELINE configs[1]: about a second), so those go through the grid-wide two-stage sum.
+  bool big = false;
+  for (int i = 0; i < count; i++) big = big || n[i] > ((int64_t)1 << 22);
+  if (!big) {
+    sqnorms_kernel<<<count, 1024, 0, ctx->stream>>>(a, out_dev);
+    PPX_CHECK_LAUNCH(ctx);
+    return PPX_OK;
+  }
+  ppx_ws_reset(ctx);
+  const int blocks = ctx->sm_count * 8;
+  double *partial = (double *)ppx_ws_alloc(ctx, sizeof(double) * blocks);
+  if (!partial) return ppx_set_err(ctx, PPX_ENOMEM, "workspace too small");
+  for (int i = 0; i < count; i++) {
+    sq_stage1<<<blocks, 256, 0, ctx->stream>>>(X[i], n[i], partial);
+    PPX_CHECK_LAUNCH(ctx);
+    int rc = ppx_sum_partials(ctx, partial, blocks, out_dev + i);
+    if (rc) return rc;
+  }
   return PPX_OK;
 }
 

@@ -700,6 +700,18 @@ void alsCP_PP_phase_timed(Tensor<> &V, Matrix<> *W, Matrix<> *grad_W, int n_swee
   for (void *e : {e0, e1, e2, t0, t1}) ppx_event_destroy(dw.ctx, e);
 }
 
+void alsCP_DT_mttkrps(Tensor<> &V, Matrix<> *W, Matrix<> *M_out, World &dw) {
+  const int N = V.order;
+  map<string, string> parent, sibling;
+  Construct_Dimension_Tree(parent, sibling, 0, N - 1);
+  map<string, Tensor<>> mttkrp_map;
+  for (int i = 0; i < N; i++) M_out[i] = leaf_mttkrp(mttkrp_map, parent, sibling, V, W, i, dw);
+}
+
+void alsCP_PP_operators(Tensor<> &V, Matrix<> *W, map<string, Tensor<>> &ops, World &dw) {
+  build_pp_operators(ops, V, W, dw);
+}
+
 bool alsCP_PP(Tensor<> &V, Matrix<> *W, Matrix<> *grad_W, Matrix<> *F, double tol, double tol_init, double timelimit,
               int maxiter, double lambda, double ratio_step, ofstream &Plot_File, int resprint, bool bench,
               World &dw) {

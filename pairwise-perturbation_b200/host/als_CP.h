@@ -50,4 +50,11 @@ void alsCP_DT_sweeps(Tensor<> &V, Matrix<> *W, Matrix<> *grad_W, int n_sweeps, d
 void alsCP_PP_phase_timed(Tensor<> &V, Matrix<> *W, Matrix<> *grad_W, int n_sweeps, double lambda, double ratio_step,
                           World &dw, float *ms_build, float *ms_sweeps);
 
+// ---- probes for the full-size parity checks (tests/, bench.py parity_probe): what one tree pass / one operator build
+// produce at FIXED factors, through exactly the calls the sweeps make -------------------------------------------
+// M_out[i] = MTTKRP of mode i from the dimension tree (leaf_mttkrp of every mode, no update in between)
+void alsCP_DT_mttkrps(Tensor<> &V, Matrix<> *W, Matrix<> *M_out, World &dw);
+// all pair operators and singles of a PP phase built at W (build_pp_operators; key = contracted modes)
+void alsCP_PP_operators(Tensor<> &V, Matrix<> *W, map<string, Tensor<>> &ops, World &dw);
+
 #endif

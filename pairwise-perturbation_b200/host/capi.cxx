@@ -266,6 +266,40 @@ int ppxh_cp_pp_phase_timed(void *V, void **W, void **grad_W, int N, int n_sweeps
   });
 }
 
+// ---- probes at fixed factors (full-size parity checks) -----------------------------------------------------------
+int ppxh_cp_dt_mttkrps(void *V, void **W, void **M, int N, void *w) {
+  return guarded([&] {
+    MatArray Wa(W, N), Ma(M, N);
+    alsCP_DT_mttkrps(*(Tensor<> *)V, Wa.ptr(), Ma.ptr(), *(World *)w);
+  });
+}
+// builds every PP operator at W; returns a handle to the map (NULL on error)
+void *ppxh_cp_pp_ops_build(void *V, void **W, int N, void *w) {
+  map<string, Tensor<>> *ops = new map<string, Tensor<>>();
+  if (guarded([&] {
+        MatArray Wa(W, N);
+        alsCP_PP_operators(*(Tensor<> *)V, Wa.ptr(), *ops, *(World *)w);
+      })) {
+    delete ops;
+    return nullptr;
+  }
+  return ops;
+}
+int64_t ppxh_cp_pp_ops_size(void *h, const char *key) {
+  auto *ops = (map<string, Tensor<>> *)h;
+  auto it = ops->find(key);
+  return it == ops->end() ? -1 : it->second.size;
+}
+int ppxh_cp_pp_ops_read(void *h, const char *key, double *host) {
+  return guarded([&] {
+    auto *ops = (map<string, Tensor<>> *)h;
+    auto it = ops->find(key);
+    if (it == ops->end()) throw std::runtime_error(std::string("no PP operator with key ") + key);
+    it->second.read_all(host);
+  });
+}
+void ppxh_cp_pp_ops_free(void *h) { delete (map<string, Tensor<>> *)h; }
+
 // ---- OO path (src/CP.h + src/optimizer) ---------------------------------------------------------------------
 // kind: 3 = CPDTLROptimizer, 4 = CPMSDTLROptimizer  (run.cxx -pp 2 / 3)
 void *ppxh_cpd_create_lr(int kind, int order, int size, int r, int update_rank, int randomsvd, void *w) {

@@ -24,7 +24,7 @@ def load_host_library():
     lib = C.CDLL(HOST_LIB_PATH, mode=C.RTLD_GLOBAL)
     lib.ppxh_last_error.restype = C.c_char_p
     for name in ("ppxh_world_create", "ppxh_world_ctx", "ppxh_tensor_create", "ppxh_matrix_create", "ppxh_tensor_data",
-                 "ppxh_cpd_create", "ppxh_cpd_create_lr", "ppxh_tucker_create"):
+                 "ppxh_cpd_create", "ppxh_cpd_create_lr", "ppxh_tucker_create", "ppxh_cp_pp_ops_build"):
         getattr(lib, name).restype = _vp
     lib.ppxh_world_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_size_t]
     lib.ppxh_world_destroy.argtypes = [_vp]
@@ -79,6 +79,12 @@ def load_host_library():
     lib.ppxh_alsTucker_DT.argtypes = [_vp, _vp, PV, C.c_int, d, d, C.c_int, C.c_char_p, C.c_int, C.c_int, _vp, PI]
     lib.ppxh_alsTucker_PP.argtypes = [_vp, _vp, PV, C.c_int, d, d, d, C.c_int, C.c_char_p, C.c_int, C.c_int, _vp, PI]
     lib.ppxh_alsTucker.argtypes = [_vp, _vp, PV, C.c_int, d, d, C.c_int, _vp, PI]
+    lib.ppxh_cp_dt_mttkrps.argtypes = [_vp, PV, PV, C.c_int, _vp]
+    lib.ppxh_cp_pp_ops_build.argtypes = [_vp, PV, C.c_int, _vp]
+    lib.ppxh_cp_pp_ops_size.argtypes = [_vp, C.c_char_p]
+    lib.ppxh_cp_pp_ops_size.restype = _i64
+    lib.ppxh_cp_pp_ops_read.argtypes = [_vp, C.c_char_p, _vp]
+    lib.ppxh_cp_pp_ops_free.argtypes = [_vp]
     lib.ppxh_tucker_create.argtypes = [C.c_int, PI, PI, _vp]
     lib.ppxh_tucker_destroy.argtypes = [_vp]
     lib.ppxh_tucker_init.argtypes = [_vp, _vp]
@@ -273,6 +279,37 @@ def cp_pp_phase_timed(world, V, W, grad_W, n_sweeps, lam=0.0, ratio_step=1.0):
     _ck(world.lib.ppxh_cp_pp_phase_timed(V.h, _harr(W), _harr(grad_W), len(W), n_sweeps, lam, ratio_step, world.h,
                                          C.byref(a), C.byref(b)))
     return a.value, b.value
+
+
+def cp_dt_mttkrps(world, V, W):
+    """MTTKRP of every mode from ONE pass over the dimension tree at fixed W (the calls alsCP_DT's sweep makes, without the
+    updates in between); returns device matrices."""
+    M = [Matrix(world, w.lens[0], w.lens[1]) for w in W]
+    _ck(world.lib.ppxh_cp_dt_mttkrps(V.h, _harr(W), _harr(M), len(W), world.h))
+    return M
+
+
+class PPOperators:
+    """The operators of one PP phase built at W (Build_mttkrp_map for all pairs, then all singles)."""
+
+    def __init__(self, world, V, W):
+        self.lib = world.lib
+        self.h = self.lib.ppxh_cp_pp_ops_build(V.h, _harr(W), len(W), world.h)
+        if not self.h:
+            raise PpxError(self.lib.ppxh_last_error().decode())
+
+    def get(self, key, shape):
+        n = self.lib.ppxh_cp_pp_ops_size(self.h, key.encode())
+        if n < 0:
+            raise KeyError(key)
+        out = np.empty(n)
+        _ck(self.lib.ppxh_cp_pp_ops_read(self.h, key.encode(), out.ctypes.data_as(_vp)))
+        return out.reshape(shape, order="F")
+
+    def free(self):
+        if self.h:
+            self.lib.ppxh_cp_pp_ops_free(self.h)
+            self.h = None
 
 
 class CPD:

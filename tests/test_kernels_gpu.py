@@ -261,6 +261,9 @@ def test_sqnorms_and_diff_update(ctx):
     out = ctx.empty(2)
     ctx.sqnorms([ctx.to_device(a), ctx.to_device(b)], out)
     assert np.allclose(ctx.to_host(out, (2,)), [np.sum(a * a), np.sum(b * b)], rtol=1e-13)
+    big, small = rnd((5_000_001,), 97), rnd((77,), 98)  # tensor-sized arrays take the grid-wide two-stage sum
+    ctx.sqnorms([ctx.to_device(big), ctx.to_device(small)], out)
+    assert np.allclose(ctx.to_host(out, (2,)), [np.sum(big * big), np.sum(small * small)], rtol=1e-13)
     Wp, dW, sq = ctx.to_device(b), ctx.empty(1234), ctx.empty(2)
     ctx.diff_update(ctx.to_device(a), Wp, dW, sq)
     assert np.array_equal(ctx.to_host(dW, (1234,)), a - b)

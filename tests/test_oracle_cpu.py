@@ -339,3 +339,28 @@ def test_contract_blas_path_equals_einsum(shape, iT, x, monkeypatch):
     monkeypatch.setattr(o, "_FAST_MIN_ELEMS", 10 ** 15)
     ref = o.contract(out, T, iT, W, x + "*")
     assert fast.shape == ref.shape and np.abs(fast - ref).max() <= 1e-13 * np.abs(ref).max()
+
+
+# ---- the closed-form known answers used for the full-size GPU parity checks ---------------------------------------
+@pytest.mark.parametrize("lens,R", [((7, 6, 5, 4), 3), ((5, 4, 6), 2), ((4, 3, 4, 3, 4, 3), 2)])
+def test_closed_form_known_answers_match_the_oracle(lens, R):
+    """pairwise-perturbation_b200/kat.py (MTTKRP and PP pair operators of an exact CP tensor from the small matrices
+    A_m^T W_m) against the oracle's contractions of the materialised tensor, and on a mode-0 shard."""
+    kat = importlib.import_module("pairwise-perturbation_b200.kat")
+    N = len(lens)
+    A = [o.fill_uniform((l, R), 1, i) for i, l in enumerate(lens)]
+    W = [o.fill_uniform((l, R), 2, i) for i, l in enumerate(lens)]
+    V = o.build_V(A)
+    C = kat.cross_grams(A, W)
+    seq = o.letters(N)
+    ops = o.build_pp_operators(V, W)
+    for i in range(N):
+        ref = o.KhatriRao_contract(V, W, [j for j in range(N) if j != i] + [i])
+        assert kat.max_rel_err(kat.mttkrp(A, C, i), ref) < 1e-13
+        assert kat.max_rel_err(kat.mttkrp(A, C, i), ops[seq.replace(seq[i], "")]) < 1e-13
+        for j in range(i + 1, N):
+            key = seq.replace(seq[i], "").replace(seq[j], "")
+            assert kat.max_rel_err(kat.pair_operator(A, C, i, j), ops[key]) < 1e-13
+    b, e = 1, lens[0] - 1
+    assert np.array_equal(kat.mttkrp(A, C, 0, rows=(b, e)), kat.mttkrp(A, C, 0)[b:e])
+    assert np.allclose(kat.pair_operator(A, C, 0, 1, rows_i=(b, e)), kat.pair_operator(A, C, 0, 1)[b:e], rtol=1e-15)
