@@ -16,8 +16,10 @@
 //   * B is packed once per call (krp_pack_kernel) into per-chunk slabs [chunk][8*NT + TAIL columns][20] with the same k
 //     permutation, zero padded in k and in the columns, so a stage's slab is ONE contiguous bulk copy.
 // Layouts:  KMAJOR (L == 1): tensor map 2-D {K, M}, one 16 x 128 box per stage;
-//           M-major (L > 1): 128 l of one t per row tile -- one 4-D box of a {16, K, L/16, Rt} view when L % 16 == 0,
-//                            else eight 16(l) x 16(k) boxes of the 3-D map {L, K, Rt};
+//           M-major (L > 1): 128 l of one t per row tile -- one 4-D box of a {16, K, L/16, Rt} view for every row tile
+//                            made of whole groups of 16 l; the last row tile of a t when L % 16 != 0 (a mode-0 shard
+//                            of 37 or 38 rows gives L = 11100 / 11400) takes eight 16(l) x 16(k) boxes of the 3-D map
+//                            {L, K, Rt}, whose out-of-bounds rows read as zero;
 //           M-major, short L (128-row tiles would idle > 6 %): 16 l x 8 consecutive t per row tile, one 3-D box.
 // ppx_ttm_tma_try returns 1 (caller falls back to the cp.async kernel) when the shape is not TMA-friendly: odd
 // extents (TMA needs 16-byte global strides), unaligned base, R > 64, or an L that would waste > 6 % of a row tile.
@@ -49,7 +51,8 @@ struct TmaParams {
   int num_tiles;
   int nk, ksplit, cps;
   int inplace, accumulate;
-  int onebox;  // M-major with L % 16 == 0: the eight 16 x 16 boxes of a stage are one 4-D box (see ppx_ttm_tma_try)
+  int onebox;  // M-major: the eight 16 x 16 boxes of a stage are one 4-D box (see ppx_ttm_tma_try)
+  int64_t L16; // onebox: rows [0, L16) are whole groups of 16 l; a row tile reaching past L16 uses the 3-D map instead
   int tmulti;  // M-major with a short L: a row tile is 16 l x 8 consecutive t (one 3-D box); tiles_per_t = l groups
 };
 
@@ -210,7 +213,8 @@ __global__ void __launch_bounds__(256) tma_split_reduce_kernel(const double *__r
 // DFMA per thread (about 2.9*TAIL DMMA-equivalents) instead of the 16 DMMA of a padded tile.  Each lane accumulates
 // the partial sum over its own k positions; the four lanes of a group are combined by shuffles in the epilogue.
 template <int NT, int TAIL, bool KMAJOR>
-__global__ void __launch_bounds__(TTHREADS, 2) ttm_tma_kernel(const __grid_constant__ CUtensorMap tmap, TmaParams p) {
+__global__ void __launch_bounds__(TTHREADS, 2) ttm_tma_kernel(const __grid_constant__ CUtensorMap tmap,
+                                                              const __grid_constant__ CUtensorMap tmap3, TmaParams p) {
   extern __shared__ uint8_t smem_raw[];
   constexpr int NCOLS = 8 * NT + TAIL;
   constexpr int W_STAGE_BYTES = NCOLS * TLDW * 8;
@@ -307,11 +311,11 @@ __global__ void __launch_bounds__(TTHREADS, 2) ttm_tma_kernel(const __grid_const
       const int l0 = (ld.tile - t * p.tiles_per_t) * TBM;
       if (p.tmulti) {
         tma_load_3d(As, &tmap, &full[stage], (ld.tile - t * p.tiles_per_t) * 16, chunk * TBK, t * 8);
-      } else if (p.onebox) {
+      } else if (p.onebox && l0 + TBM <= p.L16) {
         tma_load_4d(As, &tmap, &full[stage], 0, chunk * TBK, l0 >> 4, t);
       } else {
 #pragma unroll
-        for (int b = 0; b < 8; b++) tma_load_3d(As + b * 2048, &tmap, &full[stage], l0 + 16 * b, chunk * TBK, t);
+        for (int b = 0; b < 8; b++) tma_load_3d(As + b * 2048, &tmap3, &full[stage], l0 + 16 * b, chunk * TBK, t);
       }
     }
     bulk_load(W_base + stage * W_STAGE_BYTES, p.Wpp + (int64_t)chunk * (NCOLS * TLDW), W_STAGE_BYTES, &full[stage]);
@@ -513,7 +517,7 @@ constexpr int TAIL_MAX = 4;  // leftover columns done as DFMA; 5..7 leftover col
 constexpr int NT_MAX = 8;
 
 // (NT, TAIL) table of the instantiated kernels: NT = 1..8 with TAIL = 0, NT = 1..7 with TAIL = 1..4
-typedef void (*TmaKernel)(const CUtensorMap, TmaParams);
+typedef void (*TmaKernel)(const CUtensorMap, const CUtensorMap, TmaParams);
 struct TmaEntry {
   TmaKernel kern[2];  // [kmajor]
   size_t smem;
@@ -538,11 +542,12 @@ inline void tma_split_rank(int R, int *nt, int *tail) {
   *tail = t;
 }
 
-int launch_tma(ppx_ctx *ctx, const CUtensorMap &map, const TmaParams &p, int nt, int tail, bool kmajor) {
+int launch_tma(ppx_ctx *ctx, const CUtensorMap &map, const CUtensorMap &map3, const TmaParams &p, int nt, int tail,
+               bool kmajor) {
   const TmaEntry &e = g_tma_table[nt - 1][tail];
   const int units = p.num_tiles * p.ksplit;
   const int gx = units < 2 * ctx->sm_count ? units : 2 * ctx->sm_count;
-  e.kern[kmajor ? 1 : 0]<<<gx, TTHREADS, e.smem, ctx->stream>>>(map, p);
+  e.kern[kmajor ? 1 : 0]<<<gx, TTHREADS, e.smem, ctx->stream>>>(map, map3, p);
   PPX_CHECK_LAUNCH(ctx);
   return PPX_OK;
 }
@@ -630,7 +635,10 @@ int ppx_ttm_tma_try(ppx_ctx *ctx, const double *V, int64_t L, int64_t K, int64_t
   p.inplace = inplace;
   p.accumulate = accumulate;
   p.tmulti = tmulti ? 1 : 0;
-  p.onebox = (!kmajor && !tmulti && L % 16 == 0) ? 1 : 0;
+  // one 4-D box per stage for every row tile made of whole groups of 16 l (needs at least one such tile); with
+  // L % 16 != 0 the last row tile of each t goes through the 3-D map (zero fill past L), everything else is unchanged
+  p.onebox = (!kmajor && !tmulti && L >= TBM && !getenv("PPX_NO_ONEBOX")) ? 1 : 0;
+  p.L16 = (L % 16 == 0) ? ((int64_t)1 << 62) : (L / 16) * 16;  // L % 16 == 0: every tile, the 4-D view zero-fills past L
   int nt, tail;
   tma_split_rank(R, &nt, &tail);
   const int ncols = 8 * nt + tail;
@@ -655,8 +663,8 @@ int ppx_ttm_tma_try(ppx_ctx *ctx, const double *V, int64_t L, int64_t K, int64_t
     }
   }
 
-  // tensor map of V
-  CUtensorMap map;
+  // tensor map(s) of V
+  CUtensorMap map, map3;
   CUresult cr;
   if (kmajor) {
     cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)Mtot};
@@ -678,6 +686,17 @@ int ppx_ttm_tma_try(ppx_ctx *ctx, const double *V, int64_t L, int64_t K, int64_t
     cr = g_encode(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, (void *)V, dims, strides, box, es,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr == CUDA_SUCCESS && L % 16 != 0) {  // the last row tile of each t
+      cuuint64_t dims3[3] = {(cuuint64_t)L, (cuuint64_t)K, (cuuint64_t)Rt};
+      cuuint64_t strides3[2] = {(cuuint64_t)L * 8, (cuuint64_t)L * (cuuint64_t)K * 8};
+      cuuint32_t box3[3] = {16, TBK, 1};
+      cuuint32_t es3[3] = {1, 1, 1};
+      cr = g_encode(&map3, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void *)V, dims3, strides3, box3, es3,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    } else {
+      map3 = map;
+    }
   } else {
     cuuint64_t dims[3] = {(cuuint64_t)L, (cuuint64_t)K, (cuuint64_t)Rt};
     cuuint64_t strides[2] = {(cuuint64_t)L * 8, (cuuint64_t)L * (cuuint64_t)K * 8};
@@ -689,6 +708,7 @@ int ppx_ttm_tma_try(ppx_ctx *ctx, const double *V, int64_t L, int64_t K, int64_t
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   }
   if (cr != CUDA_SUCCESS) return 1;
+  if (!p.onebox) map3 = map;  // the 3-D (or 2-D) map is the only one
 
   // pack B
   PackArgs a;
@@ -707,7 +727,7 @@ int ppx_ttm_tma_try(ppx_ctx *ctx, const double *V, int64_t L, int64_t K, int64_t
     PPX_CHECK_LAUNCH(ctx);
   }
   p.Wpp = Wpp;
-  int rc = launch_tma(ctx, map, p, nt, tail, kmajor);
+  int rc = launch_tma(ctx, map, map3, p, nt, tail, kmajor);
   if (rc) return rc;
   if (p.ksplit > 1) {
     const int64_t n = Mtot * (int64_t)R;

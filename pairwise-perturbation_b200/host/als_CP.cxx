@@ -156,13 +156,18 @@ void dt_sweep(Tensor<> &V, Matrix<> *W, Matrix<> *grad_W, Matrix<> *F, double la
 // nothing is read back to the host), so the FIRST sweep of a driver call runs eagerly -- it also fills the pool --, the
 // SECOND is captured and launched, and every later one is a single graph launch.  At BASELINE configs[0] (order 3,
 // s = 200, R = 10) a sweep is ~30 launches of a few microseconds of work each: launch-bound when enqueued one by one.
-// One GPU only (the NCCL all-reduces stay eager); any allocation that misses the pool during the capture abandons it.
+// With several GPUs the NCCL all-reduces of the sweep are captured with it (NCCL collectives are capturable; the first,
+// eager sweep has already made NCCL set up its channels); every rank issues the same sequence of collectives whether it
+// replays its graph or, after a failed capture, runs eagerly, so the ranks need not agree on that.  PPX_NO_MG_GRAPH
+// keeps multi-GPU sweeps eager.  Any allocation that misses the pool during the capture abandons it.
 struct DtSweepGraph {
   World &dw;
   void *graph = nullptr;
   bool disabled = false;
   int eager_done = 0;
-  explicit DtSweepGraph(World &w) : dw(w) { disabled = !(w.use_graph && w.np == 1) || getenv("PPX_NO_DT_GRAPH"); }
+  explicit DtSweepGraph(World &w) : dw(w) {
+    disabled = !w.use_graph || getenv("PPX_NO_DT_GRAPH") || (w.np > 1 && getenv("PPX_NO_MG_GRAPH"));
+  }
   DtSweepGraph(const DtSweepGraph &) = delete;
   ~DtSweepGraph() {
     if (graph) ppx_graph_destroy(dw.ctx, graph);
@@ -382,27 +387,103 @@ void Build_mttkrp_map(map<string, Tensor<>> &mttkrp_map, Tensor<> &V, Matrix<> *
 
 namespace {
 
-// all pair operators, then all singles (als_CP.cxx:676-694); afterwards only the operators the PP sweep reads are
-// kept (the reference leaves the 3 level-1 tensors -- 32 GB at N=4, s=300, R=50 -- in the map until the next clear)
+// All pair operators, then all singles (als_CP.cxx:676-694); afterwards only the operators the PP sweep reads are
+// kept (the reference leaves the level-1 tensors -- 32 GB at N=4, s=300, R=50 -- in the map until the next clear).
+//
+// Keys and results are the reference's (key = contracted modes in increasing order, als_CP.cxx:352-409); the ORDER in
+// which the modes of a key are contracted is not: Build_mttkrp_map contracts them in increasing order (prefix = key
+// minus its last letter), here the highest mode goes first (prefix = key minus its FIRST letter).  The operators are
+// the same sums; what changes is the shape of the work:
+//   * the tensor-sized first contraction always removes a trailing mode, so its row extent L = prod of the earlier
+//     extents stays long.  With the leading mode sharded over GPUs the reference order contracts mode 1 of a slab with
+//     37 rows (row tiles 71 % idle: the operator build reached only 4.3x on 8 GPUs in round 1);
+//   * the sharded mode 0 is contracted LAST in every chain, so the only partial sums that cross GPUs are the finished
+//     s x s x R operators and the s x R singles, never a level-1 tensor;
+//   * a chain nobody else shares whose modes are adjacent ("ab" for N = 4, "abcd" for N = 6) is ONE fused GEMM against the
+//     Khatri-Rao rows (ppx_ttm_multi): its level-1 tensor is never written.
+struct PPBuildPlan {
+  map<string, int> uses;  // how many target chains pass through a node (keyed like the map)
+  static string suffix(const string &key, size_t from) { return key.substr(from); }
+  explicit PPBuildPlan(const vector<string> &targets) {
+    for (const string &k : targets)
+      for (size_t f = 0; f < k.size(); f++) uses[suffix(k, f)]++;
+  }
+  bool private_adjacent_chain(const string &key) const {
+    for (size_t j = 1; j < key.size(); j++)
+      if (key[j] != key[j - 1] + 1) return false;
+    auto it = uses.find(string(1, key.back()));
+    return key.size() >= 2 && it != uses.end() && it->second == 1;
+  }
+};
+
+void build_key_last_first(map<string, Tensor<>> &m, Tensor<> &V, Matrix<> *W, const string &key, const PPBuildPlan &plan,
+                          World &dw) {
+  if (m.find(key) != m.end()) return;
+  const int N = V.order;
+  const int R = (int)W[0].ncol;
+  if (plan.private_adjacent_chain(key) && key.size() <= 8) {
+    const int x_first = key[0] - 'a', n = (int)key.size();
+    int64_t out_lens[17];
+    int k = 0;
+    for (int i = 0; i < N; i++)
+      if (i < x_first || i >= x_first + n) out_lens[k++] = V.lens[i];
+    out_lens[k++] = R;
+    Tensor<> out(k, out_lens, dw, false);
+    const double *wp[8];
+    int64_t ld[8];
+    for (int j = 0; j < n; j++) {
+      wp[j] = W[x_first + j].data;
+      ld[j] = W[x_first + j].nrow;
+    }
+    PPXCK(dw, ppx_ttm_multi(dw.ctx, V.data, V.lens, N, x_first, n, wp, ld, R, out.data));
+    m[key] = std::move(out);
+    return;
+  }
+  if (key.size() == 1) {  // level 1: the first contraction with V (als_CP.cxx:360-380)
+    m[key] = contract_mode(V, all_modes(N), false, key[0], W[key[0] - 'a'], dw);
+    return;
+  }
+  const string prefix = key.substr(1);
+  build_key_last_first(m, V, W, prefix, plan, dw);
+  string kept;
+  for (int i = 0; i < N; i++)
+    if (prefix.find((char)('a' + i)) == string::npos) kept.push_back((char)('a' + i));
+  const char x = key[0];
+  m[key] = contract_mode(m[prefix], kept, true, x, W[x - 'a'], dw);  // als_CP.cxx:407-408
+}
+
 void build_pp_operators(map<string, Tensor<>> &mttkrp_map, Tensor<> &V, Matrix<> *W, World &dw) {
   const int N = V.order;
   const string seq = all_modes(N);
   mttkrp_map.clear();
-  auto finish = [&](const string &key) {
-    // an operator that has contracted the sharded mode holds a partial sum over the local slab
-    if (dw.np > 1 && key.find((char)('a' + dw.shard_mode)) != string::npos)
-      dw.allreduce(mttkrp_map[key].data, mttkrp_map[key].size);
-  };
+  const char sh = (char)('a' + dw.shard_mode);
+  vector<string> pairs, singles;
   for (int ii = 0; ii < N; ii++)
-    for (int jj = ii + 1; jj < N; jj++) {
-      const string key = without(seq, ii, jj);
+    for (int jj = ii + 1; jj < N; jj++) pairs.push_back(without(seq, ii, jj));
+  for (int ii = 0; ii < N; ii++) singles.push_back(without(seq, ii));
+  if (getenv("PPX_PP_BUILD_REFERENCE_ORDER")) {  // the reference's contraction order (A/B timing, parity tests)
+    for (const string &key : pairs) {
       Build_mttkrp_map(mttkrp_map, V, W, key.c_str(), dw);
-      finish(key);
+      if (dw.np > 1 && key.find(sh) != string::npos) dw.allreduce(mttkrp_map[key].data, mttkrp_map[key].size);
     }
-  for (int ii = 0; ii < N; ii++) {
-    const string key = without(seq, ii);
-    Build_mttkrp_map(mttkrp_map, V, W, key.c_str(), dw);
-    // built from an already reduced pair operator: complete, nothing to reduce
+    for (const string &key : singles) Build_mttkrp_map(mttkrp_map, V, W, key.c_str(), dw);  // from reduced pair operators
+  } else {
+    const PPBuildPlan plan(pairs);
+    // a result is a partial sum over the local slab iff this step contracted the sharded mode
+    auto finish = [&](const string &key, bool from_V) {
+      if (dw.np == 1 || key.find(sh) == string::npos) return;
+      if (from_V || key.substr(1).find(sh) == string::npos) dw.allreduce(mttkrp_map[key].data, mttkrp_map[key].size);
+    };
+    for (const string &key : pairs) {
+      const bool had = mttkrp_map.find(key) != mttkrp_map.end();
+      build_key_last_first(mttkrp_map, V, W, key, plan, dw);
+      if (!had) finish(key, plan.private_adjacent_chain(key));
+    }
+    const PPBuildPlan none(vector<string>{});
+    for (const string &key : singles) {
+      build_key_last_first(mttkrp_map, V, W, key, none, dw);
+      finish(key, false);
+    }
   }
   for (auto it = mttkrp_map.begin(); it != mttkrp_map.end();) {
     if ((int)it->first.size() < N - 2) it = mttkrp_map.erase(it);
@@ -452,6 +533,7 @@ double alsCP_DT_sub(Tensor<> &V, Matrix<> *W, Matrix<> *grad_W, Matrix<> *dW, Ma
   Construct_Dimension_Tree(parent, sibling, 0, N - 1);
   GramCache gc;
   gc.init(W, N, dw);
+  DtSweepGraph sweep_graph(dw);
   for (; iter <= maxiter; iter++) {
     if (iter % resprint == 0 || iter == maxiter) {  // :457-498
       const double st_time1 = synced_time(dw);
@@ -462,7 +544,8 @@ double alsCP_DT_sub(Tensor<> &V, Matrix<> *W, Matrix<> *grad_W, Matrix<> *dW, Ma
       log_row(V, iter, projnorm, tol, 0, diffnorm_V, dtime, Plot_File, dw);
       if (projnorm < tol || wall_time() - st_time > timelimit) break;
     }
-    dt_sweep(V, W, grad_W, nullptr, lambda, false, parent, sibling, gc, S, dw);  // :499-592
+    sweep_graph.run([&]() { dt_sweep(V, W, grad_W, nullptr, lambda, false, parent, sibling, gc, S, dw); },
+                    maxiter - iter);  // :499-592
     if (trace_sink()) trace_sink()->sweeps.push_back({0, iter});
     // :594-605  dW = W - W_prev; W_prev = W; switch when every ||dW_i||/||W_i|| < tol_init
     for (int i = 0; i < N; i++)
@@ -519,7 +602,7 @@ struct PPPhase {
     build_pp_operators(ops, V, W, dw);
     // The sweep touches a fixed set of buffers from here on: capture it now (capturing enqueues nothing), so that
     // every approximate sweep of the phase -- including the first, the one pp_bench times -- is one graph launch.
-    if (dw.use_graph && dw.np == 1 && !graph) {
+    if (dw.use_graph && !(dw.np > 1 && getenv("PPX_NO_MG_GRAPH")) && !graph) {
       PPXCK(dw, ppx_graph_begin(dw.ctx));
       try {
         enqueue_sweep();

@@ -837,7 +837,7 @@ def test_cli_reads_a_raw_tensor_file(tmp_path, pp):
                          timeout=300).stdout
     assert "Read the tensor from file" in out and "Read dataset finished" in out
     m = re.search(r"Vnorm= (\S+)", out)
-    assert m and abs(float(m.group(1)) - vnorm) <= 1e-10 * vnorm
+    assert m and abs(float(m.group(1)) - vnorm) <= 2e-6 * vnorm  # printed with the stream's default six digits
     rows, events, _ = _stdout_numbers(out)
     if pp:
         assert events == list(tr.events)

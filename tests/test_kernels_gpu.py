@@ -43,6 +43,9 @@ TTM_CASES = [
     ((128, 21, 3), 1, 41), ((640, 7, 2), 1, 58), ((256, 12, 3), 1, 59),
     # M-major with L % 16 != 0: eight 16 x 16 boxes per stage instead of the single 4-D box
     ((250, 12, 3), 1, 50), ((378, 9, 2), 1, 33), ((122, 40, 2), 1, 26),
+    # L % 16 != 0 with several row tiles (a mode-0 shard of 37 rows gives L = 37 * s): one 4-D box per stage for the tiles
+    # made of whole groups of 16 l, eight 3-D boxes for the last tile of each t
+    ((1110, 24), 1, 50), ((1110, 12, 3), 1, 50), ((1140, 9, 2), 1, 26), ((270, 6, 2), 1, 64), ((130, 16, 2), 1, 33),
     # M-major with a short L: 16 l x 8 t row tiles (one 3-D box per stage)
     ((300, 20, 16), 1, 50), ((46, 17, 40), 1, 27), ((300, 7, 4, 6), 1, 35), ((94, 33, 8), 1, 64), ((16, 40, 24), 1, 25),
     # streaming kernels (X <= 64 and R <= 16, k1_ttm_stream.cu): lanes along l with one or two rows per thread
@@ -369,6 +372,8 @@ MULTI_CASES = [
     ((256, 6, 5, 3), 1, 2, 4), ((128, 30, 40), 1, 2, 50), ((10, 12, 130, 3), 0, 2, 50),  # TMA-eligible fused cases
     ((640, 4, 5, 6), 1, 3, 10), ((128, 9, 11), 1, 2, 26), ((12, 14, 140), 0, 2, 11), ((256, 5, 4, 3), 1, 3, 43),
     ((46, 6, 5, 16), 1, 2, 26),
+    # the 8-GPU shard shape in small: L = 37 * 30 = 1110 rows (L % 16 != 0), two trailing modes fused, split K
+    ((37, 30, 40, 24), 2, 2, 50), ((38, 30, 24, 16), 2, 2, 26), ((37, 30, 20, 24), 0, 2, 50),
 ]
 
 
