@@ -258,6 +258,10 @@ class Ctx:
     def gram(self, W, s, R, G, ldw=None):
         self._ck(self.lib.ppx_gram(self.h, _ptr(W), s, ldw if ldw is not None else s, R, _ptr(G)))
 
+    def spd_inverse_g(self, Gs, skip, lam, R, mode, S_out, Sinv_out):
+        self._ck(self.lib.ppx_spd_inverse_g(self.h, _ptrs(Gs), len(Gs), skip, lam, R, mode,
+                                            _ptr(S_out) if S_out is not None else None, _ptr(Sinv_out)))
+
     def hadamard_grams(self, Gs, skip, R, lam, S):
         self._ck(self.lib.ppx_hadamard_grams(self.h, _ptrs(Gs), len(Gs), skip, R, lam, _ptr(S)))
 

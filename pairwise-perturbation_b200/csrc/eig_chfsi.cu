@@ -486,6 +486,9 @@ int ppx_eig_chfsi(ppx_ctx *ctx, double *A, int n, int r, double *U, double *eval
     products++;
     chfsi_cross_gram_kernel<<<ppx_cdiv((int64_t)pa * pa * 32, 256), 256, 0, ctx->stream>>>(Xa, AX, n, ld, pa, H);
     PPX_CHECK_LAUNCH(ctx);
+    // (a two-sided Jacobi with H itself in shared memory -- rotation from three entries, no reductions -- was measured
+    // SLOWER, 0.71 vs 0.60 ms per step at p = 64: on these graded Ritz matrices, one outlier 1e6 x the bulk, it needs
+    // many more sweeps to push the small off-diagonal entries below the relative threshold)
     chfsi_jacobi_smem_kernel<<<1, 1024, jac_smem, ctx->stream>>>(H, pa, Zr, theta);
     PPX_CHECK_LAUNCH(ctx);
     CHK(right_mult(ctx, Xa, n, ld, pa, Zr, 0, T));

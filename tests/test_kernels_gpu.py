@@ -214,6 +214,36 @@ def test_solve_update(ctx, ppx, mode, s, R):
     assert rel_err(ctx.to_host(Wd, (s, R)), o.cholesky_solve(M, S)) < 1e-9
 
 
+@pytest.mark.parametrize("R", [1, 2, 7, 8, 9, 16, 23, 40, 50, 56, 57, 64, 77, 100, 112])
+def test_spd_inverse_blocked(ctx, R):
+    """S^-1 of the Gram-Hadamard matrix by the blocked LDL^T kernel (8 columns per step; cholesky_solve semantics,
+    common.cxx:727-737) for every padding class of R, against NumPy, with and without lambda, and on a matrix with a wide
+    spectrum (Hadamard product of three Grams of nearly collinear factors)."""
+    s = 3 * R + 5
+    for trial, lam in enumerate((0.0, 1e-3, 0.0)):
+        Ws = [rnd((s, R), 400 + 7 * trial + j) for j in range(4)]
+        if trial == 2:  # nearly collinear columns: condition number ~1e7..1e9
+            Ws = [0.05 * w + np.ones((s, 1)) * rnd((1, R), 440 + j) for j, w in enumerate(Ws)]
+        Gs = []
+        for w in Ws:
+            G = ctx.empty(R * R)
+            ctx.gram(ctx.to_device(w), s, R, G)
+            Gs.append(G)
+        S = np.ones((R, R))
+        for j in (0, 2, 3):
+            S = S * (Ws[j].T @ Ws[j])
+        S = S + lam * np.eye(R)
+        S_out, Sinv = ctx.empty(R * R), ctx.empty(R * R)
+        ctx.spd_inverse_g(Gs, 1, lam, R, 0, S_out, Sinv)
+        got = ctx.to_host(Sinv, (R, R))
+        assert rel_err(ctx.to_host(S_out, (R, R)), S) < 1e-12
+        cond = np.linalg.cond(S)
+        assert np.abs(got @ S - np.eye(R)).max() < 1e-14 * max(cond, 1e3) * R
+        assert np.abs(got - got.T).max() == 0.0
+        ref = np.linalg.inv(S)
+        assert rel_err(got, ref) < 1e-13 * max(cond, 1e3)
+
+
 def test_normalize(ctx):
     sizes, R = [13, 40, 7, 300], 6
     W = [rnd((s, R), 90 + i) * (i + 1) for i, s in enumerate(sizes)]
@@ -275,7 +305,12 @@ def test_sqnorms_and_diff_update(ctx):
 
 
 @pytest.mark.parametrize("lens,R", [((12, 10, 8, 6), 4), ((13, 9, 11), 5), ((5, 6, 4, 5, 3, 4), 3), ((130, 35), 50),
-                                    ((7, 200), 3)])
+                                    ((7, 200), 3),
+                                    # >= 65536 elements: the tensor-pipe kernel (128-row tiles, 64-column chunks of the last
+                                    # mode, ragged in both; R padded to a multiple of 4; every leading dimension class)
+                                    ((40, 30, 20, 35), 50), ((64, 33, 50), 10), ((130, 35, 300), 3), ((7, 9, 11, 13, 9), 27),
+                                    ((300, 250), 64), ((50, 40, 60), 100), ((129, 8, 8, 70), 1), ((33, 2000), 12),
+                                    ((50, 40, 60), 101)])
 def test_cp_residual_and_reconstruct(ctx, lens, R):
     N = len(lens)
     W = [rnd((lens[i], R), 100 + i) for i in range(N)]
