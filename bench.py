@@ -710,15 +710,18 @@ def main():
     hlib = H.load_host_library()
 
     def e2e_step():
+        # pinned host -> device on the engine's stream (stream order makes them visible to the sweep), the driver call,
+        # device -> pinned host, ONE synchronise at the end of the step: the results are on the host when it returns
         for t_, w in zip(pin, W):
-            hlib.ppxh_tensor_write(w.h, C.c_void_p(t_.data_ptr()))
+            hlib.ppxh_tensor_write_async(w.h, C.c_void_p(t_.data_ptr()))
         for t_, g in zip(pin_g, G):
-            hlib.ppxh_tensor_write(g.h, C.c_void_p(t_.data_ptr()))
+            hlib.ppxh_tensor_write_async(g.h, C.c_void_p(t_.data_ptr()))
         H.alsCP_DT(world, V, W, G, F, 0.0, 0, lam=0.0, resprint=1 << 30, bench=True)  # exactly one sweep
         for t_, w in zip(pin_out, W):
-            hlib.ppxh_tensor_read(w.h, C.c_void_p(t_.data_ptr()))
+            hlib.ppxh_tensor_read_async(w.h, C.c_void_p(t_.data_ptr()))
         for t_, g in zip(pin_g, G):
-            hlib.ppxh_tensor_read(g.h, C.c_void_p(t_.data_ptr()))
+            hlib.ppxh_tensor_read_async(g.h, C.c_void_p(t_.data_ptr()))
+        hlib.ppxh_world_sync(world.h)
 
     with H.Trace(quiet=True, skip_residual=True):
         for _ in range(max(1, min(args.warmup, 2))):

@@ -246,6 +246,13 @@ int ppx_comm_rank(ppx_ctx *ctx);
 /* in-place sum over ranks of n buffers as ONE NCCL group (bufs/sizes: HOST arrays; no-op when nranks == 1). */
 int ppx_allreduce_packed(ppx_ctx *ctx, double *const *bufs, const int64_t *sizes, int n);
 
+/* Personalised exchange (one NCCL group of send/recv pairs): sendcounts[k] doubles from sendbufs[k] go to rank k,
+ * recvcounts[k] doubles from rank k land in recvbufs[k]; the entry of the calling rank is a device copy.  HOST arrays
+ * of comm_size entries.  Used for the mode-0 unfolding Gram of a tensor sharded along mode 0 (HOSVD on several GPUs):
+ * every rank gets ALL rows of its share of the last mode instead of moving the whole tensor through all-reduces. */
+int ppx_alltoallv(ppx_ctx *ctx, const double *const *sendbufs, const int64_t *sendcounts, double *const *recvbufs,
+                  const int64_t *recvcounts);
+
 #ifdef __cplusplus
 }
 #endif

@@ -28,6 +28,8 @@ struct NcclApi {
   ncclResult_e (*CommInitRank)(ncclComm_p *, int, ncclUniqueId_t, int) = nullptr;
   ncclResult_e (*CommDestroy)(ncclComm_p) = nullptr;
   ncclResult_e (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_p, cudaStream_t) = nullptr;
+  ncclResult_e (*Send)(const void *, size_t, int, int, ncclComm_p, cudaStream_t) = nullptr;
+  ncclResult_e (*Recv)(void *, size_t, int, int, ncclComm_p, cudaStream_t) = nullptr;
   ncclResult_e (*GroupStart)() = nullptr;
   ncclResult_e (*GroupEnd)() = nullptr;
   const char *(*GetErrorString)(ncclResult_e) = nullptr;
@@ -46,6 +48,8 @@ bool load_nccl() {
   LOAD(CommInitRank);
   LOAD(CommDestroy);
   LOAD(AllReduce);
+  LOAD(Send);
+  LOAD(Recv);
   LOAD(GroupStart);
   LOAD(GroupEnd);
   LOAD(GetErrorString);
@@ -194,6 +198,35 @@ int ppx_allreduce_packed(ppx_ctx *ctx, double *const *bufs, const int64_t *sizes
     return ppx_set_err(ctx, PPX_ENCCL, "ncclAllReduce failed: %s",
                        g_nccl.GetErrorString ? g_nccl.GetErrorString(r ? r : r2) : "?");
   ctx->launches += n;
+  return PPX_OK;
+}
+
+int ppx_alltoallv(ppx_ctx *ctx, const double *const *sendbufs, const int64_t *sendcounts, double *const *recvbufs,
+                  const int64_t *recvcounts) {
+  if (ctx->nranks == 1) return PPX_OK;
+  PPX_REQUIRE(ctx, ctx->comm != nullptr, "communicator initialised (ppx_comm_init)");
+  PPX_REQUIRE(ctx, sendbufs && sendcounts && recvbufs && recvcounts, "non-null arrays");
+  if (!g_nccl.Send || !g_nccl.Recv) return ppx_set_err(ctx, PPX_ENCCL, "this NCCL has no ncclSend/ncclRecv");
+  ncclResult_e r = g_nccl.GroupStart();
+  for (int k = 0; k < ctx->nranks && !r; k++) {
+    if (k == ctx->rank) continue;
+    if (sendcounts[k] > 0)
+      r = g_nccl.Send(sendbufs[k], (size_t)sendcounts[k], NCCL_FLOAT64, k, (ncclComm_p)ctx->comm, ctx->stream);
+    if (!r && recvcounts[k] > 0)
+      r = g_nccl.Recv(recvbufs[k], (size_t)recvcounts[k], NCCL_FLOAT64, k, (ncclComm_p)ctx->comm, ctx->stream);
+  }
+  ncclResult_e r2 = g_nccl.GroupEnd();
+  if (r || r2)
+    return ppx_set_err(ctx, PPX_ENCCL, "ncclSend/ncclRecv failed: %s",
+                       g_nccl.GetErrorString ? g_nccl.GetErrorString(r ? r : r2) : "?");
+  // the piece a rank keeps for itself is a plain copy
+  const int me = ctx->rank;
+  if (sendcounts[me] > 0 && recvbufs[me] && recvbufs[me] != sendbufs[me]) {
+    PPX_REQUIRE(ctx, recvcounts[me] == sendcounts[me], "self counts agree");
+    PPX_CUDA(ctx, cudaMemcpyAsync(recvbufs[me], sendbufs[me], sizeof(double) * (size_t)sendcounts[me],
+                                  cudaMemcpyDeviceToDevice, ctx->stream));
+  }
+  ctx->launches += ctx->nranks;
   return PPX_OK;
 }
 

@@ -233,166 +233,12 @@ __global__ void __launch_bounds__(INV_B *INV_B) spd_inverse_ldl_kernel(HadArgs h
   PPX_PROF(4);
 }
 
-// ---- R x R SPD inverse, BLOCKED: the critical path of the PP approximate sweep ------------------------------------------
-// The column-by-column kernel above runs R dependent elimination steps of ~1080 cycles each (37 us at R = 50, longer
-// than the PP correction it should hide behind).  Here the factorisation advances 8 columns per step:
-//     S = L D L^T,   D = diag(D_0 .. D_{nb-1}) with 8 x 8 SPD blocks (NOT factored further),  L unit block-lower,
-//     step k:  Dinv_k = D_k^-1                      one warp, in-register Gauss-Jordan (8 rounds of shuffles)
-//              L_ik   = S_ik Dinv_k          (i > k)       panel, one thread per element
-//              S_ij  -= L_ik S_jk^T          (i >= j > k)  trailing update, one thread per element
-//     Y = L^-1 by block forward substitution (in place),  S^-1 = Y^T (Dinv Y).
-// nb = ceil(R / 8) sequential steps instead of R (7 instead of 50), every phase spread over the 256 threads of the CTA.
-// The matrix (padded with identity to a multiple of 8) lives in shared memory, column-major with an odd leading
-// dimension.  Checked against the column kernel and NumPy in tests/test_kernels_gpu.py; design notes and a NumPy
-// model of the scheme: tools/inv_blocked_proto.py.
-constexpr int BLK = 8;
-constexpr int INVB_THREADS = 256;
-
-__global__ void __launch_bounds__(INVB_THREADS) spd_inverse_blocked_kernel(HadArgs h, int R, double lambda,
-                                                                           double *__restrict__ S_out,
-                                                                           double *__restrict__ Sinv) {
-  extern __shared__ double sm[];
-  const int nb = (R + BLK - 1) / BLK, RP = nb * BLK, LD = RP + 1;
-  double *A = sm;                       // [RP][LD]: S, trailing matrices; later T = Dinv Y
-  double *L = A + (size_t)RP * LD;      // [RP][LD]: L, then Y = L^-1 in place
-  double *D = L + (size_t)RP * LD;      // [nb][64]: Dinv_k, column-major 8 x 8
-  const int tid = threadIdx.x, nt = INVB_THREADS, lane = tid & 31, warp = tid >> 5;
-  // identity padding / initial L = I
-  for (int e = tid; e < RP * RP; e += nt) {
-    const int j = e / RP, i = e - j * RP;
-    L[j * LD + i] = i == j ? 1.0 : 0.0;
-    if (i >= R || j >= R) A[j * LD + i] = i == j ? 1.0 : 0.0;
-  }
-  // S = Hadamard product (+ lambda I): four independent elements per thread and pass keep the loads in flight
-  for (int e0 = tid; e0 < R * R; e0 += 4 * nt) {
-    double v[4];
-#pragma unroll
-    for (int u = 0; u < 4; u++) {
-      const int e = e0 + u * nt;
-      v[u] = e < R * R ? h.g[0][e] : 0.0;
-    }
-#pragma unroll 1
-    for (int m = 1; m < h.n; m++) {
-      const double *g = h.g[m];
-#pragma unroll
-      for (int u = 0; u < 4; u++) {
-        const int e = e0 + u * nt;
-        if (e < R * R) v[u] *= g[e];
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < 4; u++) {
-      const int e = e0 + u * nt;
-      if (e < R * R) {
-        const int j = e / R, i = e - j * R;
-        if (i == j) v[u] += lambda;
-        if (S_out) S_out[e] = v[u];
-        A[j * LD + i] = v[u];
-      }
-    }
-  }
-  __syncthreads();
-  for (int k = 0; k < nb; k++) {
-    const int k0 = k * BLK;
-    if (warp == 0) {
-      // in-place Gauss-Jordan inverse of the 8 x 8 pivot block; lane holds (i, jj) and (i, jj + 4)
-      const int i = lane & 7, jj = lane >> 3;
-      double a0 = A[(k0 + jj) * LD + k0 + i], a1 = A[(k0 + jj + 4) * LD + k0 + i];
-#pragma unroll
-      for (int r = 0; r < BLK; r++) {
-        const double colr = r < 4 ? a0 : a1;  // column r lives in register r / 4 of the lanes with jj == r % 4
-        const double air = __shfl_sync(0xffffffffu, colr, i + 8 * (r & 3));
-        const double arr = __shfl_sync(0xffffffffu, colr, r + 8 * (r & 3));
-        const double arj0 = __shfl_sync(0xffffffffu, a0, r + 8 * jj);
-        const double arj1 = __shfl_sync(0xffffffffu, a1, r + 8 * jj);
-        const double piv = inv_pivot(arr);
-        if (i == r) {
-          a0 = (jj == r) ? piv : arj0 * piv;
-          a1 = (jj + 4 == r) ? piv : arj1 * piv;
-        } else {
-          const double f = air * piv;
-          a0 = (jj == r) ? -f : fma(-f, arj0, a0);
-          a1 = (jj + 4 == r) ? -f : fma(-f, arj1, a1);
-        }
-      }
-      D[k * 64 + jj * 8 + i] = a0;
-      D[k * 64 + (jj + 4) * 8 + i] = a1;
-    }
-    __syncthreads();
-    const int m = RP - k0 - BLK;  // rows below the pivot block
-    if (m > 0) {
-      const double *Dk = D + k * 64;
-      // panel: L[ri, k0 + c] = sum_t A[ri, k0 + t] Dk[t, c]
-      for (int e = tid; e < m * BLK; e += nt) {
-        const int c = e / m, ri = k0 + BLK + (e - c * m);
-        double acc = 0.0;
-#pragma unroll
-        for (int t = 0; t < BLK; t++) acc = fma(A[(k0 + t) * LD + ri], Dk[c * 8 + t], acc);
-        L[(k0 + c) * LD + ri] = acc;
-      }
-      __syncthreads();
-      // trailing update of the block-lower triangle (diagonal blocks in full): A[ri, cj] -= sum_t L[ri, k0+t] A[cj, k0+t]
-      for (int e = tid; e < m * m; e += nt) {
-        const int cjl = e / m, ril = e - cjl * m;
-        if ((cjl >> 3) > (ril >> 3)) continue;
-        const int ri = k0 + BLK + ril, cj = k0 + BLK + cjl;
-        double acc = A[cj * LD + ri];
-#pragma unroll
-        for (int t = 0; t < BLK; t++) acc = fma(-L[(k0 + t) * LD + ri], A[(k0 + t) * LD + cj], acc);
-        A[cj * LD + ri] = acc;
-      }
-      __syncthreads();
-    }
-  }
-  // Y = L^-1, block row by block row: Y[ri, cc] = -(L[ri, cc] + sum_{q = 8(block(cc)+1)}^{8 bi - 1} L[ri, q] Y[q, cc])
-  for (int bi = 1; bi < nb; bi++) {
-    const int r0 = bi * BLK, ncols = bi * BLK;
-    double val[2] = {0.0, 0.0};  // 8 * ncols <= 8 * 104 elements over 256 threads: at most 4; RP <= 112 -> <= 4
-    double val2[2] = {0.0, 0.0};
-    int cnt = 0;
-    for (int e = tid; e < BLK * ncols; e += nt, cnt++) {
-      const int cc = e / BLK, ri = r0 + (e - cc * BLK);
-      double acc = L[cc * LD + ri];
-      for (int q = ((cc >> 3) + 1) * BLK; q < r0; q++) acc = fma(L[q * LD + ri], L[cc * LD + q], acc);
-      if (cnt < 2) val[cnt] = -acc;
-      else val2[cnt - 2] = -acc;
-    }
-    __syncthreads();
-    cnt = 0;
-    for (int e = tid; e < BLK * ncols; e += nt, cnt++) {
-      const int cc = e / BLK, ri = r0 + (e - cc * BLK);
-      L[cc * LD + ri] = cnt < 2 ? val[cnt] : val2[cnt - 2];
-    }
-    __syncthreads();
-  }
-  // T = Dinv Y (block row bm of Y times Dinv_bm), into A:  T[mrow, c] = sum_t Dinv_bm[mrow % 8, t] Y[8 bm + t, c]
-  for (int e = tid; e < RP * RP; e += nt) {
-    const int c = e / RP, mrow = e - c * RP;
-    const int bm = mrow >> 3;
-    if ((c >> 3) > bm) continue;  // Y is block lower triangular
-    const double *Dm = D + bm * 64;
-    double acc = 0.0;
-#pragma unroll
-    for (int t = 0; t < BLK; t++) acc = fma(Dm[t * 8 + (mrow & 7)], L[c * LD + bm * BLK + t], acc);
-    A[c * LD + mrow] = acc;
-  }
-  __syncthreads();
-  // S^-1[i, j] = sum_{m >= 8 block(i)} Y[m, i] T[m, j]   (i >= j), mirrored
-  for (int e = tid; e < R * R; e += nt) {
-    const int j = e / R, i = e - j * R;
-    if (i < j) continue;
-    double acc0 = 0.0, acc1 = 0.0;
-    int mm = (i >> 3) * BLK;
-    for (; mm + 1 < RP; mm += 2) {
-      acc0 = fma(L[i * LD + mm], A[j * LD + mm], acc0);
-      acc1 = fma(L[i * LD + mm + 1], A[j * LD + mm + 1], acc1);
-    }
-    if (mm < RP) acc0 = fma(L[i * LD + mm], A[j * LD + mm], acc0);
-    const double v = acc0 + acc1;
-    Sinv[i + R * j] = v;
-    Sinv[j + R * i] = v;
-  }
-}
+// (A BLOCKED variant -- 8 columns per step: in-register Gauss-Jordan of the 8 x 8 pivot block by one warp, panel and
+// trailing update with one thread per element, Y = L^-1 by block forward substitution, S^-1 = Y^T Dinv Y; NumPy model in
+// tools/inv_blocked_proto.py -- was written and measured in round 2: 36.8 us at R = 50 and 123 us at R = 100 against
+// 32.8 / 86.0 us for the kernel above.  One CTA runs at the latency of its dependent shared-memory loads and FMAs
+// whichever way the work is cut; the seven block steps each pay an 8-round pivot inversion plus three barriers, and
+// the two triangular products that the column kernel folds into its loop come on top.  Not adopted.)
 
 // Cyclic Jacobi (parallel round-robin ordering) on a symmetric matrix in shared memory.
 // A[n][ld], Q[n][ld]; n even (padded with an identity row/column when R is odd).
@@ -682,14 +528,6 @@ int inverse_launch(ppx_ctx *ctx, const HadArgs &h, int R, double lambda, int mod
                    double *Linv = nullptr) {
   if (mode == PPX_SOLVE_CHOL) {
     if (R > 112) return ppx_set_err(ctx, PPX_EUNSUPPORTED, "solve: R=%d too large for the one-CTA inverse (max 112)", R);
-    static const bool column_kernel = getenv("PPX_INV_COLUMN") != nullptr;  // A/B timing against the column-by-column kernel
-    if (!Linv && Sinv && !column_kernel) {
-      const int RP = ((R + BLK - 1) / BLK) * BLK;
-      const size_t smem_b = sizeof(double) * (2 * (size_t)RP * (RP + 1) + (size_t)(RP / BLK) * 64);
-      spd_inverse_blocked_kernel<<<1, INVB_THREADS, smem_b, ctx->stream>>>(h, R, lambda, S_out, Sinv);
-      PPX_CHECK_LAUNCH(ctx);
-      return PPX_OK;
-    }
     const int T = (R + INV_B - 1) / INV_B;
     const size_t smem = sizeof(double) * (2 * ((size_t)INV_B * T + 2) + (size_t)R * (R + 1));
 #define PPX_INV_LAUNCH(T) \
@@ -792,7 +630,6 @@ int ppx_k45_init(ppx_ctx *ctx) {
   PPX_CUDA(ctx, cudaFuncSetAttribute(spd_inverse_ldl_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   PPX_CUDA(ctx, cudaFuncSetAttribute(spd_inverse_ldl_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   PPX_CUDA(ctx, cudaFuncSetAttribute(sym_inverse_jacobi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-  PPX_CUDA(ctx, cudaFuncSetAttribute(spd_inverse_blocked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   PPX_CUDA(ctx, cudaFuncSetAttribute(solve_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   return PPX_OK;
 }

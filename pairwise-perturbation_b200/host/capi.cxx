@@ -136,6 +136,19 @@ int ppxh_tensor_write(void *t, const double *host) {
 int ppxh_tensor_read(void *t, double *host) {
   return guarded([&] { ((Tensor<> *)t)->read_all(host); });
 }
+// the same without the stream synchronise: `host` must be pinned and stay valid until ppxh_world_sync (stream order
+// makes a write visible to every later kernel, and a read complete after the sync)
+int ppxh_tensor_write_async(void *t_, const double *host) {
+  Tensor<> *t = (Tensor<> *)t_;
+  return guarded([&] { PPXCK(*t->wrld, ppx_memcpy_h2d(t->wrld->ctx, t->data, host, sizeof(double) * t->size)); });
+}
+int ppxh_tensor_read_async(void *t_, double *host) {
+  Tensor<> *t = (Tensor<> *)t_;
+  return guarded([&] { PPXCK(*t->wrld, ppx_memcpy_d2h(t->wrld->ctx, host, t->data, sizeof(double) * t->size)); });
+}
+int ppxh_world_sync(void *w) {
+  return guarded([&] { ((World *)w)->sync(); });
+}
 void *ppxh_tensor_data(void *t) { return ((Tensor<> *)t)->data; }
 int64_t ppxh_tensor_size(void *t) { return ((Tensor<> *)t)->size; }
 int ppxh_tensor_order(void *t) { return ((Tensor<> *)t)->order; }

@@ -37,6 +37,9 @@ def load_host_library():
     lib.ppxh_tensor_destroy.argtypes = [_vp]
     lib.ppxh_tensor_write.argtypes = [_vp, _vp]
     lib.ppxh_tensor_read.argtypes = [_vp, _vp]
+    lib.ppxh_tensor_write_async.argtypes = [_vp, _vp]
+    lib.ppxh_tensor_read_async.argtypes = [_vp, _vp]
+    lib.ppxh_world_sync.argtypes = [_vp]
     lib.ppxh_tensor_data.argtypes = [_vp]
     lib.ppxh_tensor_size.argtypes = [_vp]
     lib.ppxh_tensor_size.restype = _i64

@@ -47,15 +47,17 @@ def free_all(*groups):
             t.free()
 
 
-def check_rows(rows_gpu, rows_ref, vnorm, grad_floor=1e-6):
+def check_rows(rows_gpu, rows_ref, vnorm, grad_floor=1e-6, grad_rtol=FIT_RTOL):
     """grad_floor: gradient norms below grad_floor * ||V|| are compared absolutely (an exactly representable problem
-    converges to rounding noise, which is not reproducible digit for digit)."""
+    converges to rounding noise, which is not reproducible digit for digit).  grad_rtol: the gradient -M + W S is a
+    difference of nearly equal matrices, so its norm carries cond(S) times the rounding of the R x R solve; the fitness
+    tolerance of the north star (1e-10) applies to the residual column."""
     assert len(rows_gpu) == len(rows_ref)
     for rg, rr in zip(rows_gpu, rows_ref):
         it_g, gn_g, pp_g, dv_g = rg[0], rg[1], rg[2], rg[3]
         it_r, gn_r, pp_r, dv_r = rr
         assert int(it_g) == it_r and int(pp_g) == pp_r
-        assert abs(gn_g - gn_r) <= FIT_RTOL * max(abs(gn_r), vnorm * grad_floor), (rg, rr)
+        assert abs(gn_g - gn_r) <= grad_rtol * max(abs(gn_r), vnorm * grad_floor), (rg, rr)
         # the residual is a norm of a difference: compare relative to ||V|| (fitness = 1 - residual/||V||)
         assert abs(dv_g - dv_r) <= FIT_RTOL * vnorm, (rg, rr)
 
@@ -438,7 +440,9 @@ def test_baseline_config0_cp_n3_s200_r10(H, world, pp):
             H.alsCP_PP(world, Vd, Wd, Gd, Fd, 1e-10 * vnorm, 1e-2, maxiter, resprint=10)
     if pp:
         assert t.events == [(0 if k == "DT" else 1, it) for k, it in tr.events]
-    check_rows(t.rows, tr.rows, vnorm)
+    # gradient norm at 1e-9 (as tests/test_reference_pin.py compares the oracle with the reference): the oracle solves
+    # with an SVD pseudo-inverse, the CUDA path with LDL^T, and S is ill-conditioned near convergence of this exact problem
+    check_rows(t.rows, tr.rows, vnorm, grad_rtol=1e-9)
     check_factors(Wd, W_ref)
     free_all(Vd, Wd, Gd, Fd)
 

@@ -130,18 +130,32 @@ def _sharded_tucker(rank, nranks, port, lens, R, out_dir):
     def local_ttm(T, x, Wx):  # a contraction of mode 0 sums over the local rows only
         return ttm_saved(T, x, Wx[b:e] if x == 0 else Wx)
 
-    # HOSVD: modes != 0 all-reduce the local Gram; mode 0 gathers the slab panel by panel along the last mode
+    # HOSVD: modes != 0 all-reduce the local Gram.  Mode 0 (gram_mode0_sharded in host/als_Tucker.cxx): ONE personalised
+    # exchange -- rank k receives, from every rank, that rank's rows of k's share [tb_k, te_k) of the LAST mode -- then
+    # the Gram of the full-height panel and one all-reduce of the partial Grams
+    n_exchange = 0
     W = []
     for i in range(N):
         if i != 0:
             MTM = allreduce(o.unroll_tensor_contraction(Vl, i))
         else:
-            MTM = np.zeros((lens[0], lens[0]))
-            for pid, t0 in enumerate(range(0, lens[-1], 2)):
-                full = gather_mode0(Vl[..., t0:t0 + 2])
-                if pid % nranks == rank:
-                    MTM += o.unroll_tensor_contraction(full, 0)
-            MTM = allreduce(MTM)
+            tr = [ppx.shard_range(lens[-1], nranks, k) for k in range(nranks)]
+            rr = [ppx.shard_range(lens[0], nranks, k) for k in range(nranks)]
+            send = [torch.from_numpy(np.ascontiguousarray(Vl[..., tr[k][0]:tr[k][1]])) for k in range(nranks)]
+            recv = [torch.empty((rr[k][1] - rr[k][0],) + tuple(lens[1:-1]) + (tr[rank][1] - tr[rank][0],),
+                                dtype=torch.float64) for k in range(nranks)]
+            reqs = []
+            for k in range(nranks):
+                if k == rank:
+                    recv[k].copy_(send[k])
+                else:
+                    reqs.append(dist.isend(send[k], k))
+                    reqs.append(dist.irecv(recv[k], k))
+            for q in reqs:
+                q.wait()
+            n_exchange += 1
+            full = np.concatenate([t.numpy() for t in recv], axis=0)   # all rows of my share of the last mode
+            MTM = allreduce(o.unroll_tensor_contraction(full, 0))
         W.append(o.top_left_singular(MTM, R))
     # two HOOI sweeps with the dimension tree
     parent, sibling = {}, {}
@@ -156,7 +170,7 @@ def _sharded_tucker(rank, nranks, port, lens, R, out_dir):
                 W[i] = o.top_left_singular(o.unroll_tensor_contraction(Y, i), R)
     finally:
         o.ttm = ttm_saved
-    np.savez(os.path.join(out_dir, "trank%d.npz" % rank), n_allreduce=n_allreduce,
+    np.savez(os.path.join(out_dir, "trank%d.npz" % rank), n_allreduce=n_allreduce, n_exchange=n_exchange,
              **{"W%d" % i: w for i, w in enumerate(W)})
     dist.destroy_process_group()
 
@@ -184,6 +198,6 @@ def test_mode0_sharded_hooi_equals_unsharded(tmp_path, lens, R):
         for p in parts:       # replicated factors: same subspace on every rank as the unsharded run
             A, B = p["W%d" % i], W[i]
             assert np.abs(A @ A.T - B @ B.T).max() < 1e-9
-    # HOSVD: N-1 Gram all-reduces + (panels + 1) for mode 0; HOOI: one exchange per mode update
-    panels = (lens[-1] + 1) // 2
-    assert int(parts[0]["n_allreduce"]) == (N - 1) + panels + 1 + 2 * N
+    # HOSVD: N Gram all-reduces + ONE personalised exchange for mode 0; HOOI: one exchange per mode update
+    assert int(parts[0]["n_allreduce"]) == N + 2 * N
+    assert int(parts[0]["n_exchange"]) == 1
