@@ -103,14 +103,28 @@ __global__ void __launch_bounds__(RS_THREADS) cp_reconstruct_kernel(const double
 // owns 128 rows m.  Per tile it puts into shared memory, in DMMA operand layout (leading dimension = 4 mod 16:
 // conflict-free fragment loads), the Khatri-Rao rows K of the tile and as many rows of W_last as fit (all 300 at
 // R = 50: 178 KB together) -- ONE barrier per tile (per super-chunk of W_last when the last mode is long).  After it
-// the warps run free: warp (mg, nh) takes rows 32 mg .. 32 mg + 31 and every other group of 32 columns, computes
-// 32 x 32 with mma.sync m8n8k4 f64 -- accumulators in the very fragment layout whose V elements it needs: the 32 values
-// of V a lane compares against are requested BEFORE the 13 k-steps of the group, so their latency hides behind them --
-// and squares the differences in registers while other warps are in their MMA loops (a first version with W_last in
-// double-buffered 64-column chunks put two barriers around every chunk: all warps computed, then all warps compared;
-// ncu showed the DMMA pipe 52 % busy).  V is read exactly once, in 64-byte pieces (8 consecutive rows per column).
-constexpr int RD_TM = 128;
-constexpr int RD_THREADS = 256;
+// the warps run on their own -- no CTA barrier in steady state: a warp takes a STRIP of 16 rows, keeps its DMMA A
+// fragments (the Khatri-Rao rows of the strip, 2 x 13 doubles per lane at R = 50, formed from independent loads of the
+// factors) in REGISTERS for the whole strip, and walks the columns 13 blocks (104 columns) at a time: 26 independent
+// accumulators, B fragments from the resident W_last, then the 64-byte pieces of V that match its accumulator fragments
+// (8 consecutive rows of a column), squared differences in registers.  The grid is persistent (one CTA of 8 warps per
+// SM); W_last is fetched once per CTA.  V is read exactly once.
+// History at BASELINE configs[1] (78 ms for the DFMA kernel), each step measured on a B200:
+//   60 ms    128-row tile per CTA, K in shared memory built by one thread per row walking k (a dependent product chain)
+//   45.7 ms  W_last in double-buffered 64-column chunks, two barriers around every chunk (ncu: DMMA pipe 52 % busy)
+//   43.2 ms  W_last resident, one bulk copy per tile, V prefetched into the accumulator layout before the MMA loop
+//   42.5 / 44.6 / 42.8 ms  16 warps as 4 x 4, then 8 x 2 balanced + persistent, then without the prefetch whose register
+//            pressure made ptxas schedule the two k-steps of one accumulator back to back
+//   ablation (PPX_K7_DBG): without the V loads 41.3 ms, without the MMA loop 18.6, without both 11.8 -- the per-tile work
+//            outside the MMA (two barriers, 64-bit index arithmetic, the shared-memory image of K) was 8 us of a 30 us tile
+//            and nothing overlapped it, because a tile-wide barrier keeps all warps in the same phase
+//   40.4 ms  strips with K in registers, no barrier (strided strips, Krest recomputed per strip)
+//   41.2 ms  contiguous strip ranges per warp with Krest cached (this version): ablation 7.7 ms without V loads and MMA,
+//            14.6 without the MMA, 32.3 without the V loads -- the three parts add up to the total: with two warps per
+//            scheduler partition (255 registers each) a warp's address/load phase is not covered by the other warp's
+//            MMA phase often enough.  The MMA loop itself now runs at 93 % of the pipe (24.6 ms for 22.9 ms of DMMA).
+//            More warps need fewer registers per thread, i.e. K fragments back in shared memory: open.
+constexpr int RD_THREADS = 256;  // 8 independent warps per CTA
 
 __device__ __forceinline__ uint32_t rd_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void rd_mbar_init(uint64_t *bar, int count) {
@@ -159,165 +173,191 @@ __global__ void __launch_bounds__(256) rd_pack_last_kernel(const double *__restr
     Bp[i] = (k < R && n < slast) ? wl[n + slast * k] : 0.0;
   }
 }
-constexpr int RD_NQ_MAX = 34;  // distinct "other modes" rows of a tile: 128 / lens[0] + 2 with lens[0] >= 4
 
-template <bool WRITE>
+constexpr int RD_NB = 13;  // column blocks per pass: 2 x 13 = 26 independent DMMA accumulators per warp
+
+template <bool WRITE, int NKS>
 __global__ void __launch_bounds__(RD_THREADS, 1) cp_reconstruct_dmma_kernel(const double *__restrict__ V, ResArgs a,
                                                                             int KP, int ld, int ncap,
                                                                             const double *__restrict__ Bp,
+                                                                            int64_t nstrips, int dbg,
                                                                             double *__restrict__ Vout,
                                                                             double *__restrict__ partial) {
   extern __shared__ double sm[];
-  double *As = sm;                          // [RD_TM][ld]
-  double *Bs = sm + RD_TM * ld;             // [ncap][ld]: rows n0s .. n0s + ncap - 1 of W_last
-  double *Kr = Bs + (size_t)ncap * ld;      // [RD_NQ_MAX][KP]
+  double *Bs = sm;                       // [ncap][ld]: rows n0s .. n0s + ncap - 1 of W_last
+  double *Ks = sm + (size_t)ncap * ld;   // [NKS][RD_THREADS]: per-lane Krest slots
   __shared__ double red[32];
   __shared__ uint64_t bar;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t4 = lane & 3;
-  const int mg = warp & 3, nh = warp >> 2;
   const int R = a.R;
-  const int64_t m0 = (int64_t)blockIdx.x * RD_TM;
+  const int ksteps = KP >> 2;
   const int64_t slast = a.lens[a.N - 1];
   const int64_t slast_pad = (slast + 7) & ~(int64_t)7;
+  const int64_t s0 = a.lens[0];
+  const int64_t gw = (int64_t)blockIdx.x * (RD_THREADS / 32) + warp, nw = (int64_t)gridDim.x * (RD_THREADS / 32);
   if (tid == 0) rd_mbar_init(&bar, 1);
-  {
-    // Khatri-Rao rows of the tile, K[m, k] = W_0[i_0(m), k] * Krest[q(m), k], q = m / lens[0] (the other N-2 modes):
-    // a 128-row tile touches nq <= 128 / lens[0] + 2 consecutive q, so Krest is formed once per tile, then every
-    // thread forms 26 entries of K from independent, coalesced loads of W_0 (one thread per row walking k with a
-    // dependent product chain per entry took ~9 us per tile, more than the tile's DMMA work).
-    const int64_t s0 = a.lens[0];
-    const int64_t q_first = m0 / s0;
-    const int64_t m_last = (m0 + RD_TM <= a.P1 ? m0 + RD_TM : a.P1) - 1;
-    const int nq = (int)(m_last / s0 - q_first) + 1;
-    for (int e = tid; e < nq * KP; e += RD_THREADS) {
-      const int qi = e / KP, k = e - qi * KP;
-      double v = 0.0;
-      if (k < R) {
-        v = 1.0;
-        int64_t q = q_first + qi;
-        for (int j = 1; j < a.N - 1; j++) {
-          const int64_t ij = q % a.lens[j];
-          q /= a.lens[j];
-          v *= __ldg(a.w[j] + ij + a.lens[j] * k);
-        }
-      }
-      Kr[qi * KP + k] = v;
-    }
-    __syncthreads();  // (also publishes the mbarrier)
-    if (tid == 0) {   // the first super-chunk of W_last arrives while K is being formed
-      const int64_t nr = slast_pad < ncap ? slast_pad : ncap;
-      const uint32_t bytes = (uint32_t)(nr * ld * sizeof(double));
-      rd_mbar_expect_tx(&bar, bytes);
-      rd_bulk_load(Bs, Bp, bytes, &bar);
-    }
-    const int ml = tid & (RD_TM - 1), half = tid >> 7;
-    const int64_t m = m0 + ml;
-    const bool live = m < a.P1;
-    const int64_t q = (live ? m : m0) / s0;
-    const int64_t i0 = (live ? m : m0) - q * s0;
-    const double *kr = Kr + (int)(q - q_first) * KP;
-    const double *w0 = a.w[0] + i0;
-    for (int kb = half; kb < KP; kb += 32) {  // 16 independent loads in flight per thread and batch
-      double v[16];
-#pragma unroll
-      for (int u = 0; u < 16; u++) {
-        const int k = kb + 2 * u;
-        v[u] = (live && k < R) ? __ldg(w0 + s0 * k) : 0.0;
-      }
-#pragma unroll
-      for (int u = 0; u < 16; u++) {
-        const int k = kb + 2 * u;
-        if (k < KP) As[ml * ld + k] = k < R ? v[u] * kr[k] : 0.0;
-      }
-    }
-  }
-  double ss = 0.0;
-  const int ksteps = KP >> 2;
-  const double *Arow = As + (32 * mg + g) * ld + t4;
-  int sc = 0;
-  for (int64_t n0s = 0; n0s < slast; n0s += ncap, sc++) {  // super-chunks of W_last (one at BASELINE sizes)
+  __syncthreads();
+  double ss4[4] = {0.0, 0.0, 0.0, 0.0};  // four chains: a single running sum would be 156 dependent DFMAs per strip
+  int nload = 0;
+  for (int64_t n0s = 0; n0s < slast; n0s += ncap) {  // super-chunks of W_last: ONE, loaded once per CTA, at BASELINE sizes
     const int nrows_pad = (int)(slast_pad - n0s < ncap ? slast_pad - n0s : ncap);
-    if (n0s > 0) {
-      __syncthreads();  // everyone is done with the previous rows of W_last
-      if (tid == 0) {
-        const uint32_t bytes = (uint32_t)((size_t)nrows_pad * ld * sizeof(double));
-        rd_mbar_expect_tx(&bar, bytes);
-        rd_bulk_load(Bs, Bp + n0s * ld, bytes, &bar);
-      }
+    if (n0s > 0) __syncthreads();  // everyone is done with the previous rows of W_last
+    if (tid == 0) {
+      const uint32_t bytes = (uint32_t)((size_t)nrows_pad * ld * sizeof(double));
+      rd_mbar_expect_tx(&bar, bytes);
+      rd_bulk_load(Bs, Bp + n0s * ld, bytes, &bar);
     }
-    rd_mbar_wait(&bar, sc & 1);
-    if (n0s == 0) __syncthreads();  // K is complete
+    rd_mbar_wait(&bar, nload & 1);
+    nload++;
     const int nblk_all = nrows_pad >> 3;
-    for (int b0 = 4 * nh; b0 < nblk_all; b0 += 8) {  // groups of 4 column blocks, alternating between the warp columns
-      const int cnt = nblk_all - b0 < 4 ? nblk_all - b0 : 4;
-      const int64_t n0 = n0s + 8 * b0;
-      double vreg[4][4][2];
-      if (!WRITE) {
+    // from here to the end of the super-chunk every warp runs on its own: a CONTIGUOUS range of 16-row strips, no CTA
+    // barrier.  Contiguous, so that consecutive strips share the indices of modes 1 .. N-2: their product Krest[k] is
+    // recomputed (two divisions per mode and 13 x (N-2) loads) only when a strip starts a new value of m / lens[0];
+    // in between a strip costs 26 independent loads of W_0 and 26 multiplications.
+    const int64_t per_warp = (nstrips + nw - 1) / nw;
+    const int64_t strip_b = gw * per_warp, strip_e = strip_b + per_warp < nstrips ? strip_b + per_warp : nstrips;
+    // Krest of the current value of m / lens[0] lives in shared memory, one private slot per lane and k-step (13 more
+    // doubles per lane do not fit beside 26 accumulators, 26 A fragments and the B fragments)
+    double *krs = Ks + (size_t)tid;  // slot of k-step ks at krs[ks * RD_THREADS]
+    int64_t q_cached_a = -1;
+    auto krest = [&](int64_t q, double *kr) {
 #pragma unroll
-        for (int i = 0; i < 4; i++)
+      for (int ks = 0; ks < NKS; ks++) kr[ks] = 1.0;
+      for (int j = 1; j < a.N - 1; j++) {
+        const int64_t ij = q % a.lens[j];
+        q /= a.lens[j];
+        const double *wj = a.w[j] + ij;
 #pragma unroll
-          for (int j = 0; j < 4; j++)
-#pragma unroll
-            for (int e = 0; e < 2; e++) {
-              const int64_t m = m0 + 32 * mg + 8 * i + g;
-              const int64_t n = n0 + 8 * j + 2 * t4 + e;
-              vreg[i][j][e] = (j < cnt && m < a.P1 && n < slast) ? rd_ld_stream(V + m + a.P1 * n) : 0.0;
-            }
-      }
-      double acc[4][4][2];
-#pragma unroll
-      for (int i = 0; i < 4; i++)
-#pragma unroll
-        for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
-      const double *Brow = Bs + (8 * b0 + g) * ld + t4;
-      if (cnt == 4) {
-#pragma unroll 2
-        for (int ks = 0; ks < ksteps; ks++) {
-          double af[4], bf[4];
-#pragma unroll
-          for (int i = 0; i < 4; i++) af[i] = Arow[(8 * i) * ld + 4 * ks];
-#pragma unroll
-          for (int j = 0; j < 4; j++) bf[j] = Brow[(8 * j) * ld + 4 * ks];
-#pragma unroll
-          for (int j = 0; j < 4; j++)
-#pragma unroll
-            for (int i = 0; i < 4; i++) ppx_dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
-        }
-      } else {
-        for (int ks = 0; ks < ksteps; ks++) {
-          double af[4], bf[4];
-#pragma unroll
-          for (int i = 0; i < 4; i++) af[i] = Arow[(8 * i) * ld + 4 * ks];
-#pragma unroll
-          for (int j = 0; j < 4; j++) bf[j] = j < cnt ? Brow[(8 * j) * ld + 4 * ks] : 0.0;
-#pragma unroll
-          for (int j = 0; j < 4; j++)
-            if (j < cnt) {
-#pragma unroll
-              for (int i = 0; i < 4; i++) ppx_dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
-            }
+        for (int ks = 0; ks < NKS; ks++) {
+          const int k = 4 * ks + t4;
+          if (ks < ksteps && k < R) kr[ks] *= __ldg(wj + a.lens[j] * k);
         }
       }
+    };
+    for (int64_t strip = strip_b; strip < strip_e; strip++) {
+      const int64_t m0 = strip * 16;
+      // ---- this lane's A fragments, in registers for the whole strip:  areg[i][ks] = K[m0 + 8 i + g, 4 ks + t4],
+      // K[m, k] = W_0[i_0(m), k] * Krest[m / lens[0], k]
+      double areg[2][NKS];
+      {
+        const int64_t ma = m0 + g, mb = m0 + 8 + g;
+        const bool la = ma < a.P1, lb = mb < a.P1;
+        // m / lens[0] without a division in the common case: the previous strip's quotient, advanced when the row passes
+        // the end of its mode-0 fibre
+        int64_t qa, qb;
+        if (q_cached_a >= 0 && ma - q_cached_a * s0 < s0) qa = q_cached_a;
+        else qa = (la ? ma : 0) / s0;
+        if (mb - qa * s0 < s0) qb = qa;
+        else qb = (lb ? mb : 0) / s0;
+        const int64_t ia = (la ? ma : 0) - qa * s0, ib = (lb ? mb : 0) - qb * s0;
+        const double *wa = a.w[0] + ia, *wb = a.w[0] + ib;
+        double wva[NKS], wvb[NKS];
 #pragma unroll
-      for (int i = 0; i < 4; i++)
+        for (int ks = 0; ks < NKS; ks++) {
+          const int k = 4 * ks + t4;
+          wva[ks] = (ks < ksteps && k < R && la) ? __ldg(wa + s0 * k) : 0.0;
+          wvb[ks] = (ks < ksteps && k < R && lb) ? __ldg(wb + s0 * k) : 0.0;
+        }
+        // (the choice is per lane: the 8 rows of a block may straddle a boundary)
+        if (qa != q_cached_a) {
+          double kr[NKS];
+          krest(qa, kr);
 #pragma unroll
-        for (int j = 0; j < 4; j++)
+          for (int ks = 0; ks < NKS; ks++) krs[ks * RD_THREADS] = kr[ks];
+          q_cached_a = qa;
+        }
 #pragma unroll
-          for (int e = 0; e < 2; e++) {
-            if (WRITE) {
-              const int64_t m = m0 + 32 * mg + 8 * i + g;
-              const int64_t n = n0 + 8 * j + 2 * t4 + e;
-              if (j < cnt && m < a.P1 && n < slast) Vout[m + a.P1 * n] = acc[i][j][e];
-            } else {
-              // positions outside the tensor: vreg = 0 and acc = 0 (zero Khatri-Rao row / zero row of W_last)
-              const double df = vreg[i][j][e] - (j < cnt ? acc[i][j][e] : 0.0);
-              ss = fma(df, df, ss);
+        for (int ks = 0; ks < NKS; ks++) areg[0][ks] = wva[ks] * krs[ks * RD_THREADS];
+        if (qb == qa) {
+#pragma unroll
+          for (int ks = 0; ks < NKS; ks++) areg[1][ks] = wvb[ks] * krs[ks * RD_THREADS];
+        } else {  // rare: the second row block has passed the end of the fibre
+          double kr[NKS];
+          krest(qb, kr);
+#pragma unroll
+          for (int ks = 0; ks < NKS; ks++) areg[1][ks] = wvb[ks] * kr[ks];
+        }
+      }
+      for (int b0 = 0; b0 < nblk_all; b0 += RD_NB) {
+        const int cnt = nblk_all - b0 < RD_NB ? nblk_all - b0 : RD_NB;
+        const int64_t n0 = n0s + 8 * b0;
+        double acc[2][RD_NB][2];
+#pragma unroll
+        for (int i = 0; i < 2; i++)
+#pragma unroll
+          for (int j = 0; j < RD_NB; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+        const double *Brow = Bs + (8 * b0 + g) * ld + t4;
+        if (!(dbg & 2)) {
+          if (cnt == RD_NB) {
+#pragma unroll
+            for (int ks = 0; ks < NKS; ks++) {
+              if (ks < ksteps) {
+                double bf[RD_NB];
+#pragma unroll
+                for (int j = 0; j < RD_NB; j++) bf[j] = Brow[(8 * j) * ld + 4 * ks];
+#pragma unroll
+                for (int j = 0; j < RD_NB; j++) {
+                  ppx_dmma(acc[0][j][0], acc[0][j][1], areg[0][ks], bf[j]);
+                  ppx_dmma(acc[1][j][0], acc[1][j][1], areg[1][ks], bf[j]);
+                }
+              }
+            }
+          } else {
+#pragma unroll
+            for (int ks = 0; ks < NKS; ks++) {
+              if (ks < ksteps) {
+#pragma unroll
+                for (int j = 0; j < RD_NB; j++)
+                  if (j < cnt) {
+                    const double bfj = Brow[(8 * j) * ld + 4 * ks];
+                    ppx_dmma(acc[0][j][0], acc[0][j][1], areg[0][ks], bfj);
+                    ppx_dmma(acc[1][j][0], acc[1][j][1], areg[1][ks], bfj);
+                  }
+              }
             }
           }
+        }
+        // epilogue: V in the accumulators' own layout, 16 values per batch (64-byte pieces: 8 consecutive rows of a column)
+#pragma unroll
+        for (int j0 = 0; j0 < RD_NB; j0 += 4) {
+          double v[2][4][2];
+          if (!WRITE) {
+#pragma unroll
+            for (int i = 0; i < 2; i++)
+#pragma unroll
+              for (int j = 0; j < 4; j++)
+#pragma unroll
+                for (int e = 0; e < 2; e++) {
+                  const int64_t m = m0 + 8 * i + g;
+                  const int64_t n = n0 + 8 * (j0 + j) + 2 * t4 + e;
+                  v[i][j][e] = (j0 + j < cnt && m < a.P1 && n < slast && !(dbg & 1)) ? rd_ld_stream(V + m + a.P1 * n) : 0.0;
+                }
+          }
+#pragma unroll
+          for (int i = 0; i < 2; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+#pragma unroll
+              for (int e = 0; e < 2; e++) {
+                if (j0 + j < RD_NB) {
+                  if (WRITE) {
+                    const int64_t m = m0 + 8 * i + g;
+                    const int64_t n = n0 + 8 * (j0 + j) + 2 * t4 + e;
+                    if (j0 + j < cnt && m < a.P1 && n < slast) Vout[m + a.P1 * n] = acc[i][j0 + j][e];
+                  } else {
+                    // positions outside the tensor: v = 0 and acc = 0 (zero Khatri-Rao row / zero row of W_last)
+                    const double df = v[i][j][e] - (j0 + j < cnt ? acc[i][j0 + j][e] : 0.0);
+                    ss4[2 * i + e] = fma(df, df, ss4[2 * i + e]);
+                  }
+                }
+              }
+        }
+      }
     }
   }
   if (!WRITE) {
+    double ss = (ss4[0] + ss4[1]) + (ss4[2] + ss4[3]);
     ss = ppx_block_sum(ss, red);
     if (tid == 0) partial[blockIdx.x] = ss;
   }
@@ -326,18 +366,15 @@ __global__ void __launch_bounds__(RD_THREADS, 1) cp_reconstruct_dmma_kernel(cons
 // leading dimension of the shared operands: >= KP and = 4 (mod 16), so that the 32 lanes of a fragment load (8 rows x
 // 4 consecutive k) fall into 32 different 8-byte banks per half-warp
 inline int rd_ld(int KP) { return KP + ((4 - KP % 16 + 16) % 16); }
-// rows of W_last kept in shared memory at a time: all of them when they fit beside K and Krest in 220 KB
-inline int rd_ncap(int KP, int ld, int64_t slast) {
-  const int64_t budget = 220 * 1024 / 8 - (int64_t)RD_TM * ld - (int64_t)RD_NQ_MAX * KP;
-  int64_t cap = budget / ld;
-  cap &= ~(int64_t)63;  // whole 64-column pairs of warp groups
+// rows of W_last kept in shared memory at a time: all of them when they fit in 172 KB
+inline int rd_ncap(int ld, int64_t slast) {
+  int64_t cap = (172 * 1024 / 8) / ld;  // + 13 x 256 doubles of Krest slots = 26 KB
+  cap &= ~(int64_t)7;
   const int64_t need = (slast + 7) & ~(int64_t)7;
   if (cap > need) cap = need;
   return (int)cap;
 }
-inline size_t rd_smem(int KP, int ld, int ncap) {
-  return sizeof(double) * ((size_t)(RD_TM + ncap) * ld + (size_t)RD_NQ_MAX * KP);
-}
+inline size_t rd_smem(int ld, int ncap) { return sizeof(double) * ((size_t)ncap * ld + 13 * (size_t)RD_THREADS); }
 
 }  // namespace
 
@@ -347,10 +384,38 @@ int ppx_k7_init(ppx_ctx *ctx) {
   const int big = 200 * 1024;
   PPX_CUDA(ctx, cudaFuncSetAttribute(cp_reconstruct_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   PPX_CUDA(ctx, cudaFuncSetAttribute(cp_reconstruct_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-  const int dmma_max = 220 * 1024;
-  PPX_CUDA(ctx, cudaFuncSetAttribute(cp_reconstruct_dmma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dmma_max));
-  PPX_CUDA(ctx, cudaFuncSetAttribute(cp_reconstruct_dmma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dmma_max));
+  const int dmma_max = 204 * 1024;
+#define PPX_K7_ATTR(W, NKS) \
+  PPX_CUDA(ctx, cudaFuncSetAttribute(cp_reconstruct_dmma_kernel<W, NKS>, cudaFuncAttributeMaxDynamicSharedMemorySize, dmma_max))
+  PPX_K7_ATTR(true, 3);
+  PPX_K7_ATTR(true, 7);
+  PPX_K7_ATTR(true, 13);
+  PPX_K7_ATTR(false, 3);
+  PPX_K7_ATTR(false, 7);
+  PPX_K7_ATTR(false, 13);
+#undef PPX_K7_ATTR
   return PPX_OK;
+}
+
+// The strip kernel is used where the FP64 pipe is the limit: 24 <= R <= 52 (k-steps held in registers: 7 or 13 of
+// them), a tensor big enough to care and a leading extent that keeps a 16-row strip within two values of the other
+// modes' indices.  At R = 10 the residual is bandwidth bound and the DFMA kernel above is the faster one (order 6,
+// s = 40: 18.6 ms = 1.76 TB/s against 22.6 ms; measured, profiles/).  PPX_K7_FORCE_DMMA / PPX_K7_DFMA override.
+static bool rd_eligible(const ResArgs &a) {
+  if (getenv("PPX_K7_DFMA")) return false;
+  const bool shape_ok = a.R <= 52 && a.P1 * a.lens[a.N - 1] >= (1 << 16) && a.lens[0] >= 16;
+  return shape_ok && (a.R >= 24 || getenv("PPX_K7_FORCE_DMMA"));
+}
+template <bool WRITE>
+static void rd_launch(ppx_ctx *ctx, int grid, size_t smem, const double *V, const ResArgs &a, int KP, int ld, int ncap,
+                      const double *Bp, int64_t nstrips, int dbg, double *Vout, double *partial) {
+  const int ks = KP >> 2;
+  if (ks <= 3)
+    cp_reconstruct_dmma_kernel<WRITE, 3><<<grid, RD_THREADS, smem, ctx->stream>>>(V, a, KP, ld, ncap, Bp, nstrips, dbg, Vout, partial);
+  else if (ks <= 7)
+    cp_reconstruct_dmma_kernel<WRITE, 7><<<grid, RD_THREADS, smem, ctx->stream>>>(V, a, KP, ld, ncap, Bp, nstrips, dbg, Vout, partial);
+  else
+    cp_reconstruct_dmma_kernel<WRITE, 13><<<grid, RD_THREADS, smem, ctx->stream>>>(V, a, KP, ld, ncap, Bp, nstrips, dbg, Vout, partial);
 }
 
 // packs W_last into the workspace (after whatever the caller allocated there); NULL when the workspace is too small
@@ -394,14 +459,17 @@ int ppx_cp_residual(ppx_ctx *ctx, const double *V, const int64_t *lens, int N, c
   double *partial = (double *)ppx_ws_alloc(ctx, sizeof(double) * (size_t)blocks);
   if (!partial) return ppx_set_err(ctx, PPX_ENOMEM, "cp_residual needs %lld bytes of workspace", (long long)blocks * 8);
   const int KP = (R + 3) & ~3, ld = rd_ld(KP);
-  const int ncap = rd_ncap(KP, ld, a.lens[N - 1]);
-  // tensor-pipe kernel whenever its operands fit in shared memory and the tensor is big enough to care
+  const int ncap = rd_ncap(ld, a.lens[N - 1]);
   double *Bp = nullptr;
-  if (ncap >= 8 && a.P1 * a.lens[N - 1] >= (1 << 16) && a.lens[0] >= 4 && !getenv("PPX_K7_DFMA"))
-    Bp = rd_pack_last(ctx, a, ld);
+  if (ncap >= 8 && rd_eligible(a)) Bp = rd_pack_last(ctx, a, ld);
   if (Bp) {
-    cp_reconstruct_dmma_kernel<false><<<(unsigned)blocks, RD_THREADS, rd_smem(KP, ld, ncap), ctx->stream>>>(
-        V, a, KP, ld, ncap, Bp, nullptr, partial);
+    const int64_t nstrips = (a.P1 + 15) / 16;
+    const int64_t want = (nstrips + RD_THREADS / 32 - 1) / (RD_THREADS / 32);
+    const int grid = (int)(want < ctx->sm_count ? want : ctx->sm_count);  // persistent; partial[] has >= grid entries
+    const int dbg = getenv("PPX_K7_DBG") ? atoi(getenv("PPX_K7_DBG")) : 0;  // timing experiments: 1 no V loads, 2 no MMA
+    rd_launch<false>(ctx, grid, rd_smem(ld, ncap), V, a, KP, ld, ncap, Bp, nstrips, dbg, nullptr, partial);
+    PPX_CHECK_LAUNCH(ctx);
+    return ppx_sum_partials(ctx, partial, grid, sq_out_dev);
   } else {
     const size_t smem = sizeof(double) * (size_t)R * (RS_TM + RS_TD);
     cp_reconstruct_kernel<false><<<(unsigned)blocks, RS_THREADS, smem, ctx->stream>>>(V, a, nullptr, partial);
@@ -418,15 +486,17 @@ int ppx_cp_reconstruct(ppx_ctx *ctx, const int64_t *lens, int N, const double *c
   const int64_t blocks = (a.P1 + RS_TM - 1) / RS_TM;
   if (blocks > 0x7fffffffLL) return ppx_set_err(ctx, PPX_EUNSUPPORTED, "cp_reconstruct: grid too large");
   const int KP = (R + 3) & ~3, ld = rd_ld(KP);
-  const int ncap = rd_ncap(KP, ld, a.lens[N - 1]);
+  const int ncap = rd_ncap(ld, a.lens[N - 1]);
   double *Bp = nullptr;
-  if (ncap >= 8 && a.P1 * a.lens[N - 1] >= (1 << 16) && a.lens[0] >= 4 && !getenv("PPX_K7_DFMA")) {
+  if (ncap >= 8 && rd_eligible(a)) {
     ppx_ws_reset(ctx);
     Bp = rd_pack_last(ctx, a, ld);
   }
   if (Bp) {
-    cp_reconstruct_dmma_kernel<true><<<(unsigned)blocks, RD_THREADS, rd_smem(KP, ld, ncap), ctx->stream>>>(
-        nullptr, a, KP, ld, ncap, Bp, V_out, nullptr);
+    const int64_t nstrips = (a.P1 + 15) / 16;
+    const int64_t want = (nstrips + RD_THREADS / 32 - 1) / (RD_THREADS / 32);
+    const int grid = (int)(want < ctx->sm_count ? want : ctx->sm_count);
+    rd_launch<true>(ctx, grid, rd_smem(ld, ncap), nullptr, a, KP, ld, ncap, Bp, nstrips, 0, V_out, nullptr);
   } else {
     const size_t smem = sizeof(double) * (size_t)R * (RS_TM + RS_TD);
     cp_reconstruct_kernel<true><<<(unsigned)blocks, RS_THREADS, smem, ctx->stream>>>(nullptr, a, V_out, nullptr);

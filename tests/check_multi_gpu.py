@@ -30,8 +30,11 @@ if rank == 0:
 dist.broadcast(idt, 0)
 
 ok_all = True
-for lens, R, maxiter, tol_init in [((13, 12, 11, 10), 4, 40, 0.1), ((9, 10, 11), 3, 30, 0.1), ((6, 7, 6, 5, 6, 7), 3, 40, 0.1)]:
+for lens, R, maxiter, tol_init in [((13, 12, 11, 10), 4, 40, 0.1), ((9, 10, 11), 3, 30, 0.1), ((6, 7, 6, 5, 6, 7), 3, 40, 0.1),
+                                   ((37, 9, 8, 7), 3, 24, 0.1)]:
     N = len(lens)
+    if lens[0] < nranks:  # every rank needs at least one row of the sharded mode
+        lens = (nranks,) + tuple(lens[1:])
     b, e = ppx.shard_range(lens[0], nranks, rank)
     if world.np == 1:
         world.comm_init(bytes(idt.cpu().tolist()), nranks, rank, 0, lens[0], b, e)  # NCCL communicator, once

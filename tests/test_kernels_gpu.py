@@ -310,7 +310,11 @@ def test_sqnorms_and_diff_update(ctx):
                                     # mode, ragged in both; R padded to a multiple of 4; every leading dimension class)
                                     ((40, 30, 20, 35), 50), ((64, 33, 50), 10), ((130, 35, 300), 3), ((7, 9, 11, 13, 9), 27),
                                     ((300, 250), 64), ((50, 40, 60), 100), ((129, 8, 8, 70), 1), ((33, 2000), 12),
-                                    ((50, 40, 60), 101)])
+                                    ((50, 40, 60), 101),
+                                    # the strip kernel's register classes (3 / 7 / 13 k-steps), strips that cross a
+                                    # boundary of the leading mode, two super-chunks of the last factor
+                                    ((17, 19, 23, 40), 28), ((300, 30, 304), 52), ((20, 20, 20, 20), 13),
+                                    ((18, 5000), 9), ((16, 16, 16, 16, 16), 5)])
 def test_cp_residual_and_reconstruct(ctx, lens, R):
     N = len(lens)
     W = [rnd((lens[i], R), 100 + i) for i in range(N)]
