@@ -86,8 +86,11 @@ def proj_err(A, B):
     return float(np.abs(A @ A.T - B @ B.T).max())
 
 
-for lens, R, tol_init in [((12, 13, 14), 3, 0.3), ((9, 10, 8, 7), 3, 0.3)]:
+for lens, R, tol_init in [((12, 13, 14), 3, 0.3), ((9, 10, 8, 7), 3, 0.3), ((3, 13, 14), 3, 0.3), ((3, 7, 6, 5), 2, 0.3),
+                          ((6, 13, 14), 3, 0.3)]:
     N = len(lens)
+    if lens[0] < nranks:
+        lens = (nranks,) + tuple(lens[1:])
     b, e = ppx.shard_range(lens[0], nranks, rank)
     world.set_shard(0, lens[0], b, e)
     V = o.make_tensor_r2(lens)
@@ -97,8 +100,12 @@ for lens, R, tol_init in [((12, 13, 14), 3, 0.3), ((9, 10, 8, 7), 3, 0.3)]:
     Wd = [H.Matrix(world, lens[i], R) for i in range(N)]
     cored = H.Tensor(world, (R,) * N)
     H.hosvd(world, Vd, cored, Wd, [R] * N)
-    ok = all(proj_err(Wd[i].numpy(), W_ref[i]) < 1e-8 for i in range(N))
+    hosvd_err = [proj_err(Wd[i].numpy(), W_ref[i]) for i in range(N)]
+    ok = all(x < 1e-8 for x in hosvd_err)
     ok &= abs(np.linalg.norm(cored.numpy()) - np.linalg.norm(core_ref)) < 1e-10 * vnorm
+    if not ok and rank == 0:
+        print(f"  Tucker lens {lens}: hosvd itself differs: proj_err {hosvd_err} core norm {np.linalg.norm(cored.numpy())} "
+              f"vs {np.linalg.norm(core_ref)}", flush=True)
     W2 = [w.copy() for w in W_ref]
     ok_ref, rows_ref, _ = o.alsTucker_DT(V, core_ref, W2, 1e-10 * vnorm, 12, resprint=4)
     with H.Trace(quiet=True) as t:
@@ -111,6 +118,9 @@ for lens, R, tol_init in [((12, 13, 14), 3, 0.3), ((9, 10, 8, 7), 3, 0.3)]:
     ok &= all(proj_err(Wd[i].numpy(), W2[i]) < 1e-7 for i in range(N))
     print(f"rank {rank} Tucker lens {lens} R {R} hosvd+DT: {'OK' if ok else 'MISMATCH'} rows {len(t.rows)} "
           f"fit_err {worst:.2e}", flush=True)
+    if not ok and rank == 0:  # what differs: the HOSVD subspaces, the core, or the logged rows
+        print("  hosvd proj_err", [proj_err(Wd[i].numpy(), W2[i]) for i in range(N)], "rows gpu", [tuple(r[:4]) for r in t.rows],
+              "rows ref", rows_ref, flush=True)
     ok_all &= ok
     for x in Wd + [cored]:
         x.free()
