@@ -156,6 +156,70 @@ def cpu_build_V(np, o, Wt, rows0):
     return V2.reshape(tuple(lens[:0:-1]) + (rows0,)).T  # F-contiguous view with shape (rows0, s_1, .., s_{N-1})
 
 
+def openblas_path():
+    """The OpenBLAS shared library NumPy ships (numpy.libs/libscipy_openblas64_*.so), for the stand-in's DGEMM path."""
+    try:
+        import glob
+
+        import numpy
+
+        hits = glob.glob(os.path.join(os.path.dirname(numpy.__file__), "..", "numpy.libs", "libscipy_openblas*.so"))
+        return os.path.abspath(hits[0]) if hits else None
+    except Exception:
+        return None
+
+
+def reference_sources_crosscheck(R, N, small=100, sweeps=2):
+    """For the record (not the baseline): the reference's OWN alsCP_DT -- oracle/_ref/test_ALS, the unmodified sources on
+    the CTF stand-in with its DGEMM path switched on -- against the NumPy port on the same small cube, both on the same
+    BLAS and thread count.  It answers "is the port a strawman?": the reference's code copies the tensor into V_front for
+    every first-level tree node (common.cxx:31-33) and materialises every level-1 intermediate, so it is the slower one."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "test_ALS")
+    blas = openblas_path()
+    if not os.path.exists(exe) or not blas:
+        return None
+    import re
+
+    import numpy as np
+    from oracle import pp_oracle as o
+    try:
+        env = dict(os.environ, CTF_STANDIN_BLAS=blas)
+        with tempfile.TemporaryDirectory() as td:
+            out = subprocess.run([exe, "-model", "CP", "-tensor", "r", "-dim", str(N), "-size", str(small), "-rank", str(R),
+                                  "-pp", "0", "-maxiter", str(sweeps), "-resprint", "1000000", "-filename",
+                                  os.path.join(td, "x.csv")], capture_output=True, text=True, timeout=600, cwd=td, env=env).stdout
+        m = re.findall(r"\[iter\]=\s+%d\s.*\[dtime\]\s+(\S+)" % sweeps, out)
+        if not m:
+            return {"error": "no [dtime] line"}
+        ref_sec = float(m[-1]) / sweeps
+        lens = (small,) * N
+        Wt = [o.fill_uniform((l, R), 1, i) for i, l in enumerate(lens)]
+        V = cpu_build_V(np, o, Wt, small)
+        W = [o.fill_uniform((l, R), 2, i) for i, l in enumerate(lens)]
+        parent, sibling = {}, {}
+        o.construct_dimension_tree(parent, sibling, 0, N - 1)
+
+        def sweep():
+            mm = {}
+            for i in range(N):
+                M = o._leaf_M(mm, parent, sibling, V, W, i)
+                S = o.gram_hadamard(W, i, 0.0, True)
+                W[i] = o.SVD_solve(M, S)
+            o.normalize(W)
+
+        sweep()
+        t0 = time.perf_counter()
+        for _ in range(sweeps):
+            sweep()
+        port_sec = (time.perf_counter() - t0) / sweeps
+        return {"size": small, "reference_sources_s_per_sweep": ref_sec, "numpy_port_s_per_sweep": port_sec,
+                "what": "oracle/_ref/test_ALS (the reference's unmodified sources; CTF stand-in with its DGEMM path, same "
+                        "OpenBLAS and threads) vs oracle/pp_oracle.py on an order-%d cube of size %d, R=%d; residual "
+                        "evaluations off the clock in both" % (N, small, R)}
+    except Exception as exc:  # noqa: BLE001
+        return {"error": "%s: %s" % (type(exc).__name__, exc)}
+
+
 def run_reference_child(args):
     """The reference arm proper (runs with the BLAS thread count fixed by the parent): the reference's sweep on the host
     cores, NumPy + OpenBLAS port (oracle/pp_oracle.py), full tensor when the host memory allows."""
@@ -237,7 +301,9 @@ def run_reference_child(args):
         "cpu_baseline": {"value": val, "unit": "sweeps/s", "cores": cores, "kind": "port", "sample": sample,
                          "full_tensor": full, "blas_pools": pools, "host_threads_available": host_threads()},
         "e2e": {"value": val, "unit": "sweeps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0, "wall_s": time.perf_counter() - t_start,
+        "gpu_launches": 0,
+        "reference_sources_on_blas_standin": reference_sources_crosscheck(R, N) if (args.dump_factors is None and len(set(lens)) == 1) else None,
+        "wall_s": time.perf_counter() - t_start,
         "reference_note": "Cyclops CTF / MPI / ScaLAPACK are absent from this image and cannot be installed (no network); "
                           "oracle/_ref (the reference's own sources on a loop-based CTF stand-in) is a correctness checker "
                           "and would be an unfairly slow baseline, so the BLAS-backed port is what is timed",

@@ -9,6 +9,11 @@
  * D["ij"]`, `+=`, `-=`, repeated indices = diagonals, indices absent from the output are summed) evaluated with plain
  * loops; svd (one-sided Jacobi), qr, cholesky, solve_tri; norm2, write, read_local, read_dense_from_file, fill_random;
  * Transform<>; Timer/Timer_epoch; World; the handful of MPI symbols the mains call.
+ * Optional: with CTF_STANDIN_BLAS=<path of an OpenBLAS shared library> (bench.py's CPU arm points it at the one NumPy
+ * ships) a product of two tensors whose index pattern folds into a matrix product -- the tensor-times-matrix and
+ * Hadamard-batched contractions of the dimension tree, the Grams, the solves -- is handed to DGEMM slice by slice, the
+ * way CTF itself maps a contraction to local GEMMs; everything else, and everything when the variable is unset (all
+ * parity tests), runs through the plain loops.  tests/test_reference_pin.py checks the two paths against each other.
  * What it is not: CTF.  Summation order, the SVD algorithm and fill_random's stream differ from the real library, so
  * agreement with a CTF build holds to rounding (and up to the sign of singular vectors), not bit for bit.
  * fill_random(lo, hi) draws u(seed, id, linear_index) from the repo's counter-based generator (oracle/pp_oracle.py
@@ -26,6 +31,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <dlfcn.h>
 #include <fstream>
 #include <functional>
 #include <iomanip>
@@ -35,6 +41,7 @@
 #include <set>
 #include <sstream>
 #include <string>
+#include <thread>
 #include <vector>
 
 /* ---------------------------------------------------------------- MPI symbols the mains use (one process) */
@@ -321,11 +328,223 @@ inline void accumulate(vector<double> &acc, const TensorBase *out, const string 
     if (d == nd) break;
   }
 }
+/* ---- optional DGEMM path (CTF_STANDIN_BLAS) ---------------------------------------------------------------------- */
+typedef void (*dgemm64_t)(int order, int ta, int tb, int64_t m, int64_t n, int64_t k, double alpha, const double *a,
+                          int64_t lda, const double *b, int64_t ldb, double beta, double *c, int64_t ldc);
+typedef void (*dgemm32_t)(int order, int ta, int tb, int m, int n, int k, double alpha, const double *a, int lda,
+                          const double *b, int ldb, double beta, double *c, int ldc);
+struct Blas {
+  dgemm64_t g64 = nullptr;
+  dgemm32_t g32 = nullptr;
+  void (*set_threads)(int) = nullptr;
+  Blas() {
+    const char *path = getenv("CTF_STANDIN_BLAS");
+    if (!path || !*path) return;
+    void *lib = dlopen(path, RTLD_NOW | RTLD_LOCAL);
+    if (!lib) {
+      fprintf(stderr, "ctf stand-in: cannot load %s: %s\n", path, dlerror());
+      return;
+    }
+    for (const char *n : {"scipy_cblas_dgemm64_", "cblas_dgemm64_"})
+      if (!g64) g64 = (dgemm64_t)dlsym(lib, n);
+    if (!g64) g32 = (dgemm32_t)dlsym(lib, "cblas_dgemm");
+    for (const char *n : {"scipy_openblas_set_num_threads64_", "openblas_set_num_threads64_", "openblas_set_num_threads"})
+      if (!set_threads) set_threads = (void (*)(int))dlsym(lib, n);
+  }
+  bool ok() const { return g64 || g32; }
+  /* column-major C (m x n, ldc) += alpha op(A) op(B) */
+  void gemm(bool ta, bool tb, int64_t m, int64_t n, int64_t k, double alpha, const double *a, int64_t lda, const double *b,
+            int64_t ldb, double *c, int64_t ldc) const {
+    if (g64) g64(102, ta ? 112 : 111, tb ? 112 : 111, m, n, k, alpha, a, lda, b, ldb, 1.0, c, ldc);
+    else g32(102, ta ? 112 : 111, tb ? 112 : 111, (int)m, (int)n, (int)k, alpha, a, (int)lda, b, (int)ldb, 1.0, c, (int)ldc);
+  }
+};
+inline const Blas &blas() {
+  static Blas b;
+  return b;
+}
+struct IdxInfo {
+  int64_t ext, sa, sb, so; /* stride in A, B, out; -1 when absent */
+};
+/* merges, in increasing order of `key`, the indices of `grp` that are contiguous in both tensors of the group:
+ * returns the merged extent, fills the two strides, moves what is left to `rest` */
+inline int64_t merge_group(vector<IdxInfo> grp, int which1, int which2, int64_t &s1, int64_t &s2, vector<IdxInfo> &rest) {
+  auto st = [](const IdxInfo &x, int w) { return w == 0 ? x.sa : (w == 1 ? x.sb : x.so); };
+  if (grp.empty()) {
+    s1 = s2 = 1;
+    return 1;
+  }
+  sort(grp.begin(), grp.end(), [&](const IdxInfo &x, const IdxInfo &y) { return st(x, which2) < st(y, which2); });
+  int64_t ext = grp[0].ext;
+  s1 = st(grp[0], which1);
+  s2 = st(grp[0], which2);
+  size_t used = 1;
+  while (used < grp.size() && st(grp[used], which1) == s1 * ext && st(grp[used], which2) == s2 * ext) {
+    ext *= grp[used].ext;
+    used++;
+  }
+  for (size_t i = used; i < grp.size(); i++) rest.push_back(grp[i]);
+  return ext;
+}
+/* acc += coef * A * B through DGEMM when the index pattern allows it; false = not taken (nothing written) */
+inline bool accumulate_blas(vector<double> &acc, const TensorBase *out, const string &oidx, const Prod &q) {
+  const Blas &bl = blas();
+  if (!bl.ok() || q.f.size() != 2) return false;
+  const Leaf &A = q.f[0], &B = q.f[1];
+  auto has_repeat = [](const string &x) {
+    for (size_t i = 0; i < x.size(); i++)
+      if (x.find(x[i]) != i) return true;
+    return false;
+  };
+  if (has_repeat(A.idx) || has_repeat(B.idx) || has_repeat(oidx)) return false;
+  vector<int64_t> stA, stB, stO;
+  strides_of(A.t, stA);
+  strides_of(B.t, stB);
+  strides_of(out, stO);
+  string chars = oidx;
+  for (char c : A.idx + B.idx)
+    if (chars.find(c) == string::npos) chars.push_back(c);
+  vector<IdxInfo> Mg, Ng, Kg, loops;
+  int64_t work = 1;
+  for (char c : chars) {
+    IdxInfo x{0, -1, -1, -1};
+    size_t pa = A.idx.find(c), pb = B.idx.find(c), po = oidx.find(c);
+    if (pa != string::npos) x.sa = stA[pa], x.ext = A.t->lens[pa];
+    if (pb != string::npos) {
+      if (pa != string::npos && B.t->lens[pb] != x.ext) return false;
+      x.sb = stB[pb], x.ext = B.t->lens[pb];
+    }
+    if (po != string::npos) {
+      if (x.ext && out->lens[po] != x.ext) return false;
+      x.so = stO[po], x.ext = out->lens[po];
+    }
+    if (x.ext == 0) return true; /* empty contraction: nothing to add */
+    work *= x.ext;
+    const bool a = x.sa >= 0, b = x.sb >= 0, o = x.so >= 0;
+    if (a && b && o) loops.push_back(x); /* batch (Hadamard) index */
+    else if (a && !b && o) Mg.push_back(x);
+    else if (!a && b && o) Ng.push_back(x);
+    else if (a && b && !o) Kg.push_back(x);
+    else return false; /* summed over one operand only, or broadcast: plain loops */
+  }
+  if (work < 4096) return false; /* tiny: not worth a library call */
+  int64_t am, cm, bn, cn, ak, bk;
+  const int64_t M = merge_group(Mg, 0, 2, am, cm, loops);
+  const int64_t N = merge_group(Ng, 1, 2, bn, cn, loops);
+  const int64_t K = merge_group(Kg, 1, 0, bk, ak, loops);
+  /* leftover indices become loops; absent strides count as 0 */
+  for (auto &x : loops) {
+    if (x.sa < 0) x.sa = 0;
+    if (x.sb < 0) x.sb = 0;
+    if (x.so < 0) x.so = 0;
+  }
+  /* orientation: C column-major needs a unit stride along m (or n, then C^T = B^T A^T) */
+  bool swap_roles = false;
+  if (!(cm == 1 || M == 1)) {
+    if (cn == 1 || N == 1) swap_roles = true;
+    else return false;
+  }
+  int64_t m = M, n = N, k = K, a_m = am, a_k = ak, b_k = bk, b_n = bn, c_m = cm, c_n = cn;
+  const double *pa0 = A.t->data.data(), *pb0 = B.t->data.data();
+  vector<IdxInfo> lp = loops;
+  if (swap_roles) { /* C^T (n x m) = B^T (n x k) A^T (k x m) */
+    m = N, n = M;
+    a_m = bn, a_k = bk, b_k = ak, b_n = am, c_m = cn, c_n = cm;
+    std::swap(pa0, pb0);
+    for (auto &x : lp) std::swap(x.sa, x.sb);
+  }
+  bool ta, tb;
+  int64_t lda, ldb, ldc;
+  if (a_m == 1 || m == 1) ta = false, lda = (k == 1 ? std::max<int64_t>(m, 1) : a_k);
+  else if (a_k == 1 || k == 1) ta = true, lda = a_m;
+  else return false;
+  if (b_k == 1 || k == 1) tb = false, ldb = (n == 1 ? std::max<int64_t>(k, 1) : b_n);
+  else if (b_n == 1 || n == 1) tb = true, ldb = b_k;
+  else return false;
+  ldc = (n == 1 ? std::max<int64_t>(m, 1) : c_n);
+  if (lda < (ta ? k : m) || ldb < (tb ? n : k) || ldc < m) return false;
+  int64_t nloop = 1;
+  for (auto &x : lp) nloop *= x.ext;
+  /* indices that are summed (K leftovers) make different loop iterations write the same C: those stay serial */
+  bool loops_disjoint = true;
+  for (auto &x : lp)
+    if (x.so == 0 && x.ext > 1) loops_disjoint = false;
+  auto run = [&](int64_t it0, int64_t it1) {
+    vector<int64_t> ctr(lp.size(), 0);
+    int64_t oa = 0, ob = 0, oc = 0, rem = it0;
+    for (size_t d = 0; d < lp.size(); d++) {
+      ctr[d] = rem % lp[d].ext;
+      rem /= lp[d].ext;
+      oa += ctr[d] * lp[d].sa, ob += ctr[d] * lp[d].sb, oc += ctr[d] * lp[d].so;
+    }
+    for (int64_t it = it0; it < it1; it++) {
+      bl.gemm(ta, tb, m, n, k, q.coef, pa0 + oa, lda, pb0 + ob, ldb, acc.data() + oc, ldc);
+      for (size_t d = 0; d < lp.size(); d++) {
+        ctr[d]++;
+        oa += lp[d].sa, ob += lp[d].sb, oc += lp[d].so;
+        if (ctr[d] < lp[d].ext) break;
+        oa -= lp[d].sa * lp[d].ext, ob -= lp[d].sb * lp[d].ext, oc -= lp[d].so * lp[d].ext;
+        ctr[d] = 0;
+      }
+    }
+  };
+  /* many small products: one BLAS thread each, the loop spread over the cores; few large ones: BLAS threads */
+  const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+  const char *nt_env = getenv("OMP_NUM_THREADS");
+  const unsigned nthr = nt_env ? (unsigned)std::max(1, atoi(nt_env)) : hw;
+  const double flops_each = 2.0 * (double)m * (double)n * (double)k;
+  if (loops_disjoint && nthr > 1 && nloop >= 4 * (int64_t)nthr && flops_each < 2e8 && bl.set_threads) {
+    bl.set_threads(1);
+    vector<std::thread> pool;
+    for (unsigned t = 0; t < nthr; t++)
+      pool.emplace_back(run, nloop * t / nthr, nloop * (t + 1) / nthr);
+    for (auto &th : pool) th.join();
+    bl.set_threads((int)nthr);
+  } else {
+    run(0, nloop);
+  }
+  return true;
+}
+/* out (+)= coef * A with identical index strings: a plain vector update (the residual V - V_build of als_CP.cxx:183-187) */
+inline bool accumulate_axpy(vector<double> &acc, const TensorBase *out, const string &oidx, const Prod &q) {
+  if (!blas().ok() || q.f.size() != 1 || q.f[0].idx != oidx || q.f[0].t->data.size() != acc.size()) return false;
+  for (size_t i = 0; i < oidx.size(); i++)
+    if (oidx.find(oidx[i]) != i) return false;
+  const double *a = q.f[0].t->data.data();
+  const double c = q.coef;
+  const size_t n = acc.size();
+  const unsigned nthr = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+  if (n < (1u << 22)) {
+    for (size_t i = 0; i < n; i++) acc[i] += c * a[i];
+  } else {
+    vector<std::thread> pool;
+    for (unsigned t = 0; t < nthr; t++)
+      pool.emplace_back([&, t]() {
+        for (size_t i = n * t / nthr; i < n * (t + 1) / nthr; i++) acc[i] += c * a[i];
+      });
+    for (auto &th : pool) th.join();
+  }
+  return true;
+}
+
 /* mode 0: out = rhs, +1: out += rhs, -1: out -= rhs.  The right-hand side is evaluated completely first (it may
  * mention the output tensor). */
 inline void assign(TensorBase *out, const string &oidx, const Term &rhs, int mode) {
   vector<double> acc(out->data.size(), 0.0);
-  for (const auto &q : rhs.p) accumulate(acc, out, oidx, q);
+  static const bool verbose = getenv("CTF_STANDIN_VERBOSE") != nullptr;
+  for (const auto &q : rhs.p) {
+    const double t0 = verbose ? MPI_Wtime() : 0.0;
+    int path = 0;
+    if (accumulate_blas(acc, out, oidx, q)) path = 1;
+    else if (accumulate_axpy(acc, out, oidx, q)) path = 2;
+    else accumulate(acc, out, oidx, q);
+    if (verbose && MPI_Wtime() - t0 > 0.05) {
+      string desc;
+      for (const auto &l : q.f) desc += l.idx + " ";
+      fprintf(stderr, "ctf stand-in: %s-> %s  %s  %.3f s\n", desc.c_str(), oidx.c_str(),
+              path == 1 ? "dgemm" : (path == 2 ? "axpy" : "loops"), MPI_Wtime() - t0);
+    }
+  }
   bool repeated = false;
   for (size_t i = 0; i < oidx.size(); i++)
     if (oidx.find(oidx[i]) != i) repeated = true;

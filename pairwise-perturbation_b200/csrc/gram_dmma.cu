@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(GB_THREADS, 2) gram_dmma_kernel(GramParams p) 
         double *dst = (isA ? As + row * GB_LDK : Bs + (row - GB_M) * GB_LDK) + 2 * kp;
         const double *src = base + lg + p.L * pg;
         if (p.vec) {
-          ppx_cp_async16(dst, (rv && kv) ? src : p.T, (rv && kv == 2) ? 16 : 0);
+          ppx_cp_async16(dst, (rv && kv) ? src : p.T, !rv ? 0 : (kv == 2 ? 16 : (kv == 1 ? 8 : 0)));
         } else {
           ppx_cp_async8(dst, (rv && kv >= 1) ? src : p.T, (rv && kv >= 1) ? 8 : 0);
           ppx_cp_async8(dst + 1, (rv && kv == 2) ? src + 1 : p.T, (rv && kv == 2) ? 8 : 0);
@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(GB_THREADS, 2) gram_dmma_kernel(GramParams p) 
           double *dst = As + k * GB_LDM + ml;
           const double *src = p.T + pg + p.X * (c0 + k);
           if (p.vec) {
-            ppx_cp_async16(dst, (cv && pv) ? src : p.T, (cv && pv == 2) ? 16 : 0);
+            ppx_cp_async16(dst, (cv && pv) ? src : p.T, !cv ? 0 : (pv == 2 ? 16 : (pv == 1 ? 8 : 0)));
           } else {
             ppx_cp_async8(dst, (cv && pv >= 1) ? src : p.T, (cv && pv >= 1) ? 8 : 0);
             ppx_cp_async8(dst + 1, (cv && pv == 2) ? src + 1 : p.T, (cv && pv == 2) ? 8 : 0);
@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(GB_THREADS, 2) gram_dmma_kernel(GramParams p) 
           double *dst = Bs + k * GB_LDN + nl;
           const double *src = p.T + qg + p.X * (c0 + k);
           if (p.vec) {
-            ppx_cp_async16(dst, (cv && qv) ? src : p.T, (cv && qv == 2) ? 16 : 0);
+            ppx_cp_async16(dst, (cv && qv) ? src : p.T, !cv ? 0 : (qv == 2 ? 16 : (qv == 1 ? 8 : 0)));
           } else {
             ppx_cp_async8(dst, (cv && qv >= 1) ? src : p.T, (cv && qv >= 1) ? 8 : 0);
             ppx_cp_async8(dst + 1, (cv && qv == 2) ? src + 1 : p.T, (cv && qv == 2) ? 8 : 0);

@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(THREADS, 2) ttm_first_kernel(TtmParams p) {
         const double *src = p.V + (mv ? (mg * p.X + kg) : 0);
         double *dst = As + m * LDK + 2 * kp;
         if (p.vecA) {
-          ppx_cp_async16(dst, (mv && kv) ? src : p.V, (mv && kv == 2) ? 16 : 0);
+          ppx_cp_async16(dst, (mv && kv) ? src : p.V, !mv ? 0 : (kv == 2 ? 16 : (kv == 1 ? 8 : 0)));
         } else {
           ppx_cp_async8(dst, (mv && kv >= 1) ? src : p.V, (mv && kv >= 1) ? 8 : 0);
           ppx_cp_async8(dst + 1, (mv && kv == 2) ? src + 1 : p.V, (mv && kv == 2) ? 8 : 0);
@@ -212,7 +212,10 @@ __global__ void __launch_bounds__(THREADS, 2) ttm_first_kernel(TtmParams p) {
         const double *src = p.W + (kv ? ((int64_t)col * p.ldw + kg) : 0);
         double *dst = Ws + n * LDK + 2 * kp;
         if (p.vecW) {
-          ppx_cp_async16(dst, src, kv == 2 ? 16 : 0);
+          // kv == 1: the last row of an odd-length factor slice whose leading dimension is even (rows b..e of a
+          // replicated factor in a sharded run): 8 bytes are copied, the other 8 zero-filled.  (Until round 2 this
+          // copied nothing, dropping the slice's last row: wrong Tucker cores on shards with an odd number of rows.)
+          ppx_cp_async16(dst, src, kv == 2 ? 16 : (kv == 1 ? 8 : 0));
         } else {
           ppx_cp_async8(dst, src, kv >= 1 ? 8 : 0);
           ppx_cp_async8(dst + 1, kv == 2 ? src + 1 : p.W, kv == 2 ? 8 : 0);

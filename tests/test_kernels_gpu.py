@@ -332,6 +332,45 @@ def test_cp_residual_and_reconstruct(ctx, lens, R):
     assert np.sqrt(ctx.to_host(sq, (1,))[0]) <= 1e-12 * np.linalg.norm(ref)
 
 
+@pytest.mark.parametrize("nranks", [2, 3, 4, 8])
+@pytest.mark.parametrize("lens,Q", [((12, 13, 14), 3), ((4, 13, 14), 3), ((9, 10, 8, 7), 3), ((6, 13, 14), 3), ((4, 7, 6, 5), 2),
+                                    ((300, 20, 30), 10), ((37, 300, 6), 50)])
+def test_mode0_contraction_on_shards_sums_to_the_whole(ctx, ppx, lens, Q, nranks):
+    """What every rank of a sharded run does with mode 0 (host/als_Tucker.cxx ttm_mode, host/als_CP.cxx): contract its
+    slab T[b:e] with rows b..e of the REPLICATED factor -- the factor's pointer advanced by b, its leading dimension the
+    global extent -- for the Tucker TTM (rank in place), the CP first contraction (rank last) and the Hadamard-batched
+    one.  The sum of the partial results over the ranks must be the contraction of the whole tensor.  Shards of one, two
+    and three rows, odd offsets (round 2: the 4- and 8-GPU parity runs found the sum wrong for some of these)."""
+    N = len(lens)
+    if lens[0] < nranks:
+        pytest.skip("fewer rows than ranks")
+    T = rnd(lens, 700)
+    W = rnd((lens[0], Q), 701)
+    Wd = ctx.to_device(W)
+    rest = lens[1:]
+    ref_ttm = o.ttm(T, 0, W)
+    ref_first = o.contract(o.letters(N)[1:] + "*", T, o.letters(N), W, "a*")
+    Th = rnd(tuple(lens) + (Q,), 702)
+    ref_mttv = o.contract(o.letters(N)[1:] + "*", Th, o.letters(N) + "*", W, "a*")
+    acc_ttm, acc_first, acc_mttv = np.zeros_like(ref_ttm), np.zeros_like(ref_first), np.zeros_like(ref_mttv)
+    for r in range(nranks):
+        b, e = ppx.shard_range(lens[0], nranks, r)
+        ll = (e - b,) + tuple(rest)
+        Wr = Wd[b:]  # rows b.. of every column: the same buffer, pointer advanced by b, leading dimension lens[0]
+        out = ctx.empty(Q * int(np.prod(rest)))
+        ctx.ttm(ctx.to_device(T[b:e]), ll, 0, Wr, Q, out, ldw=lens[0])
+        acc_ttm += ctx.to_host(out, (Q,) + tuple(rest))
+        out1 = ctx.empty(Q * int(np.prod(rest)))
+        ctx.ttm_first(ctx.to_device(T[b:e]), ll, 0, Wr, Q, out1, ldw=lens[0])
+        acc_first += ctx.to_host(out1, tuple(rest) + (Q,))
+        out2 = ctx.empty(Q * int(np.prod(rest)))
+        ctx.mttv(ctx.to_device(Th[b:e]), ll, 0, Wr, Q, out2, ldw=lens[0])
+        acc_mttv += ctx.to_host(out2, tuple(rest) + (Q,))
+    assert rel_err(acc_ttm, ref_ttm) < 1e-12
+    assert rel_err(acc_first, ref_first) < 1e-12
+    assert rel_err(acc_mttv, ref_mttv) < 1e-12
+
+
 @pytest.mark.parametrize("lens,x,Q", [((13, 9, 11), 0, 4), ((13, 9, 11), 1, 4), ((13, 9, 11), 2, 4),
                                       ((12, 10, 8, 6), 1, 3), ((40, 7, 40), 2, 40), ((5, 1, 6), 1, 2),
                                       # TMA path with the rank written in place (+ DFMA tail columns)

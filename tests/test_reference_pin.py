@@ -386,3 +386,41 @@ def test_reference_tree_code_cannot_do_order_3(tmp_path):
     assert bad.returncode != 0  # SIGSEGV from the unbounded recursion
     good = rh.run_cli("run", args)
     assert "Iters" in good["stdout"]
+
+
+def test_standin_dgemm_path_matches_the_plain_loops(tmp_path):
+    """CTF_STANDIN_BLAS switches the stand-in's contraction engine to DGEMM for products that fold into a matrix product
+    (bench.py's CPU arm times the reference's own main that way).  Same main, same inputs, both engines: identical
+    switching iterations, printed values equal to rounding."""
+    import glob
+
+    hits = glob.glob(os.path.join(os.path.dirname(np.__file__), "..", "numpy.libs", "libscipy_openblas*.so"))
+    if not hits:
+        pytest.skip("no OpenBLAS shared library beside NumPy")
+    N, s, R = 4, 16, 4
+    args = ["-model", "CP", "-tensor", "r", "-dim", str(N), "-size", str(s), "-rank", str(R), "-pp", "1", "-maxiter", "30",
+            "-pp_res_tol", "0.1", "-resprint", "3", "-filename", os.path.join(str(tmp_path), "a.csv")]
+    fills = [(1, i) for i in range(N)] + [p for i in range(N) for p in ((2, i), (3, i))]
+    plain = rh.run_cli("test_ALS", args, fills=fills)
+    os.environ["CTF_STANDIN_BLAS"] = os.path.abspath(hits[0])
+    try:
+        fast = rh.run_cli("test_ALS", args, fills=fills)
+    finally:
+        del os.environ["CTF_STANDIN_BLAS"]
+    assert fast["events"] == plain["events"] and len(fast["rows"]) == len(plain["rows"]) >= 5
+    for a, b in zip(fast["rows"], plain["rows"]):
+        assert a[0] == b[0] and a[2] == b[2]
+        assert abs(a[1] - b[1]) <= 1e-9 * max(abs(b[1]), 1.0) and abs(a[3] - b[3]) <= 1e-9 * max(abs(b[3]), 1.0)
+    # Tucker too (TTMs with the rank in place, the unfolding Gram with its ^ & indices)
+    targs = ["-model", "Tucker", "-tensor", "r2", "-dim", "4", "-size", "9", "-rank", "3", "-pp", "1", "-maxiter", "12",
+             "-pp_res_tol", "0.3", "-resprint", "3", "-filename", os.path.join(str(tmp_path), "t.csv")]
+    tf = [(1, 100)] + [p for i in range(4) for p in ((2, i), (3, i))]
+    plain = rh.run_cli("test_ALS", targs, fills=tf)
+    os.environ["CTF_STANDIN_BLAS"] = os.path.abspath(hits[0])
+    try:
+        fast = rh.run_cli("test_ALS", targs, fills=tf)
+    finally:
+        del os.environ["CTF_STANDIN_BLAS"]
+    assert fast["events"] == plain["events"] and len(fast["rows"]) == len(plain["rows"]) >= 3
+    for a, b in zip(fast["rows"], plain["rows"]):
+        assert abs(a[1] - b[1]) <= 1e-8 * max(abs(b[1]), 1.0) and abs(a[3] - b[3]) <= 1e-9 * max(abs(b[3]), 1.0)
