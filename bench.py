@@ -732,10 +732,44 @@ def main():
             pp["k3_pp_correct"] = {"us": 1e3 * k3_ms, "algorithmic_bytes": k3_bytes, "gbs": k3_bytes / k3_ms / 1e6,
                                    "frac_hbm": k3_bytes / k3_ms / 1e6 / hbm_peak,
                                    "timing": "20 back-to-back launches, CUDA events (launch ramp included)"}
-            for t_ in ops + [M0, Mo]:
+            # the solve kernels of one mode update alone ("solve kernels as HBM GB/s"): Hadamard of the Grams
+            # + R x R inverse (one CTA), then W = M S^-1 with gradient and dW (row tiles); both are latency-size work --
+            # 8 (5 s R + 2 R^2) bytes -- and are reported as what they are
+            Gs = [H.Matrix(world, R, R) for _ in range(N)]
+            for j_, g_ in enumerate(Gs):
+                rc_ = lib.ppx_gram(world.ctx_handle(), C.c_void_p(W[j_].data_ptr()), lens_local[j_], lens_local[j_], R,
+                                   C.c_void_p(g_.data_ptr()))
+                assert rc_ == 0
+            gp = (C.c_void_p * N)(*[g_.data_ptr() for g_ in Gs])
+            S_, Si_ = H.Matrix(world, R, R), H.Matrix(world, R, R)
+            Wc, Gc, Dc = H.Matrix(world, s_i, R), H.Matrix(world, s_i, R), H.Matrix(world, s_i, R)
+
+            def inv():
+                rc_ = lib.ppx_spd_inverse_g(world.ctx_handle(), gp, N, i_mode, 0.0, R, 0, C.c_void_p(S_.data_ptr()),
+                                            C.c_void_p(Si_.data_ptr()))
+                assert rc_ == 0, lib.ppx_last_error(world.ctx_handle())
+
+            def app():
+                rc_ = lib.ppx_solve_apply(world.ctx_handle(), C.c_void_p(Mo.data_ptr()), C.c_void_p(S_.data_ptr()),
+                                          C.c_void_p(Si_.data_ptr()), C.c_void_p(Wc.data_ptr()), s_i, R,
+                                          C.c_void_p(W[i_mode].data_ptr()), 1.0, C.c_void_p(Gc.data_ptr()),
+                                          C.c_void_p(Dc.data_ptr()))
+                assert rc_ == 0, lib.ppx_last_error(world.ctx_handle())
+
+            for _ in range(5):
+                inv()
+                app()
+            inv_ms, app_ms = timed(inv, 50), timed(app, 50)
+            solve_bytes = 8.0 * (5 * s_i * R + 2 * R * R)
+            pp["solve"] = {"inverse_us": 1e3 * inv_ms, "apply_us": 1e3 * app_ms, "algorithmic_bytes": solve_bytes,
+                           "gbs": solve_bytes / (inv_ms + app_ms) / 1e6, "frac_hbm": solve_bytes / (inv_ms + app_ms) / 1e6 / hbm_peak,
+                           "note": "latency bound: one CTA factorises the R x R matrix (R dependent elimination steps), the "
+                                   "apply kernel moves 0.6 MB; 50 back-to-back launches each, CUDA events"}
+            for t_ in ops + [M0, Mo, S_, Si_, Wc, Gc, Dc] + Gs:
                 t_.free()
         except Exception as exc:  # noqa: BLE001
-            pp["k3_pp_correct"] = {"error": "%s: %s" % (type(exc).__name__, exc)}
+            pp.setdefault("k3_pp_correct", {"error": "%s: %s" % (type(exc).__name__, exc)})
+            pp["solve"] = pp.get("solve") or {"error": "%s: %s" % (type(exc).__name__, exc)}
         # the mixed run: alsCP_PP exactly as `test_ALS -pp 1 -maxiter M` drives it (als_CP.cxx:1082-1137), residual
         # evaluations skipped (the reference takes them off its clock, :189); wall clock, synchronised on both sides
         try:

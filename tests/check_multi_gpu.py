@@ -43,8 +43,35 @@ for lens, R, maxiter, tol_init in [((13, 12, 11, 10), 4, 40, 0.1), ((9, 10, 11),
     V, _ = o.make_tensor_r(lens, R)
     W, G = o.init_factors(lens, R), o.init_grad(lens, R)
     vnorm = np.linalg.norm(V)
-    for driver in ("DT", "PP", "PPpart"):
+    for driver in ("DT", "PP", "PPpart", "plain"):
         W_ref, G_ref = [w.copy() for w in W], [g.copy() for g in G]
+        if driver == "plain":
+            # alsCP (als_CP.cxx:20-115): a full MTTKRP per mode, gradient_CP from scratch at iterations 0 and maxiter --
+            # the partial MTTKRPs of gradient_CP must be reduced too, or the ranks disagree on the stopping test and
+            # the next collective hangs (round-1 advisor finding).  Same normal equations as the DT sweeps.
+            o.alsCP_DT(V, W_ref, G_ref, 0.0, 5, resprint=100, want_residual=False)
+            Vd = H.Tensor.from_numpy(world, np.ascontiguousarray(V[b:e]))
+            Wd = [H.Tensor.from_numpy(world, (w[b:e] if i == 0 else w), matrix=True) for i, w in enumerate(W)]
+            Gd = [H.Tensor.from_numpy(world, (g[b:e] if i == 0 else g), matrix=True) for i, g in enumerate(G)]
+            Fd = [H.Matrix(world, w.lens[0], R) for w in Wd]
+            with H.Trace(quiet=True) as t:
+                H.alsCP(world, Vd, Wd, Gd, Fd, 0.0, 5)
+            worst_fac = 0.0
+            for i in range(N):
+                ref = W_ref[i][b:e] if i == 0 else W_ref[i]
+                worst_fac = max(worst_fac, float(np.abs(Wd[i].numpy() - ref).max() / max(1.0, np.abs(ref).max())))
+            # the projected-gradient norms alsCP logs are global quantities: every rank must have logged the same ones
+            pn = torch.tensor([r[1] for r in t.rows], dtype=torch.float64, device="cuda")
+            lo, hi = pn.clone(), pn.clone()
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+            dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+            ok = worst_fac <= 1e-8 and len(t.rows) == 2 and bool(torch.all(hi - lo <= 1e-12 * hi.abs().clamp(min=1.0)))
+            print(f"rank {rank} lens {lens} R {R} plain alsCP: {'OK' if ok else 'MISMATCH'} factor_err {worst_fac:.2e} "
+                  f"projnorm {[float(x) for x in pn]}", flush=True)
+            ok_all &= ok
+            for x in [Vd] + Wd + Gd + Fd:
+                x.free()
+            continue
         if driver == "DT":
             _, tr = o.alsCP_DT(V, W_ref, G_ref, 1e-10 * vnorm, 12, resprint=4, F=None)
         elif driver == "PP":
