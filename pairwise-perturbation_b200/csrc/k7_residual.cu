@@ -124,7 +124,10 @@ __global__ void __launch_bounds__(RS_THREADS) cp_reconstruct_kernel(const double
 //            scheduler partition (255 registers each) a warp's address/load phase is not covered by the other warp's
 //            MMA phase often enough.  The MMA loop itself now runs at 93 % of the pipe (24.6 ms for 22.9 ms of DMMA).
 //            More warps need fewer registers per thread, i.e. K fragments back in shared memory: open.
-constexpr int RD_THREADS = 256;  // 8 independent warps per CTA
+#ifndef PPX_RD_THREADS
+#define PPX_RD_THREADS 256
+#endif
+constexpr int RD_THREADS = PPX_RD_THREADS;  // 8 independent warps per CTA (-DPPX_RD_THREADS: A/B builds)
 
 __device__ __forceinline__ uint32_t rd_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void rd_mbar_init(uint64_t *bar, int count) {
@@ -174,7 +177,10 @@ __global__ void __launch_bounds__(256) rd_pack_last_kernel(const double *__restr
   }
 }
 
-constexpr int RD_NB = 13;  // column blocks per pass: 2 x 13 = 26 independent DMMA accumulators per warp
+#ifndef PPX_RD_NB
+#define PPX_RD_NB 13
+#endif
+constexpr int RD_NB = PPX_RD_NB;  // column blocks per pass: 2 x 13 = 26 independent DMMA accumulators per warp
 
 template <bool WRITE, int NKS>
 __global__ void __launch_bounds__(RD_THREADS, 1) cp_reconstruct_dmma_kernel(const double *__restrict__ V, ResArgs a,
