@@ -240,6 +240,160 @@ __global__ void __launch_bounds__(INV_B *INV_B) spd_inverse_ldl_kernel(HadArgs h
 // whichever way the work is cut; the seven block steps each pay an 8-round pivot inversion plus three barriers, and
 // the two triangular products that the column kernel folds into its loop come on top.  Not adopted.)
 
+// ---- R x R SPD inverse for R <= 64: symmetric sweep with the matrix in registers, two columns per step ---------------
+// The column kernel above spends its 33 us at R = 50 on latency: a step is a barrier of 8 warps, a shared-memory
+// broadcast, a reciprocal chain and two dependent-issue FMA groups, R times in sequence.  This kernel halves the
+// number of sequential steps and shortens each:
+//   * four threads own a COLUMN (thread (j, h): rows [h NR/4, (h+1) NR/4) of column j, NR = R rounded up to 8; the
+//     threads of a warp share h, so every lane reads the SAME 16 bytes of a published column: one wavefront per load);
+//   * the loop over the pivot blocks is unrolled, every register index is compile-time;
+//   * a step eliminates the 2 x 2 pivot block K = {k, k+1} (the symmetric sweep operator in block form):
+//         P = A_KK^-1,   (u1, u2)_j = P (a_kj, a_k+1,j),   a_ij -= a_ik u1_j + a_i,k+1 u2_j  (i, j not in K),
+//         a_Kj = (u1, u2)_j,   a_iK = a_iK P,   A_KK = -P;
+//     after R/2 steps the registers hold -S^-1.  Only the PUBLISHED columns k, k+1 are read (a_jk stands in for a_kj,
+//     equal up to rounding, so the rows never travel); the columns' own threads start from zero with (u1, u2) =
+//     -(column of P), which gives a_iK P and -P by the same FMAs;
+//   * the owners of columns k+2, k+3 update those first, one of them (a shuffle brings the third element) forms
+//     the next P = adj / det with a Newton reciprocal while its remaining FMAs issue, and publishes columns and P
+//     through double-buffered shared vectors: ONE barrier per two columns, no divisions.
+// An odd R is padded with an identity row and column.  The result is symmetrised through shared memory on the way out
+// (the sweep keeps symmetry only up to rounding).  NumPy model of the scalar form: tools/inv_sweep_proto.py.
+// Measured (tools/time_inverse.py, 200 back-to-back launches): see profiles/r02x_inverse_*.json.
+__device__ __forceinline__ double rcp_newton(double d) {
+  double x;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(d));  // MUFU.RCP64H: about 20 bits
+  // x (1 + e + e^2 + e^3)(1 + e^4), e = 1 - d x: 2^-80 in four dependent operations
+  const double e = fma(-d, x, 1.0);
+  const double e2 = e * e;
+  const double y = fma(x, e, x);
+  const double z = fma(y, e2, y);
+  return fma(z, e2 * e2, z);
+}
+
+#ifdef PPX_INV_PROFILE  // tools/inv_bench.cu: clock probes of the middle step taken by the thread that publishes P
+#define PPX_PROF_STEP(slot) if (K == (R / 4) * 2 && j == K + 2 && hh == (K + 2) / NH) g_prof[slot] = clock64()
+#else
+#define PPX_PROF_STEP(slot)
+#endif
+
+constexpr int SWEEP_H = 4;  // threads per column
+
+template <int NR>
+struct SweepSmem {
+  double col[2][2][NR];  // [buffer][column k or k+1][row]
+  double P[2][4];        // [buffer]: P00, P01, P11
+  double st[NR][NR + 1];
+};
+
+template <int NR, int K>
+struct SweepSteps {
+  static constexpr int NH = NR / SWEEP_H;
+  __device__ __forceinline__ static void run(double (&c)[NH], SweepSmem<NR> &sm, int R, int j, int hh) {
+    if (K < R) {
+      PPX_PROF_STEP(16);
+      constexpr int b = (K / 2) & 1;
+      const double *ca = sm.col[b][0], *cb = sm.col[b][1];
+      const double P00 = sm.P[b][0], P01 = sm.P[b][1], P11 = sm.P[b][2];
+      const double cj1 = ca[j], cj2 = cb[j];
+      const bool own1 = (j == K), own2 = (j == K + 1);
+      double u1 = fma(P00, cj1, P01 * cj2), u2 = fma(P01, cj1, P11 * cj2);
+      if (own1) u1 = -P00, u2 = -P01;
+      if (own2) u1 = -P01, u2 = -P11;
+      double va[NH], vb[NH];
+      const double2 *a2 = reinterpret_cast<const double2 *>(ca + hh * NH);
+      const double2 *b2 = reinterpret_cast<const double2 *>(cb + hh * NH);
+#pragma unroll
+      for (int i = 0; i < NH; i += 2) {
+        const double2 t = a2[i / 2], w = b2[i / 2];
+        va[i] = t.x, va[i + 1] = t.y, vb[i] = w.x, vb[i + 1] = w.y;
+      }
+      if (own1 || own2) {  // the two columns of the block start from zero (one warp per row block takes the branch)
+#pragma unroll
+        for (int i = 0; i < NH; i++) c[i] = 0.0;
+      }
+      PPX_PROF_STEP(17);
+      constexpr int kl = K % NH, kh = K / NH, nl = (K + 2) % NH, nh = ((K + 2) / NH) % SWEEP_H;
+      // rows k+2, k+3 first: in columns k+2, k+3 they are the next pivot block
+      c[nl] = fma(-vb[nl], u2, fma(-va[nl], u1, c[nl]));
+      c[nl + 1] = fma(-vb[nl + 1], u2, fma(-va[nl + 1], u1, c[nl + 1]));
+      const double pa = c[nl], pb = c[nl + 1], pd = __shfl_down_sync(0xffffffffu, c[nl + 1], 1);
+      const double rdet = rcp_newton(fma(pa, pd, -pb * pb));
+      double n00 = pd * rdet, n01 = -pb * rdet, n11 = pa * rdet;
+#pragma unroll
+      for (int i = 0; i < NH; i++)
+        if (i != nl && i != nl + 1) c[i] = fma(-vb[i], u2, fma(-va[i], u1, c[i]));
+      if (hh == kh) c[kl] = u1, c[kl + 1] = u2;
+      asm volatile("" : "+d"(n00), "+d"(n01), "+d"(n11));
+      PPX_PROF_STEP(19);
+      if (K + 2 < R) {
+        if (j == K + 2 || j == K + 3) {
+          double2 *dst = reinterpret_cast<double2 *>(sm.col[b ^ 1][j - (K + 2)] + hh * NH);
+#pragma unroll
+          for (int i = 0; i < NH; i += 2) dst[i / 2] = make_double2(c[i], c[i + 1]);
+          if (j == K + 2 && hh == nh) sm.P[b ^ 1][0] = n00, sm.P[b ^ 1][1] = n01, sm.P[b ^ 1][2] = n11;
+        }
+      }
+      PPX_PROF_STEP(20);
+      __syncthreads();
+      PPX_PROF_STEP(21);
+    }
+    SweepSteps<NR, K + 2>::run(c, sm, R, j, hh);
+  }
+};
+template <int NR>
+struct SweepSteps<NR, NR> {
+  __device__ __forceinline__ static void run(double (&)[NR / SWEEP_H], SweepSmem<NR> &, int, int, int) {}
+};
+
+template <int NR>
+__global__ void __launch_bounds__(SWEEP_H *((NR + 31) / 32) * 32)
+    spd_inverse_sweep_kernel(HadArgs h, int R, double lambda, double *__restrict__ S_out, double *__restrict__ Sinv) {
+  constexpr int NH = NR / SWEEP_H, NRP = (NR + 31) / 32 * 32;
+  __shared__ __align__(16) SweepSmem<NR> sm;
+  const int hh = threadIdx.x / NRP, j = threadIdx.x % NRP, r0 = hh * NH;
+  double c[NH];
+  PPX_PROF(8);
+  // S = Hadamard product (+ lambda I), read through its symmetry (element (j, row)) so that a warp reads rows
+#pragma unroll
+  for (int i = 0; i < NH; i++) c[i] = (r0 + i < R && j < R) ? h.g[0][j + R * (r0 + i)] : 0.0;
+#pragma unroll 1
+  for (int m = 1; m < h.n; m++) {
+    const double *g = h.g[m];
+#pragma unroll
+    for (int i = 0; i < NH; i++)
+      if (r0 + i < R && j < R) c[i] *= g[j + R * (r0 + i)];
+  }
+#pragma unroll
+  for (int i = 0; i < NH; i++) {
+    if (r0 + i == j && lambda != 0.0) c[i] += lambda;
+    if (S_out && r0 + i < R && j < R) S_out[j + R * (r0 + i)] = c[i];
+    if (r0 + i == j && j >= R) c[i] = 1.0;  // identity padding: an odd R shares its last pivot block with index R
+  }
+  {  // block 0: columns 0, 1 and P
+    const double pd = __shfl_down_sync(0xffffffffu, c[1], 1);
+    const double rdet = rcp_newton(fma(c[0], pd, -c[1] * c[1]));
+    if (j < 2) {
+#pragma unroll
+      for (int i = 0; i < NH; i++) sm.col[0][j][r0 + i] = c[i];
+      if (j == 0 && hh == 0) sm.P[0][0] = pd * rdet, sm.P[0][1] = -c[1] * rdet, sm.P[0][2] = c[0] * rdet;
+    }
+  }
+  __syncthreads();
+  PPX_PROF(9);
+  SweepSteps<NR, 0>::run(c, sm, R, j, hh);
+  PPX_PROF(10);
+  // -S^-1 is in the registers: symmetrise through shared memory and write
+  if (j < NR) {
+#pragma unroll
+    for (int i = 0; i < NH; i++) sm.st[r0 + i][j] = c[i];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < NH; i++)
+    if (r0 + i < R && j < R) Sinv[j + R * (r0 + i)] = -0.5 * (c[i] + sm.st[j][r0 + i]);
+  PPX_PROF(11);
+}
+
 // Cyclic Jacobi (parallel round-robin ordering) on a symmetric matrix in shared memory.
 // A[n][ld], Q[n][ld]; n even (padded with an identity row/column when R is odd).
 __device__ void jacobi_eig_shared(double *A, double *Q, double *cs, int n, int ld, int max_sweeps) {
@@ -526,7 +680,22 @@ __global__ void __launch_bounds__(1024) normalize_norms_kernel(NormNormsArgs a, 
 
 int inverse_launch(ppx_ctx *ctx, const HadArgs &h, int R, double lambda, int mode, double *S_out, double *Sinv,
                    double *Linv = nullptr) {
-  if (mode == PPX_SOLVE_CHOL) {
+  static const bool inv_column = getenv("PPX_INV_COLUMN") != nullptr;  // A/B: the column kernel for every R
+  if (mode == PPX_SOLVE_CHOL && R <= 64 && !Linv && !inv_column) {
+#define PPX_SWEEP_LAUNCH(NR) \
+  spd_inverse_sweep_kernel<NR><<<1, SWEEP_H *((NR + 31) / 32) * 32, 0, ctx->stream>>>(h, R, lambda, S_out, Sinv)
+    switch ((R + 7) / 8) {
+      case 1: PPX_SWEEP_LAUNCH(8); break;
+      case 2: PPX_SWEEP_LAUNCH(16); break;
+      case 3: PPX_SWEEP_LAUNCH(24); break;
+      case 4: PPX_SWEEP_LAUNCH(32); break;
+      case 5: PPX_SWEEP_LAUNCH(40); break;
+      case 6: PPX_SWEEP_LAUNCH(48); break;
+      case 7: PPX_SWEEP_LAUNCH(56); break;
+      default: PPX_SWEEP_LAUNCH(64); break;
+    }
+#undef PPX_SWEEP_LAUNCH
+  } else if (mode == PPX_SOLVE_CHOL) {
     if (R > 112) return ppx_set_err(ctx, PPX_EUNSUPPORTED, "solve: R=%d too large for the one-CTA inverse (max 112)", R);
     const int T = (R + INV_B - 1) / INV_B;
     const size_t smem = sizeof(double) * (2 * ((size_t)INV_B * T + 2) + (size_t)R * (R + 1));

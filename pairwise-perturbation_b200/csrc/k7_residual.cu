@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(RS_THREADS) cp_reconstruct_kernel(const double
 //            MMA phase often enough.  The MMA loop itself now runs at 93 % of the pipe (24.6 ms for 22.9 ms of DMMA).
 //            More warps need fewer registers per thread, i.e. K fragments back in shared memory: open.
 #ifndef PPX_RD_THREADS
-#define PPX_RD_THREADS 256
+#define PPX_RD_THREADS 384
 #endif
 constexpr int RD_THREADS = PPX_RD_THREADS;  // 8 independent warps per CTA (-DPPX_RD_THREADS: A/B builds)
 
@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(256) rd_pack_last_kernel(const double *__restr
 }
 
 #ifndef PPX_RD_NB
-#define PPX_RD_NB 13
+#define PPX_RD_NB 5
 #endif
 constexpr int RD_NB = PPX_RD_NB;  // column blocks per pass: 2 x 13 = 26 independent DMMA accumulators per warp
 

@@ -214,10 +214,10 @@ def test_solve_update(ctx, ppx, mode, s, R):
     assert rel_err(ctx.to_host(Wd, (s, R)), o.cholesky_solve(M, S)) < 1e-9
 
 
-@pytest.mark.parametrize("R", [1, 2, 7, 8, 9, 16, 23, 40, 50, 56, 57, 64, 77, 100, 112])
+@pytest.mark.parametrize("R", [1, 2, 3, 7, 8, 9, 10, 16, 17, 23, 24, 25, 32, 33, 40, 41, 48, 49, 50, 56, 57, 64, 65, 77, 100, 112])
 def test_spd_inverse(ctx, R):
-    """S^-1 of the Gram-Hadamard matrix by the one-CTA LDL^T kernel (cholesky_solve semantics, common.cxx:727-737) for
-    every register-tile class of R, against NumPy, with and without lambda, and on a matrix with a wide
+    """S^-1 of the Gram-Hadamard matrix (cholesky_solve semantics, common.cxx:727-737) by the register-resident sweep
+    kernel (R <= 64, every 8-column class and its edges) and the one-CTA LDL^T kernel (R > 64, every register-tile class), against NumPy, with and without lambda, and on a matrix with a wide
     spectrum (Hadamard product of three Grams of nearly collinear factors)."""
     s = 3 * R + 5
     for trial, lam in enumerate((0.0, 1e-3, 0.0)):

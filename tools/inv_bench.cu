@@ -56,6 +56,27 @@ int main(int argc, char **argv) {
            prof[1] - prof[0], prof[2] - prof[1], (double)(prof[2] - prof[1]) / R, prof[4] - prof[2]);
     printf("\n");
   }
+  if (R <= 64) {  // the register-resident sweep kernel (R <= 64)
+    for (int rep = 0; rep < 5; rep++) {
+      cudaEventRecord(e0);
+      switch ((R + 7) / 8) {
+        case 2: spd_inverse_sweep_kernel<16><<<1, SWEEP_H * 32>>>(h, R, 0.0, dS, dSi); break;
+        case 5: spd_inverse_sweep_kernel<40><<<1, SWEEP_H * 64>>>(h, R, 0.0, dS, dSi); break;
+        case 7: spd_inverse_sweep_kernel<56><<<1, SWEEP_H * 64>>>(h, R, 0.0, dS, dSi); break;
+        default: spd_inverse_sweep_kernel<64><<<1, SWEEP_H * 64>>>(h, R, 0.0, dS, dSi); break;
+      }
+      cudaEventRecord(e1);
+      cudaEventSynchronize(e1);
+      float ms;
+      cudaEventElapsedTime(&ms, e0, e1);
+      long long prof[64];
+      cudaMemcpyFromSymbol(prof, g_prof, sizeof(prof));
+      printf("sweep rep %d: %.1f us; cycles: load %lld, loop %lld (%.0f/step), store %lld; step R/2 of the publisher: "
+             "read+u %lld, fma %lld, publish %lld, barrier %lld\n", rep, ms * 1e3, prof[9] - prof[8],
+             prof[10] - prof[9], (double)(prof[10] - prof[9]) / R, prof[11] - prof[10], prof[17] - prof[16],
+             prof[19] - prof[17], prof[20] - prof[19], prof[21] - prof[20]);
+    }
+  }
   // check: S * Sinv = I
   std::vector<double> S(R * R), Si(R * R);
   cudaMemcpy(S.data(), dS, 8 * R * R, cudaMemcpyDeviceToHost);

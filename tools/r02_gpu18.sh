@@ -3,7 +3,7 @@
 mkdir -p gpurun_out
 T=${1:-r02v}
 echo "base"; timeout 200 python tools/time_k7.py > gpurun_out/${T}_k7_base.json 2>gpurun_out/${T}_k7_base.err; echo rc=$?
-for v in 384_7 384_5 512_5; do
+for v in $(ls tools/k7_variants | sed "s/libppx_k7_//; s/.so//"); do
   echo "$v"; PPX_LIB=$PWD/tools/k7_variants/libppx_k7_$v.so timeout 200 python tools/time_k7.py > gpurun_out/${T}_k7_$v.json 2>gpurun_out/${T}_k7_$v.err; echo rc=$?
 done
 python - <<PY
