@@ -174,6 +174,16 @@ int ppx_rank_expand_acc(ppx_ctx *ctx, const double *T, int64_t Mtot, int r, cons
 int ppx_side_begin(ppx_ctx *ctx);
 int ppx_side_end(ppx_ctx *ctx);
 int ppx_side_join(ppx_ctx *ctx);
+/* The same with four independent lanes (ppx_side_* is lane 0): the PP sweep runs the R x R inverse of mode i on lane 0
+ * and the part of mode i+1's correction that does not depend on mode i's update on lane 1 (als_CP.cxx:774-812 has no
+ * such overlap: CTF executes one contraction at a time).  Entry points that take scratch from the context workspace
+ * must not run on two lanes at once; ppx_pp_correct does not split its grid (no scratch) while a lane is open.   */
+int ppx_lane_begin(ppx_ctx *ctx, int lane);
+int ppx_lane_end(ppx_ctx *ctx);
+int ppx_lane_join(ppx_ctx *ctx, int lane);
+/* Diagnostics: writes the GPU's nanosecond clock (%globaltimer) to *dev_slot, in stream order on the current stream or
+ * lane -- a timeline of a captured sweep without a profiler (PPX_PP_TRACE=1, host/als_CP.cxx). */
+int ppx_stamp(ppx_ctx *ctx, unsigned long long *dev_slot);
 /* Normalize (common.cxx:680-688): every W_i scaled to the geometric mean of the Frobenius norms.  W, s: HOST
  * arrays.  If G != NULL, G[i] (cached Gram of W_i) is rescaled consistently. */
 int ppx_normalize(ppx_ctx *ctx, double *const *W, const int64_t *s, int N, int R, double *const *G);

@@ -81,6 +81,10 @@ SIGNATURES = {
     "ppx_side_begin": (C.c_int, [_vp]),
     "ppx_side_end": (C.c_int, [_vp]),
     "ppx_side_join": (C.c_int, [_vp]),
+    "ppx_lane_begin": (C.c_int, [_vp, C.c_int]),
+    "ppx_lane_end": (C.c_int, [_vp]),
+    "ppx_lane_join": (C.c_int, [_vp, C.c_int]),
+    "ppx_stamp": (C.c_int, [_vp, _vp]),
     "ppx_normalize_norms": (C.c_int, [_vp, C.POINTER(_dp), C.POINTER(_dp), C.POINTER(_i64), C.c_int, C.c_int,
                                       C.POINTER(_dp), _dp]),
     "ppx_normalize": (C.c_int, [_vp, C.POINTER(_dp), C.POINTER(_i64), C.c_int, C.c_int, C.POINTER(_dp)]),

@@ -552,7 +552,8 @@ int ppx_pp_correct(ppx_ctx *ctx, const double *M0, const double *const *ops, con
   double *part = nullptr;
   int nz = 1;
   static const bool no_split = getenv("PPX_NO_FLAT") != nullptr;  // experiments only
-  if (!no_split && ctas < 2 * ctx->sm_count && max_sj >= 256) {
+  // (not on a lane: the partial sums live in the context workspace, which the main stream may be using)
+  if (!no_split && ctx->open_lane < 0 && ctas < 2 * ctx->sm_count && max_sj >= 256) {
     nz = (int)((4 * (int64_t)ctx->sm_count + ctas - 1) / ctas);
     if (nz > (max_sj + 63) / 64) nz = (int)((max_sj + 63) / 64);
     if (nz > 64) nz = 64;

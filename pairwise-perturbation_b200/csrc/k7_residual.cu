@@ -99,16 +99,15 @@ __global__ void __launch_bounds__(RS_THREADS) cp_reconstruct_kernel(const double
 
 // ---- the same on the FP64 tensor pipe -----------------------------------------------------------------------------
 // Vhat[m, d] = sum_r K[m, r] W_last[d, r] is a GEMM with a short inner dimension (R); the kernel above does it with
-// DFMA out of shared memory (measured 10 TFLOP/s at BASELINE configs[1]: 78 ms per residual).  Here a CTA of 8 warps
-// owns 128 rows m.  Per tile it puts into shared memory, in DMMA operand layout (leading dimension = 4 mod 16:
-// conflict-free fragment loads), the Khatri-Rao rows K of the tile and as many rows of W_last as fit (all 300 at
-// R = 50: 178 KB together) -- ONE barrier per tile (per super-chunk of W_last when the last mode is long).  After it
-// the warps run on their own -- no CTA barrier in steady state: a warp takes a STRIP of 16 rows, keeps its DMMA A
-// fragments (the Khatri-Rao rows of the strip, 2 x 13 doubles per lane at R = 50, formed from independent loads of the
-// factors) in REGISTERS for the whole strip, and walks the columns 13 blocks (104 columns) at a time: 26 independent
-// accumulators, B fragments from the resident W_last, then the 64-byte pieces of V that match its accumulator fragments
-// (8 consecutive rows of a column), squared differences in registers.  The grid is persistent (one CTA of 8 warps per
-// SM); W_last is fetched once per CTA.  V is read exactly once.
+// DFMA out of shared memory (measured 10 TFLOP/s at BASELINE configs[1]: 78 ms per residual).  Here the grid is
+// persistent, one CTA of 12 warps per SM.  W_last lives in shared memory for the whole kernel in DMMA operand layout
+// (leading dimension = 4 mod 16: conflict-free fragment loads; all 300 rows at R = 50, super-chunks when the last mode
+// is long), fetched once per CTA by a bulk copy.  After that one barrier the warps run on their own: a warp takes a
+// contiguous range of STRIPS of 16 rows m, keeps the DMMA A fragments of a strip (its Khatri-Rao rows, 2 x 13 doubles
+// per lane at R = 50, formed from independent loads of the factors; the part that is constant along the strip range
+// cached in per-lane shared slots) in REGISTERS, and walks the columns RD_NB blocks (8 RD_NB columns) at a time: 2 RD_NB
+// independent accumulators, B fragments from the resident W_last, then the 64-byte pieces of V that match its
+// accumulator fragments (8 consecutive rows of a column), squared differences in registers.  V is read exactly once.
 // History at BASELINE configs[1] (78 ms for the DFMA kernel), each step measured on a B200:
 //   60 ms    128-row tile per CTA, K in shared memory built by one thread per row walking k (a dependent product chain)
 //   45.7 ms  W_last in double-buffered 64-column chunks, two barriers around every chunk (ncu: DMMA pipe 52 % busy)
@@ -123,11 +122,15 @@ __global__ void __launch_bounds__(RS_THREADS) cp_reconstruct_kernel(const double
 //            14.6 without the MMA, 32.3 without the V loads -- the three parts add up to the total: with two warps per
 //            scheduler partition (255 registers each) a warp's address/load phase is not covered by the other warp's
 //            MMA phase often enough.  The MMA loop itself now runs at 93 % of the pipe (24.6 ms for 22.9 ms of DMMA).
-//            More warps need fewer registers per thread, i.e. K fragments back in shared memory: open.
+//   29.6 ms  the same kernel with 12 warps per CTA and 5 column blocks per pass (this version): three warps per
+//            scheduler at <= 168 registers -- 2 x 5 accumulators per warp instead of 2 x 13, so a third warp fits and
+//            one warp's address/V-load phase is covered by the other two.  Grid of the A/B (threads_blocks, ms;
+//            profiles/r02w_k7_warps_ab.json): 256_13 41.4, 320_4 35.7, 384_3 30.5, 384_4 29.8, 384_5 29.6, 384_6 32.2
+//            (spills), 448_3 33.2, 512_3 30.2, 512_4 32.3.  27.3 TFLOP/s = 0.77 of the DGEMM peak.
 #ifndef PPX_RD_THREADS
 #define PPX_RD_THREADS 384
 #endif
-constexpr int RD_THREADS = PPX_RD_THREADS;  // 8 independent warps per CTA (-DPPX_RD_THREADS: A/B builds)
+constexpr int RD_THREADS = PPX_RD_THREADS;  // 12 independent warps per CTA (-DPPX_RD_THREADS: A/B builds)
 
 __device__ __forceinline__ uint32_t rd_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void rd_mbar_init(uint64_t *bar, int count) {
@@ -180,7 +183,7 @@ __global__ void __launch_bounds__(256) rd_pack_last_kernel(const double *__restr
 #ifndef PPX_RD_NB
 #define PPX_RD_NB 5
 #endif
-constexpr int RD_NB = PPX_RD_NB;  // column blocks per pass: 2 x 13 = 26 independent DMMA accumulators per warp
+constexpr int RD_NB = PPX_RD_NB;  // column blocks per pass: 2 x RD_NB independent DMMA accumulators per warp
 
 template <bool WRITE, int NKS>
 __global__ void __launch_bounds__(RD_THREADS, 1) cp_reconstruct_dmma_kernel(const double *__restrict__ V, ResArgs a,

@@ -49,9 +49,12 @@ int ppx_ctx_create(int device, void *stream, size_t workspace_bytes, ppx_ctx **o
     ctx->own_stream = true;
   }
   ctx->main_stream = ctx->stream;
-  e = cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking);
-  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
-  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
+  e = cudaSuccess;
+  for (int l = 0; l < ppx_ctx::N_LANES && e == cudaSuccess; l++) {
+    e = cudaStreamCreateWithFlags(&ctx->lane_stream[l], cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_fork[l], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_join[l], cudaEventDisableTiming);
+  }
   if (e != cudaSuccess) { delete ctx; return ppx_set_err(nullptr, PPX_ECUDA, "side stream: %s", cudaGetErrorString(e)); }
   if (workspace_bytes < ((size_t)8 << 20)) workspace_bytes = (size_t)8 << 20;
   e = cudaMalloc((void **)&ctx->ws, workspace_bytes);
@@ -78,12 +81,15 @@ int ppx_ctx_destroy(ppx_ctx *ctx) {
   if (!ctx) return PPX_OK;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->main_stream);
-  cudaStreamSynchronize(ctx->side_stream);
+  for (int l = 0; l < ppx_ctx::N_LANES; l++)
+    if (ctx->lane_stream[l]) cudaStreamSynchronize(ctx->lane_stream[l]);
   ppx_comm_destroy_internal(ctx);
   if (ctx->ws) cudaFree(ctx->ws);
-  if (ctx->side_stream) cudaStreamDestroy(ctx->side_stream);
-  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
-  if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+  for (int l = 0; l < ppx_ctx::N_LANES; l++) {
+    if (ctx->lane_stream[l]) cudaStreamDestroy(ctx->lane_stream[l]);
+    if (ctx->ev_fork[l]) cudaEventDestroy(ctx->ev_fork[l]);
+    if (ctx->ev_join[l]) cudaEventDestroy(ctx->ev_join[l]);
+  }
   if (ctx->own_stream) cudaStreamDestroy(ctx->main_stream);
   delete ctx;
   return PPX_OK;
@@ -94,24 +100,46 @@ int ppx_sync(ppx_ctx *ctx) {
   return PPX_OK;
 }
 // Fork/join for work that may overlap the main stream (works eagerly and inside a graph capture):
-//   ppx_side_begin  : the side stream waits for everything enqueued so far; later calls go to the side stream
-//   ppx_side_end    : later calls go to the main stream again (the side work keeps running concurrently)
-//   ppx_side_join   : the main stream waits for the side work enqueued between begin and end
-int ppx_side_begin(ppx_ctx *ctx) {
-  PPX_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->main_stream));
-  PPX_CUDA(ctx, cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0));
-  ctx->stream = ctx->side_stream;
+//   ppx_lane_begin(l): lane l waits for everything enqueued on the main stream so far; later calls go to lane l
+//   ppx_lane_end      : later calls go to the main stream again (the lane's work keeps running concurrently)
+//   ppx_lane_join(l)  : the main stream waits for the work enqueued on lane l up to its last ppx_lane_end
+//   ppx_side_*        : lane 0
+int ppx_lane_begin(ppx_ctx *ctx, int lane) {
+  PPX_REQUIRE(ctx, lane >= 0 && lane < ppx_ctx::N_LANES, "0 <= lane < 4");
+  PPX_REQUIRE(ctx, ctx->stream == ctx->main_stream, "ppx_lane_begin inside an open lane");
+  PPX_CUDA(ctx, cudaEventRecord(ctx->ev_fork[lane], ctx->main_stream));
+  PPX_CUDA(ctx, cudaStreamWaitEvent(ctx->lane_stream[lane], ctx->ev_fork[lane], 0));
+  ctx->stream = ctx->lane_stream[lane];
+  ctx->open_lane = lane;
   return PPX_OK;
 }
-int ppx_side_end(ppx_ctx *ctx) {
-  PPX_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->side_stream));
+int ppx_lane_end(ppx_ctx *ctx) {
+  if (ctx->open_lane >= 0) PPX_CUDA(ctx, cudaEventRecord(ctx->ev_join[ctx->open_lane], ctx->lane_stream[ctx->open_lane]));
+  ctx->open_lane = -1;
   ctx->stream = ctx->main_stream;
   return PPX_OK;
 }
-int ppx_side_join(ppx_ctx *ctx) {
-  PPX_CUDA(ctx, cudaStreamWaitEvent(ctx->main_stream, ctx->ev_join, 0));
+int ppx_lane_join(ppx_ctx *ctx, int lane) {
+  PPX_REQUIRE(ctx, lane >= 0 && lane < ppx_ctx::N_LANES, "0 <= lane < 4");
+  PPX_CUDA(ctx, cudaStreamWaitEvent(ctx->main_stream, ctx->ev_join[lane], 0));
   return PPX_OK;
 }
+// diagnostics: the GPU's nanosecond clock into a device slot, on the current stream (a timeline of a captured sweep
+// without a profiler: PPX_PP_TRACE=1 in the PP phase of host/als_CP.cxx)
+__global__ void stamp_kernel(unsigned long long *slot) {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  *slot = t;
+}
+int ppx_stamp(ppx_ctx *ctx, unsigned long long *dev_slot) {
+  PPX_REQUIRE(ctx, dev_slot != nullptr, "dev_slot != NULL");
+  stamp_kernel<<<1, 1, 0, ctx->stream>>>(dev_slot);
+  PPX_CHECK_LAUNCH(ctx);
+  return PPX_OK;
+}
+int ppx_side_begin(ppx_ctx *ctx) { return ppx_lane_begin(ctx, 0); }
+int ppx_side_end(ppx_ctx *ctx) { return ppx_lane_end(ctx); }
+int ppx_side_join(ppx_ctx *ctx) { return ppx_lane_join(ctx, 0); }
 const char *ppx_last_error(ppx_ctx *ctx) { return ctx ? ctx->err.c_str() : ""; }
 void *ppx_stream(ppx_ctx *ctx) { return (void *)ctx->main_stream; }
 int ppx_device(ppx_ctx *ctx) { return ctx->device; }

@@ -12,8 +12,11 @@ struct ppx_ctx {
   int sm_count = 148;
   cudaStream_t stream = nullptr;       // the stream operators are enqueued on (main, or side between side_begin/end)
   cudaStream_t main_stream = nullptr;
-  cudaStream_t side_stream = nullptr;  // for work that may overlap the main stream (ppx_side_*)
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  // lanes: streams for work that may overlap the main stream (ppx_lane_*; ppx_side_* is lane 0)
+  static constexpr int N_LANES = 4;
+  cudaStream_t lane_stream[N_LANES] = {};
+  cudaEvent_t ev_fork[N_LANES] = {}, ev_join[N_LANES] = {};
+  int open_lane = -1;  // the lane `stream` points at, -1: the main stream
   bool own_stream = false;
   char *ws = nullptr;  // workspace arena (bump allocated per call)
   size_t ws_bytes = 0;

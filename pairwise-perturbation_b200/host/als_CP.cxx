@@ -502,9 +502,13 @@ void build_pp_operators(map<string, Tensor<>> &mttkrp_map, Tensor<> &V, Matrix<>
   }
 }
 
-// PP-corrected MTTKRP of mode i (als_CP.cxx:774-794), all operators in one launch
+// PP-corrected MTTKRP of mode i (als_CP.cxx:774-794), all operators in one launch.
+// part = PP_ALL: the whole sum.  The sweep splits it so that only the term that depends on the mode updated just before
+// sits on the critical path: PP_EARLY = M0 + every term except j = i-1 (enqueued on a lane while mode i-1 is being
+// solved: dW_j for j < i-1 is final by then, dW_j for j > i is last sweep's), PP_LATE = M += the j = i-1 term.
+enum PPPart { PP_ALL, PP_EARLY, PP_LATE };
 void pp_corrected_mttkrp(map<string, Tensor<>> &mttkrp_map, Matrix<> *W, Matrix<> *dW, int i, int N, Matrix<> &M,
-                         Matrix<> &zero_M, World &dw) {
+                         Matrix<> &zero_M, World &dw, PPPart part = PP_ALL) {
   const string seq = all_modes(N);
   const double *ops[16], *dws[16];
   int which[16];
@@ -513,6 +517,8 @@ void pp_corrected_mttkrp(map<string, Tensor<>> &mttkrp_map, Matrix<> *W, Matrix<
   const bool reduce = dw.np > 1 && i != dw.shard_mode;
   for (int j = 0; j < N; j++) {
     if (j == i) continue;
+    if (part == PP_EARLY && j == i - 1) continue;
+    if (part == PP_LATE && j != i - 1) continue;
     // multi-GPU: P^(shard,i) is contracted over the sharded index -> partial sums; the replicated terms are added
     // on rank 0 only and the result is summed over ranks
     if (reduce && dw.rank != 0 && j != dw.shard_mode) continue;
@@ -523,9 +529,11 @@ void pp_corrected_mttkrp(map<string, Tensor<>> &mttkrp_map, Matrix<> *W, Matrix<
     s_other[n] = dW[j].nrow;
     n++;
   }
-  const double *M0 = (reduce && dw.rank != 0) ? zero_M.data : mttkrp_map[without(seq, i)].data;  // :778
-  PPXCK(dw, ppx_pp_correct(dw.ctx, M0, ops, which, dws, s_other, n, W[i].nrow, (int)W[i].ncol, M.data));
-  if (reduce) dw.allreduce(M.data, M.size);
+  const double *M0 = part == PP_LATE ? M.data  // in place: every element is read and written by the same thread
+                                     : (reduce && dw.rank != 0) ? zero_M.data : mttkrp_map[without(seq, i)].data;  // :778
+  if (part != PP_LATE || n > 0)
+    PPXCK(dw, ppx_pp_correct(dw.ctx, M0, ops, which, dws, s_other, n, W[i].nrow, (int)W[i].ncol, M.data));
+  if (reduce && part != PP_EARLY) dw.allreduce(M.data, M.size);
 }
 
 }  // namespace
@@ -588,6 +596,27 @@ struct PPPhase {
   Matrix<> S, Sinv, zero_M;
   GramCache gc;
   void *graph = nullptr;
+  // PPX_PP_TRACE=1: %globaltimer stamps between the kernels of the sweep, printed after the first two replays
+  unsigned long long *trace_dev = nullptr;
+  vector<string> trace_labels;
+  int trace_prints = 0;
+  void stamp(const char *label) {
+    if (!trace_dev || trace_labels.size() >= 256) return;
+    trace_labels.push_back(label);
+    PPXCK(dw, ppx_stamp(dw.ctx, trace_dev + trace_labels.size() - 1));
+  }
+  void trace_print() {
+    if (!trace_dev || trace_prints >= 2 || dw.rank != 0) return;
+    trace_prints++;
+    dw.sync();
+    vector<unsigned long long> t(trace_labels.size());
+    PPXCK(dw, ppx_memcpy_d2h(dw.ctx, t.data(), trace_dev, sizeof(unsigned long long) * t.size()));
+    dw.sync();
+    unsigned long long t0 = ~0ull;
+    for (auto x : t) t0 = std::min(t0, x);
+    fprintf(stderr, "ppx: PP sweep timeline (us since the first stamp)\n");
+    for (size_t k = 0; k < t.size(); k++) fprintf(stderr, "  %8.2f  %s\n", (t[k] - t0) * 1e-3, trace_labels[k].c_str());
+  }
 
   PPPhase(Tensor<> &V_, Matrix<> *W_, Matrix<> *grad_W_, Matrix<> *dW_, double lambda_, double ratio_step_, World &dw_)
       : V(V_), W(W_), grad_W(grad_W_), dW(dW_), lambda(lambda_), ratio_step(ratio_step_), dw(dw_), N(V_.order),
@@ -600,9 +629,11 @@ struct PPPhase {
       zero_M = Matrix<>(smax, R, dw);
     }
     gc.init(W, N, dw);
+    if (getenv("PPX_PP_TRACE")) PPXCK(dw, ppx_malloc(dw.ctx, 256 * sizeof(unsigned long long), (void **)&trace_dev));
   }
   ~PPPhase() {
     if (graph) ppx_graph_destroy(dw.ctx, graph);
+    if (trace_dev) ppx_free(dw.ctx, trace_dev);
   }
   // W_init = W, dW = 0, build all pair operators and singles (:672-694)
   void build() {
@@ -631,19 +662,40 @@ struct PPPhase {
   // per mode: correction -> Gram-Hadamard -> solve (+grad, dW) -> Gram; then Normalize and the 2N squared norms
   // the switching test needs, copied to pinned host memory (:754-825, :657-664)
   void enqueue_sweep() {
+    static const bool split = getenv("PPX_PP_NO_SPLIT") == nullptr;  // A/B: the correction of a mode in one launch
+    trace_labels.clear();
+    stamp("sweep begin");
     for (int i = 0; i < N; i++) {
       // S from the CURRENT W (:796-802) and its inverse depend only on the Grams: they run on the side stream while
       // the main stream forms the corrected MTTKRP (:774-794); then gradient + SVD_solve_mod (:811-812)
       const double *gp[16];
       for (int j = 0; j < N; j++) gp[j] = gc.G[j].data;
-      PPXCK(dw, ppx_side_begin(dw.ctx));
+      PPXCK(dw, ppx_lane_begin(dw.ctx, 0));
+      stamp("  lane0 inverse >");
       PPXCK(dw, ppx_spd_inverse_g(dw.ctx, gp, N, i, lambda, R, dw.solver, S.data, Sinv.data));
-      PPXCK(dw, ppx_side_end(dw.ctx));
-      pp_corrected_mttkrp(ops, W, dW, i, N, M[i], zero_M, dw);
-      PPXCK(dw, ppx_side_join(dw.ctx));
+      stamp("  lane0 inverse <");
+      PPXCK(dw, ppx_lane_end(dw.ctx));
+      if (split && i > 0) PPXCK(dw, ppx_lane_join(dw.ctx, 1));
+      stamp("main correction (late or all) >");
+      pp_corrected_mttkrp(ops, W, dW, i, N, M[i], zero_M, dw, (split && i > 0) ? PP_LATE : PP_ALL);
+      stamp("main correction <");
+      // the correction of mode i+1 minus its dW_i term reads nothing this mode writes: lane 1, forked AFTER this
+      // mode's own term so that the two do not share the HBM (started together, the short one finishes with the long
+      // one); it then runs under the solve and the Gram of this mode, which move almost nothing
+      if (split && i + 1 < N) {
+        PPXCK(dw, ppx_lane_begin(dw.ctx, 1));
+        stamp("    lane1 early >");
+        pp_corrected_mttkrp(ops, W, dW, i + 1, N, M[i + 1], zero_M, dw, PP_EARLY);
+        stamp("    lane1 early <");
+        PPXCK(dw, ppx_lane_end(dw.ctx));
+      }
+      PPXCK(dw, ppx_lane_join(dw.ctx, 0));
+      stamp("main apply >");
       PPXCK(dw, ppx_solve_apply(dw.ctx, M[i].data, S.data, Sinv.data, W[i].data, W[i].nrow, R, W_init[i].data,
                                 ratio_step, grad_W[i].data, dW[i].data));
+      stamp("main gram >");
       gc.refresh(W, i, dw);
+      stamp("main gram <");
     }
     // Normalize after dW was taken -- W_init is never rescaled (:825) -- and the 2N squared norms of the switching test
     if (dw.np == 1) {
@@ -670,11 +722,13 @@ struct PPPhase {
         PPXCK(dw, ppx_sqnorms(dw.ctx, xs + b, ns + b, std::min(16, 2 * N - b), dw.scal_dev + b));
       dw.allreduce(dw.scal_dev + 2 * dw.shard_mode, 2);
     }
+    stamp("sweep end (normalised, norms taken)");
     PPXCK(dw, ppx_memcpy_d2h(dw.ctx, dw.scal_host, dw.scal_dev, sizeof(double) * 2 * N));
   }
   void sweep() {
     if (graph) PPXCK(dw, ppx_graph_launch(dw.ctx, graph));
     else enqueue_sweep();
+    trace_print();
   }
 };
 
