@@ -550,14 +550,44 @@ __global__ void __launch_bounds__(32 * AP_ROWS) solve_apply_kernel(const double 
   const int lane = threadIdx.x, row = threadIdx.y;
   const int tid = row * 32 + lane, nt = 32 * AP_ROWS;
   const int64_t i = (int64_t)blockIdx.x * AP_ROWS + row;
-  // (compact loops: the kernel runs once per launch on cold instruction caches, code size is latency)
-#pragma unroll 1
-  for (int idx = tid; idx < R * R; idx += nt) {
-    Ss[idx] = grad_out ? S[idx] : 0.0;
-    Si[idx] = Sinv[idx];
+  // (compact compute loops: the kernel runs once per launch on cold instruction caches, code size is latency.  The
+  // loads are the opposite: issued one dependent round trip at a time they were 8 of the kernel's 13 us, so every
+  // thread now has its row elements and eight elements of each matrix in flight before the first one is stored.)
+  double mv[2], wv[2];
+#pragma unroll
+  for (int u = 0; u < 2; u++) {
+    const int r = lane + 32 * u;
+    mv[u] = (i < s && r < R) ? M[i + s * r] : 0.0;
+    wv[u] = (i < s && r < R) ? W[i + s * r] : 0.0;
   }
 #pragma unroll 1
-  for (int r = lane; r < R; r += 32) {
+  for (int idx0 = tid; idx0 < R * R; idx0 += 8 * nt) {
+    double a[8], b[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      const int idx = idx0 + u * nt;
+      a[u] = (grad_out && idx < R * R) ? S[idx] : 0.0;
+      b[u] = idx < R * R ? Sinv[idx] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      const int idx = idx0 + u * nt;
+      if (idx < R * R) {
+        Ss[idx] = a[u];
+        Si[idx] = b[u];
+      }
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < 2; u++) {
+    const int r = lane + 32 * u;
+    if (r < R) {
+      Mt[row * R + r] = mv[u];
+      Wt[row * R + r] = wv[u];
+    }
+  }
+#pragma unroll 1
+  for (int r = lane + 64; r < R; r += 32) {  // R > 64
     Mt[row * R + r] = (i < s) ? M[i + s * r] : 0.0;
     Wt[row * R + r] = (i < s) ? W[i + s * r] : 0.0;
   }
@@ -659,13 +689,22 @@ __global__ void __launch_bounds__(1024) normalize_norms_kernel(NormNormsArgs a, 
   const double *d = a.dw[m];
   const int64_t n = a.n[m];
   double sw = 0.0, sd = 0.0;
-  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
-    const double v = f * x[i];
-    x[i] = v;
-    sw += v * v;
-    if (d) {
-      const double e = d[i];
-      sd += e * e;
+  // eight elements of W and dW per thread in flight at a time (one block per mode: the loop is latency, not bandwidth)
+  for (int64_t i0 = threadIdx.x; i0 < n; i0 += 8 * (int64_t)blockDim.x) {
+    double xv[8], dv[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      const int64_t i = i0 + u * (int64_t)blockDim.x;
+      xv[u] = i < n ? x[i] : 0.0;
+      dv[u] = (d && i < n) ? d[i] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      const int64_t i = i0 + u * (int64_t)blockDim.x;
+      const double v = f * xv[u];
+      if (i < n) x[i] = v;
+      sw += v * v;
+      sd += dv[u] * dv[u];
     }
   }
   double *g = a.g[m];

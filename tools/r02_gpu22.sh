@@ -7,5 +7,5 @@ for l in sys.stdin:
         d=json.loads(l); print('$*', 'approx_sweep_ms', d['pp']['approx_sweep_ms'], 'value', d['value'], 'inv', d['pp']['solve']['inverse_us'])"; }
 run A=1
 run PPX_INV_NO_ISOLATE=1
-run PPX_PP_NO_SPLIT=1
-run PPX_PP_NO_SPLIT=1 PPX_INV_NO_ISOLATE=1
+run PPX_PP_SPLIT=1
+run PPX_PP_SPLIT=1 PPX_INV_NO_ISOLATE=1
