@@ -684,7 +684,9 @@ def main():
         ar_ms = max_over_ranks(timed(ar, 50))
         buf.free()
         comm = {"allreduce_sxR_us": 1e3 * ar_ms, "bytes": 8 * max(lens[1:]) * R, "per_sweep": "%d of s x R + 1 of R x R" % (N - 1),
-                "timing": "50 back-to-back NCCL all-reduces on the engine's stream, CUDA events, max over ranks"}
+                "path": ("one kernel over NVLink peer memory (stage, flag every peer, sum the staged copies in rank order)"
+                         if lib.ppx_comm_p2p(world.ctx_handle()) else "NCCL"),
+                "timing": "50 back-to-back ppx_allreduce_packed calls on the engine's stream, CUDA events, max over ranks"}
 
     # ---- PP phase (pp_bench protocol): operator build + approximate sweeps; the -pp 1 mixed run -------------------
     pp = None

@@ -251,6 +251,12 @@ int ppx_comm_init(ppx_ctx *ctx, const void *id128, int nranks, int rank);
  * over TCP on addr:port (it listens, they connect, retrying for up to timeout_s seconds), then every rank calls
  * ppx_comm_init.  One node or several; nothing else ever goes over that socket. */
 int ppx_comm_bootstrap(ppx_ctx *ctx, int nranks, int rank, const char *addr, int port, int timeout_s);
+/* 1 when small all-reduces (ppx_allreduce_packed, up to 96 Ki doubles per call and 8 buffers) run as ONE kernel over
+ * NVLink peer memory instead of NCCL: every rank stages its values in a buffer all peers have mapped (cudaIpc), raises
+ * an epoch flag in every peer's memory, waits for the peers' flags and adds the P staged copies in rank order (bit-
+ * identical on every rank).  Set up collectively inside ppx_comm_init; 0 when any rank could not map a peer (other
+ * node, no peer access, IPC not permitted) or PPX_NO_P2P is set -- then every call is NCCL. */
+int ppx_comm_p2p(ppx_ctx *ctx);
 int ppx_comm_size(ppx_ctx *ctx);
 int ppx_comm_rank(ppx_ctx *ctx);
 /* in-place sum over ranks of n buffers as ONE NCCL group (bufs/sizes: HOST arrays; no-op when nranks == 1). */

@@ -109,6 +109,7 @@ SIGNATURES = {
     "ppx_comm_bootstrap": (C.c_int, [_vp, C.c_int, C.c_int, C.c_char_p, C.c_int, C.c_int]),
     "ppx_comm_size": (C.c_int, [_vp]),
     "ppx_comm_rank": (C.c_int, [_vp]),
+    "ppx_comm_p2p": (C.c_int, [_vp]),
     "ppx_allreduce_packed": (C.c_int, [_vp, C.POINTER(_dp), C.POINTER(_i64), C.c_int]),
     "ppx_alltoallv": (C.c_int, [_vp, C.POINTER(_dp), C.POINTER(_i64), C.POINTER(_dp), C.POINTER(_i64)]),
 }

@@ -20,7 +20,7 @@ namespace {
 typedef struct { char internal[128]; } ncclUniqueId_t;
 typedef void *ncclComm_p;
 typedef int ncclResult_e;  // 0 == ncclSuccess
-enum { NCCL_FLOAT64 = 8, NCCL_SUM = 0 };
+enum { NCCL_UINT64 = 5, NCCL_FLOAT64 = 8, NCCL_SUM = 0 };
 
 struct NcclApi {
   void *lib = nullptr;
@@ -61,9 +61,243 @@ bool load_nccl() {
   return true;
 }
 
+// ---- one-shot all-reduce over NVLink peer memory ---------------------------------------------------------------------
+// What crosses GPUs in a sweep is small (an s x R partial MTTKRP: 120 KB at BASELINE configs[1]; an R x R Gram; a few
+// scalars) and sits on the critical path of every mode update, so its cost is latency: NCCL needs 29 us for 120 KB on
+// 8 GPUs.  Every rank owns a staging buffer that all peers have mapped (cudaIpc); the kernel
+//   1. copies its slice of the input to its own staging buffer, fences, and writes the call's epoch into a flag word in
+//      EVERY peer's memory (one remote store per peer and CTA);
+//   2. spins on its own flag words until every peer's epoch has arrived (the peers' data are then visible);
+//   3. reads the slice from every peer's staging buffer through NVLink, adds the P values in rank order -- every rank
+//      forms bit-identical sums, replicated quantities stay replicated -- and writes the result in place.
+// CTA c talks only to CTA c of the peers (flags per CTA), so there is no grid-wide barrier; staging and flags are double
+// buffered by the parity of the epoch, which needs no closing barrier: a rank can only start call e+2 (same parity as e)
+// after completing e+1, and that took every peer's flag e+1, which a peer writes after it has finished reading in
+// call e.  The epoch lives in device memory and is advanced by the kernel itself, so the kernel can sit in a captured
+// CUDA graph.  Several buffers go through one launch (ppx_allreduce_packed).  A spin that sees no flag for 20 s gives
+// up, reports through a device-side error word and lets the stream drain instead of hanging the GPU.
+constexpr int P2P_MAXR = 8;       // ranks (one NVSwitch domain)
+constexpr int P2P_MAXB = 8;       // buffers per launch
+constexpr int P2P_MAXCTA = 16;    // CTAs per launch
+constexpr int P2P_THREADS = 512;
+constexpr size_t P2P_CAP = 96 * 1024;  // doubles per call and parity (768 KB)
+
+struct P2PState {
+  int nranks = 0, rank = 0;
+  char *base[P2P_MAXR] = {};  // mapped regions, [rank] is the local allocation
+  bool opened[P2P_MAXR] = {};
+};
+// region layout (bytes)
+constexpr size_t P2P_OFF_FLAGS = 0;                                               // [2][MAXCTA][MAXR] u64
+constexpr size_t P2P_OFF_EPOCH = P2P_OFF_FLAGS + 2 * P2P_MAXCTA * P2P_MAXR * 8;   // [MAXCTA] u64
+constexpr size_t P2P_OFF_ERR = P2P_OFF_EPOCH + P2P_MAXCTA * 8;                    // u64
+constexpr size_t P2P_OFF_STAGE = 4096;                                            // [2][CAP] double
+constexpr size_t P2P_BYTES = P2P_OFF_STAGE + 2 * P2P_CAP * 8;
+static_assert(P2P_OFF_ERR + 8 <= P2P_OFF_STAGE, "header fits");
+
+struct P2PArgs {
+  char *base[P2P_MAXR];
+  double *buf[P2P_MAXB];
+  long long off[P2P_MAXB + 1];  // packed offsets of the buffers, off[nbuf] = total
+  int nranks, rank, nbuf;
+};
+
+__device__ __forceinline__ unsigned long long p2p_ld_acquire(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void p2p_st_release(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ double p2p_ld_data(const double *p) {
+  double v;
+  asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(P2P_THREADS) allreduce_oneshot_kernel(P2PArgs a) {
+  const int c = blockIdx.x, tid = threadIdx.x;
+  char *mine = a.base[a.rank];
+  unsigned long long *epoch = reinterpret_cast<unsigned long long *>(mine + P2P_OFF_EPOCH) + c;
+  const unsigned long long e = *epoch + 1;  // only this CTA writes this word (at the end)
+  const int par = (int)(e & 1);
+  const long long total = a.off[a.nbuf];
+  long long chunk = (total + gridDim.x - 1) / gridDim.x;
+  const long long lo = c * chunk, hi = lo + chunk < total ? lo + chunk : total;
+  double *stage = reinterpret_cast<double *>(mine + P2P_OFF_STAGE) + (size_t)par * P2P_CAP;
+  // 1. own slice -> own staging (four elements per thread and round, loads first)
+  constexpr int U = 4;
+  for (long long i0 = lo + tid; i0 < hi; i0 += U * P2P_THREADS) {
+    double v[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const long long i = i0 + u * P2P_THREADS;
+      if (i < hi) {
+        int b = 0;
+        while (i >= a.off[b + 1]) b++;
+        v[u] = a.buf[b][i - a.off[b]];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const long long i = i0 + u * P2P_THREADS;
+      if (i < hi) stage[i] = v[u];
+    }
+  }
+  // the barrier orders every thread's staging stores before the release stores below (release is cumulative)
+  __syncthreads();
+  const size_t fslot = ((size_t)par * P2P_MAXCTA + c) * P2P_MAXR;
+  if (tid < a.nranks && tid != a.rank) {
+    p2p_st_release(reinterpret_cast<unsigned long long *>(a.base[tid] + P2P_OFF_FLAGS) + fslot + a.rank, e);
+    // 2. wait for that peer's epoch
+    const unsigned long long *f = reinterpret_cast<const unsigned long long *>(mine + P2P_OFF_FLAGS) + fslot + tid;
+    unsigned long long t0 = 0;
+    int spins = 0;
+    while (p2p_ld_acquire(f) < e) {
+      if (++spins < 4096) continue;  // (the clock is read only once the wait is long)
+      unsigned long long t1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (t0 == 0) t0 = t1;
+      if (t1 - t0 > 20000000000ull) {  // a peer never arrived: do not hang the GPU
+        *reinterpret_cast<unsigned long long *>(mine + P2P_OFF_ERR) = e;
+        printf("ppx: one-shot all-reduce: rank %d saw no flag from rank %d for 20 s (call %llu, CTA %d); results are wrong\n",
+               a.rank, tid, e, c);
+        break;
+      }
+    }
+  }
+  __syncthreads();
+  // 3. sum in rank order; all P x U loads of a round are in flight before the first addition
+  for (long long i0 = lo + tid; i0 < hi; i0 += U * P2P_THREADS) {
+    double v[P2P_MAXR][U];
+#pragma unroll
+    for (int r = 0; r < P2P_MAXR; r++) {
+      if (r < a.nranks) {
+        const double *src = reinterpret_cast<const double *>(a.base[r] + P2P_OFF_STAGE) + (size_t)par * P2P_CAP;
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          const long long i = i0 + u * P2P_THREADS;
+          v[r][u] = i < hi ? (r == a.rank ? stage[i] : p2p_ld_data(src + i)) : 0.0;
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const long long i = i0 + u * P2P_THREADS;
+      if (i < hi) {
+        double sum = v[0][u];
+#pragma unroll
+        for (int r = 1; r < P2P_MAXR; r++)
+          if (r < a.nranks) sum += v[r][u];
+        int b = 0;
+        while (i >= a.off[b + 1]) b++;
+        a.buf[b][i - a.off[b]] = sum;
+      }
+    }
+  }
+  __syncthreads();
+  if (tid == 0) *epoch = e;
+}
+
+void p2p_teardown(ppx_ctx *ctx, bool live = false) {
+  P2PState *st = (P2PState *)ctx->p2p;
+  if (!st) return;
+  if (live && ctx->comm) {
+    // a peer may still be reading this rank's staging buffer in its last call: nobody unmaps before everybody is done
+    unsigned long long *w = reinterpret_cast<unsigned long long *>(st->base[st->rank] + P2P_OFF_ERR) + 1;
+    cudaStreamSynchronize(ctx->main_stream);
+    if (g_nccl.AllReduce(w, w, 1, NCCL_UINT64, NCCL_SUM, (ncclComm_p)ctx->comm, ctx->main_stream) == 0)
+      cudaStreamSynchronize(ctx->main_stream);
+    cudaGetLastError();
+  }
+  for (int r = 0; r < st->nranks; r++) {
+    if (r == st->rank) {
+      if (st->base[r]) cudaFree(st->base[r]);
+    } else if (st->opened[r]) {
+      cudaIpcCloseMemHandle(st->base[r]);
+    }
+  }
+  delete st;
+  ctx->p2p = nullptr;
+}
+
+// Collective over the communicator: map every peer's staging region.  Any failure on any rank (peers on another node,
+// no peer access, IPC not permitted in this container, PPX_NO_P2P set) leaves every rank on NCCL.
+void p2p_setup(ppx_ctx *ctx) {
+  const int P = ctx->nranks;
+  if (P < 2 || P > P2P_MAXR) return;
+  P2PState *st = new P2PState();
+  st->nranks = P;
+  st->rank = ctx->rank;
+  unsigned long long fail = getenv("PPX_NO_P2P") != nullptr;
+  cudaIpcMemHandle_t mine;
+  memset(&mine, 0, sizeof(mine));
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "64-byte IPC handles");
+  if (!fail) {
+    if (cudaMalloc((void **)&st->base[ctx->rank], P2P_BYTES) != cudaSuccess ||
+        cudaMemset(st->base[ctx->rank], 0, P2P_BYTES) != cudaSuccess ||
+        cudaIpcGetMemHandle(&mine, st->base[ctx->rank]) != cudaSuccess) {
+      cudaGetLastError();
+      fail = 1;
+    }
+  }
+  // all-gather of the handles (+ a failure count) as an NCCL sum of zero-padded u64 words
+  const int words = P * 8 + 1;
+  unsigned long long *dev = nullptr, host[P2P_MAXR * 8 + 1];
+  memset(host, 0, sizeof(host));
+  memcpy(host + 8 * ctx->rank, &mine, 64);
+  host[P * 8] = fail;
+  bool ok = cudaMalloc((void **)&dev, sizeof(unsigned long long) * words) == cudaSuccess &&
+            cudaMemcpyAsync(dev, host, sizeof(unsigned long long) * words, cudaMemcpyHostToDevice, ctx->stream) == cudaSuccess &&
+            g_nccl.AllReduce(dev, dev, (size_t)words, NCCL_UINT64, NCCL_SUM, (ncclComm_p)ctx->comm, ctx->stream) == 0 &&
+            cudaMemcpyAsync(host, dev, sizeof(unsigned long long) * words, cudaMemcpyDeviceToHost, ctx->stream) == cudaSuccess &&
+            cudaStreamSynchronize(ctx->stream) == cudaSuccess;
+  if (!ok) {  // cannot even agree: NCCL only (the other ranks fail the same collective or see our absence as an error)
+    cudaGetLastError();
+    if (dev) cudaFree(dev);
+    ctx->p2p = st;
+    p2p_teardown(ctx);
+    return;
+  }
+  unsigned long long bad = host[P * 8];
+  if (!bad) {
+    for (int r = 0; r < P; r++) {
+      if (r == ctx->rank) continue;
+      cudaIpcMemHandle_t h;
+      memcpy(&h, host + 8 * r, 64);
+      void *ptr = nullptr;
+      if (cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        cudaGetLastError();
+        bad = 1;
+        break;
+      }
+      st->base[r] = (char *)ptr;
+      st->opened[r] = true;
+    }
+  }
+  // second agreement: did every rank map every peer?
+  host[0] = bad;
+  ok = cudaMemcpyAsync(dev, host, sizeof(unsigned long long), cudaMemcpyHostToDevice, ctx->stream) == cudaSuccess &&
+       g_nccl.AllReduce(dev, dev, 1, NCCL_UINT64, NCCL_SUM, (ncclComm_p)ctx->comm, ctx->stream) == 0 &&
+       cudaMemcpyAsync(host, dev, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream) == cudaSuccess &&
+       cudaStreamSynchronize(ctx->stream) == cudaSuccess;
+  cudaFree(dev);
+  ctx->p2p = st;
+  if (!ok || host[0] != 0) {
+    cudaGetLastError();
+    p2p_teardown(ctx);
+    if (getenv("PPX_COMM_VERBOSE") && ctx->rank == 0) fprintf(stderr, "ppx: peer-memory all-reduce unavailable, using NCCL\n");
+    return;
+  }
+  if (getenv("PPX_COMM_VERBOSE") && ctx->rank == 0)
+    fprintf(stderr, "ppx: one-shot all-reduce over peer memory enabled (%d ranks, up to %zu doubles per call)\n", P, P2P_CAP);
+}
+
 }  // namespace
 
 void ppx_comm_destroy_internal(ppx_ctx *ctx) {
+  p2p_teardown(ctx, true);
   if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_p)ctx->comm);
   ctx->comm = nullptr;
 }
@@ -95,6 +329,7 @@ int ppx_comm_init(ppx_ctx *ctx, const void *id128, int nranks, int rank) {
   if (r)
     return ppx_set_err(ctx, PPX_ENCCL, "ncclCommInitRank failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
   ctx->comm = comm;
+  p2p_setup(ctx);
   return PPX_OK;
 }
 
@@ -178,6 +413,7 @@ int ppx_comm_bootstrap(ppx_ctx *ctx, int nranks, int rank, const char *addr, int
   return ppx_comm_init(ctx, id, nranks, rank);
 }
 
+int ppx_comm_p2p(ppx_ctx *ctx) { return ctx->p2p != nullptr; }
 int ppx_comm_size(ppx_ctx *ctx) { return ctx->nranks; }
 int ppx_comm_rank(ppx_ctx *ctx) { return ctx->rank; }
 
@@ -189,6 +425,31 @@ int ppx_allreduce_packed(ppx_ctx *ctx, double *const *bufs, const int64_t *sizes
   if (skip) return PPX_OK;
   PPX_REQUIRE(ctx, ctx->comm != nullptr, "communicator initialised (ppx_comm_init)");
   PPX_REQUIRE(ctx, bufs && sizes && n > 0, "bufs, sizes non-null");
+  if (ctx->p2p && n <= P2P_MAXB) {
+    P2PState *st = (P2PState *)ctx->p2p;
+    P2PArgs a;
+    a.nranks = st->nranks;
+    a.rank = st->rank;
+    a.nbuf = 0;
+    a.off[0] = 0;
+    for (int i = 0; i < n; i++)
+      if (sizes[i] > 0) {
+        a.buf[a.nbuf] = bufs[i];
+        a.off[a.nbuf + 1] = a.off[a.nbuf] + sizes[i];
+        a.nbuf++;
+      }
+    const long long total = a.off[a.nbuf];
+    if (total == 0) return PPX_OK;
+    if ((size_t)total <= P2P_CAP) {
+      for (int r = 0; r < P2P_MAXR; r++) a.base[r] = r < st->nranks ? st->base[r] : nullptr;
+      int nblk = (int)((total + 1023) / 1024);
+      nblk = nblk < 1 ? 1 : nblk > P2P_MAXCTA ? P2P_MAXCTA : nblk;
+      // the number of CTAs is a function of the sizes alone: every rank launches the same grid
+      allreduce_oneshot_kernel<<<nblk, P2P_THREADS, 0, ctx->stream>>>(a);
+      PPX_CHECK_LAUNCH(ctx);
+      return PPX_OK;
+    }
+  }
   ncclResult_e r = g_nccl.GroupStart();
   for (int i = 0; i < n && !r; i++)
     if (sizes[i] > 0)

@@ -717,18 +717,14 @@ __global__ void __launch_bounds__(1024) normalize_norms_kernel(NormNormsArgs a, 
   }
 }
 
-size_t g_sweep_fill[8];  // dynamic shared memory that fills an SM, per instantiation of the sweep kernel (ppx_k45_init)
-
 int inverse_launch(ppx_ctx *ctx, const HadArgs &h, int R, double lambda, int mode, double *S_out, double *Sinv,
                    double *Linv = nullptr) {
   static const bool inv_column = getenv("PPX_INV_COLUMN") != nullptr;  // A/B: the column kernel for every R
   if (mode == PPX_SOLVE_CHOL && R <= 64 && !Linv && !inv_column) {
-    // the kernel is one latency-bound CTA: asking for all the shared memory of an SM keeps CTAs of kernels running on
-    // other lanes (the HBM-bound PP correction) off its SM, where they would take its issue slots
-    static const bool isolate = getenv("PPX_INV_NO_ISOLATE") == nullptr;
-#define PPX_SWEEP_LAUNCH(NR)                                                                                        \
-  spd_inverse_sweep_kernel<NR><<<1, SWEEP_H *((NR + 31) / 32) * 32, isolate ? g_sweep_fill[NR / 8 - 1] : 0, ctx->stream>>>( \
-      h, R, lambda, S_out, Sinv)
+    // (asking for all the shared memory of an SM, so that CTAs of kernels on other lanes stay off this one's SM, was
+    // tried: no measurable effect on the PP sweep)
+#define PPX_SWEEP_LAUNCH(NR) \
+  spd_inverse_sweep_kernel<NR><<<1, SWEEP_H *((NR + 31) / 32) * 32, 0, ctx->stream>>>(h, R, lambda, S_out, Sinv)
     switch ((R + 7) / 8) {
       case 1: PPX_SWEEP_LAUNCH(8); break;
       case 2: PPX_SWEEP_LAUNCH(16); break;
@@ -844,17 +840,6 @@ int ppx_k45_init(ppx_ctx *ctx) {
   PPX_CUDA(ctx, cudaFuncSetAttribute(spd_inverse_ldl_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   PPX_CUDA(ctx, cudaFuncSetAttribute(spd_inverse_ldl_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   PPX_CUDA(ctx, cudaFuncSetAttribute(sym_inverse_jacobi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-#define PPX_SWEEP_INIT(NR)                                                                                          \
-  {                                                                                                                 \
-    cudaFuncAttributes fa;                                                                                          \
-    PPX_CUDA(ctx, cudaFuncGetAttributes(&fa, spd_inverse_sweep_kernel<NR>));                                        \
-    g_sweep_fill[NR / 8 - 1] = 227 * 1024 - fa.sharedSizeBytes;                                                     \
-    PPX_CUDA(ctx, cudaFuncSetAttribute(spd_inverse_sweep_kernel<NR>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
-                                       (int)g_sweep_fill[NR / 8 - 1]));                                             \
-  }
-  PPX_SWEEP_INIT(8) PPX_SWEEP_INIT(16) PPX_SWEEP_INIT(24) PPX_SWEEP_INIT(32) PPX_SWEEP_INIT(40) PPX_SWEEP_INIT(48)
-  PPX_SWEEP_INIT(56) PPX_SWEEP_INIT(64)
-#undef PPX_SWEEP_INIT
   PPX_CUDA(ctx, cudaFuncSetAttribute(solve_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   return PPX_OK;
 }

@@ -26,6 +26,7 @@ struct ppx_ctx {
   // pinned staging for pointer tables handed to kernels
   void *comm = nullptr;  // ncclComm_t
   int nranks = 1, rank = 0;
+  void *p2p = nullptr;   // peer-memory state of the one-shot all-reduce (comm.cu), nullptr: NCCL only
 };
 
 int ppx_set_err(ppx_ctx *ctx, int code, const char *fmt, ...);

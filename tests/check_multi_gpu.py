@@ -29,7 +29,36 @@ if rank == 0:
     idt = torch.tensor(list(ppx.comm_unique_id()), dtype=torch.uint8, device="cuda")
 dist.broadcast(idt, 0)
 
+
+
+def check_allreduce():
+    """ppx_allreduce_packed alone (the one-shot peer-memory kernel when the ranks could map each other, else NCCL):
+    integer-valued doubles, so the sum is exact whatever the order -- bit-exact against the closed form, over sizes
+    from one word to beyond the staging capacity, packed calls, and 60 back-to-back calls (flag epochs, double
+    buffering)."""
+    import ctypes as C
+    lib = ppx.load_library()
+    h = world.ctx_handle()
+    p2p = bool(lib.ppx_comm_p2p(h))
+    good = True
+    sizes = [1, 2, 7, 50 * 50, 300 * 50, 2049, 96 * 1024, 96 * 1024 + 3, 200000]
+    for rep in range(60):
+        group = [sizes[(rep + k) % len(sizes)] for k in range(1 + rep % 3)]
+        host = [np.arange(n, dtype=np.float64) % 11 + (rank + 1) * (rep + 1 + k) for k, n in enumerate(group)]
+        bufs = [H.Tensor.from_numpy(world, x.reshape(-1, 1), matrix=True) for x in host]
+        bp = (C.c_void_p * len(bufs))(*[b.data_ptr() for b in bufs])
+        bn = (C.c_int64 * len(bufs))(*group)
+        assert lib.ppx_allreduce_packed(h, bp, bn, len(bufs)) == 0
+        for k, (b_, n) in enumerate(zip(bufs, group)):
+            want = nranks * (np.arange(n, dtype=np.float64) % 11) + (rep + 1 + k) * nranks * (nranks + 1) / 2
+            good &= bool(np.array_equal(b_.numpy().reshape(-1), want))
+            b_.free()
+    print(f"rank {rank} all-reduce ({'peer memory' if p2p else 'NCCL'}): {'OK' if good else 'MISMATCH'}", flush=True)
+    return good
+
+
 ok_all = True
+allreduce_checked = False
 for lens, R, maxiter, tol_init in [((13, 12, 11, 10), 4, 40, 0.1), ((9, 10, 11), 3, 30, 0.1), ((6, 7, 6, 5, 6, 7), 3, 40, 0.1),
                                    ((37, 9, 8, 7), 3, 24, 0.1)]:
     N = len(lens)
@@ -40,6 +69,9 @@ for lens, R, maxiter, tol_init in [((13, 12, 11, 10), 4, 40, 0.1), ((9, 10, 11),
         world.comm_init(bytes(idt.cpu().tolist()), nranks, rank, 0, lens[0], b, e)  # NCCL communicator, once
     else:
         world.set_shard(0, lens[0], b, e)  # only the shard layout changes between problems
+    if not allreduce_checked:
+        allreduce_checked = True
+        ok_all &= check_allreduce()
     V, _ = o.make_tensor_r(lens, R)
     W, G = o.init_factors(lens, R), o.init_grad(lens, R)
     vnorm = np.linalg.norm(V)
