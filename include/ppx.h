@@ -108,6 +108,16 @@ int ppx_ttm_multi(ppx_ctx *ctx, const double *V, const int64_t *lens, int N, int
  * replaces common.cxx:83,128; als_CP.cxx:258-259,407-408; cp_dt_optimizer.cxx:184-185. */
 int ppx_mttv(ppx_ctx *ctx, const double *T, const int64_t *lens, int k, int x, const double *Wx, int64_t ldw, int R,
              double *out);
+/* The three Hadamard contractions of ONE order-3 (+ rank) tensor in one pass over it -- what Build_mttkrp_map does to a
+ * level-1 tensor with several consumers (als_CP.cxx:394-408: "ijkr,ir->jkr", "ijkr,jr->ikr", "ijkr,kr->ijr" read the
+ * same intermediate once each):
+ *   T[l, x, t, r], lens3 = {s_l, s_x, s_t};  out_l[x,t,r] = sum_l T Wl[l,r];  out_x[l,t,r] = sum_x T Wx[x,r];
+ *   out_t[l,x,r] = sum_t T Wt[t,r].  A NULL output is skipped (its factor may be NULL too).
+ * Streams T through shared memory with bulk copies; out_x is summed over x-tiles in a fixed order (workspace scratch).
+ * Shapes the one-pass kernel does not take (odd s_l, a single requested output, small tensors, no scratch) run as one
+ * ppx_mttv per output. */
+int ppx_mttv3(ppx_ctx *ctx, const double *T, const int64_t *lens3, int R, const double *Wl, int64_t ldl,
+              const double *Wx, int64_t ldx, const double *Wt, int64_t ldt, double *out_l, double *out_x, double *out_t);
 /* two factors at once (leaf under a 3-mode node): out[rest'', r] = sum_{x1,x2} T * W1[x1,r] * W2[x2,r], x1 < x2.
  * replaces als_CP.cxx:281-283. */
 int ppx_mttv2(ppx_ctx *ctx, const double *T, const int64_t *lens, int k, int x1, const double *W1, int64_t ldw1,

@@ -62,6 +62,7 @@ SIGNATURES = {
     "ppx_ttm_multi": (C.c_int, [_vp, _dp, C.POINTER(_i64), C.c_int, C.c_int, C.c_int, C.POINTER(_dp), C.POINTER(_i64),
                                 C.c_int, _dp]),
     "ppx_mttv": (C.c_int, [_vp, _dp, C.POINTER(_i64), C.c_int, C.c_int, _dp, _i64, C.c_int, _dp]),
+    "ppx_mttv3": (C.c_int, [_vp, _vp, C.POINTER(_i64), C.c_int, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _vp]),
     "ppx_mttv2": (C.c_int, [_vp, _dp, C.POINTER(_i64), C.c_int, C.c_int, _dp, _i64, C.c_int, _dp, _i64, C.c_int, _dp]),
     "ppx_ttm_first_mttv": (C.c_int, [_vp, _dp, C.POINTER(_i64), C.c_int, C.c_int, _dp, _i64, C.c_int, _dp, _i64,
                                      C.c_int, _dp]),
@@ -247,6 +248,13 @@ class Ctx:
     def mttv(self, T, lens, x, W, R, out, ldw=None):
         self._ck(self.lib.ppx_mttv(self.h, _ptr(T), _lens(lens), len(lens), x, _ptr(W),
                                    ldw if ldw is not None else lens[x], R, _ptr(out)))
+
+    def mttv3(self, T, lens3, Wl, Wx, Wt, R, out_l, out_x, out_t):
+        """All (non-None) Hadamard contractions of one order-3 (+rank) tensor in one pass (ppx_mttv3)."""
+        def p(x):
+            return _ptr(x) if x is not None else None
+        self._ck(self.lib.ppx_mttv3(self.h, _ptr(T), _lens(lens3), R, p(Wl), lens3[0], p(Wx), lens3[1], p(Wt), lens3[2],
+                                    p(out_l), p(out_x), p(out_t)))
 
     def mttv2(self, T, lens, x1, W1, x2, W2, R, out):
         self._ck(self.lib.ppx_mttv2(self.h, _ptr(T), _lens(lens), len(lens), x1, _ptr(W1), lens[x1], x2, _ptr(W2),

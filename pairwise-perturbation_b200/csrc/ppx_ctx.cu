@@ -65,6 +65,7 @@ int ppx_ctx_create(int device, void *stream, size_t workspace_bytes, ppx_ctx **o
     if (!rc) rc = ppx_k1_tma_init(ctx);
     if (!rc) rc = ppx_k45_init(ctx);
     if (!rc) rc = ppx_k7_init(ctx);
+    if (!rc) rc = ppx_k2x3_init(ctx);
     if (!rc) rc = ppx_gram_init(ctx);
     if (rc) {
       fprintf(stderr, "ppx: kernel init failed: %s\n", ctx->err.c_str());

@@ -51,6 +51,7 @@ int ppx_gram_dmma(ppx_ctx *ctx, const double *T, int64_t L, int64_t X, int64_t R
 int ppx_gram_init(ppx_ctx *ctx);
 int ppx_k45_init(ppx_ctx *ctx);
 int ppx_k7_init(ppx_ctx *ctx);
+int ppx_k2x3_init(ppx_ctx *ctx);
 void ppx_comm_destroy_internal(ppx_ctx *ctx);
 int ppx_sum_partials(ppx_ctx *ctx, const double *partial, int n, double *out);
 

@@ -108,6 +108,28 @@ def test_mttv(ctx, lens, x, R):
     assert rel_err(ctx.to_host(out, ref.shape), ref) < 1e-12
 
 
+@pytest.mark.parametrize("lens,R,which", [
+    ((64, 70, 60), 16, (1, 1, 1)),   # one-pass kernel, even x-tiles
+    ((38, 101, 90), 13, (1, 1, 1)),  # rows not a multiple of the warp, a short last x-tile
+    ((300, 31, 29), 17, (1, 1, 0)),  # the level-1 tensor with two consumers (PP build, mode c)
+    ((120, 64, 50), 11, (0, 1, 1)), ((120, 64, 50), 11, (1, 0, 1)),
+    ((2, 600, 500), 7, (1, 1, 1)),   # one x-tile holds everything: no partial sums
+    ((37, 80, 75), 20, (1, 1, 1)),   # odd row extent: the separate kernels
+    ((9, 8, 7), 4, (1, 1, 1)), ((9, 8, 7), 4, (0, 1, 0))])
+def test_mttv3_all_hadamard_contractions_in_one_pass(ctx, lens, R, which):
+    """ppx_mttv3 = the Hadamard contractions of one level-1 tensor along each of its three modes (als_CP.cxx:394-408),
+    every requested output against the einsum of the oracle."""
+    T = rnd(tuple(lens) + (R,), 21)
+    Ws = [rnd((lens[i], R), 22 + i) for i in range(3)]
+    refs = [o.contract("abc".replace("abc"[i], "") + "*", T, "abc*", Ws[i], "abc"[i] + "*") for i in range(3)]
+    outs = [ctx.empty(refs[i].size) if which[i] else None for i in range(3)]
+    dW = [ctx.to_device(w) if which[i] else None for i, w in enumerate(Ws)]
+    ctx.mttv3(ctx.to_device(T), lens, dW[0], dW[1], dW[2], R, outs[0], outs[1], outs[2])
+    for i in range(3):
+        if which[i]:
+            assert rel_err(ctx.to_host(outs[i], refs[i].shape), refs[i]) < 1e-12, "output %d" % i
+
+
 @pytest.mark.parametrize("lens,x1,x2,R", [((9, 8, 7), 0, 1, 4), ((9, 8, 7), 1, 2, 4), ((9, 8, 7), 0, 2, 4),
                                           ((40, 40, 40), 0, 1, 10)])
 def test_mttv2(ctx, lens, x1, x2, R):
