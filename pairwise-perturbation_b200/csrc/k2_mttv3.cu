@@ -288,7 +288,10 @@ int ppx_mttv3(ppx_ctx *ctx, const double *T, const int64_t *lens3, int R, const 
   if (XT > M3_CK * NG) XT = M3_CK * NG;
   if (XT > sx) XT = (int)sx;
   const size_t smem = sizeof(double) * ((size_t)M3_NST * M3_STAGE_DOUBLES + M3_WX + st);
-  bool fused = !off && sl % 2 == 0 && NG >= 1 && XT >= 2 && smem <= 220 * 1024 && ((uintptr_t)T & 15) == 0 &&
+  // rows of at least 192: below that the column pass wastes most of its ten loads per lane and the tile's x are spread
+  // over row groups -- measured on a 38-row shard (8 GPUs) the one-pass kernel made the operator build 13.8 ms instead
+  // of 11.9 with one kernel per output
+  bool fused = !off && sl % 2 == 0 && sl >= 192 && NG >= 1 && XT >= 2 && smem <= 220 * 1024 && ((uintptr_t)T & 15) == 0 &&
                (out_l != nullptr) + (out_x != nullptr) + (out_t != nullptr) >= 2 && sl * sx * st * R >= (1 << 22) && st >= 2;
   int ntiles = 0, nparts = 0;
   double *part = nullptr;

@@ -109,11 +109,11 @@ def test_mttv(ctx, lens, x, R):
 
 
 @pytest.mark.parametrize("lens,R,which", [
-    ((64, 70, 60), 16, (1, 1, 1)),   # one-pass kernel, even x-tiles
-    ((38, 101, 90), 13, (1, 1, 1)),  # rows not a multiple of the warp, a short last x-tile
+    ((300, 31, 29), 17, (1, 1, 1)),  # one-pass kernel: two x-tiles (23 + 8), rows not a multiple of the warp
     ((300, 31, 29), 17, (1, 1, 0)),  # the level-1 tensor with two consumers (PP build, mode c)
-    ((120, 64, 50), 11, (0, 1, 1)), ((120, 64, 50), 11, (1, 0, 1)),
-    ((2, 600, 500), 7, (1, 1, 1)),   # one x-tile holds everything: no partial sums
+    ((192, 40, 37), 15, (0, 1, 1)), ((192, 40, 37), 15, (1, 0, 1)),
+    ((320, 20, 66), 10, (1, 1, 1)),  # the longest row the kernel takes; one x-tile: no partial sums
+    ((64, 70, 60), 16, (1, 1, 1)), ((38, 101, 90), 13, (1, 1, 1)),  # short rows: the separate kernels
     ((37, 80, 75), 20, (1, 1, 1)),   # odd row extent: the separate kernels
     ((9, 8, 7), 4, (1, 1, 1)), ((9, 8, 7), 4, (0, 1, 0))])
 def test_mttv3_all_hadamard_contractions_in_one_pass(ctx, lens, R, which):
