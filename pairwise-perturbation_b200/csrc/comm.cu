@@ -91,9 +91,10 @@ struct P2PState {
 constexpr size_t P2P_OFF_FLAGS = 0;                                               // [2][MAXCTA][MAXR] u64
 constexpr size_t P2P_OFF_EPOCH = P2P_OFF_FLAGS + 2 * P2P_MAXCTA * P2P_MAXR * 8;   // [MAXCTA] u64
 constexpr size_t P2P_OFF_ERR = P2P_OFF_EPOCH + P2P_MAXCTA * 8;                    // u64
+constexpr size_t P2P_OFF_DONE = P2P_OFF_ERR + 64;                                 // [MAXR] u64: teardown handshake
 constexpr size_t P2P_OFF_STAGE = 4096;                                            // [2][CAP] double
 constexpr size_t P2P_BYTES = P2P_OFF_STAGE + 2 * P2P_CAP * 8;
-static_assert(P2P_OFF_ERR + 8 <= P2P_OFF_STAGE, "header fits");
+static_assert(P2P_OFF_DONE + 8 * P2P_MAXR <= P2P_OFF_STAGE, "header fits");
 
 struct P2PArgs {
   char *base[P2P_MAXR];
@@ -203,12 +204,24 @@ __global__ void __launch_bounds__(P2P_THREADS) allreduce_oneshot_kernel(P2PArgs 
 void p2p_teardown(ppx_ctx *ctx, bool live = false) {
   P2PState *st = (P2PState *)ctx->p2p;
   if (!st) return;
-  if (live && ctx->comm) {
-    // a peer may still be reading this rank's staging buffer in its last call: nobody unmaps before everybody is done
-    unsigned long long *w = reinterpret_cast<unsigned long long *>(st->base[st->rank] + P2P_OFF_ERR) + 1;
+  if (live && st->base[st->rank]) {
+    // A peer may still be reading this rank's staging buffer in its last call: nobody frees before everybody is done.
+    // Host-side handshake through the mapped regions, bounded (3 s): a peer that died or never tears down must not
+    // hang this rank, which an NCCL barrier here would.
     cudaStreamSynchronize(ctx->main_stream);
-    if (g_nccl.AllReduce(w, w, 1, NCCL_UINT64, NCCL_SUM, (ncclComm_p)ctx->comm, ctx->main_stream) == 0)
-      cudaStreamSynchronize(ctx->main_stream);
+    const unsigned long long one = 1;
+    for (int r = 0; r < st->nranks; r++)
+      if (r != st->rank && st->opened[r])
+        cudaMemcpy(st->base[r] + P2P_OFF_DONE + 8 * st->rank, &one, 8, cudaMemcpyDefault);
+    for (int tries = 0; tries < 15000; tries++) {
+      unsigned long long seen[P2P_MAXR] = {};
+      if (cudaMemcpy(seen, st->base[st->rank] + P2P_OFF_DONE, sizeof(seen), cudaMemcpyDefault) != cudaSuccess) break;
+      bool all = true;
+      for (int r = 0; r < st->nranks; r++)
+        if (r != st->rank && st->opened[r] && !seen[r]) all = false;
+      if (all) break;
+      usleep(200);
+    }
     cudaGetLastError();
   }
   for (int r = 0; r < st->nranks; r++) {
