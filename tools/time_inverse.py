@@ -1,5 +1,6 @@
-"""Times the R x R SPD inverse (ppx_spd_inverse_g: Hadamard of three Grams + blocked LDL^T inverse) alone, CUDA events
-around 200 back-to-back launches.   PPX_INV_COLUMN=1: the column-by-column kernel of round 1, for A/B."""
+"""Times the R x R SPD inverse (ppx_spd_inverse_g: Hadamard of three Grams + the register-resident sweep kernel for
+R <= 64, the column LDL^T kernel above) alone, CUDA events around 200 back-to-back launches.
+PPX_INV_COLUMN=1: the column kernel for every R, for A/B."""
 import ctypes as C
 import importlib
 import json
