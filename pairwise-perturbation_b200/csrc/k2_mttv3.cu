@@ -8,7 +8,7 @@
 //
 // The tensor is streamed through shared memory by bulk (TMA) copies: for a fixed (t, r) the rows of an x-tile are ONE
 // contiguous run of s_l * XT doubles, so a stage is a single cp.async.bulk of up to 56 KB issued by one elected thread
-// of a producer warp; three stages are in flight per CTA.  The eight consumer warps read the staged tile three ways:
+// of a producer warp; three stages are in flight per CTA.  Fourteen consumer warps read the staged tile:
 //   out_t, out_x : a thread is a row l (and, for short rows, one of NG groups of the tile's x): ONE shared-memory read
 //           of T[l, x, t] feeds both -- the accumulator of (l, x) over t in a register, and the sum over the thread's x,
 //           which is complete in the thread: a PARTIAL sum over x-tiles (and groups), written to scratch and added in
@@ -26,8 +26,12 @@
 
 namespace {
 
-constexpr int M3_CONSUMERS = 320;              // 10 consumer warps
-constexpr int M3_THREADS = M3_CONSUMERS + 32;  // + the producer warp
+constexpr int M3_CONSUMERS = 320;              // 10 row warps (thread = row l)
+#ifndef PPX_M3_COLW
+#define PPX_M3_COLW 4
+#endif
+constexpr int M3_COLW = PPX_M3_COLW;                     // column warps (warp = column x): the sum over l, beside the row warps
+constexpr int M3_THREADS = M3_CONSUMERS + 32 * M3_COLW + 32;  // + the producer warp (the last one)
 #ifndef PPX_M3_NST
 #define PPX_M3_NST 3
 #endif
@@ -94,7 +98,7 @@ __global__ void __launch_bounds__(M3_THREADS, 1) mttv3_kernel(M3Args a) {
   if (tid == 0) {
     for (int s = 0; s < M3_NST; s++) {
       m3_mbar_init(&full[s], 1);
-      m3_mbar_init(&empty[s], M3_CONSUMERS / 32);  // one arrival per consumer warp
+      m3_mbar_init(&empty[s], M3_CONSUMERS / 32 + M3_COLW);  // one arrival per consumer warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -102,7 +106,7 @@ __global__ void __launch_bounds__(M3_THREADS, 1) mttv3_kernel(M3Args a) {
   const long long plane = a.sl * a.sx;  // one t
   const long long cube = plane * a.st;  // one r
 
-  if (warp == M3_CONSUMERS / 32) {
+  if (warp == M3_CONSUMERS / 32 + M3_COLW) {
     // ---- producer: one elected lane ----
     if (lane == 0) {
       long long g = 0;  // stage counter over the whole kernel
@@ -135,7 +139,69 @@ __global__ void __launch_bounds__(M3_THREADS, 1) mttv3_kernel(M3Args a) {
     return;
   }
 
-  // ---- consumers ----
+  if (warp >= M3_CONSUMERS / 32) {
+    // ---- column warps: out_l[x, t] = sum_l T[l, x, t] Wl[l], warp = column, lanes stride the rows (ten per lane,
+    // s_l <= 320, Wl in registers).  Three columns go together: thirty loads in flight, three FMA chains, one
+    // interleaved shuffle reduction.  They run BESIDE the row warps on the same staged tile (in the first versions
+    // every warp did its rows, then its columns: 2.48 ms for three outputs against 1.80 for the rows alone).
+    const int cw = warp - M3_CONSUMERS / 32;
+    const int sl = (int)a.sl;
+    long long g = 0;
+    for (int nit = 0;; nit++) {
+      {
+        const int s = (int)(g % M3_NST);
+        m3_mbar_wait(&full[s], (uint32_t)((g / M3_NST) & 1));
+      }
+      const int w = item_slot[nit & 1];
+      if (w < 0) break;
+      const int tile = w % a.ntiles, r = w / a.ntiles;
+      const long long x0 = (long long)tile * a.XT;
+      const int xc = (int)(a.sx - x0 < a.XT ? a.sx - x0 : a.XT);
+      double wlr[10];
+#pragma unroll
+      for (int q = 0; q < 10; q++) wlr[q] = (a.out_l && lane + 32 * q < sl) ? a.Wl[lane + 32 * q + a.ldl * r] : 0.0;
+      double *pl = a.out_l ? a.out_l + (size_t)r * (size_t)(a.sx * a.st) + x0 : nullptr;
+      for (long long t = 0; t < a.st; t++, g++) {
+        const int s = (int)(g % M3_NST);
+        if (t > 0) m3_mbar_wait(&full[s], (uint32_t)((g / M3_NST) & 1));
+        const double *S = stage + (size_t)s * M3_STAGE_DOUBLES;
+        if (pl && !(a.dbg & 2)) {
+          for (int xb = 0; xb < xc; xb += 3 * M3_COLW) {
+            double d[3] = {0.0, 0.0, 0.0};
+            double cv[3][10];
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+              const int xx = xb + cw + M3_COLW * j;
+              const double *col = S + sl * (xx < xc ? xx : 0);
+#pragma unroll
+              for (int q = 0; q < 10; q++) {
+                const int i = lane + 32 * q;
+                cv[j][q] = col[i < sl ? i : sl - 1];
+              }
+            }
+#pragma unroll
+            for (int q = 0; q < 10; q++)
+#pragma unroll
+              for (int j = 0; j < 3; j++) d[j] = fma(cv[j][q], wlr[q], d[j]);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+              for (int j = 0; j < 3; j++) d[j] += __shfl_xor_sync(0xffffffffu, d[j], o);
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+              const int xx = xb + cw + M3_COLW * j;
+              if (lane == 0 && xx < xc) pl[xx + a.sx * t] = d[j];
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) m3_mbar_arrive(&empty[s]);
+      }
+    }
+    return;
+  }
+
+  // ---- row warps ----
   long long g = 0;
   for (int nit = 0;; nit++) {
     {  // the first stage of the item carries its id
@@ -155,16 +221,11 @@ __global__ void __launch_bounds__(M3_THREADS, 1) mttv3_kernel(M3Args a) {
     if (a.out_t)
       for (int i = tid; i < a.st; i += M3_CONSUMERS) wt[i] = a.Wt[i + a.ldt * r];
     for (int i = tid; i < M3_WX; i += M3_CONSUMERS) wx[i] = (a.part_x && i < xc) ? a.Wx[x0 + i + a.ldx * r] : 0.0;
-    // Wl in registers: lane <-> rows lane, lane + 32, ... (s_l <= 320), zero beyond the extent
-    double wlr[10];
-#pragma unroll
-    for (int q = 0; q < 10; q++) wlr[q] = (a.out_l && lane + 32 * q < sl) ? a.Wl[lane + 32 * q + a.ldl * r] : 0.0;
     asm volatile("bar.sync 1, %0;" ::"n"(M3_CONSUMERS) : "memory");
     double acc[M3_CK];
 #pragma unroll
     for (int k = 0; k < M3_CK; k++) acc[k] = 0.0;
     double *px = a.part_x ? a.part_x + (((size_t)tile * a.NG + xg) * a.R + r) * (size_t)(a.sl * a.st) : nullptr;
-    double *pl = a.out_l ? a.out_l + (size_t)r * (size_t)(a.sx * a.st) + x0 : nullptr;
     const bool want_t = a.out_t != nullptr;
     for (long long t = 0; t < a.st; t++, g++) {
       const int s = (int)(g % M3_NST);
@@ -207,38 +268,6 @@ __global__ void __launch_bounds__(M3_THREADS, 1) mttv3_kernel(M3Args a) {
           }
         }
         if (px) px[l + a.sl * t] = b0 + b1;
-      }
-      // out_l: warp = column x, lanes stride the rows (ten per lane, s_l <= 320).  The warp's (up to three) columns
-      // go together: thirty loads in flight, three FMA chains, one interleaved shuffle reduction
-      if (pl && !(a.dbg & 2)) {
-        constexpr int NW = M3_CONSUMERS / 32;
-        for (int xb = 0; xb < xc; xb += 3 * NW) {  // one round at configs[1] (22 columns); more for short rows
-          double d[3] = {0.0, 0.0, 0.0};
-          double cv[3][10];
-#pragma unroll
-          for (int j = 0; j < 3; j++) {
-            const int xx = xb + warp + NW * j;
-            const double *col = S + sl * (xx < xc ? xx : 0);
-#pragma unroll
-            for (int q = 0; q < 10; q++) {
-              const int i = lane + 32 * q;
-              cv[j][q] = col[i < sl ? i : sl - 1];
-            }
-          }
-#pragma unroll
-          for (int q = 0; q < 10; q++)
-#pragma unroll
-            for (int j = 0; j < 3; j++) d[j] = fma(cv[j][q], wlr[q], d[j]);
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-            for (int j = 0; j < 3; j++) d[j] += __shfl_xor_sync(0xffffffffu, d[j], o);
-#pragma unroll
-          for (int j = 0; j < 3; j++) {
-            const int xx = xb + warp + NW * j;
-            if (lane == 0 && xx < xc) pl[xx + a.sx * t] = d[j];
-          }
-        }
       }
       __syncwarp();
       if (lane == 0) m3_mbar_arrive(&empty[s]);
