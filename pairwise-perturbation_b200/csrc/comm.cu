@@ -74,7 +74,7 @@ bool load_nccl() {
 // buffered by the parity of the epoch, which needs no closing barrier: a rank can only start call e+2 (same parity as e)
 // after completing e+1, and that took every peer's flag e+1, which a peer writes after it has finished reading in
 // call e.  The epoch lives in device memory and is advanced by the kernel itself, so the kernel can sit in a captured
-// CUDA graph.  Several buffers go through one launch (ppx_allreduce_packed).  A spin that sees no flag for 20 s gives
+// CUDA graph.  Several buffers go through one launch (ppx_allreduce_packed).  A spin that sees no flag for 300 s gives
 // up, reports through a device-side error word and lets the stream drain instead of hanging the GPU.
 constexpr int P2P_MAXR = 8;       // ranks (one NVSwitch domain)
 constexpr int P2P_MAXB = 8;       // buffers per launch
@@ -160,9 +160,9 @@ __global__ void __launch_bounds__(P2P_THREADS) allreduce_oneshot_kernel(P2PArgs 
       unsigned long long t1;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
       if (t0 == 0) t0 = t1;
-      if (t1 - t0 > 20000000000ull) {  // a peer never arrived: do not hang the GPU
+      if (t1 - t0 > 300000000000ull) {  // a peer never arrived: do not hang the GPU
         *reinterpret_cast<unsigned long long *>(mine + P2P_OFF_ERR) = e;
-        printf("ppx: one-shot all-reduce: rank %d saw no flag from rank %d for 20 s (call %llu, CTA %d); results are wrong\n",
+        printf("ppx: one-shot all-reduce: rank %d saw no flag from rank %d for 300 s (call %llu, CTA %d); results are wrong\n",
                a.rank, tid, e, c);
         break;
       }
