@@ -705,7 +705,8 @@ struct PPPhase {
     // PPX_PP_SPLIT=1: the correction of mode i+1 minus its dW_i term on lane 1 under the solve of mode i, only the
     // dW_i term on the critical path.  Measured at cfg2 (stamps, PPX_PP_TRACE): the critical-path term drops from 24
     // to 11 us, but the 38-CTA apply kernel running beside the 500-CTA lane kernel takes 25-33 us instead of 10, and
-    // the sweep is 0.197 ms against 0.173 in one launch per mode -- off by default.
+    // the sweep is 0.197 ms against 0.173 in one launch per mode -- off by default (a timing experiment: the parity
+    // suite runs the default path only).
     static const bool split = getenv("PPX_PP_SPLIT") != nullptr;
     trace_labels.clear();
     stamp("sweep begin");
